@@ -1,0 +1,44 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+@pytest.fixture(scope="session")
+def sdss_mock():
+    d = golden("sdss_cww_mock.npz")
+    return d["phot_obs"], d["phot_err"], d["redshifts"]
+
+
+def same_special(a, b):
+    """inf / nan positions agree."""
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return (np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.isposinf(a), np.isposinf(b))
+            and np.array_equal(np.isneginf(a), np.isneginf(b)))
+
+
+def max_rel(a, b, floor=0.0):
+    """max |a-b| / max(|b|, floor) over entries where b is finite."""
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    ok = np.isfinite(b)
+    if not ok.any():
+        return 0.0
+    den = np.maximum(np.abs(b[ok]), floor) if floor > 0 else np.abs(b[ok])
+    num = np.abs(a[ok] - b[ok])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r = np.where(num == 0, 0.0, num / den)
+    return float(np.max(r))
