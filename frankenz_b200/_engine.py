@@ -1,0 +1,230 @@
+"""Thin host-side driver of one libfzb200 handle (numpy in / numpy out).
+
+Only marshals arguments across the C ABI; all arithmetic of the path runs in the CUDA
+library.  `Engine` is shared by `BruteForce`, `NearestNeighbors` and `pdf.loglike`.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import FzbConfig, FzbFitOut, FzbStats, dptr, f64, iptr
+
+_LPROB_KEYS = ("free_scale", "ignore_model_err", "dim_prior", "ltol", "return_scale", "lnprior", "precision")
+
+
+def default_device():
+    for key in ("FZB_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(key, "") != "":
+            return int(os.environ[key])
+    return 0
+
+
+def make_config(lprob_kwargs=None, kde_kwargs=None, track_scale=False):
+    """Translate the reference's keyword arguments (pdf.py:238-240, :444-445, :529-531) into FzbConfig."""
+    lk = dict(lprob_kwargs or {})
+    kk = dict(kde_kwargs or {})
+    unknown = [k for k in lk if k not in _LPROB_KEYS]
+    if unknown:
+        raise TypeError("unsupported lprob_kwargs for the built-in logprob: %s" % unknown)
+    cfg = FzbConfig()
+    cfg.free_scale = 1 if lk.get("free_scale", False) else 0
+    ime = lk.get("ignore_model_err", False)
+    # pdf.py:197 tests `ignore_model_err is not True`: a truthy non-bool still iterates
+    cfg.ignore_model_err = 1 if ime is True else (2 if ime else 0)
+    cfg.dim_prior = 1 if lk.get("dim_prior", True) else 0
+    cfg.track_scale = 1 if track_scale else 0
+    cfg.ltol = float(lk.get("ltol", 1e-4))
+    wt, cdf = kk.get("wt_thresh", 1e-3), kk.get("cdf_thresh", 2e-4)
+    cfg.use_wt_thresh = 0 if wt is None else 1
+    cfg.use_cdf_thresh = 0 if cdf is None else 1
+    cfg.wt_thresh = 0.0 if wt is None else float(wt)
+    cfg.cdf_thresh = 0.0 if cdf is None else float(cdf)
+    prec = lk.get("precision", "auto")
+    cfg.precision = {"auto": _lib.PREC_AUTO, "fp64": _lib.PREC_FP64, "fp32": _lib.PREC_FP32}[prec]
+    return cfg
+
+
+def clean_inplace(data, data_err, data_mask):
+    """Vectorised form of the reference's per-object in-place cleaning (pdf.py:310-311).
+
+    The reference mutates the caller's arrays one row at a time; the drop-in does the same
+    for all rows at once so callers observe identical arrays afterwards.
+    """
+    with np.errstate(invalid="ignore"):
+        bad = ~(np.isfinite(data) & np.isfinite(data_err) & (data_err > 0.))
+    if bad.any():
+        data[bad], data_err[bad], data_mask[bad] = 0., 1., False
+    return data, data_err, data_mask
+
+
+class Engine(object):
+    def __init__(self, models, models_err, models_mask, device=None):
+        self.lib = _lib.load()
+        self.h = C.c_void_p()
+        self.device = default_device() if device is None else int(device)
+        _lib.check(self.lib.fzb_create(self.device, C.byref(self.h)))
+        m, me, mm = f64(models), f64(models_err), f64(models_mask)
+        if m.ndim != 2 or me.shape != m.shape or mm.shape != m.shape:
+            raise ValueError("models, models_err and models_mask must share one (Nmodel, Nfilt) shape")
+        self.Nm, self.Nf = m.shape
+        _lib.check(self.lib.fzb_set_models(self.h, dptr(m), dptr(me), dptr(mm), self.Nm, self.Nf))
+        self._kde_key = None
+        self.Ng = 0
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            try:
+                self.lib.fzb_destroy(self.h)
+            except Exception:
+                pass
+            self.h = None
+
+    __del__ = close
+
+    # ---- configuration -------------------------------------------------------------------------
+    def set_lnprior(self, lnprior):
+        if lnprior is None:
+            _lib.check(self.lib.fzb_set_lnprior(self.h, None, 0))
+        else:
+            lp = f64(lnprior)
+            if lp.shape != (self.Nm,):
+                raise ValueError("lnprior must have shape (Nmodel,)")
+            _lib.check(self.lib.fzb_set_lnprior(self.h, dptr(lp), self.Nm))
+
+    def set_kde(self, model_labels, model_label_errs, label_dict=None, label_grid=None, kde_kwargs=None):
+        """Upload the KDE tables and per-model label indices (pdf.py:800-852 / :499-502)."""
+        if label_dict is None and label_grid is None:
+            raise ValueError("`label_dict` or `label_grid` must be specified.")
+        kk = kde_kwargs or {}
+        y, ye = f64(model_labels), f64(model_label_errs)
+        if label_dict is not None:
+            widths = np.ascontiguousarray(label_dict.sigma_width, dtype=np.int32)
+            lens = np.array([len(k) for k in label_dict.sigma_dict], dtype=np.int64)
+            koff = np.zeros(len(lens) + 1, dtype=np.int64)
+            koff[1:] = np.cumsum(lens)
+            kern = f64(np.concatenate(label_dict.sigma_dict)) if koff[-1] else np.zeros(1)
+            kcdf = f64(np.concatenate(label_dict.sigma_dict_cdf)) if koff[-1] else np.zeros(1)
+            _lib.check(self.lib.fzb_set_kde_dict(self.h, int(label_dict.Ngrid), int(label_dict.Ndict),
+                                                 widths.ctypes.data_as(_lib.c_int32_p), iptr(koff), dptr(kern),
+                                                 dptr(kcdf)))
+            yi, si = label_dict.fit(y, ye)
+            yi = np.ascontiguousarray(yi, dtype=np.int64)
+            si = np.ascontiguousarray(si, dtype=np.int64)
+            _lib.check(self.lib.fzb_set_labels_dict(self.h, iptr(yi), iptr(si), len(yi)))
+            self.Ng = int(label_dict.Ngrid)
+        else:
+            x = f64(label_grid)
+            nx = len(x)
+            dx = kk.get("dx", None)
+            if dx is None:
+                dx = x[1] - x[0]
+            sig = kk.get("sig_thresh", 5.)
+            # pdf.py:499-502: truncation toward zero, upper-exclusive windows clipped to the grid
+            centers = np.array((y - x[0]) / dx, dtype="int")
+            offsets = np.array(sig * ye / dx, dtype="int")
+            uppers, lowers = centers + offsets, centers - offsets
+            uppers[uppers > nx], lowers[lowers < 0] = nx, 0
+            # python slice semantics of x[lower:upper]: a negative upper bound counts from the end
+            lowers = np.minimum(lowers, nx)
+            uppers = np.where(uppers < 0, np.maximum(uppers + nx, 0), uppers)
+            uppers = np.maximum(uppers, lowers)
+            _lib.check(self.lib.fzb_set_kde_grid(self.h, dptr(x), nx))
+            lo = np.ascontiguousarray(lowers, dtype=np.int64)
+            up = np.ascontiguousarray(uppers, dtype=np.int64)
+            _lib.check(self.lib.fzb_set_labels_grid(self.h, dptr(y), dptr(ye), iptr(lo), iptr(up), len(y)))
+            self.Ng = nx
+
+    # ---- compute ------------------------------------------------------------------------------
+    @staticmethod
+    def _objects(data, data_err, data_mask):
+        x, xe, xm = f64(data), f64(data_err), f64(data_mask)
+        if x.ndim != 2 or xe.shape != x.shape or xm.shape != x.shape:
+            raise ValueError("data, data_err and data_mask must share one (Ndata, Nfilt) shape")
+        return x, xe, xm
+
+    def fit(self, data, data_err, data_mask, cfg, want=("lnprior", "lnlike", "lnprob", "Ndim", "chi2", "scale",
+                                                       "scale_err"), out=None):
+        """Full (Ndata x Nmodel) fit arrays (bruteforce.py:182-205)."""
+        x, xe, xm = self._objects(data, data_err, data_mask)
+        if x.shape[1] != self.Nf:
+            raise ValueError("data has %d filters, models have %d" % (x.shape[1], self.Nf))
+        no = len(x)
+        res = dict(out or {})
+        for name in want:
+            if name not in res:
+                res[name] = np.empty((no, self.Nm), dtype=np.int64 if name == "Ndim" else np.float64)
+        o = FzbFitOut()
+        for name in ("lnprior", "lnlike", "lnprob", "chi2", "scale", "scale_err"):
+            setattr(o, name, dptr(res.get(name)))
+        o.Ndim = iptr(res.get("Ndim"))
+        _lib.check(self.lib.fzb_fit(self.h, dptr(x), dptr(xe), dptr(xm), no, C.byref(cfg), C.byref(o)))
+        return res
+
+    def fit_predict(self, data, data_err, data_mask, cfg, want_pdf=True):
+        """Fused fit + PDF (bruteforce.py:602-631, save_fits=False)."""
+        x, xe, xm = self._objects(data, data_err, data_mask)
+        if x.shape[1] != self.Nf:
+            raise ValueError("data has %d filters, models have %d" % (x.shape[1], self.Nf))
+        no = len(x)
+        pdfs = np.empty((no, self.Ng)) if want_pdf else None
+        lmap, levid = np.empty(no), np.empty(no)
+        best = np.empty(no, dtype=np.int64)
+        bchi2, bscale = np.empty(no), np.empty(no)
+        _lib.check(self.lib.fzb_fit_predict(self.h, dptr(x), dptr(xe), dptr(xm), no, C.byref(cfg), dptr(pdfs),
+                                            dptr(lmap), dptr(levid), iptr(best), dptr(bchi2), dptr(bscale)))
+        return pdfs, lmap, levid, best, bchi2, bscale
+
+    def predict_logwt(self, logwt, cfg, neighbors=None, nneighbors=None):
+        """PDFs from a log-weight matrix (bruteforce.py:358-372; knn.py:541-555 with neighbours)."""
+        lw = f64(logwt)
+        no, w = lw.shape
+        nb = nn = None
+        if neighbors is not None:
+            nb = np.ascontiguousarray(neighbors, dtype=np.int64)
+            nn = np.ascontiguousarray(nneighbors, dtype=np.int64)
+        pdfs, lmap, levid = np.empty((no, self.Ng)), np.empty(no), np.empty(no)
+        _lib.check(self.lib.fzb_predict_logwt(self.h, dptr(lw), no, w, iptr(nb), iptr(nn), C.byref(cfg), dptr(pdfs),
+                                              dptr(lmap), dptr(levid)))
+        return pdfs, lmap, levid
+
+    def knn_build(self, feats):
+        f = np.ascontiguousarray(feats, dtype=np.float32)
+        K, nm, nf = f.shape
+        _lib.check(self.lib.fzb_knn_build(self.h, f.ctypes.data_as(_lib.c_float_p), K, nm, nf))
+        self.K = K
+
+    def knn_query(self, qfeats, k, p=2, return_dist=True):
+        q = f64(np.atleast_2d(qfeats))
+        no = len(q)
+        idx = np.empty((no, self.K, k), dtype=np.int64)
+        dist = np.empty((no, self.K, k)) if return_dist else None
+        pp = 0.0 if np.isinf(p) else float(p)
+        _lib.check(self.lib.fzb_knn_query(self.h, dptr(q), no, k, pp, iptr(idx), dptr(dist)))
+        return idx, dist
+
+    def knn_fit(self, qfeats, data, data_err, data_mask, k, p, cfg):
+        x, xe, xm = self._objects(data, data_err, data_mask)
+        q = f64(qfeats)
+        no = len(x)
+        w = self.K * k
+        res = dict(lnprior=np.empty((no, w)), lnlike=np.empty((no, w)), lnprob=np.empty((no, w)),
+                   Ndim=np.empty((no, w), dtype=np.int64), chi2=np.empty((no, w)), scale=np.empty((no, w)),
+                   scale_err=np.empty((no, w)))
+        nb = np.empty((no, w), dtype=np.int64)
+        nn = np.empty(no, dtype=np.int64)
+        o = FzbFitOut()
+        for name in ("lnprior", "lnlike", "lnprob", "chi2", "scale", "scale_err"):
+            setattr(o, name, dptr(res[name]))
+        o.Ndim = iptr(res["Ndim"])
+        pp = 0.0 if np.isinf(p) else float(p)
+        _lib.check(self.lib.fzb_knn_fit(self.h, dptr(q), dptr(x), dptr(xe), dptr(xm), no, k, pp, C.byref(cfg),
+                                        iptr(nb), iptr(nn), C.byref(o)))
+        res["neighbors"], res["Nneighbors"] = nb, nn
+        return res
+
+    def stats(self):
+        s = FzbStats()
+        _lib.check(self.lib.fzb_get_stats(self.h, C.byref(s)))
+        return {name: getattr(s, name) for name, _ in FzbStats._fields_}

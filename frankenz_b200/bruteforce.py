@@ -1,0 +1,185 @@
+"""`BruteForce` estimator with the reference's interface (frankenz/bruteforce.py:30-631).
+
+Every object is scored against every model on the GPU.  The per-object Python loop of the
+reference is replaced by batched calls into libfzb200; the generator twins (`_fit`,
+`_predict`, `_fit_predict`) still yield one object at a time so streaming callers keep
+working, but the work is done up front.
+"""
+import sys
+
+import numpy as np
+
+from . import pdf as _pdf
+from ._engine import Engine, clean_inplace, make_config
+
+__all__ = ["BruteForce"]
+
+
+def _check_lprob_func(lprob_func):
+    if lprob_func is None or lprob_func is _pdf.logprob:
+        return
+    raise NotImplementedError(
+        "frankenz_b200 evaluates the likelihood inside CUDA kernels and cannot call a Python `lprob_func`. "
+        "Use lprob_func=None with `lprob_kwargs` (free_scale, ignore_model_err, dim_prior, ltol) and pass a "
+        "per-model log-prior as lprob_kwargs['lnprior'] (uniform if omitted).")
+
+
+def _check_args(args, name):
+    if args is not None and len(args) > 0:
+        raise NotImplementedError("positional `%s` are not supported; use the keyword form" % name)
+
+
+class BruteForce(object):
+    """Fits data and generates predictions with a brute-force scan of all models."""
+
+    def __init__(self, models, models_err, models_mask):
+        # the reference keeps references to the caller's arrays (bruteforce.py:54-56)
+        self.models = models
+        self.models_err = models_err
+        self.models_mask = models_mask
+        self.NMODEL, self.NDIM = models.shape
+        self.NDATA = None
+        self.fit_lnprior = None
+        self.fit_lnlike = None
+        self.fit_lnprob = None
+        self.fit_Ndim = None
+        self.fit_chi2 = None
+        self.fit_scale = None
+        self.fit_scale_err = None
+        self._engine = None
+        self._lnprior_id = None
+
+    # ---- internals -----------------------------------------------------------------------------
+    def _eng(self):
+        if self._engine is None:
+            self._engine = Engine(self.models, self.models_err, self.models_mask)
+        return self._engine
+
+    def _setup(self, lprob_func, lprob_args, lprob_kwargs, track_scale, kde_kwargs=None):
+        _check_lprob_func(lprob_func)
+        _check_args(lprob_args, "lprob_args")
+        lk = dict(lprob_kwargs or {})
+        if track_scale and not (lk.get("free_scale", False) and lk.get("return_scale", False)):
+            # the reference indexes results[5] of a 5-tuple here (bruteforce.py:200-202)
+            raise IndexError("tuple index out of range: `track_scale` needs lprob_kwargs free_scale=True and "
+                             "return_scale=True")
+        eng = self._eng()
+        eng.set_lnprior(lk.get("lnprior", None))
+        return eng, make_config(lk, kde_kwargs, track_scale=track_scale)
+
+    def _store(self, res, Ndata):
+        self.fit_lnprior, self.fit_lnlike, self.fit_lnprob = res["lnprior"], res["lnlike"], res["lnprob"]
+        self.fit_Ndim, self.fit_chi2 = res["Ndim"], res["chi2"]
+        self.fit_scale, self.fit_scale_err = res["scale"], res["scale_err"]
+        self.NDATA = Ndata
+
+    @staticmethod
+    def _rows(res, i, track_scale):
+        out = (res["lnprior"][i], res["lnlike"][i], res["lnprob"][i], res["Ndim"][i], res["chi2"][i])
+        if track_scale:
+            out = out + (res["scale"][i], res["scale_err"][i])
+        return out
+
+    # ---- fit -----------------------------------------------------------------------------------
+    def fit(self, data, data_err, data_mask, lprob_func=None, lprob_args=None, lprob_kwargs=None,
+            track_scale=False, verbose=True):
+        """Fit all models to all objects; results land in the `fit_*` attributes (bruteforce.py:66-125)."""
+        Ndata = len(data)
+        for i, _ in enumerate(self._fit(data, data_err, data_mask, lprob_func=lprob_func, lprob_args=lprob_args,
+                                        lprob_kwargs=lprob_kwargs, track_scale=track_scale, save_fits=True)):
+            pass
+        if verbose:
+            sys.stderr.write('\rFitting object {0}/{1}\n'.format(Ndata, Ndata))
+            sys.stderr.flush()
+
+    def _fit(self, data, data_err, data_mask, lprob_func=None, lprob_args=None, lprob_kwargs=None,
+             track_scale=False, save_fits=True):
+        """Generator over objects yielding the `logprob` tuple of each (bruteforce.py:127-205)."""
+        eng, cfg = self._setup(lprob_func, lprob_args, lprob_kwargs, track_scale)
+        clean_inplace(data, data_err, data_mask)
+        Ndata = len(data)
+        self.NDATA = Ndata
+        res = eng.fit(data, data_err, data_mask, cfg)
+        if save_fits:
+            self._store(res, Ndata)
+        for i in range(Ndata):
+            yield self._rows(res, i, track_scale)
+
+    # ---- predict -------------------------------------------------------------------------------
+    def predict(self, model_labels, model_label_errs, label_dict=None, label_grid=None, logwt=None, kde_args=None,
+                kde_kwargs=None, return_gof=False, verbose=True):
+        """1-D PDFs from stored fits or supplied log-weights (bruteforce.py:207-301)."""
+        pdfs, lmap, levid = self._predict_all(model_labels, model_label_errs, label_dict, label_grid, logwt,
+                                              kde_args, kde_kwargs)
+        if verbose:
+            sys.stderr.write('\rGenerating PDF {0}/{1}\n'.format(len(pdfs), len(pdfs)))
+            sys.stderr.flush()
+        if return_gof:
+            return pdfs, (lmap, levid)
+        return pdfs
+
+    def _predict_all(self, model_labels, model_label_errs, label_dict, label_grid, logwt, kde_args, kde_kwargs):
+        _check_args(kde_args, "kde_args")
+        if logwt is None:
+            logwt = self.fit_lnprob
+        if label_dict is None and label_grid is None:
+            raise ValueError("`label_dict` or `label_grid` must be specified.")
+        if logwt is None:
+            raise ValueError("Fits have not been computed and weights have not been provided.")
+        eng = self._eng()
+        eng.set_kde(model_labels, model_label_errs, label_dict=label_dict, label_grid=label_grid,
+                    kde_kwargs=kde_kwargs)
+        cfg = make_config(None, kde_kwargs)
+        return eng.predict_logwt(logwt, cfg)
+
+    def _predict(self, model_labels, model_label_errs, label_dict=None, label_grid=None, logwt=None, kde_args=None,
+                 kde_kwargs=None):
+        """Generator twin of `predict` (bruteforce.py:303-372): yields (pdf, (lmap, levid))."""
+        pdfs, lmap, levid = self._predict_all(model_labels, model_label_errs, label_dict, label_grid, logwt,
+                                              kde_args, kde_kwargs)
+        for i in range(len(pdfs)):
+            yield pdfs[i], (lmap[i], levid[i])
+
+    # ---- fit_predict ---------------------------------------------------------------------------
+    def fit_predict(self, data, data_err, data_mask, model_labels, model_label_errs, lprob_func=None,
+                    label_dict=None, label_grid=None, kde_args=None, kde_kwargs=None, lprob_args=None,
+                    lprob_kwargs=None, return_gof=False, track_scale=False, verbose=True, save_fits=True):
+        """Fit and predict in one go (bruteforce.py:374-503).  With `save_fits=False` the
+        (Ndata x Nmodel) arrays are never formed: the fused kernels reduce on the fly."""
+        pdfs, lmap, levid = self._fit_predict_all(data, data_err, data_mask, model_labels, model_label_errs,
+                                                  lprob_func, label_dict, label_grid, kde_args, kde_kwargs,
+                                                  lprob_args, lprob_kwargs, track_scale, save_fits)
+        if verbose:
+            sys.stderr.write('\rGenerating PDF {0}/{1}\n'.format(len(pdfs), len(pdfs)))
+            sys.stderr.flush()
+        if return_gof:
+            return pdfs, (lmap, levid)
+        return pdfs
+
+    def _fit_predict_all(self, data, data_err, data_mask, model_labels, model_label_errs, lprob_func, label_dict,
+                         label_grid, kde_args, kde_kwargs, lprob_args, lprob_kwargs, track_scale, save_fits):
+        _check_args(kde_args, "kde_args")
+        if label_dict is None and label_grid is None:
+            raise ValueError("`label_dict` or `label_grid` must be specified.")
+        eng, cfg = self._setup(lprob_func, lprob_args, lprob_kwargs, track_scale, kde_kwargs)
+        eng.set_kde(model_labels, model_label_errs, label_dict=label_dict, label_grid=label_grid,
+                    kde_kwargs=kde_kwargs)
+        clean_inplace(data, data_err, data_mask)
+        Ndata = len(data)
+        if save_fits:
+            res = eng.fit(data, data_err, data_mask, cfg)
+            self._store(res, Ndata)
+            return eng.predict_logwt(res["lnprob"], cfg)
+        pdfs, lmap, levid, best, bchi2, bscale = eng.fit_predict(data, data_err, data_mask, cfg)
+        self.best_idx, self.best_chi2, self.best_scale = best, bchi2, bscale   # extras of the fused path
+        return pdfs, lmap, levid
+
+    def _fit_predict(self, data, data_err, data_mask, model_labels, model_label_errs, lprob_func=None,
+                     label_dict=None, label_grid=None, kde_args=None, kde_kwargs=None, lprob_args=None,
+                     lprob_kwargs=None, track_scale=False, save_fits=True):
+        """Generator twin of `fit_predict` (bruteforce.py:505-631): yields (pdf, (lmap, levid))."""
+        pdfs, lmap, levid = self._fit_predict_all(data, data_err, data_mask, model_labels, model_label_errs,
+                                                  lprob_func, label_dict, label_grid, kde_args, kde_kwargs,
+                                                  lprob_args, lprob_kwargs, track_scale, save_fits)
+        for i in range(len(pdfs)):
+            yield pdfs[i], (lmap[i], levid[i])

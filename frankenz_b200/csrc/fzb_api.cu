@@ -1,0 +1,504 @@
+// C-ABI entry points of libfzb200 (see include/frankenz_b200.h): handle management, host<->device
+// staging, and dispatch between the fp32 register-tiled path (fzb_fast.cu) and the generic
+// float64 path (fzb_generic.cu).
+#include <cmath>
+#include <cstdarg>
+
+#include "fzb_common.cuh"
+
+static thread_local std::string g_err;
+
+void fzb_set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+namespace {
+
+struct Timer {
+    fzb_context* h;
+    explicit Timer(fzb_context* hh) : h(hh) { cudaEventRecord(h->ev[0], h->stream); }
+    int stop() {
+        FZB_CUDA(cudaEventRecord(h->ev[1], h->stream));
+        FZB_CUDA(cudaEventSynchronize(h->ev[1]));
+        float ms = 0.f;
+        FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        h->stats.ms_total = ms;
+        return 0;
+    }
+};
+
+int use_device(fzb_context* h) {
+    FZB_CHECK(h != nullptr, "null handle");
+    FZB_CUDA(cudaSetDevice(h->device));
+    return 0;
+}
+
+template <class T>
+int upload(fzb_context* h, DevBuf& b, const T* src, size_t n) {
+    if (b.reserve(n * sizeof(T) + 16)) return 1;
+    if (n) FZB_CUDA(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+template <class T>
+int download(fzb_context* h, T* dst, const void* src, size_t n) {
+    if (n && dst) FZB_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    return 0;
+}
+
+void reset_stats(fzb_context* h) { h->stats = FzbStats{}; }
+
+int check_models(fzb_context* h) {
+    FZB_CHECK(h->Nm > 0 && h->Nf > 0, "no models loaded: call fzb_set_models first");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fzb_last_error(void) { return g_err.c_str(); }
+int fzb_version(void) { return 100; }
+
+int fzb_device_count(int* count) {
+    FZB_CHECK(count != nullptr, "null pointer");
+    *count = 0;
+    FZB_CUDA(cudaGetDeviceCount(count));
+    return 0;
+}
+
+int fzb_create(int device, fzb_handle* out) {
+    FZB_CHECK(out != nullptr, "null output pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        fzb_set_error("no usable CUDA device (%s); frankenz_b200 has no CPU fallback",
+                      e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return 3;
+    }
+    FZB_CHECK(device >= 0 && device < n, "device %d out of range (found %d)", device, n);
+    FZB_CUDA(cudaSetDevice(device));
+    fzb_context* h = new fzb_context();
+    h->device = device;
+    cudaDeviceProp prop;
+    FZB_CUDA(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    FZB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& ev : h->ev) FZB_CUDA(cudaEventCreate(&ev));
+    *out = h;
+    return 0;
+}
+
+int fzb_destroy(fzb_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->models, &h->models_err, &h->models_mask, &h->lnprior, &h->widths, &h->koff, &h->kernels,
+                      &h->kcdf, &h->yidx, &h->ysidx, &h->grid, &h->y, &h->ystd, &h->lowers, &h->uppers, &h->rows,
+                      &h->knn_feats, &h->fast.recs, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
+                      &h->fast.d_slot_sidx};
+    for (auto* b : bufs) b->release();
+    for (auto& b : h->obj_in) b.release();
+    for (auto& b : h->out_f64) b.release();
+    for (auto& b : h->out_i64) b.release();
+    for (auto& b : h->misc) b.release();
+    for (auto& ev : h->ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int fzb_synchronize(fzb_handle h) {
+    if (use_device(h)) return 2;
+    FZB_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int fzb_get_stats(fzb_handle h, FzbStats* out) {
+    FZB_CHECK(h && out, "null pointer");
+    *out = h->stats;
+    return 0;
+}
+
+int fzb_set_models(fzb_handle h, const double* models, const double* models_err, const double* models_mask,
+                   int64_t Nm, int32_t Nf) {
+    if (use_device(h)) return 2;
+    FZB_CHECK(models && models_err && models_mask, "null model array");
+    FZB_CHECK(Nm > 0 && Nf > 0, "empty model set (Nm=%lld, Nf=%d)", (long long)Nm, Nf);
+    FZB_CHECK(Nf <= FZB_MAXF, "Nf=%d exceeds the supported maximum %d", Nf, FZB_MAXF);
+    size_t n = (size_t)Nm * Nf;
+    bool all_one = true, all_zero = true, finite = true;
+    for (size_t i = 0; i < n; ++i) {
+        all_one &= (models_mask[i] == 1.0);
+        all_zero &= (models_err[i] == 0.0);
+        finite &= std::isfinite(models[i]) && std::isfinite(models_err[i]);
+    }
+    h->mask_all_one = all_one;
+    h->err_all_zero = all_zero;
+    h->models_finite = finite;
+    if (upload(h, h->models, models, n) || upload(h, h->models_err, models_err, n) ||
+        upload(h, h->models_mask, models_mask, n))
+        return 1;
+    FZB_CUDA(cudaStreamSynchronize(h->stream));
+    h->Nm = Nm;
+    h->Nf = Nf;
+    h->has_lnprior = false;
+    h->labels_dict_set = h->labels_grid_set = false;
+    h->fast_dirty = true;
+    return 0;
+}
+
+int fzb_set_lnprior(fzb_handle h, const double* lnprior, int64_t Nm) {
+    if (use_device(h) || check_models(h)) return 2;
+    if (lnprior == nullptr) {
+        h->has_lnprior = false;
+        h->fast_dirty = true;
+        return 0;
+    }
+    FZB_CHECK(Nm == h->Nm, "lnprior has %lld entries, model set has %lld", (long long)Nm, (long long)h->Nm);
+    if (upload(h, h->lnprior, lnprior, (size_t)Nm)) return 1;
+    FZB_CUDA(cudaStreamSynchronize(h->stream));
+    h->has_lnprior = true;
+    h->fast_dirty = true;
+    return 0;
+}
+
+int fzb_set_kde_dict(fzb_handle h, int32_t Ngrid, int32_t Ndict, const int32_t* widths, const int64_t* koff,
+                     const double* kernels, const double* kcdf) {
+    if (use_device(h)) return 2;
+    FZB_CHECK(Ngrid > 0 && Ndict > 0 && widths && koff && kernels && kcdf, "bad dictionary arguments");
+    FZB_CHECK(Ngrid <= FZB_MAX_NGRID, "PDF grid of %d points exceeds the supported maximum %d", Ngrid, FZB_MAX_NGRID);
+    for (int i = 0; i < Ndict; ++i)
+        FZB_CHECK(koff[i + 1] - koff[i] == 2 * (int64_t)widths[i] + 1 || koff[i + 1] - koff[i] >= 0,
+                  "malformed kernel table");
+    h->h_widths.assign(widths, widths + Ndict);
+    h->h_koff.assign(koff, koff + Ndict + 1);
+    size_t tot = (size_t)koff[Ndict];
+    if (upload(h, h->widths, widths, (size_t)Ndict) || upload(h, h->koff, koff, (size_t)Ndict + 1) ||
+        upload(h, h->kernels, kernels, tot) || upload(h, h->kcdf, kcdf, tot))
+        return 1;
+    FZB_CUDA(cudaStreamSynchronize(h->stream));
+    h->Ng = Ngrid;
+    h->Ndict = Ndict;
+    h->kde_mode = FZB_KDE_DICT;
+    h->labels_dict_set = false;
+    h->fast_dirty = true;
+    return 0;
+}
+
+int fzb_set_labels_dict(fzb_handle h, const int64_t* y_idx, const int64_t* y_std_idx, int64_t Nm) {
+    if (use_device(h) || check_models(h)) return 2;
+    FZB_CHECK(h->kde_mode == FZB_KDE_DICT, "call fzb_set_kde_dict first");
+    FZB_CHECK(Nm == h->Nm, "labels have %lld entries, model set has %lld", (long long)Nm, (long long)h->Nm);
+    // The reference raises (shape mismatch / IndexError) when a selected model's kernel misses the grid
+    // or uses a wrapped (malformed) dictionary entry (pdf.py:612-620, :814-818); refuse such labels up front.
+    for (int64_t j = 0; j < Nm; ++j) {
+        int64_t si = y_std_idx[j];
+        FZB_CHECK(si >= 0 && si < h->Ndict, "label %lld: dictionary index %lld out of range", (long long)j,
+                  (long long)si);
+        int64_t w = h->h_widths[si];
+        FZB_CHECK(h->h_koff[si + 1] - h->h_koff[si] == 2 * w + 1,
+                  "label %lld uses dictionary kernel %lld which is wider than the grid (malformed in the reference, "
+                  "pdf.py:814-818)", (long long)j, (long long)si);
+        int64_t pos = y_idx[j];
+        FZB_CHECK(pos + w >= 0 && pos - w <= h->Ng - 1 && pos - w < h->Ng && pos + w + 1 > 0,
+                  "label %lld lies further outside the grid than its kernel width (the reference raises here)",
+                  (long long)j);
+    }
+    h->h_yidx.assign(y_idx, y_idx + Nm);
+    h->h_ysidx.assign(y_std_idx, y_std_idx + Nm);
+    if (upload(h, h->yidx, y_idx, (size_t)Nm) || upload(h, h->ysidx, y_std_idx, (size_t)Nm)) return 1;
+    FZB_CUDA(cudaStreamSynchronize(h->stream));
+    h->labels_dict_set = true;
+    h->fast_dirty = true;
+    return 0;
+}
+
+int fzb_set_kde_grid(fzb_handle h, const double* grid, int32_t Ngrid) {
+    if (use_device(h)) return 2;
+    FZB_CHECK(grid && Ngrid > 0, "bad grid arguments");
+    FZB_CHECK(Ngrid <= FZB_MAX_NGRID, "PDF grid of %d points exceeds the supported maximum %d", Ngrid, FZB_MAX_NGRID);
+    if (upload(h, h->grid, grid, (size_t)Ngrid)) return 1;
+    FZB_CUDA(cudaStreamSynchronize(h->stream));
+    h->Ng = Ngrid;
+    h->kde_mode = FZB_KDE_GRID;
+    h->labels_grid_set = false;
+    h->fast_dirty = true;
+    return 0;
+}
+
+int fzb_set_labels_grid(fzb_handle h, const double* y, const double* y_std, const int64_t* lowers,
+                        const int64_t* uppers, int64_t Nm) {
+    if (use_device(h) || check_models(h)) return 2;
+    FZB_CHECK(h->kde_mode == FZB_KDE_GRID, "call fzb_set_kde_grid first");
+    FZB_CHECK(Nm == h->Nm, "labels have %lld entries, model set has %lld", (long long)Nm, (long long)h->Nm);
+    for (int64_t j = 0; j < Nm; ++j)
+        FZB_CHECK(lowers[j] >= 0 && uppers[j] <= h->Ng, "label %lld: window [%lld, %lld) outside the grid",
+                  (long long)j, (long long)lowers[j], (long long)uppers[j]);
+    if (upload(h, h->y, y, (size_t)Nm) || upload(h, h->ystd, y_std, (size_t)Nm) ||
+        upload(h, h->lowers, lowers, (size_t)Nm) || upload(h, h->uppers, uppers, (size_t)Nm))
+        return 1;
+    FZB_CUDA(cudaStreamSynchronize(h->stream));
+    h->labels_grid_set = true;
+    h->fast_dirty = true;
+    return 0;
+}
+
+int fzb_fit(fzb_handle h, const double* data, const double* data_err, const double* data_mask, int64_t No,
+            const FzbConfig* cfg, const FzbFitOut* out) {
+    if (use_device(h) || check_models(h)) return 2;
+    FZB_CHECK(cfg && out, "null config / output struct");
+    FZB_CHECK(No >= 0, "negative object count");
+    reset_stats(h);
+    if (No == 0) return 0;
+    const int64_t Nm = h->Nm;
+    const int Nf = h->Nf;
+    // chunk the objects so that the staged (chunk x Nm) outputs stay within ~6 GB of HBM
+    int nout = (out->lnprior != nullptr) + (out->lnlike != nullptr) + (out->lnprob != nullptr) +
+               (out->Ndim != nullptr) + (out->chi2 != nullptr) + (out->scale != nullptr) + (out->scale_err != nullptr);
+    size_t per_obj = (size_t)Nm * 8 * (size_t)(nout > 0 ? nout : 1);
+    int64_t chunk = (int64_t)(((size_t)6 << 30) / per_obj);
+    if (chunk < 1) chunk = 1;
+    if (chunk > No) chunk = No;
+    size_t cn = (size_t)chunk * Nm;
+    double* d_o[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double* hostp[6] = {out->lnprior, out->lnlike, out->lnprob, out->chi2, out->scale, out->scale_err};
+    for (int i = 0; i < 6; ++i)
+        if (hostp[i]) {
+            if (h->out_f64[i].reserve(cn * 8)) return 1;
+            d_o[i] = h->out_f64[i].as<double>();
+        }
+    int64_t* d_nd = nullptr;
+    if (out->Ndim) {
+        if (h->out_i64[0].reserve(cn * 8)) return 1;
+        d_nd = h->out_i64[0].as<int64_t>();
+    }
+    Timer t(h);
+    for (int64_t o0 = 0; o0 < No; o0 += chunk) {
+        int64_t nc = No - o0 < chunk ? No - o0 : chunk;
+        size_t nin = (size_t)nc * Nf;
+        if (upload(h, h->obj_in[0], data + o0 * Nf, nin) || upload(h, h->obj_in[1], data_err + o0 * Nf, nin) ||
+            upload(h, h->obj_in[2], data_mask + o0 * Nf, nin))
+            return 1;
+        if (fzb_generic_fit_dev(h, h->obj_in[0].as<double>(), h->obj_in[1].as<double>(), h->obj_in[2].as<double>(), nc,
+                                *cfg, d_o[0], d_o[1], d_o[2], d_nd, d_o[3], d_o[4], d_o[5]))
+            return 1;
+        size_t no = (size_t)nc * Nm;
+        for (int i = 0; i < 6; ++i)
+            if (download(h, hostp[i] ? hostp[i] + (size_t)o0 * Nm : nullptr, d_o[i], no)) return 1;
+        if (download(h, out->Ndim ? out->Ndim + (size_t)o0 * Nm : nullptr, d_nd, no)) return 1;
+        FZB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return t.stop();
+}
+
+int fzb_fit_predict_dev(fzb_handle h, const double* d_data, const double* d_err, const double* d_mask, int64_t No,
+                        const FzbConfig* cfg, double* d_pdfs, double* d_lmap, double* d_levid, int64_t* d_best_idx,
+                        double* d_best_chi2, double* d_best_scale) {
+    if (use_device(h) || check_models(h)) return 2;
+    FZB_CHECK(cfg != nullptr, "null config");
+    reset_stats(h);
+    if (No == 0) return 0;
+    Timer t(h);
+    int rc;
+    if (cfg->precision != FZB_PREC_FP64 && fzb_fast_supported(h, *cfg)) {
+        rc = fzb_fast_fit_predict_dev(h, d_data, d_err, d_mask, No, *cfg, d_pdfs, d_lmap, d_levid, d_best_idx,
+                                      d_best_chi2, d_best_scale);
+    } else {
+        FZB_CHECK(cfg->precision != FZB_PREC_FP32, "the fp32 path does not support this configuration");
+        rc = fzb_generic_fit_predict_dev(h, d_data, d_err, d_mask, No, nullptr, 0, *cfg, d_pdfs, d_lmap, d_levid,
+                                         d_best_idx, d_best_chi2, d_best_scale);
+    }
+    if (rc) return rc;
+    return t.stop();
+}
+
+int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, const double* data_mask, int64_t No,
+                    const FzbConfig* cfg, double* pdfs, double* lmap, double* levid, int64_t* best_idx,
+                    double* best_chi2, double* best_scale) {
+    if (use_device(h) || check_models(h)) return 2;
+    FZB_CHECK(cfg != nullptr, "null config");
+    FZB_CHECK(No >= 0, "negative object count");
+    if (No == 0) { reset_stats(h); return 0; }
+    const int Nf = h->Nf;
+    const int Ng = h->Ng;
+    size_t nin = (size_t)No * Nf;
+    if (upload(h, h->obj_in[0], data, nin) || upload(h, h->obj_in[1], data_err, nin) ||
+        upload(h, h->obj_in[2], data_mask, nin))
+        return 1;
+    if (pdfs && h->out_f64[0].reserve((size_t)No * Ng * 8)) return 1;
+    if (h->out_f64[1].reserve((size_t)No * 8) || h->out_f64[2].reserve((size_t)No * 8) ||
+        h->out_f64[3].reserve((size_t)No * 8) || h->out_f64[4].reserve((size_t)No * 8) ||
+        h->out_i64[0].reserve((size_t)No * 8))
+        return 1;
+    int rc = fzb_fit_predict_dev(h, h->obj_in[0].as<double>(), h->obj_in[1].as<double>(), h->obj_in[2].as<double>(),
+                                 No, cfg, pdfs ? h->out_f64[0].as<double>() : nullptr, h->out_f64[1].as<double>(),
+                                 h->out_f64[2].as<double>(), h->out_i64[0].as<int64_t>(), h->out_f64[3].as<double>(),
+                                 h->out_f64[4].as<double>());
+    if (rc) return rc;
+    if (download(h, pdfs, h->out_f64[0].p, (size_t)No * Ng) || download(h, lmap, h->out_f64[1].p, (size_t)No) ||
+        download(h, levid, h->out_f64[2].p, (size_t)No) || download(h, best_idx, h->out_i64[0].p, (size_t)No) ||
+        download(h, best_chi2, h->out_f64[3].p, (size_t)No) || download(h, best_scale, h->out_f64[4].p, (size_t)No))
+        return 1;
+    FZB_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int fzb_predict_logwt(fzb_handle h, const double* logwt, int64_t No, int64_t W, const int64_t* neighbors,
+                      const int64_t* nneighbors, const FzbConfig* cfg, double* pdfs, double* lmap, double* levid) {
+    if (use_device(h) || check_models(h)) return 2;
+    FZB_CHECK(cfg && logwt && pdfs, "null argument");
+    FZB_CHECK((neighbors == nullptr) == (nneighbors == nullptr), "neighbors and nneighbors go together");
+    if (!neighbors) FZB_CHECK(W == h->Nm, "logwt has %lld columns, model set has %lld", (long long)W, (long long)h->Nm);
+    reset_stats(h);
+    if (No == 0) return 0;
+    const int Ng = h->Ng;
+    // chunk so that the staged log-weights stay within ~8 GB
+    int64_t chunk = (int64_t)(((size_t)8 << 30) / ((size_t)W * 8 * (neighbors ? 2 : 1)));
+    if (chunk < 1) chunk = 1;
+    if (chunk > No) chunk = No;
+    if (h->out_f64[0].reserve((size_t)chunk * Ng * 8) || h->out_f64[1].reserve((size_t)chunk * 8) ||
+        h->out_f64[2].reserve((size_t)chunk * 8))
+        return 1;
+    Timer t(h);
+    for (int64_t o0 = 0; o0 < No; o0 += chunk) {
+        int64_t nc = No - o0 < chunk ? No - o0 : chunk;
+        if (upload(h, h->misc[0], logwt + (size_t)o0 * W, (size_t)nc * W)) return 1;
+        const int64_t *d_nb = nullptr, *d_nn = nullptr;
+        if (neighbors) {
+            if (upload(h, h->misc[1], neighbors + (size_t)o0 * W, (size_t)nc * W) ||
+                upload(h, h->misc[2], nneighbors + o0, (size_t)nc))
+                return 1;
+            d_nb = h->misc[1].as<int64_t>();
+            d_nn = h->misc[2].as<int64_t>();
+        }
+        if (fzb_generic_predict_logwt_dev(h, h->misc[0].as<double>(), nc, W, d_nb, d_nn, *cfg,
+                                          h->out_f64[0].as<double>(), h->out_f64[1].as<double>(),
+                                          h->out_f64[2].as<double>()))
+            return 1;
+        if (download(h, pdfs + (size_t)o0 * Ng, h->out_f64[0].p, (size_t)nc * Ng) ||
+            download(h, lmap ? lmap + o0 : nullptr, h->out_f64[1].p, (size_t)nc) ||
+            download(h, levid ? levid + o0 : nullptr, h->out_f64[2].p, (size_t)nc))
+            return 1;
+        FZB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return t.stop();
+}
+
+int fzb_shard_pass1_dev(fzb_handle h, const double* d_data, const double* d_err, const double* d_mask, int64_t No,
+                        const FzbConfig* cfg, double* d_pmax, double* d_psum, int64_t* d_pbest) {
+    if (use_device(h) || check_models(h)) return 2;
+    FZB_CHECK(cfg != nullptr, "null config");
+    reset_stats(h);
+    if (No == 0) return 0;
+    Timer t(h);
+    if (fzb_generic_shard_pass1_dev(h, d_data, d_err, d_mask, No, *cfg, d_pmax, d_psum, d_pbest)) return 1;
+    return t.stop();
+}
+
+int fzb_shard_pass2_dev(fzb_handle h, const double* d_data, const double* d_err, const double* d_mask, int64_t No,
+                        const FzbConfig* cfg, const double* d_lmap, const double* d_levid, double* d_pdf_partial) {
+    if (use_device(h) || check_models(h)) return 2;
+    FZB_CHECK(cfg != nullptr, "null config");
+    reset_stats(h);
+    if (No == 0) return 0;
+    Timer t(h);
+    if (fzb_generic_shard_pass2_dev(h, d_data, d_err, d_mask, No, *cfg, d_lmap, d_levid, d_pdf_partial)) return 1;
+    return t.stop();
+}
+
+int fzb_knn_build(fzb_handle h, const float* feats, int32_t K, int64_t Nm, int32_t Nf) {
+    if (use_device(h)) return 2;
+    FZB_CHECK(feats && K > 0 && Nm > 0 && Nf > 0, "bad kNN build arguments");
+    FZB_CHECK(Nf <= FZB_MAXF, "Nf=%d exceeds the supported maximum %d", Nf, FZB_MAXF);
+    if (upload(h, h->knn_feats, feats, (size_t)K * Nm * Nf)) return 1;
+    FZB_CUDA(cudaStreamSynchronize(h->stream));
+    h->knn_K = K;
+    h->knn_Nm = Nm;
+    h->knn_Nf = Nf;
+    return 0;
+}
+
+int fzb_knn_query(fzb_handle h, const double* qfeats, int64_t No, int32_t k, double p, int64_t* idx, double* dist) {
+    if (use_device(h)) return 2;
+    FZB_CHECK(h->knn_K > 0, "call fzb_knn_build first");
+    FZB_CHECK(qfeats && idx, "null argument");
+    FZB_CHECK(k > 0 && k <= h->knn_Nm, "k=%d must be in [1, Nmodel=%lld]", k, (long long)h->knn_Nm);
+    reset_stats(h);
+    if (No == 0) return 0;
+    size_t nout = (size_t)No * h->knn_K * k;
+    if (upload(h, h->obj_in[0], qfeats, (size_t)No * h->knn_Nf) || h->out_i64[0].reserve(nout * 8) ||
+        h->out_f64[0].reserve(nout * 8))
+        return 1;
+    Timer t(h);
+    if (fzb_knn_query_dev(h, h->obj_in[0].as<double>(), No, k, p, h->out_i64[0].as<int64_t>(),
+                          h->out_f64[0].as<double>()))
+        return 1;
+    if (download(h, idx, h->out_i64[0].p, nout) || download(h, dist, h->out_f64[0].p, nout)) return 1;
+    return t.stop();
+}
+
+int fzb_knn_fit(fzb_handle h, const double* qfeats, const double* data, const double* data_err,
+                const double* data_mask, int64_t No, int32_t k, double p, const FzbConfig* cfg, int64_t* neighbors,
+                int64_t* nneighbors, const FzbFitOut* out) {
+    if (use_device(h) || check_models(h)) return 2;
+    FZB_CHECK(h->knn_K > 0, "call fzb_knn_build first");
+    FZB_CHECK(h->knn_Nm == h->Nm && h->knn_Nf == h->Nf, "kNN features (%lld x %d) do not match the model set (%lld x %d)",
+              (long long)h->knn_Nm, h->knn_Nf, (long long)h->Nm, h->Nf);
+    FZB_CHECK(qfeats && data && data_err && data_mask && cfg && neighbors && nneighbors && out, "null argument");
+    FZB_CHECK(k > 0 && k <= h->knn_Nm, "k=%d must be in [1, Nmodel=%lld]", k, (long long)h->knn_Nm);
+    reset_stats(h);
+    if (No == 0) return 0;
+    const int Nf = h->Nf;
+    const int64_t W = (int64_t)h->knn_K * k;
+    // chunk the objects: 2 int64 + 7 output arrays of width W
+    int64_t chunk = (int64_t)(((size_t)8 << 30) / ((size_t)W * 8 * 10));
+    if (chunk < 1) chunk = 1;
+    if (chunk > No) chunk = No;
+    size_t cn = (size_t)chunk * W;
+    double* hostp[6] = {out->lnprior, out->lnlike, out->lnprob, out->chi2, out->scale, out->scale_err};
+    double* d_o[6] = {};
+    for (int i = 0; i < 6; ++i)
+        if (hostp[i]) {
+            if (h->out_f64[i].reserve(cn * 8)) return 1;
+            d_o[i] = h->out_f64[i].as<double>();
+        }
+    int64_t* d_nd = nullptr;
+    if (out->Ndim) {
+        if (h->out_i64[1].reserve(cn * 8)) return 1;
+        d_nd = h->out_i64[1].as<int64_t>();
+    }
+    if (h->out_i64[0].reserve(cn * 8) || h->misc[3].reserve(cn * 8) || h->misc[4].reserve((size_t)chunk * 8)) return 1;
+    Timer t(h);
+    for (int64_t o0 = 0; o0 < No; o0 += chunk) {
+        int64_t nc = No - o0 < chunk ? No - o0 : chunk;
+        size_t nin = (size_t)nc * Nf;
+        if (upload(h, h->obj_in[0], data + o0 * Nf, nin) || upload(h, h->obj_in[1], data_err + o0 * Nf, nin) ||
+            upload(h, h->obj_in[2], data_mask + o0 * Nf, nin) || upload(h, h->misc[5], qfeats + o0 * Nf, nin))
+            return 1;
+        int64_t* d_idx = h->out_i64[0].as<int64_t>();
+        int64_t* d_nb = h->misc[3].as<int64_t>();
+        int64_t* d_nn = h->misc[4].as<int64_t>();
+        if (fzb_knn_query_dev(h, h->misc[5].as<double>(), nc, k, p, d_idx, nullptr)) return 1;
+        if (fzb_knn_union_dev(h, d_idx, nc, (int)W, d_nb, d_nn)) return 1;
+        if (fzb_generic_gather_fit_dev(h, h->obj_in[0].as<double>(), h->obj_in[1].as<double>(),
+                                       h->obj_in[2].as<double>(), nc, W, d_nb, d_nn, *cfg, d_o[0], d_o[1], d_o[2],
+                                       d_nd, d_o[3], d_o[4], d_o[5]))
+            return 1;
+        size_t no = (size_t)nc * W;
+        for (int i = 0; i < 6; ++i)
+            if (download(h, hostp[i] ? hostp[i] + (size_t)o0 * W : nullptr, d_o[i], no)) return 1;
+        if (download(h, out->Ndim ? out->Ndim + (size_t)o0 * W : nullptr, d_nd, no) ||
+            download(h, neighbors + (size_t)o0 * W, d_nb, no) || download(h, nneighbors + o0, d_nn, (size_t)nc))
+            return 1;
+        FZB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return t.stop();
+}
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+// Shared declarations of libfzb200: context, error handling, launch bookkeeping.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/frankenz_b200.h"
+
+#define FZB_MAXF 64          // generic fp64 path: filters per object
+#define FZB_FAST_MAXF 8      // register-tiled fp32 path: filters per object
+#define FZB_MAX_NGRID 16384  // PDF grid points held in shared memory (fp64)
+
+void fzb_set_error(const char* fmt, ...);
+
+#define FZB_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            fzb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return 1;                                                                       \
+        }                                                                                   \
+    } while (0)
+
+#define FZB_CHECK(cond, ...)          \
+    do {                              \
+        if (!(cond)) {                \
+            fzb_set_error(__VA_ARGS__); \
+            return 2;                 \
+        }                             \
+    } while (0)
+
+// Growable device buffer (never shrinks; freed with the context).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            fzb_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            return 1;
+        }
+        cap = bytes;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+enum { FZB_KDE_NONE = 0, FZB_KDE_DICT = 1, FZB_KDE_GRID = 2 };
+
+// Per-model constants of the fp32 fast path, laid out for bulk (TMA) staging into shared memory.
+struct FastModels {
+    bool valid = false;
+    int nf = 0;
+    int64_t nm = 0;        // models
+    int64_t nm_pad = 0;    // padded to a multiple of the tile
+    int rec = 0;           // floats per model record
+    DevBuf recs;           // [nm_pad][rec] float: see fzb_fast.cu for the record layout
+    DevBuf perm;           // int32 [nm_pad]: sorted position -> original model index (-1 = padding)
+    DevBuf bins;           // int32 [nm_pad]: KDE histogram bin (slot*Ng + pos) of each sorted model, -1 = none
+    DevBuf invnorm;        // float [nm_pad]: 1 / kernel normalisation of each sorted model
+    int nslot = 0;         // distinct dictionary widths in use
+    std::vector<int32_t> slot_sidx;  // slot -> dictionary index
+    DevBuf d_slot_sidx;
+};
+
+struct fzb_context {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+
+    // model set (fp64 originals, row-major Nm x Nf)
+    int64_t Nm = 0;
+    int Nf = 0;
+    DevBuf models, models_err, models_mask, lnprior;
+    bool has_lnprior = false;
+    bool mask_all_one = false;     // every model mask entry == 1
+    bool err_all_zero = false;     // every model error == 0
+    bool models_finite = false;
+
+    // KDE tables
+    int kde_mode = FZB_KDE_NONE;
+    int Ng = 0;
+    int Ndict = 0;
+    std::vector<int32_t> h_widths;
+    std::vector<int64_t> h_koff;
+    DevBuf widths, koff, kernels, kcdf;     // dictionary
+    DevBuf yidx, ysidx;                     // int64 per model
+    std::vector<int64_t> h_yidx, h_ysidx;
+    bool labels_dict_set = false;
+    DevBuf grid, y, ystd, lowers, uppers;   // exact-Gaussian KDE
+    bool labels_grid_set = false;
+
+    // scratch
+    DevBuf rows;            // generic kernels: per-CTA row state
+    DevBuf obj_in[3];       // staged inputs
+    DevBuf out_f64[8];      // staged outputs
+    DevBuf out_i64[2];
+    DevBuf misc[8];
+
+    FastModels fast;
+    bool fast_dirty = true;
+
+    // kNN
+    DevBuf knn_feats;       // float32 K x Nm x Nf
+    int knn_K = 0;
+    int64_t knn_Nm = 0;
+    int knn_Nf = 0;
+
+    FzbStats stats = {};
+};
+
+static inline void fzb_count_launch(fzb_context* h, int64_t n = 1) { h->stats.kernel_launches += n; }
+
+// ---- generic fp64 path (fzb_generic.cu) ------------------------------------------------------
+int fzb_generic_fit_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm, int64_t No,
+                        const FzbConfig& cfg, double* d_lnprior, double* d_lnlike, double* d_lnprob,
+                        int64_t* d_ndim, double* d_chi2, double* d_scale, double* d_scale_err);
+int fzb_generic_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm,
+                                int64_t No, const int32_t* d_objsel, int64_t Nsel, const FzbConfig& cfg,
+                                double* d_pdfs, double* d_lmap, double* d_levid, int64_t* d_best_idx,
+                                double* d_best_chi2, double* d_best_scale);
+int fzb_generic_predict_logwt_dev(fzb_context* h, const double* d_logwt, int64_t No, int64_t W,
+                                  const int64_t* d_neighbors, const int64_t* d_nneighbors, const FzbConfig& cfg,
+                                  double* d_pdfs, double* d_lmap, double* d_levid);
+int fzb_generic_shard_pass1_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm,
+                                int64_t No, const FzbConfig& cfg, double* d_pmax, double* d_psum, int64_t* d_pbest);
+int fzb_generic_shard_pass2_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm,
+                                int64_t No, const FzbConfig& cfg, const double* d_lmap, const double* d_levid,
+                                double* d_pdf_partial);
+int fzb_generic_gather_fit_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm,
+                               int64_t No, int64_t W, const int64_t* d_neighbors, const int64_t* d_nneighbors,
+                               const FzbConfig& cfg, double* d_lnprior, double* d_lnlike, double* d_lnprob,
+                               int64_t* d_ndim, double* d_chi2, double* d_scale, double* d_scale_err);
+
+// ---- fp32 fast path (fzb_fast.cu) ------------------------------------------------------------
+bool fzb_fast_supported(const fzb_context* h, const FzbConfig& cfg);
+int fzb_fast_prepare(fzb_context* h);
+int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm, int64_t No,
+                             const FzbConfig& cfg, double* d_pdfs, double* d_lmap, double* d_levid,
+                             int64_t* d_best_idx, double* d_best_chi2, double* d_best_scale);
+
+// ---- kNN (fzb_knn.cu) -------------------------------------------------------------------------
+int fzb_knn_query_dev(fzb_context* h, const double* d_q, int64_t No, int k, double p, int64_t* d_idx, double* d_dist);
+int fzb_knn_union_dev(fzb_context* h, const int64_t* d_idx, int64_t No, int Kk, int64_t* d_neighbors,
+                      int64_t* d_nneighbors);

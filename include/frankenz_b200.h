@@ -1,0 +1,170 @@
+/*
+ * frankenz_b200 -- C ABI of the B200-native brute-force photometric likelihood path.
+ *
+ * This header is the drop-in boundary: a maintainer of joshspeagle/frankenz would
+ * bind exactly these entry points (ctypes stub shown in INTEGRATION.md) to replace
+ * the per-object Python loops of
+ *     frankenz/pdf.py:238-411          loglike / logprob
+ *     frankenz/bruteforce.py:127-205   BruteForce._fit
+ *     frankenz/bruteforce.py:303-372   BruteForce._predict
+ *     frankenz/bruteforce.py:505-631   BruteForce._fit_predict
+ *     frankenz/knn.py:158-188          NearestNeighbors._train_kdtrees
+ *     frankenz/knn.py:281-388, 486-558, 722-874   NearestNeighbors._fit/_predict/_fit_predict
+ *
+ * Conventions
+ *   - plain C types only; every array is C-contiguous; "host" pointers are ordinary
+ *     (pageable or pinned) CPU memory, "dev" pointers are CUDA device memory on the
+ *     handle's device.
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from fzb_last_error() (thread-local).
+ *   - a handle owns one CUDA stream; a handle is thread-compatible, not thread-safe.
+ *   - there is NO CPU fallback: every compute entry point fails if no CUDA device
+ *     is usable.
+ */
+#ifndef FRANKENZ_B200_H
+#define FRANKENZ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fzb_context* fzb_handle;
+
+/* Likelihood / KDE options.  Mirrors the keyword arguments of
+ * frankenz/pdf.py:238-240 (loglike) and frankenz/pdf.py:444-445, 529-531 (KDE). */
+typedef struct FzbConfig {
+    int32_t free_scale;        /* pdf.py:313  */
+    int32_t ignore_model_err;  /* pdf.py:76, :171, :197 */
+    int32_t dim_prior;         /* pdf.py:90, :226 */
+    int32_t track_scale;       /* return scale / scale_err (pdf.py:231-233) */
+    double  ltol;              /* pdf.py:199, default 1e-4 */
+    int32_t use_wt_thresh;     /* 1: select wt > wt_thresh*max(wt) (pdf.py:589-591) */
+    int32_t use_cdf_thresh;    /* 1 (and use_wt_thresh==0): CDF rule (pdf.py:592-597) */
+    double  wt_thresh;         /* default 1e-3 */
+    double  cdf_thresh;        /* default 2e-4 */
+    int32_t precision;         /* FZB_PREC_* */
+    int32_t reserved;
+} FzbConfig;
+
+enum {
+    FZB_PREC_AUTO = 0,   /* fused fp32 scan + fp64 where the error bound requires it */
+    FZB_PREC_FP64 = 1,   /* everything in float64, reference operation order          */
+    FZB_PREC_FP32 = 2    /* force the fp32 path (benchmarking only)                    */
+};
+
+/* Optional (Ndata x Nmodel) outputs of a full fit; any pointer may be NULL.
+ * Mirrors the arrays of frankenz/bruteforce.py:182-189. Host pointers. */
+typedef struct FzbFitOut {
+    double*  lnprior;
+    double*  lnlike;
+    double*  lnprob;
+    int64_t* Ndim;
+    double*  chi2;
+    double*  scale;
+    double*  scale_err;
+} FzbFitOut;
+
+/* Device-side counters of the last call (for bench.py's gpu_launches / roofline). */
+typedef struct FzbStats {
+    int64_t kernel_launches;   /* launches of this library's kernels in the last call   */
+    int64_t pairs_fp32;        /* object-model pairs evaluated by fp32 kernels          */
+    int64_t pairs_fp64;        /* object-model pairs evaluated by fp64 kernels          */
+    int64_t objects_fp64;      /* objects routed to the fp64 path by the error bound    */
+    double  ms_scan;           /* CUDA-event time of pass 1 (max / logsumexp / argmax)   */
+    double  ms_accum;          /* CUDA-event time of pass 2 (weights -> histogram)       */
+    double  ms_finish;         /* CUDA-event time of histogram (*) kernel + normalise    */
+    double  ms_total;          /* CUDA-event time of all device work of the call        */
+} FzbStats;
+
+const char* fzb_last_error(void);
+int fzb_version(void);
+int fzb_device_count(int* count);
+
+int fzb_create(int device, fzb_handle* out);
+int fzb_destroy(fzb_handle h);
+int fzb_synchronize(fzb_handle h);
+int fzb_get_stats(fzb_handle h, FzbStats* out);
+
+/* Model set: replaces BruteForce.__init__ (bruteforce.py:36-64) / NearestNeighbors.__init__
+ * storage (knn.py:89-101).  models/err/mask: host, (Nm x Nf) float64; mask values are
+ * used multiplicatively exactly like the reference (pdf.py:82). */
+int fzb_set_models(fzb_handle h, const double* models, const double* models_err,
+                   const double* models_mask, int64_t Nm, int32_t Nf);
+
+/* Built-in per-model ln-prior added to lnlike (north_star: replaces custom Python
+ * lprob_func).  NULL => zeros (pdf.py:406). host, [Nm]. */
+int fzb_set_lnprior(fzb_handle h, const double* lnprior, int64_t Nm);
+
+/* Dictionary KDE tables: what PDFDict.__init__ tabulates (pdf.py:800-819).
+ * widths[Ndict]; koff[Ndict+1] offsets into kernels/kcdf (each kernel has 2*w+1 entries). */
+int fzb_set_kde_dict(fzb_handle h, int32_t Ngrid, int32_t Ndict, const int32_t* widths,
+                     const int64_t* koff, const double* kernels, const double* kcdf);
+/* Per-model dictionary indices: PDFDict.fit output (pdf.py:844-850). host, [Nm]. */
+int fzb_set_labels_dict(fzb_handle h, const int64_t* y_idx, const int64_t* y_std_idx, int64_t Nm);
+
+/* Exact-Gaussian KDE (pdf.py:444-526): grid[Ngrid], per-model label / sigma and the
+ * clipped windows [lower, upper) computed as pdf.py:499-502. host. */
+int fzb_set_kde_grid(fzb_handle h, const double* grid, int32_t Ngrid);
+int fzb_set_labels_grid(fzb_handle h, const double* y, const double* y_std, const int64_t* lowers,
+                        const int64_t* uppers, int64_t Nm);
+
+/* loglike/logprob of No objects against all models, full (No x Nm) outputs.
+ * Replaces the loop bruteforce.py:192-205 -> pdf.py:326-411.  data/err/mask host (No x Nf). */
+int fzb_fit(fzb_handle h, const double* data, const double* data_err, const double* data_mask,
+            int64_t No, const FzbConfig* cfg, const FzbFitOut* out);
+
+/* Fused fit + predict without materialising the (No x Nm) matrix
+ * (bruteforce.py:602-631 with save_fits=False).  pdfs: host (No x Ngrid); lmap/levid host [No];
+ * best_* (nullable) host [No]: index / chi2 / scale of the max-lnprob model. */
+int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, const double* data_mask,
+                    int64_t No, const FzbConfig* cfg, double* pdfs, double* lmap, double* levid,
+                    int64_t* best_idx, double* best_chi2, double* best_scale);
+
+/* Same, all pointers on the device (inputs resident in HBM; used by bench.py "value"
+ * and by the multi-GPU driver). */
+int fzb_fit_predict_dev(fzb_handle h, const double* d_data, const double* d_err, const double* d_mask,
+                        int64_t No, const FzbConfig* cfg, double* d_pdfs, double* d_lmap, double* d_levid,
+                        int64_t* d_best_idx, double* d_best_chi2, double* d_best_scale);
+
+/* PDFs from a caller-supplied (No x W) log-weight matrix (bruteforce.py:358-372).
+ * neighbors == NULL: W == Nm and column j is model j.  Otherwise the kNN form
+ * (knn.py:541-555): row i uses its first nneighbors[i] columns, column c is model
+ * neighbors[i*W + c]. host pointers. */
+int fzb_predict_logwt(fzb_handle h, const double* logwt, int64_t No, int64_t W,
+                      const int64_t* neighbors, const int64_t* nneighbors, const FzbConfig* cfg,
+                      double* pdfs, double* lmap, double* levid);
+
+/* Model-sharded building blocks (one rank holds a slice of the models).  Device pointers.
+ * pass 1: per-object partial (max lnprob, sum exp(lnprob - max), argmax) over the local models;
+ * the caller merges partials across ranks (max / logsumexp all-reduce), then
+ * pass 2 accumulates the un-normalised PDF of the local models for the GLOBAL lmap, levid;
+ * the caller sums PDF partials across ranks and normalises. */
+int fzb_shard_pass1_dev(fzb_handle h, const double* d_data, const double* d_err, const double* d_mask,
+                        int64_t No, const FzbConfig* cfg, double* d_pmax, double* d_psum, int64_t* d_pbest);
+int fzb_shard_pass2_dev(fzb_handle h, const double* d_data, const double* d_err, const double* d_mask,
+                        int64_t No, const FzbConfig* cfg, const double* d_lmap, const double* d_levid,
+                        double* d_pdf_partial);
+
+/* kNN: brute-force replacement of K cKDTrees (knn.py:186, :362-365).
+ * feats: host float32 (K x Nm x Nf), the MC-realised, feature-mapped training sets
+ * (knn.py:177-184; generated by the caller's RandomState so draws match the reference). */
+int fzb_knn_build(fzb_handle h, const float* feats, int32_t K, int64_t Nm, int32_t Nf);
+/* qfeats: host float64 (No x Nf).  idx: host int64 (No x K x k), tree-major, ascending
+ * float64 Minkowski-p distance (p = 1, 2, or <=0 for infinity), exact (eps = 0).
+ * dist (nullable): host float64 (No x K x k). */
+int fzb_knn_query(fzb_handle h, const double* qfeats, int64_t No, int32_t k, double p,
+                  int64_t* idx, double* dist);
+/* Ordered union of the K*k neighbours (pandas.unique order, knn.py:368) and the likelihood
+ * of each object against its union (knn.py:375-386), padded like knn.py:342-352.
+ * neighbors: host int64 (No x K*k) filled with -99 beyond nneighbors[i]. out arrays are
+ * (No x K*k). */
+int fzb_knn_fit(fzb_handle h, const double* qfeats, const double* data, const double* data_err,
+                const double* data_mask, int64_t No, int32_t k, double p, const FzbConfig* cfg,
+                int64_t* neighbors, int64_t* nneighbors, const FzbFitOut* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRANKENZ_B200_H */
