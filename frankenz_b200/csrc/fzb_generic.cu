@@ -10,12 +10,13 @@
 #include <math_constants.h>
 
 #include "fzb_common.cuh"
+#include "fzb_pair64.cuh"
 
 namespace {
 
+using namespace fzb64;
+
 constexpr int GT = 256;  // threads per CTA
-constexpr double kLn2 = 0.69314718055994530942;
-constexpr double kLn2Pi = 1.83787706640934548356;  // ln(2*pi)
 constexpr double kSqrt2Pi = 2.50662827463100050242;
 
 enum Stage { ST_FIT = 0, ST_FIT_PREDICT = 1, ST_PASS1 = 2, ST_PASS2 = 3, ST_LOGWT = 4 };
@@ -128,106 +129,6 @@ __device__ __forceinline__ void block_argmax(double& v, long long& i, double* re
 #pragma unroll
     for (int w = 1; w < GT / 32; ++w)
         if (red[w] > v || (red[w] == v && redi[w] < i)) { v = red[w]; i = redi[w]; }
-}
-
-// ---- per-pair arithmetic (float64, reference order) --------------------------------------------
-__device__ __forceinline__ double xlogy_d(double a, double c) {
-    // scipy.special.xlogy: 0 where a == 0 and c is not NaN
-    if (a == 0.0 && !isnan(c)) return 0.0;
-    return a * log(c);
-}
-__device__ __forceinline__ double chi2_logpdf(double chi2, double a) {
-    // pdf.py:93 / :229
-    return xlogy_d(a - 1.0, chi2) - (chi2 / 2.0) - lgamma(a) - (kLn2 * a);
-}
-
-struct PairState {
-    double ndim, chi2, lnl, scale, shape;
-};
-
-// first evaluation of a pair: pdf.py:76-98 (fixed scale) or :171-194 (free scale)
-__device__ __forceinline__ void pair_first(const double* sx, const double* sxe, const double* sxm,
-                                           const double* __restrict__ m, const double* __restrict__ me,
-                                           const double* __restrict__ mm, int Nf, int free_scale, int ime,
-                                           PairState& st) {
-    double ndim = 0.0, slv = 0.0;
-    if (!free_scale) {
-        double chi2 = 0.0;
-        for (int b = 0; b < Nf; ++b) {
-            double e = me[b];
-            double var = sxe[b] * sxe[b] + (ime ? 0.0 : e * e);
-            double msk = sxm[b] * mm[b];
-            ndim += msk;
-            double r = sx[b] - m[b];
-            chi2 += msk * (r * r) / var;
-            slv += log(var);
-        }
-        st.ndim = ndim;
-        st.chi2 = chi2;
-        st.scale = 1.0;
-        st.shape = CUDART_NAN;
-        double l = -0.5 * chi2;
-        l += -0.5 * (ndim * kLn2Pi + slv);
-        st.lnl = l;
-        return;
-    }
-    double inter = 0.0, shape = 0.0;
-    for (int b = 0; b < Nf; ++b) {
-        double e = me[b];
-        double var = sxe[b] * sxe[b] + (ime ? 0.0 : e * e);
-        double msk = sxm[b] * mm[b];
-        ndim += msk;
-        inter += (msk * m[b] * sx[b]) / var;
-        shape += (msk * (m[b] * m[b])) / var;
-        slv += log(var);
-    }
-    double scale = inter / shape;
-    double chi2 = 0.0;
-    for (int b = 0; b < Nf; ++b) {
-        double e = me[b];
-        double var = sxe[b] * sxe[b] + (ime ? 0.0 : e * e);
-        double msk = sxm[b] * mm[b];
-        double r = sx[b] - scale * m[b];
-        chi2 += msk * (r * r) / var;
-    }
-    st.ndim = ndim;
-    st.chi2 = chi2;
-    st.scale = scale;
-    st.shape = shape;
-    double l = -0.5 * chi2;
-    l += -0.5 * (ndim * kLn2Pi + slv);
-    st.lnl = l;
-}
-
-// one refinement of the iterated free-scale mode: pdf.py:200-216
-__device__ __forceinline__ void pair_refine(const double* sx, const double* sxe, const double* sxm,
-                                            const double* __restrict__ m, const double* __restrict__ me,
-                                            const double* __restrict__ mm, int Nf, double ndim, double scale_prev,
-                                            double& scale_new, double& chi2_new, double& lnl_new, double& shape_new) {
-    double inter = 0.0, shape = 0.0, slv = 0.0;
-    for (int b = 0; b < Nf; ++b) {
-        double se = scale_prev * me[b];
-        double var = sxe[b] * sxe[b] + se * se;
-        double msk = sxm[b] * mm[b];
-        inter += (msk * m[b] * sx[b]) / var;
-        shape += (msk * (m[b] * m[b])) / var;
-        slv += log(var);
-    }
-    double sc = inter / shape;
-    double chi2 = 0.0;
-    for (int b = 0; b < Nf; ++b) {
-        double se = scale_prev * me[b];
-        double var = sxe[b] * sxe[b] + se * se;
-        double msk = sxm[b] * mm[b];
-        double r = sx[b] - sc * m[b];
-        chi2 += msk * (r * r) / var;
-    }
-    double l = -0.5 * chi2;
-    l += -0.5 * (ndim * kLn2Pi + slv);
-    scale_new = sc;
-    chi2_new = chi2;
-    lnl_new = l;
-    shape_new = shape;
 }
 
 // ---- KDE scatter of one selected model by one warp ----------------------------------------------
