@@ -224,6 +224,17 @@ class Engine(object):
         res["neighbors"], res["Nneighbors"] = nb, nn
         return res
 
+    def measure_peaks(self, reps=5):
+        """FP32-FMA (TFLOP/s) and MUFU (Gop/s) peaks of this device, measured with dependency-free loops."""
+        a, b = C.c_double(), C.c_double()
+        _lib.check(self.lib.fzb_measure_peaks(self.h, reps, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def fit_predict_dev(self, d_x, d_xe, d_xm, no, cfg, d_pdfs, d_lmap, d_levid, d_best, d_bchi2, d_bscale):
+        """Device-pointer form of `fit_predict` (integers = CUDA device addresses on this handle's device)."""
+        _lib.check(self.lib.fzb_fit_predict_dev(self.h, d_x, d_xe, d_xm, no, C.byref(cfg), d_pdfs, d_lmap, d_levid,
+                                                d_best, d_bchi2, d_bscale))
+
     def stats(self):
         s = FzbStats()
         _lib.check(self.lib.fzb_get_stats(self.h, C.byref(s)))

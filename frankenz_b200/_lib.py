@@ -49,6 +49,7 @@ SIGNATURES = {
     "fzb_destroy": (C.c_int, [_H]),
     "fzb_synchronize": (C.c_int, [_H]),
     "fzb_get_stats": (C.c_int, [_H, C.POINTER(FzbStats)]),
+    "fzb_measure_peaks": (C.c_int, [_H, C.c_int, c_double_p, c_double_p]),
     "fzb_set_models": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int32]),
     "fzb_set_lnprior": (C.c_int, [_H, c_double_p, C.c_int64]),
     "fzb_set_kde_dict": (C.c_int, [_H, C.c_int32, C.c_int32, c_int32_p, c_int64_p, c_double_p, c_double_p]),

@@ -114,6 +114,9 @@ struct fzb_context {
 
     FastModels fast;
     bool fast_dirty = true;
+    int fast_mode = -1;
+    int fast_wmax = 0;
+    int fast_Ngpad = 0;
 
     // kNN
     DevBuf knn_feats;       // float32 K x Nm x Nf

@@ -1,10 +1,864 @@
-// fp32 register-tiled path (placeholder until the kernels land: reports "unsupported").
-#include "fzb_common.cuh"
+// fp32 register-tiled path for the reduce-only shapes (fit_predict with save_fits=False).
+//
+// Layout: one thread owns R objects (photometry, weights and the running reduction state live in
+// registers); all threads of a CTA walk the same model tile, which a single elected thread stages
+// into shared memory with TMA bulk copies (cp.async.bulk + mbarrier, double buffered), so every
+// model value is a shared-memory broadcast.  The (N_obj x N_model) matrix never exists:
+//
+//   pass 1  k_sweep<PASS=1>  per pair: chi2 / optimal scale -> ln-likelihood (log2 units) ->
+//                            online (max, sum 2^(l-max), argmax) per object
+//   merge   k_merge          combine model splits, re-evaluate the best pair exactly in float64
+//                            (lmap, chi2, scale), levid = lmap + ln(sum), decide per object
+//                            whether the fp32 error bound allows the fp32 pass 2
+//   pass 2  k_sweep<PASS=2>  recompute l, weight = 2^(l - max) if above the wt_thresh cut, sum the
+//                            weights of each run of models that share a KDE bin in a register and
+//                            flush one RED per (object, bin) into a global histogram
+//   finish  k_finish         histogram (*) tabulated Gaussian kernel in float64, normalise, write PDF
+//
+// Models are sorted by KDE bin (dictionary width, grid position) when the labels are set, which is
+// what makes the "one flush per bin" accumulation possible.  Objects whose fp32 result cannot be
+// trusted to the 1e-5 parity bound (large best-fit chi2, extreme S/N, degenerate rows, non-finite
+// sums) are routed to the float64 kernels of fzb_generic.cu.
+//
+// Precision: inputs are split hi/lo (float64 = hi + lo); the sweep uses the hi parts and re-does
+// the residuals with the lo parts only for pairs near the running maximum of bright objects, where
+// the cancellation d - s*m would otherwise lose the low bits (hard part 1).
+#include <algorithm>
+#include <cfloat>
+#include <cstdlib>
+#include <numeric>
 
-bool fzb_fast_supported(const fzb_context*, const FzbConfig&) { return false; }
-int fzb_fast_prepare(fzb_context*) { return 0; }
-int fzb_fast_fit_predict_dev(fzb_context*, const double*, const double*, const double*, int64_t, const FzbConfig&,
-                             double*, double*, double*, int64_t*, double*, double*) {
-    fzb_set_error("fp32 path not built");
+#include "fzb_common.cuh"
+#include "fzb_pair64.cuh"
+
+namespace {
+
+constexpr int FT = 256;          // threads per CTA
+constexpr int TM = 256;          // models per shared-memory tile
+constexpr int NSTAGE = 2;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kHalfLog2e = 0.7213475204444817f;
+constexpr float kRefineMargin = 48.0f;   // log2 units below the running max that still get the lo-part redo
+
+enum FastMode { FM_FS0 = 0, FM_FX0 = 1, FM_FX1 = 2 };
+
+__host__ __device__ constexpr int rec_floats(int nf, int mode) {
+    // m[nf] (+ q[nf] = m^2 for FS0, me2[nf] for FX1) + prior2 + bin + invnorm, padded to 4 floats
+    int n = nf + ((mode == FM_FX0) ? 0 : nf) + 3;
+    return (n + 3) / 4 * 4;
+}
+
+// ---- PTX helpers: mbarrier + TMA bulk copy ----------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---- kernel parameters -------------------------------------------------------------------------
+struct SweepParams {
+    // objects, SoA [field][band][No_pad]
+    const float* od;      // d_hi
+    const float* ow;      // FS0/FX0: mask/err^2        FX1: unused
+    const float* ox;      // FS0: d*w                   FX1: err^2 (+inf where masked)
+    const float* olo;     // d_lo
+    const float* oA;      // [No_pad] (dof/2 - 1) or 0
+    const float* ocut;    // [No_pad] refine margin (log2 units) or -inf
+    int64_t No_pad;
+    int64_t No;           // objects in this launch (pass 1) / entries of objlist (pass 2)
+    // models
+    const float* recs;    // [nm][REC]
+    const float* mlo;     // [nm][NF] lo parts of the model fluxes
+    int64_t nm;
+    int tiles_per_split;
+    // pass 1 outputs: [nsplit][No_pad]
+    float* pM;
+    float* pS;
+    int32_t* pbest;
+    // pass 2
+    const int32_t* objlist;
+    const float* M2;      // [No_pad] final max (log2 units, without the per-object constant)
+    const float* thr2;    // [No_pad] selection cut in the same units
+    float* hist;          // [No_pad][hist_stride]
+    int64_t hist_stride;
+};
+
+template <int NF, int MODE>
+struct ObjRegs {
+    float d[NF];
+    float w[NF];   // FS0/FX0: weights; FX1: err^2 (+inf where masked)
+    float x[NF];   // FS0 only: d*w
+    float A, cut;
+};
+
+// hi-part evaluation of one pair.  Returns chi2; `s` is the optimal scale (FS0) or 1.
+template <int NF, int MODE>
+__device__ __forceinline__ float pair_chi2(const ObjRegs<NF, MODE>& o, const float* __restrict__ m,
+                                           const float* __restrict__ aux, float& s) {
+    float chi2;
+    if (MODE == FM_FS0) {
+        float inter = __fmul_rn(o.x[0], m[0]);
+        float shape = __fmul_rn(o.w[0], aux[0]);
+#pragma unroll
+        for (int b = 1; b < NF; ++b) {
+            inter = __fmaf_rn(o.x[b], m[b], inter);
+            shape = __fmaf_rn(o.w[b], aux[b], shape);
+        }
+        s = __fmul_rn(inter, fast_rcp(shape));
+        float r = __fmaf_rn(-s, m[0], o.d[0]);
+        chi2 = __fmul_rn(__fmul_rn(r, o.w[0]), r);
+#pragma unroll
+        for (int b = 1; b < NF; ++b) {
+            r = __fmaf_rn(-s, m[b], o.d[b]);
+            chi2 = __fmaf_rn(__fmul_rn(r, o.w[b]), r, chi2);
+        }
+    } else if (MODE == FM_FX0) {
+        s = 1.f;
+        float r = __fsub_rn(o.d[0], m[0]);
+        chi2 = __fmul_rn(__fmul_rn(r, o.w[0]), r);
+#pragma unroll
+        for (int b = 1; b < NF; ++b) {
+            r = __fsub_rn(o.d[b], m[b]);
+            chi2 = __fmaf_rn(__fmul_rn(r, o.w[b]), r, chi2);
+        }
+    } else {
+        s = 1.f;
+        float r = __fsub_rn(o.d[0], m[0]);
+        chi2 = __fmul_rn(__fmul_rn(r, fast_rcp(__fadd_rn(o.w[0], aux[0]))), r);
+#pragma unroll
+        for (int b = 1; b < NF; ++b) {
+            r = __fsub_rn(o.d[b], m[b]);
+            chi2 = __fmaf_rn(__fmul_rn(r, fast_rcp(__fadd_rn(o.w[b], aux[b]))), r, chi2);
+        }
+    }
+    return chi2;
+}
+
+// redo of the residuals with the lo parts (rare path: pairs near the maximum of bright objects)
+template <int NF, int MODE>
+__device__ __forceinline__ float pair_chi2_lo(const ObjRegs<NF, MODE>& o, const float* __restrict__ m,
+                                           const float* __restrict__ aux, float s, const float* __restrict__ olo,
+                                           int64_t ostride, const float* __restrict__ mlo) {
+    float chi2 = 0.f;
+#pragma unroll
+    for (int b = 0; b < NF; ++b) {
+        float dl = olo[b * ostride];
+        float ml = mlo[b];
+        float r, w;
+        if (MODE == FM_FS0) {
+            r = __fadd_rn(__fmaf_rn(-s, m[b], o.d[b]), __fmaf_rn(-s, ml, dl));
+            w = o.w[b];
+        } else {
+            r = __fadd_rn(__fsub_rn(o.d[b], m[b]), __fsub_rn(dl, ml));
+            w = (MODE == FM_FX0) ? o.w[b] : fast_rcp(__fadd_rn(o.w[b], aux[b]));
+        }
+        chi2 = __fmaf_rn(__fmul_rn(r, w), r, chi2);
+    }
+    return chi2;
+}
+
+template <bool DP>
+__device__ __forceinline__ float chi2_to_l2(float chi2, float A, float prior2) {
+    // ln-likelihood in log2 units without the per-object constant:
+    //   DP: (dof/2 - 1) * log2(chi2) - chi2 * log2(e)/2        (pdf.py:93 / :229, xlogy semantics)
+    //  !DP: - chi2 * log2(e)/2                                   (pdf.py:96, :192)
+    float l = __fmaf_rn(chi2, -kHalfLog2e, prior2);
+    if (DP) {
+        float t = __fmul_rn(A, fast_lg2(chi2));
+        l = __fadd_rn(l, (A == 0.f) ? 0.f : t);
+    }
+    return l;
+}
+
+template <int NF, int MODE, bool DP, int R, int PASS>
+__global__ void __launch_bounds__(FT, (R >= 4) ? 2 : 3) k_sweep(SweepParams P) {
+    constexpr int REC = rec_floats(NF, MODE);
+    constexpr int AUXOFF = NF;                                  // q / me2
+    constexpr int TAILOFF = NF + ((MODE == FM_FX0) ? 0 : NF);   // prior2, bin, invnorm
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * TM * REC * sizeof(float));
+    const int tid = threadIdx.x;
+
+    // ---- this thread's objects -----------------------------------------------------------------
+    ObjRegs<NF, MODE> ob[R];
+    int64_t oidx[R];
+    float M[R], S[R];
+    int best[R];
+    float acc[R];
+    const int64_t tile_base = (int64_t)blockIdx.x * (FT * R);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int64_t slot = tile_base + (int64_t)r * FT + tid;
+        int64_t o;
+        if (PASS == 1) o = slot < P.No_pad ? slot : P.No_pad - 1;
+        else o = slot < P.No ? P.objlist[slot] : -1;
+        oidx[r] = o;
+        int64_t oo = o < 0 ? 0 : o;
+#pragma unroll
+        for (int b = 0; b < NF; ++b) {
+            ob[r].d[b] = P.od[b * P.No_pad + oo];
+            if (MODE == FM_FX1) ob[r].w[b] = P.ox[b * P.No_pad + oo];
+            else ob[r].w[b] = P.ow[b * P.No_pad + oo];
+            if (MODE == FM_FS0) ob[r].x[b] = P.ox[b * P.No_pad + oo];
+        }
+        ob[r].A = P.oA[oo];
+        ob[r].cut = P.ocut[oo];
+        if (PASS == 1) { M[r] = -FLT_MAX; S[r] = 0.f; best[r] = 0; }
+        else { M[r] = P.M2[oo]; S[r] = P.thr2[oo]; acc[r] = 0.f; }
+    }
+
+    // ---- model tiles of this split ---------------------------------------------------------------
+    const int64_t ntiles_all = (P.nm + TM - 1) / TM;
+    const int64_t t0 = (int64_t)blockIdx.y * P.tiles_per_split;
+    int64_t t1 = t0 + P.tiles_per_split;
+    if (t1 > ntiles_all) t1 = ntiles_all;
+    const int nt = (int)(t1 - t0);
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int it) {
+        int64_t tile = t0 + it;
+        int64_t first = tile * TM;
+        int cnt = (int)((P.nm - first) < TM ? (P.nm - first) : TM);
+        uint32_t bytes = (uint32_t)cnt * REC * sizeof(float);
+        uint64_t* bar = &bars[it % NSTAGE];
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(stage + (size_t)(it % NSTAGE) * TM * REC, P.recs + first * REC, bytes, bar);
+    };
+    if (tid == 0) {
+        for (int it = 0; it < NSTAGE && it < nt; ++it) issue(it);
+    }
+    int cur_bin = -1;
+    for (int it = 0; it < nt; ++it) {
+        const int st = it % NSTAGE;
+        mbar_wait(&bars[st], (uint32_t)((it / NSTAGE) & 1));
+        const float* tile = stage + (size_t)st * TM * REC;
+        const int64_t first = (t0 + it) * TM;
+        const int cnt = (int)((P.nm - first) < TM ? (P.nm - first) : TM);
+#pragma unroll 1
+        for (int jj = 0; jj < cnt; ++jj) {
+            const float* rec = tile + jj * REC;
+            float m[NF], aux[NF];
+#pragma unroll
+            for (int b = 0; b < NF; ++b) {
+                m[b] = rec[b];
+                aux[b] = (MODE == FM_FX0) ? 0.f : rec[AUXOFF + b];
+            }
+            const float prior2 = rec[TAILOFF];
+            if (PASS == 2) {
+                const int bin = __float_as_int(rec[TAILOFF + 1]);
+                if (bin != cur_bin) {       // warp-uniform: every thread walks the same model
+                    if (cur_bin >= 0) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            if (acc[r] != 0.f && oidx[r] >= 0)
+                                atomicAdd(P.hist + oidx[r] * P.hist_stride + cur_bin, acc[r]);
+                            acc[r] = 0.f;
+                        }
+                    }
+                    cur_bin = bin;
+                }
+            }
+            const float invnorm = (PASS == 2) ? rec[TAILOFF + 2] : 0.f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float s;
+                float chi2 = pair_chi2<NF, MODE>(ob[r], m, aux, s);
+                float l2 = chi2_to_l2<DP>(chi2, ob[r].A, prior2);
+                if (l2 > M[r] - ob[r].cut) {   // bright object, pair near the maximum: redo with lo parts
+                    int64_t oo = oidx[r] < 0 ? 0 : oidx[r];
+                    chi2 = pair_chi2_lo<NF, MODE>(ob[r], m, aux, s, P.olo + oo, P.No_pad, P.mlo + (first + jj) * NF);
+                    l2 = chi2_to_l2<DP>(chi2, ob[r].A, prior2);
+                }
+                if (PASS == 1) {
+                    float delta = __fsub_rn(l2, M[r]);
+                    float e = fast_ex2(-fabsf(delta));
+                    if (delta > 0.f) {
+                        S[r] = __fmaf_rn(S[r], e, 1.f);
+                        M[r] = l2;
+                        best[r] = (int)(first + jj);
+                    } else {
+                        S[r] = __fadd_rn(S[r], e);
+                    }
+                } else {
+                    float u = fast_ex2(__fsub_rn(l2, M[r]));
+                    u = (l2 > S[r]) ? u : 0.f;      // S[r] holds the selection cut in pass 2
+                    acc[r] = __fmaf_rn(u, invnorm, acc[r]);
+                }
+            }
+        }
+        __syncthreads();   // everyone is done with this stage
+        if (tid == 0 && it + NSTAGE < nt) issue(it + NSTAGE);
+    }
+    if (PASS == 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int64_t slot = tile_base + (int64_t)r * FT + tid;
+            if (slot < P.No_pad) {
+                size_t q = (size_t)blockIdx.y * P.No_pad + slot;
+                P.pM[q] = M[r];
+                P.pS[q] = S[r];
+                P.pbest[q] = best[r];
+            }
+        }
+    } else if (cur_bin >= 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (acc[r] != 0.f && oidx[r] >= 0) atomicAdd(P.hist + oidx[r] * P.hist_stride + cur_bin, acc[r]);
+    }
+}
+
+// ---- object preparation ------------------------------------------------------------------------
+struct PrepParams {
+    const double *x, *xe, *xm;   // (No x Nf) raw inputs of this chunk
+    int64_t No, No_pad;
+    int Nf, mode, free_scale, dim_prior;
+    float *od, *ow, *ox, *olo, *oA, *ocut, *osnr;
+    float lo_snr;                // per-band S/N above which the lo-part redo is armed
+};
+
+__global__ void k_prep_objects(PrepParams P) {
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= P.No_pad) return;
+    double ndim = 0.0, snr2 = 0.0, snr_max = 0.0;
+    for (int b = 0; b < P.Nf; ++b) {
+        double d = 0.0, e = 1.0, k = 0.0;
+        if (o < P.No) {
+            d = P.x[o * P.Nf + b];
+            e = P.xe[o * P.Nf + b];
+            k = P.xm[o * P.Nf + b];
+            bool clean = isfinite(d) && isfinite(e) && (e > 0.0);   // pdf.py:310-311
+            if (!clean) { d = 0.0; e = 1.0; k = 0.0; }
+        }
+        float dh = (float)d;
+        float dl = (float)(d - (double)dh);
+        double w = k / (e * e);
+        size_t q = (size_t)b * P.No_pad + o;
+        P.od[q] = dh;
+        P.olo[q] = dl;
+        if (P.mode == FM_FX1) {
+            P.ox[q] = (k != 0.0) ? (float)(e * e) : CUDART_INF_F;
+            P.ow[q] = 0.f;
+        } else {
+            P.ow[q] = (float)w;
+            P.ox[q] = (float)(d * w);
+        }
+        ndim += k;
+        double sn = (k != 0.0) ? fabs(d) / e : 0.0;
+        snr2 += sn * sn;
+        if (sn > snr_max) snr_max = sn;
+    }
+    double a = P.free_scale ? 0.5 * (ndim - 1.0) : 0.5 * ndim;
+    P.oA[o] = P.dim_prior ? (float)(a - 1.0) : 0.f;
+    P.ocut[o] = (snr_max > P.lo_snr) ? kRefineMargin : -CUDART_INF_F;
+    P.osnr[o] = (float)sqrt(snr2);
+}
+
+// ---- merge of the model splits + exact re-evaluation of the best pair + routing -------------------
+struct MergeParams {
+    const double *x, *xe, *xm;          // raw inputs (chunk)
+    const double *m, *me, *mm;          // float64 models (original order)
+    const double* lnprior;              // nullable
+    const int32_t* perm;                // sorted position -> original model
+    int64_t No, No_pad, o_base;
+    int Nf, nsplit, free_scale, ime, dim_prior;
+    const float *pM, *pS;
+    const int32_t* pbest;
+    const float* osnr;
+    double log2_wt_thresh;              // log2(wt_thresh) or -inf
+    double chi2_max, snr_max, consist_tol;
+    int force_fp32;
+    // outputs
+    double *lmap, *levid, *best_chi2, *best_scale;   // absolute object index
+    int64_t* best_idx;
+    float *M2, *thr2;                   // chunk-local
+    int32_t *safe_list, *unsafe_list, *counts;   // counts[0]=safe, counts[1]=unsafe
+};
+
+__global__ void k_merge(MergeParams P) {
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= P.No) return;
+    float M = -FLT_MAX;
+    int bs = 0;
+    for (int s = 0; s < P.nsplit; ++s) {
+        float v = P.pM[(size_t)s * P.No_pad + o];
+        if (v > M) { M = v; bs = s; }
+    }
+    double S = 0.0;
+    bool bad = false;
+    for (int s = 0; s < P.nsplit; ++s) {
+        float v = P.pM[(size_t)s * P.No_pad + o], ss = P.pS[(size_t)s * P.No_pad + o];
+        if (!(ss == ss) || isinf(ss)) bad = true;
+        if (v > -FLT_MAX) S += (double)ss * exp2((double)v - (double)M);
+    }
+    int64_t sorted_best = P.pbest[(size_t)bs * P.No_pad + o];
+    int64_t j = P.perm[sorted_best];
+    // exact float64 evaluation of (object, best model): pdf.py:27-235 via fzb_pair64.cuh
+    double sx[FZB_FAST_MAXF], sxe[FZB_FAST_MAXF], sxm[FZB_FAST_MAXF];
+    for (int b = 0; b < P.Nf; ++b) {
+        double d = P.x[o * P.Nf + b], e = P.xe[o * P.Nf + b], k = P.xm[o * P.Nf + b];
+        bool clean = isfinite(d) && isfinite(e) && (e > 0.0);
+        sx[b] = clean ? d : 0.0;
+        sxe[b] = clean ? e : 1.0;
+        sxm[b] = clean ? k : 0.0;
+    }
+    fzb64::PairState st;
+    fzb64::pair_first(sx, sxe, sxm, P.m + j * P.Nf, P.me + j * P.Nf, P.mm + j * P.Nf, P.Nf, P.free_scale, P.ime, st);
+    double a = P.free_scale ? 0.5 * (st.ndim - 1.0) : 0.5 * st.ndim;
+    double lnl = P.dim_prior ? fzb64::chi2_logpdf(st.chi2, a) : st.lnl;
+    double lp = P.lnprior ? P.lnprior[j] : 0.0;
+    double lmap = P.lnprior ? lnl + lp : lnl;
+    // the same "varying part" the fp32 sweep tracks, in float64, for a consistency check
+    double vary = -0.5 * st.chi2 * 1.4426950408889634 + lp * 1.4426950408889634;
+    if (P.dim_prior && (a - 1.0) != 0.0) vary += (a - 1.0) * log2(st.chi2);
+    bool safe = !bad && isfinite((double)M) && M > -FLT_MAX && isfinite(S) && S >= 0.5 && isfinite(lmap) &&
+                fabs(vary - (double)M) <= P.consist_tol * fmax(1.0, fabs(vary));
+    if (!P.force_fp32) safe = safe && (st.chi2 <= P.chi2_max) && ((double)P.osnr[o] <= P.snr_max);
+    int64_t og = P.o_base + o;
+    if (P.lmap) P.lmap[og] = lmap;
+    if (P.levid) P.levid[og] = lmap + log(S);
+    if (P.best_idx) P.best_idx[og] = j;
+    if (P.best_chi2) P.best_chi2[og] = st.chi2;
+    if (P.best_scale) P.best_scale[og] = st.scale;
+    P.M2[o] = M;
+    P.thr2[o] = (float)((double)M + P.log2_wt_thresh);
+    if (safe) P.safe_list[atomicAdd(&P.counts[0], 1)] = (int32_t)o;
+    else P.unsafe_list[atomicAdd(&P.counts[1], 1)] = (int32_t)og;
+}
+
+// ---- histogram (*) kernel, normalise, write -------------------------------------------------------
+struct FinishParams {
+    const float* hist;          // [No_pad][hist_stride]
+    int64_t hist_stride;
+    const int32_t* objlist;     // chunk-local safe objects
+    int64_t o_base;
+    int Ng, Ngpad, wmax, nslot;
+    const int32_t* slot_sidx;   // slot -> dictionary index
+    const int32_t* widths;
+    const int64_t* koff;
+    const double* kernels;
+    double* pdfs;               // absolute rows
+};
+
+__global__ void __launch_bounds__(256) k_finish(FinishParams P) {
+    extern __shared__ double sm_f[];
+    double* h = sm_f;                 // Ngpad
+    double* pdf = h + P.Ngpad;        // Ng
+    __shared__ double red[8];
+    const int tid = threadIdx.x;
+    const int64_t o = P.objlist[blockIdx.x];
+    for (int g = tid; g < P.Ng; g += 256) pdf[g] = 0.0;
+    for (int s = 0; s < P.nslot; ++s) {
+        __syncthreads();
+        const float* row = P.hist + o * P.hist_stride + (size_t)s * P.Ngpad;
+        for (int g = tid; g < P.Ngpad; g += 256) h[g] = (double)row[g];
+        __syncthreads();
+        const int si = P.slot_sidx[s];
+        const int w = P.widths[si];
+        const double* kern = P.kernels + P.koff[si];
+        for (int x = tid; x < P.Ng; x += 256) {
+            double a = 0.0;
+            // model at grid position pos contributes kern[x - pos + w]; histogram index = pos + wmax
+            for (int t = -w; t <= w; ++t) a += h[x + t + P.wmax] * kern[w - t];
+            pdf[x] += a;
+        }
+    }
+    __syncthreads();
+    double part = 0.0;
+    for (int g = tid; g < P.Ng; g += 256) part += pdf[g];
+    for (int s = 16; s > 0; s >>= 1) part += __shfl_xor_sync(0xffffffffu, part, s);
+    if ((tid & 31) == 0) red[tid >> 5] = part;
+    __syncthreads();
+    double tot = 0.0;
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    double* out = P.pdfs + (size_t)(P.o_base + o) * P.Ng;
+    for (int g = tid; g < P.Ng; g += 256) out[g] = pdf[g] / tot;
+}
+
+// ---- record building ------------------------------------------------------------------------------
+struct RecParams {
+    const double *m, *me, *lnprior;
+    const int32_t* perm;
+    const int32_t* bins;
+    const float* invnorm;
+    int64_t nm;
+    int Nf, mode, rec;
+    float* recs;
+    float* mlo;
+};
+
+__global__ void k_build_records(RecParams P) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.nm) return;
+    int64_t j = P.perm[p];
+    float* r = P.recs + p * P.rec;
+    for (int b = 0; b < P.Nf; ++b) {
+        double v = P.m[j * P.Nf + b];
+        float hi = (float)v;
+        r[b] = hi;
+        P.mlo[p * P.Nf + b] = (float)(v - (double)hi);
+        if (P.mode == FM_FS0) r[P.Nf + b] = (float)(v * v);
+        else if (P.mode == FM_FX1) {
+            double e = P.me[j * P.Nf + b];
+            r[P.Nf + b] = (float)(e * e);
+        }
+    }
+    int tail = P.Nf + ((P.mode == FM_FX0) ? 0 : P.Nf);
+    r[tail] = P.lnprior ? (float)(P.lnprior[j] * 1.4426950408889634) : 0.f;
+    r[tail + 1] = __int_as_float(P.bins ? P.bins[p] : -1);
+    r[tail + 2] = P.invnorm ? P.invnorm[p] : 0.f;
+    for (int i = tail + 3; i < P.rec; ++i) r[i] = 0.f;
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+int mode_of(const FzbConfig& cfg) {
+    if (cfg.free_scale) return (cfg.ignore_model_err == 1) ? FM_FS0 : -1;
+    return cfg.ignore_model_err ? FM_FX0 : FM_FX1;
+}
+
+double env_double(const char* name, double dflt) {
+    const char* v = getenv(name);
+    return v ? atof(v) : dflt;
+}
+
+template <int NF, int MODE, bool DP, int R, int PASS>
+int launch_sweep_t(fzb_context* h, const SweepParams& P, dim3 grid) {
+    constexpr int REC = rec_floats(NF, MODE);
+    size_t smem = (size_t)NSTAGE * TM * REC * sizeof(float) + NSTAGE * sizeof(uint64_t);
+    auto kern = k_sweep<NF, MODE, DP, R, PASS>;
+    FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, FT, smem, h->stream>>>(P);
+    fzb_count_launch(h);
+    FZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int NF, int MODE, bool DP>
+int launch_sweep_r(fzb_context* h, const SweepParams& P, dim3 grid, int R, int pass) {
+    if (pass == 1) {
+        if (R == 4) return launch_sweep_t<NF, MODE, DP, 4, 1>(h, P, grid);
+        return launch_sweep_t<NF, MODE, DP, 1, 1>(h, P, grid);
+    }
+    if (R == 4) return launch_sweep_t<NF, MODE, DP, 4, 2>(h, P, grid);
+    return launch_sweep_t<NF, MODE, DP, 1, 2>(h, P, grid);
+}
+
+template <int NF>
+int launch_sweep_nf(fzb_context* h, const SweepParams& P, dim3 grid, int mode, bool dp, int R, int pass) {
+    if (mode == FM_FS0) return dp ? launch_sweep_r<NF, FM_FS0, true>(h, P, grid, R, pass)
+                                  : launch_sweep_r<NF, FM_FS0, false>(h, P, grid, R, pass);
+    if (mode == FM_FX0) return dp ? launch_sweep_r<NF, FM_FX0, true>(h, P, grid, R, pass)
+                                  : launch_sweep_r<NF, FM_FX0, false>(h, P, grid, R, pass);
+    return launch_sweep_r<NF, FM_FX1, true>(h, P, grid, R, pass);
+}
+
+int launch_sweep(fzb_context* h, const SweepParams& P, dim3 grid, int nf, int mode, bool dp, int R, int pass) {
+    switch (nf) {
+        case 4: return launch_sweep_nf<4>(h, P, grid, mode, dp, R, pass);
+        case 5: return launch_sweep_nf<5>(h, P, grid, mode, dp, R, pass);
+        case 6: return launch_sweep_nf<6>(h, P, grid, mode, dp, R, pass);
+        default: break;
+    }
+    fzb_set_error("fp32 path: unsupported filter count %d", nf);
     return 2;
+}
+
+}  // namespace
+
+bool fzb_fast_supported(const fzb_context* h, const FzbConfig& cfg) {
+    if (getenv("FZB_DISABLE_FAST")) return false;
+    int mode = mode_of(cfg);
+    if (mode < 0) return false;                                  // iterated free scale: generic path
+    if (mode == FM_FX1 && !cfg.dim_prior) return false;          // per-pair sum of ln(var): generic path
+    if (h->Nf < 4 || h->Nf > 6) return false;
+    if (!h->mask_all_one || !h->models_finite) return false;     // model masks: generic path
+    if (h->Nm >= (int64_t)1 << 31) return false;
+    if (h->kde_mode == FZB_KDE_GRID) return false;               // exact-Gaussian KDE: generic path
+    if (h->kde_mode == FZB_KDE_DICT) {
+        if (!h->labels_dict_set) return false;
+        if (!cfg.use_wt_thresh && cfg.use_cdf_thresh) return false;   // CDF rule needs a sort: generic path
+    }
+    if (cfg.use_wt_thresh && !(cfg.wt_thresh > 0.0 && cfg.wt_thresh < 1.0)) return false;
+    return true;
+}
+
+// Sort the models by KDE bin, build the fp32 records, the per-model kernel normalisations and the
+// slot table.  Depends on (models, lnprior, dictionary, labels, likelihood mode).
+static int fast_prepare_mode(fzb_context* h, int mode) {
+    FastModels& F = h->fast;
+    const int64_t nm = h->Nm;
+    const int nf = h->Nf;
+    const bool kde = (h->kde_mode == FZB_KDE_DICT && h->labels_dict_set);
+    std::vector<int32_t> perm(nm);
+    std::iota(perm.begin(), perm.end(), 0);
+    std::vector<int32_t> bins;
+    std::vector<float> invnorm;
+    F.nslot = 0;
+    F.slot_sidx.clear();
+    int wmax = 0, Ngpad = 0;
+    if (kde) {
+        // slots = distinct dictionary widths in use, ascending
+        std::vector<int32_t> slot_of(h->Ndict, -1);
+        for (int64_t j = 0; j < nm; ++j) slot_of[h->h_ysidx[j]] = 0;
+        for (int i = 0; i < h->Ndict; ++i)
+            if (slot_of[i] == 0) {
+                slot_of[i] = (int32_t)F.slot_sidx.size();
+                F.slot_sidx.push_back(i);
+                wmax = std::max(wmax, (int)h->h_widths[i]);
+            }
+        F.nslot = (int)F.slot_sidx.size();
+        Ngpad = h->Ng + 2 * wmax;
+        std::vector<int64_t> key(nm);
+        for (int64_t j = 0; j < nm; ++j)
+            key[j] = (int64_t)slot_of[h->h_ysidx[j]] * Ngpad + (h->h_yidx[j] + wmax);
+        std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return key[a] < key[b]; });
+        bins.resize(nm);
+        invnorm.resize(nm);
+        std::vector<double> kcdf((size_t)h->h_koff[h->Ndict]);
+        FZB_CUDA(cudaMemcpy(kcdf.data(), h->kcdf.p, kcdf.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int64_t p = 0; p < nm; ++p) {
+            int64_t j = perm[p];
+            bins[p] = (int32_t)key[j];
+            // edge normalisation of the truncated kernel (pdf.py:612-617)
+            int64_t si = h->h_ysidx[j], pos = h->h_yidx[j], w = h->h_widths[si];
+            const double* cdf = kcdf.data() + h->h_koff[si];
+            int64_t low = std::max<int64_t>(pos - w, 0), high = std::min<int64_t>(pos + w + 1, h->Ng);
+            int64_t lpad = low - (pos - w), hpad = high - (pos + w + 1);
+            double norm = cdf[2 * w + 1 + hpad - 1];
+            if (lpad != 0) norm -= cdf[lpad - 1];
+            invnorm[p] = (float)(1.0 / norm);
+        }
+    }
+    F.nf = nf;
+    F.nm = nm;
+    F.rec = rec_floats(nf, mode);
+    if (F.recs.reserve((size_t)nm * F.rec * sizeof(float) + 64) || F.perm.reserve((size_t)nm * 4 + 16) ||
+        h->misc[6].reserve((size_t)nm * nf * sizeof(float) + 16))
+        return 1;
+    FZB_CUDA(cudaMemcpyAsync(F.perm.p, perm.data(), (size_t)nm * 4, cudaMemcpyHostToDevice, h->stream));
+    if (kde) {
+        if (F.bins.reserve((size_t)nm * 4 + 16) || F.invnorm.reserve((size_t)nm * 4 + 16) ||
+            F.d_slot_sidx.reserve((size_t)F.nslot * 4 + 16))
+            return 1;
+        FZB_CUDA(cudaMemcpyAsync(F.bins.p, bins.data(), (size_t)nm * 4, cudaMemcpyHostToDevice, h->stream));
+        FZB_CUDA(cudaMemcpyAsync(F.invnorm.p, invnorm.data(), (size_t)nm * 4, cudaMemcpyHostToDevice, h->stream));
+        FZB_CUDA(cudaMemcpyAsync(F.d_slot_sidx.p, F.slot_sidx.data(), (size_t)F.nslot * 4, cudaMemcpyHostToDevice,
+                                 h->stream));
+    }
+    RecParams R = {};
+    R.m = h->models.as<double>();
+    R.me = h->models_err.as<double>();
+    R.lnprior = h->has_lnprior ? h->lnprior.as<double>() : nullptr;
+    R.perm = F.perm.as<int32_t>();
+    R.bins = kde ? F.bins.as<int32_t>() : nullptr;
+    R.invnorm = kde ? F.invnorm.as<float>() : nullptr;
+    R.nm = nm; R.Nf = nf; R.mode = mode; R.rec = F.rec;
+    R.recs = F.recs.as<float>();
+    R.mlo = h->misc[6].as<float>();
+    k_build_records<<<(unsigned)((nm + 255) / 256), 256, 0, h->stream>>>(R);
+    fzb_count_launch(h);
+    FZB_CUDA(cudaGetLastError());
+    FZB_CUDA(cudaStreamSynchronize(h->stream));
+    F.valid = true;
+    h->fast_dirty = false;
+    h->fast_mode = mode;
+    h->fast_wmax = wmax;
+    h->fast_Ngpad = Ngpad;
+    return 0;
+}
+
+int fzb_fast_prepare(fzb_context* h) { return 0; }
+
+int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm, int64_t No,
+                             const FzbConfig& cfg, double* d_pdfs, double* d_lmap, double* d_levid,
+                             int64_t* d_best_idx, double* d_best_chi2, double* d_best_scale) {
+    const int mode = mode_of(cfg);
+    const int nf = h->Nf;
+    const bool want_pdf = d_pdfs != nullptr;
+    if (want_pdf) FZB_CHECK(h->kde_mode == FZB_KDE_DICT && h->labels_dict_set, "dictionary KDE not configured");
+    if (h->fast_dirty || !h->fast.valid || h->fast_mode != mode) {
+        if (fast_prepare_mode(h, mode)) return 1;
+    }
+    FastModels& F = h->fast;
+    const int64_t nm = F.nm;
+    const bool kde = want_pdf;
+    const int64_t hist_stride = kde ? (int64_t)F.nslot * h->fast_Ngpad : 0;
+    FZB_CHECK(!kde || F.nslot <= 512, "too many distinct kernel widths for the fp32 path");
+
+    // chunk the objects so that the histogram stays within ~12 GB
+    int64_t chunk = No;
+    if (kde) {
+        int64_t fit = (int64_t)(((size_t)12 << 30) / ((size_t)hist_stride * 4));
+        if (fit < 1024) fit = 1024;
+        if (chunk > fit) chunk = fit;
+    }
+    const int64_t chunk_pad = (chunk + 1023) / 1024 * 1024;
+    const int R = (chunk >= 64 * 1024) ? 4 : 1;
+    const int64_t obj_tiles = (chunk_pad + (int64_t)FT * R - 1) / ((int64_t)FT * R);
+    const int64_t ntiles = (nm + TM - 1) / TM;
+    int64_t want_ctas = (int64_t)h->sm_count * 8;
+    int64_t nsplit = (want_ctas + obj_tiles - 1) / obj_tiles;
+    if (nsplit > ntiles) nsplit = ntiles;
+    if (nsplit > 256) nsplit = 256;
+    if (nsplit < 1) nsplit = 1;
+    const int tiles_per_split = (int)((ntiles + nsplit - 1) / nsplit);
+    nsplit = (ntiles + tiles_per_split - 1) / tiles_per_split;
+
+    // scratch: object SoA (4 x nf + 3 planes), partials, routing
+    DevBuf& so = h->misc[0];
+    size_t plane = (size_t)chunk_pad * sizeof(float);
+    if (so.reserve(plane * (4 * nf + 3 + 2) + 256)) return 1;
+    float* base = so.as<float>();
+    float* od = base;
+    float* ow = od + (size_t)nf * chunk_pad;
+    float* ox = ow + (size_t)nf * chunk_pad;
+    float* olo = ox + (size_t)nf * chunk_pad;
+    float* oA = olo + (size_t)nf * chunk_pad;
+    float* ocut = oA + chunk_pad;
+    float* osnr = ocut + chunk_pad;
+    float* M2 = osnr + chunk_pad;
+    float* thr2 = M2 + chunk_pad;
+    if (h->misc[1].reserve((size_t)nsplit * chunk_pad * 12 + 256)) return 1;
+    float* pM = h->misc[1].as<float>();
+    float* pS = pM + (size_t)nsplit * chunk_pad;
+    int32_t* pbest = reinterpret_cast<int32_t*>(pS + (size_t)nsplit * chunk_pad);
+    if (h->misc[2].reserve((size_t)chunk_pad * 8 + 64)) return 1;
+    int32_t* safe_list = h->misc[2].as<int32_t>();
+    int32_t* unsafe_list = safe_list + chunk_pad;
+    if (h->misc[3].reserve(64)) return 1;
+    int32_t* counts = h->misc[3].as<int32_t>();
+    if (kde && h->misc[4].reserve((size_t)chunk_pad * hist_stride * 4 + 256)) return 1;
+    float* hist = kde ? h->misc[4].as<float>() : nullptr;
+
+    const double chi2_max = env_double("FZB_FAST_CHI2_MAX", 24.0);
+    const double snr_max = env_double("FZB_FAST_SNR_MAX", 5000.0);
+    const double lo_snr = env_double("FZB_FAST_LO_SNR", 8.0);
+
+    float ms;
+    for (int64_t o0 = 0; o0 < No; o0 += chunk) {
+        const int64_t nc = std::min(chunk, No - o0);
+        const int64_t nc_pad = chunk_pad;
+        PrepParams PP = {};
+        PP.x = d_x + o0 * nf; PP.xe = d_xe + o0 * nf; PP.xm = d_xm + o0 * nf;
+        PP.No = nc; PP.No_pad = nc_pad; PP.Nf = nf; PP.mode = mode;
+        PP.free_scale = cfg.free_scale; PP.dim_prior = cfg.dim_prior;
+        PP.od = od; PP.ow = ow; PP.ox = ox; PP.olo = olo; PP.oA = oA; PP.ocut = ocut; PP.osnr = osnr;
+        PP.lo_snr = (float)lo_snr;
+        k_prep_objects<<<(unsigned)((nc_pad + 255) / 256), 256, 0, h->stream>>>(PP);
+        fzb_count_launch(h);
+        FZB_CUDA(cudaGetLastError());
+
+        SweepParams SP = {};
+        SP.od = od; SP.ow = ow; SP.ox = ox; SP.olo = olo; SP.oA = oA; SP.ocut = ocut;
+        SP.No_pad = nc_pad; SP.No = nc;
+        SP.recs = F.recs.as<float>(); SP.mlo = h->misc[6].as<float>(); SP.nm = nm;
+        SP.tiles_per_split = tiles_per_split;
+        SP.pM = pM; SP.pS = pS; SP.pbest = pbest;
+        const int64_t tiles1 = (nc + (int64_t)FT * R - 1) / ((int64_t)FT * R);
+        FZB_CUDA(cudaEventRecord(h->ev[2], h->stream));
+        if (launch_sweep(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, R, 1)) return 1;
+        FZB_CUDA(cudaEventRecord(h->ev[3], h->stream));
+        h->stats.pairs_fp32 += nc * nm;
+
+        FZB_CUDA(cudaMemsetAsync(counts, 0, 16, h->stream));
+        MergeParams MP = {};
+        MP.x = PP.x; MP.xe = PP.xe; MP.xm = PP.xm;
+        MP.m = h->models.as<double>(); MP.me = h->models_err.as<double>(); MP.mm = h->models_mask.as<double>();
+        MP.lnprior = h->has_lnprior ? h->lnprior.as<double>() : nullptr;
+        MP.perm = F.perm.as<int32_t>();
+        MP.No = nc; MP.No_pad = nc_pad; MP.o_base = o0;
+        MP.Nf = nf; MP.nsplit = (int)nsplit; MP.free_scale = cfg.free_scale; MP.ime = cfg.ignore_model_err != 0;
+        MP.dim_prior = cfg.dim_prior;
+        MP.pM = pM; MP.pS = pS; MP.pbest = pbest; MP.osnr = osnr;
+        MP.log2_wt_thresh = cfg.use_wt_thresh ? std::log2(cfg.wt_thresh) : -INFINITY;
+        MP.chi2_max = chi2_max; MP.snr_max = snr_max; MP.consist_tol = 1e-4;
+        MP.force_fp32 = (cfg.precision == FZB_PREC_FP32);
+        MP.lmap = d_lmap; MP.levid = d_levid; MP.best_chi2 = d_best_chi2; MP.best_scale = d_best_scale;
+        MP.best_idx = d_best_idx;
+        MP.M2 = M2; MP.thr2 = thr2; MP.safe_list = safe_list; MP.unsafe_list = unsafe_list; MP.counts = counts;
+        k_merge<<<(unsigned)((nc + 255) / 256), 256, 0, h->stream>>>(MP);
+        fzb_count_launch(h);
+        FZB_CUDA(cudaGetLastError());
+        int32_t hc[4] = {0, 0, 0, 0};
+        FZB_CUDA(cudaMemcpyAsync(hc, counts, 16, cudaMemcpyDeviceToHost, h->stream));
+        FZB_CUDA(cudaStreamSynchronize(h->stream));
+        FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
+        h->stats.ms_scan += ms;
+        const int64_t nsafe = hc[0], nunsafe = hc[1];
+        h->stats.objects_fp64 += nunsafe;
+
+        if (nunsafe > 0) {
+            // float64 route; objsel holds absolute object indices
+            if (fzb_generic_fit_predict_dev(h, d_x, d_xe, d_xm, No, unsafe_list, nunsafe, cfg, d_pdfs, d_lmap, d_levid,
+                                            d_best_idx, d_best_chi2, d_best_scale))
+                return 1;
+        }
+        if (kde && nsafe > 0) {
+            FZB_CUDA(cudaEventRecord(h->ev[4], h->stream));
+            FZB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nc_pad * hist_stride * 4, h->stream));
+            SP.No = nsafe; SP.objlist = safe_list; SP.M2 = M2; SP.thr2 = thr2; SP.hist = hist;
+            SP.hist_stride = hist_stride;
+            const int64_t tiles2 = (nsafe + (int64_t)FT * R - 1) / ((int64_t)FT * R);
+            if (launch_sweep(h, SP, dim3((unsigned)tiles2, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, R, 2))
+                return 1;
+            h->stats.pairs_fp32 += nsafe * nm;
+            FZB_CUDA(cudaEventRecord(h->ev[5], h->stream));
+            FinishParams FP = {};
+            FP.hist = hist; FP.hist_stride = hist_stride; FP.objlist = safe_list; FP.o_base = o0;
+            FP.Ng = h->Ng; FP.Ngpad = h->fast_Ngpad; FP.wmax = h->fast_wmax; FP.nslot = F.nslot;
+            FP.slot_sidx = F.d_slot_sidx.as<int32_t>(); FP.widths = h->widths.as<int32_t>();
+            FP.koff = h->koff.as<int64_t>(); FP.kernels = h->kernels.as<double>(); FP.pdfs = d_pdfs;
+            size_t smem = sizeof(double) * ((size_t)h->fast_Ngpad + h->Ng);
+            FZB_CUDA(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_finish<<<(unsigned)nsafe, 256, smem, h->stream>>>(FP);
+            fzb_count_launch(h);
+            FZB_CUDA(cudaGetLastError());
+            FZB_CUDA(cudaEventRecord(h->ev[6], h->stream));
+            FZB_CUDA(cudaStreamSynchronize(h->stream));
+            FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
+            h->stats.ms_accum += ms;
+            FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]));
+            h->stats.ms_finish += ms;
+        }
+    }
+    return 0;
 }

@@ -87,6 +87,11 @@ int fzb_destroy(fzb_handle h);
 int fzb_synchronize(fzb_handle h);
 int fzb_get_stats(fzb_handle h, FzbStats* out);
 
+/* Roofline denominators measured on the handle's device (MEASURED_PEAKS.json carries only HBM and
+ * bf16 tensor peaks): dependency-free FFMA and MUFU.EX2 loops over every SM, best of `reps`.
+ * fp32_tflops counts an FMA as 2 flops; mufu_gops is special-function results per second / 1e9. */
+int fzb_measure_peaks(fzb_handle h, int reps, double* fp32_tflops, double* mufu_gops);
+
 /* Model set: replaces BruteForce.__init__ (bruteforce.py:36-64) / NearestNeighbors.__init__
  * storage (knn.py:89-101).  models/err/mask: host, (Nm x Nf) float64; mask values are
  * used multiplicatively exactly like the reference (pdf.py:82). */
