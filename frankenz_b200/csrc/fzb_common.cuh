@@ -91,6 +91,7 @@ struct fzb_context {
     bool mask_all_one = false;     // every model mask entry == 1
     bool err_all_zero = false;     // every model error == 0
     bool models_finite = false;
+    bool models_f32_exact = false; // every model flux is exactly representable in float32
 
     // KDE tables
     int kde_mode = FZB_KDE_NONE;

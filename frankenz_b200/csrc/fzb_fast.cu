@@ -20,9 +20,12 @@
 // trusted to the 1e-5 parity bound (large best-fit chi2, extreme S/N, degenerate rows, non-finite
 // sums) are routed to the float64 kernels of fzb_generic.cu.
 //
-// Precision: inputs are split hi/lo (float64 = hi + lo); the sweep uses the hi parts and re-does
-// the residuals with the lo parts only for pairs near the running maximum of bright objects, where
-// the cancellation d - s*m would otherwise lose the low bits (hard part 1).
+// Precision: inputs are split hi/lo (float64 = hi + lo).  chi2 is evaluated on the hi parts and
+// corrected to first order for the lo parts, d(chi2) = 2 sum_b w_b r_b (dlo_b - s mlo_b), which is
+// exact to second order in 2^-24 (envelope theorem: the optimal scale need not be re-derived).
+// This removes the loss of the low bits in the cancellation d - s*m for bright objects
+// (hard part 1) at 5 extra FMAs per pair (10 when the models are not
+// exactly representable in fp32).
 #include <algorithm>
 #include <cfloat>
 #include <cstdlib>
@@ -36,15 +39,14 @@ namespace {
 constexpr int FT = 256;          // threads per CTA
 constexpr int TM = 256;          // models per shared-memory tile
 constexpr int NSTAGE = 2;
-constexpr float kLog2e = 1.4426950408889634f;
+constexpr int RBIG = 4;           // objects per thread of the large-shape kernels
 constexpr float kHalfLog2e = 0.7213475204444817f;
-constexpr float kRefineMargin = 48.0f;   // log2 units below the running max that still get the lo-part redo
 
 enum FastMode { FM_FS0 = 0, FM_FX0 = 1, FM_FX1 = 2 };
 
-__host__ __device__ constexpr int rec_floats(int nf, int mode) {
-    // m[nf] (+ q[nf] = m^2 for FS0, me2[nf] for FX1) + prior2 + bin + invnorm, padded to 4 floats
-    int n = nf + ((mode == FM_FX0) ? 0 : nf) + 3;
+__host__ __device__ constexpr int rec_floats(int nf, int mode, bool mlo) {
+    // m[nf] (+ q[nf] = m^2 for FS0, me2[nf] for FX1) (+ ml2[nf] = 2*m_lo) + prior2 + bin + invnorm, padded to 4
+    int n = nf + ((mode == FM_FX0) ? 0 : nf) + (mlo ? nf : 0) + 3;
     return (n + 3) / 4 * 4;
 }
 
@@ -95,16 +97,14 @@ __device__ __forceinline__ float fast_ex2(float x) {
 struct SweepParams {
     // objects, SoA [field][band][No_pad]
     const float* od;      // d_hi
-    const float* ow;      // FS0/FX0: mask/err^2        FX1: unused
-    const float* ox;      // FS0: d*w                   FX1: err^2 (+inf where masked)
-    const float* olo;     // d_lo
+    const float* ow;      // FS0/FX0: mask/err^2        FX1: err^2 (+inf where masked)
+    const float* ox;      // FS0: d*w
+    const float* odl;     // 2 * d_lo
     const float* oA;      // [No_pad] (dof/2 - 1) or 0
-    const float* ocut;    // [No_pad] refine margin (log2 units) or -inf
     int64_t No_pad;
     int64_t No;           // objects in this launch (pass 1) / entries of objlist (pass 2)
     // models
     const float* recs;    // [nm][REC]
-    const float* mlo;     // [nm][NF] lo parts of the model fluxes
     int64_t nm;
     int tiles_per_split;
     // pass 1 outputs: [nsplit][No_pad]
@@ -122,16 +122,17 @@ struct SweepParams {
 template <int NF, int MODE>
 struct ObjRegs {
     float d[NF];
-    float w[NF];   // FS0/FX0: weights; FX1: err^2 (+inf where masked)
-    float x[NF];   // FS0 only: d*w
-    float A, cut;
+    float w[NF];    // FS0/FX0: weights; FX1: err^2 (+inf where masked)
+    float x[(MODE == FM_FS0) ? NF : 1];   // FS0 only: d*w
+    float dl[NF];   // 2 * d_lo
+    float A;
 };
 
-// hi-part evaluation of one pair.  Returns chi2; `s` is the optimal scale (FS0) or 1.
-template <int NF, int MODE>
+// chi2 of one pair: hi parts + first-order lo correction.  m / aux / ml point into the shared-memory record.
+template <int NF, int MODE, bool MLO>
 __device__ __forceinline__ float pair_chi2(const ObjRegs<NF, MODE>& o, const float* __restrict__ m,
-                                           const float* __restrict__ aux, float& s) {
-    float chi2;
+                                           const float* __restrict__ aux, const float* __restrict__ ml) {
+    float chi2, corr, cm = 0.f, s = 1.f;
     if (MODE == FM_FS0) {
         float inter = __fmul_rn(o.x[0], m[0]);
         float shape = __fmul_rn(o.w[0], aux[0]);
@@ -141,76 +142,45 @@ __device__ __forceinline__ float pair_chi2(const ObjRegs<NF, MODE>& o, const flo
             shape = __fmaf_rn(o.w[b], aux[b], shape);
         }
         s = __fmul_rn(inter, fast_rcp(shape));
-        float r = __fmaf_rn(-s, m[0], o.d[0]);
-        chi2 = __fmul_rn(__fmul_rn(r, o.w[0]), r);
-#pragma unroll
-        for (int b = 1; b < NF; ++b) {
-            r = __fmaf_rn(-s, m[b], o.d[b]);
-            chi2 = __fmaf_rn(__fmul_rn(r, o.w[b]), r, chi2);
-        }
-    } else if (MODE == FM_FX0) {
-        s = 1.f;
-        float r = __fsub_rn(o.d[0], m[0]);
-        chi2 = __fmul_rn(__fmul_rn(r, o.w[0]), r);
-#pragma unroll
-        for (int b = 1; b < NF; ++b) {
-            r = __fsub_rn(o.d[b], m[b]);
-            chi2 = __fmaf_rn(__fmul_rn(r, o.w[b]), r, chi2);
-        }
-    } else {
-        s = 1.f;
-        float r = __fsub_rn(o.d[0], m[0]);
-        chi2 = __fmul_rn(__fmul_rn(r, fast_rcp(__fadd_rn(o.w[0], aux[0]))), r);
-#pragma unroll
-        for (int b = 1; b < NF; ++b) {
-            r = __fsub_rn(o.d[b], m[b]);
-            chi2 = __fmaf_rn(__fmul_rn(r, fast_rcp(__fadd_rn(o.w[b], aux[b]))), r, chi2);
-        }
     }
-    return chi2;
-}
-
-// redo of the residuals with the lo parts (rare path: pairs near the maximum of bright objects)
-template <int NF, int MODE>
-__device__ __forceinline__ float pair_chi2_lo(const ObjRegs<NF, MODE>& o, const float* __restrict__ m,
-                                           const float* __restrict__ aux, float s, const float* __restrict__ olo,
-                                           int64_t ostride, const float* __restrict__ mlo) {
-    float chi2 = 0.f;
 #pragma unroll
     for (int b = 0; b < NF; ++b) {
-        float dl = olo[b * ostride];
-        float ml = mlo[b];
-        float r, w;
-        if (MODE == FM_FS0) {
-            r = __fadd_rn(__fmaf_rn(-s, m[b], o.d[b]), __fmaf_rn(-s, ml, dl));
-            w = o.w[b];
+        float r = (MODE == FM_FS0) ? __fmaf_rn(-s, m[b], o.d[b]) : __fsub_rn(o.d[b], m[b]);
+        float w = (MODE == FM_FX1) ? fast_rcp(__fadd_rn(o.w[b], aux[b])) : o.w[b];
+        float t = __fmul_rn(r, w);
+        if (b == 0) {
+            chi2 = __fmul_rn(t, r);
+            corr = __fmul_rn(t, o.dl[0]);
+            if (MLO) cm = __fmul_rn(t, ml[0]);
         } else {
-            r = __fadd_rn(__fsub_rn(o.d[b], m[b]), __fsub_rn(dl, ml));
-            w = (MODE == FM_FX0) ? o.w[b] : fast_rcp(__fadd_rn(o.w[b], aux[b]));
+            chi2 = __fmaf_rn(t, r, chi2);
+            corr = __fmaf_rn(t, o.dl[b], corr);
+            if (MLO) cm = __fmaf_rn(t, ml[b], cm);
         }
-        chi2 = __fmaf_rn(__fmul_rn(r, w), r, chi2);
     }
+    chi2 = __fadd_rn(chi2, corr);
+    if (MLO) chi2 = __fmaf_rn(-s, cm, chi2);
     return chi2;
 }
 
 template <bool DP>
 __device__ __forceinline__ float chi2_to_l2(float chi2, float A, float prior2) {
     // ln-likelihood in log2 units without the per-object constant:
-    //   DP: (dof/2 - 1) * log2(chi2) - chi2 * log2(e)/2        (pdf.py:93 / :229, xlogy semantics)
+    //   DP: (dof/2 - 1) * log2(chi2) - chi2 * log2(e)/2        (pdf.py:93 / :229)
     //  !DP: - chi2 * log2(e)/2                                   (pdf.py:96, :192)
+    // xlogy's 0*log(0) = 0 case (A == 0, chi2 == 0) yields NaN here; the NaN poisons the object's sum and the
+    // object is then routed to the float64 path, which has the exact semantics.
     float l = __fmaf_rn(chi2, -kHalfLog2e, prior2);
-    if (DP) {
-        float t = __fmul_rn(A, fast_lg2(chi2));
-        l = __fadd_rn(l, (A == 0.f) ? 0.f : t);
-    }
+    if (DP) l = __fmaf_rn(A, fast_lg2(chi2), l);
     return l;
 }
 
-template <int NF, int MODE, bool DP, int R, int PASS>
-__global__ void __launch_bounds__(FT, (R >= 4) ? 2 : 3) k_sweep(SweepParams P) {
-    constexpr int REC = rec_floats(NF, MODE);
+template <int NF, int MODE, bool DP, bool MLO, int R, int PASS>
+__global__ void __launch_bounds__(FT, (R >= 8) ? 1 : 2) k_sweep(SweepParams P) {
+    constexpr int REC = rec_floats(NF, MODE, MLO);
     constexpr int AUXOFF = NF;                                  // q / me2
-    constexpr int TAILOFF = NF + ((MODE == FM_FX0) ? 0 : NF);   // prior2, bin, invnorm
+    constexpr int MLOFF = NF + ((MODE == FM_FX0) ? 0 : NF);     // 2*m_lo (MLO only)
+    constexpr int TAILOFF = MLOFF + (MLO ? NF : 0);             // prior2, bin, invnorm
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage = reinterpret_cast<float*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * TM * REC * sizeof(float));
@@ -218,8 +188,8 @@ __global__ void __launch_bounds__(FT, (R >= 4) ? 2 : 3) k_sweep(SweepParams P) {
 
     // ---- this thread's objects -----------------------------------------------------------------
     ObjRegs<NF, MODE> ob[R];
-    int64_t oidx[R];
-    float M[R], S[R];
+    int oidx[R];
+    float M[R], S[R];     // pass 1: running max / sum.  pass 2: final max / selection cut
     int best[R];
     float acc[R];
     const int64_t tile_base = (int64_t)blockIdx.x * (FT * R);
@@ -229,17 +199,16 @@ __global__ void __launch_bounds__(FT, (R >= 4) ? 2 : 3) k_sweep(SweepParams P) {
         int64_t o;
         if (PASS == 1) o = slot < P.No_pad ? slot : P.No_pad - 1;
         else o = slot < P.No ? P.objlist[slot] : -1;
-        oidx[r] = o;
+        oidx[r] = (int)o;
         int64_t oo = o < 0 ? 0 : o;
 #pragma unroll
         for (int b = 0; b < NF; ++b) {
             ob[r].d[b] = P.od[b * P.No_pad + oo];
-            if (MODE == FM_FX1) ob[r].w[b] = P.ox[b * P.No_pad + oo];
-            else ob[r].w[b] = P.ow[b * P.No_pad + oo];
+            ob[r].w[b] = P.ow[b * P.No_pad + oo];
+            ob[r].dl[b] = P.odl[b * P.No_pad + oo];
             if (MODE == FM_FS0) ob[r].x[b] = P.ox[b * P.No_pad + oo];
         }
         ob[r].A = P.oA[oo];
-        ob[r].cut = P.ocut[oo];
         if (PASS == 1) { M[r] = -FLT_MAX; S[r] = 0.f; best[r] = 0; }
         else { M[r] = P.M2[oo]; S[r] = P.thr2[oo]; acc[r] = 0.f; }
     }
@@ -276,51 +245,44 @@ __global__ void __launch_bounds__(FT, (R >= 4) ? 2 : 3) k_sweep(SweepParams P) {
         const int cnt = (int)((P.nm - first) < TM ? (P.nm - first) : TM);
 #pragma unroll 1
         for (int jj = 0; jj < cnt; ++jj) {
-            const float* rec = tile + jj * REC;
-            float m[NF], aux[NF];
-#pragma unroll
-            for (int b = 0; b < NF; ++b) {
-                m[b] = rec[b];
-                aux[b] = (MODE == FM_FX0) ? 0.f : rec[AUXOFF + b];
-            }
+            const float* rec = tile + jj * REC;   // every thread reads the same record: shared-memory broadcast
             const float prior2 = rec[TAILOFF];
+            float invnorm = 0.f;
             if (PASS == 2) {
                 const int bin = __float_as_int(rec[TAILOFF + 1]);
+                invnorm = rec[TAILOFF + 2];
                 if (bin != cur_bin) {       // warp-uniform: every thread walks the same model
                     if (cur_bin >= 0) {
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
                             if (acc[r] != 0.f && oidx[r] >= 0)
-                                atomicAdd(P.hist + oidx[r] * P.hist_stride + cur_bin, acc[r]);
+                                atomicAdd(P.hist + (int64_t)oidx[r] * P.hist_stride + cur_bin, acc[r]);
                             acc[r] = 0.f;
                         }
                     }
                     cur_bin = bin;
                 }
             }
-            const float invnorm = (PASS == 2) ? rec[TAILOFF + 2] : 0.f;
+            float m[NF], aux[NF], ml[NF];
+#pragma unroll
+            for (int b = 0; b < NF; ++b) {
+                m[b] = rec[b];
+                aux[b] = (MODE == FM_FX0) ? 0.f : rec[AUXOFF + b];
+                ml[b] = MLO ? rec[MLOFF + b] : 0.f;
+            }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                float s;
-                float chi2 = pair_chi2<NF, MODE>(ob[r], m, aux, s);
+                float chi2 = pair_chi2<NF, MODE, MLO>(ob[r], m, aux, ml);
                 float l2 = chi2_to_l2<DP>(chi2, ob[r].A, prior2);
-                if (l2 > M[r] - ob[r].cut) {   // bright object, pair near the maximum: redo with lo parts
-                    int64_t oo = oidx[r] < 0 ? 0 : oidx[r];
-                    chi2 = pair_chi2_lo<NF, MODE>(ob[r], m, aux, s, P.olo + oo, P.No_pad, P.mlo + (first + jj) * NF);
-                    l2 = chi2_to_l2<DP>(chi2, ob[r].A, prior2);
-                }
+                float delta = __fsub_rn(l2, M[r]);
                 if (PASS == 1) {
-                    float delta = __fsub_rn(l2, M[r]);
                     float e = fast_ex2(-fabsf(delta));
-                    if (delta > 0.f) {
-                        S[r] = __fmaf_rn(S[r], e, 1.f);
-                        M[r] = l2;
-                        best[r] = (int)(first + jj);
-                    } else {
-                        S[r] = __fadd_rn(S[r], e);
-                    }
+                    bool gt = delta > 0.f;
+                    S[r] = __fmaf_rn(S[r], gt ? e : 1.f, gt ? 1.f : e);
+                    M[r] = gt ? l2 : M[r];
+                    best[r] = gt ? (int)(first + jj) : best[r];
                 } else {
-                    float u = fast_ex2(__fsub_rn(l2, M[r]));
+                    float u = fast_ex2(delta);
                     u = (l2 > S[r]) ? u : 0.f;      // S[r] holds the selection cut in pass 2
                     acc[r] = __fmaf_rn(u, invnorm, acc[r]);
                 }
@@ -343,7 +305,8 @@ __global__ void __launch_bounds__(FT, (R >= 4) ? 2 : 3) k_sweep(SweepParams P) {
     } else if (cur_bin >= 0) {
 #pragma unroll
         for (int r = 0; r < R; ++r)
-            if (acc[r] != 0.f && oidx[r] >= 0) atomicAdd(P.hist + oidx[r] * P.hist_stride + cur_bin, acc[r]);
+            if (acc[r] != 0.f && oidx[r] >= 0)
+                atomicAdd(P.hist + (int64_t)oidx[r] * P.hist_stride + cur_bin, acc[r]);
     }
 }
 
@@ -352,14 +315,13 @@ struct PrepParams {
     const double *x, *xe, *xm;   // (No x Nf) raw inputs of this chunk
     int64_t No, No_pad;
     int Nf, mode, free_scale, dim_prior;
-    float *od, *ow, *ox, *olo, *oA, *ocut, *osnr;
-    float lo_snr;                // per-band S/N above which the lo-part redo is armed
+    float *od, *ow, *ox, *odl, *oA, *osnr;
 };
 
 __global__ void k_prep_objects(PrepParams P) {
     int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= P.No_pad) return;
-    double ndim = 0.0, snr2 = 0.0, snr_max = 0.0;
+    double ndim = 0.0, snr2 = 0.0;
     for (int b = 0; b < P.Nf; ++b) {
         double d = 0.0, e = 1.0, k = 0.0;
         if (o < P.No) {
@@ -374,10 +336,10 @@ __global__ void k_prep_objects(PrepParams P) {
         double w = k / (e * e);
         size_t q = (size_t)b * P.No_pad + o;
         P.od[q] = dh;
-        P.olo[q] = dl;
+        P.odl[q] = 2.f * dl;
         if (P.mode == FM_FX1) {
-            P.ox[q] = (k != 0.0) ? (float)(e * e) : CUDART_INF_F;
-            P.ow[q] = 0.f;
+            P.ow[q] = (k != 0.0) ? (float)(e * e) : CUDART_INF_F;
+            P.ox[q] = 0.f;
         } else {
             P.ow[q] = (float)w;
             P.ox[q] = (float)(d * w);
@@ -385,11 +347,9 @@ __global__ void k_prep_objects(PrepParams P) {
         ndim += k;
         double sn = (k != 0.0) ? fabs(d) / e : 0.0;
         snr2 += sn * sn;
-        if (sn > snr_max) snr_max = sn;
     }
     double a = P.free_scale ? 0.5 * (ndim - 1.0) : 0.5 * ndim;
     P.oA[o] = P.dim_prior ? (float)(a - 1.0) : 0.f;
-    P.ocut[o] = (snr_max > P.lo_snr) ? kRefineMargin : -CUDART_INF_F;
     P.osnr[o] = (float)sqrt(snr2);
 }
 
@@ -521,9 +481,8 @@ struct RecParams {
     const int32_t* bins;
     const float* invnorm;
     int64_t nm;
-    int Nf, mode, rec;
+    int Nf, mode, rec, mlo;
     float* recs;
-    float* mlo;
 };
 
 __global__ void k_build_records(RecParams P) {
@@ -531,18 +490,19 @@ __global__ void k_build_records(RecParams P) {
     if (p >= P.nm) return;
     int64_t j = P.perm[p];
     float* r = P.recs + p * P.rec;
+    const int mloff = P.Nf + ((P.mode == FM_FX0) ? 0 : P.Nf);
     for (int b = 0; b < P.Nf; ++b) {
         double v = P.m[j * P.Nf + b];
         float hi = (float)v;
         r[b] = hi;
-        P.mlo[p * P.Nf + b] = (float)(v - (double)hi);
+        if (P.mlo) r[mloff + b] = 2.f * (float)(v - (double)hi);
         if (P.mode == FM_FS0) r[P.Nf + b] = (float)(v * v);
         else if (P.mode == FM_FX1) {
             double e = P.me[j * P.Nf + b];
             r[P.Nf + b] = (float)(e * e);
         }
     }
-    int tail = P.Nf + ((P.mode == FM_FX0) ? 0 : P.Nf);
+    int tail = mloff + (P.mlo ? P.Nf : 0);
     r[tail] = P.lnprior ? (float)(P.lnprior[j] * 1.4426950408889634) : 0.f;
     r[tail + 1] = __int_as_float(P.bins ? P.bins[p] : -1);
     r[tail + 2] = P.invnorm ? P.invnorm[p] : 0.f;
@@ -560,11 +520,11 @@ double env_double(const char* name, double dflt) {
     return v ? atof(v) : dflt;
 }
 
-template <int NF, int MODE, bool DP, int R, int PASS>
+template <int NF, int MODE, bool DP, bool MLO, int R, int PASS>
 int launch_sweep_t(fzb_context* h, const SweepParams& P, dim3 grid) {
-    constexpr int REC = rec_floats(NF, MODE);
+    constexpr int REC = rec_floats(NF, MODE, MLO);
     size_t smem = (size_t)NSTAGE * TM * REC * sizeof(float) + NSTAGE * sizeof(uint64_t);
-    auto kern = k_sweep<NF, MODE, DP, R, PASS>;
+    auto kern = k_sweep<NF, MODE, DP, MLO, R, PASS>;
     FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, FT, smem, h->stream>>>(P);
     fzb_count_launch(h);
@@ -572,30 +532,37 @@ int launch_sweep_t(fzb_context* h, const SweepParams& P, dim3 grid) {
     return 0;
 }
 
-template <int NF, int MODE, bool DP>
+template <int NF, int MODE, bool DP, bool MLO>
 int launch_sweep_r(fzb_context* h, const SweepParams& P, dim3 grid, int R, int pass) {
     if (pass == 1) {
-        if (R == 4) return launch_sweep_t<NF, MODE, DP, 4, 1>(h, P, grid);
-        return launch_sweep_t<NF, MODE, DP, 1, 1>(h, P, grid);
+        if (R == RBIG) return launch_sweep_t<NF, MODE, DP, MLO, RBIG, 1>(h, P, grid);
+        return launch_sweep_t<NF, MODE, DP, MLO, 1, 1>(h, P, grid);
     }
-    if (R == 4) return launch_sweep_t<NF, MODE, DP, 4, 2>(h, P, grid);
-    return launch_sweep_t<NF, MODE, DP, 1, 2>(h, P, grid);
+    if (R == RBIG) return launch_sweep_t<NF, MODE, DP, MLO, RBIG, 2>(h, P, grid);
+    return launch_sweep_t<NF, MODE, DP, MLO, 1, 2>(h, P, grid);
+}
+
+template <int NF, int MODE, bool DP>
+int launch_sweep_m(fzb_context* h, const SweepParams& P, dim3 grid, bool mlo, int R, int pass) {
+    return mlo ? launch_sweep_r<NF, MODE, DP, true>(h, P, grid, R, pass)
+               : launch_sweep_r<NF, MODE, DP, false>(h, P, grid, R, pass);
 }
 
 template <int NF>
-int launch_sweep_nf(fzb_context* h, const SweepParams& P, dim3 grid, int mode, bool dp, int R, int pass) {
-    if (mode == FM_FS0) return dp ? launch_sweep_r<NF, FM_FS0, true>(h, P, grid, R, pass)
-                                  : launch_sweep_r<NF, FM_FS0, false>(h, P, grid, R, pass);
-    if (mode == FM_FX0) return dp ? launch_sweep_r<NF, FM_FX0, true>(h, P, grid, R, pass)
-                                  : launch_sweep_r<NF, FM_FX0, false>(h, P, grid, R, pass);
-    return launch_sweep_r<NF, FM_FX1, true>(h, P, grid, R, pass);
+int launch_sweep_nf(fzb_context* h, const SweepParams& P, dim3 grid, int mode, bool dp, bool mlo, int R, int pass) {
+    if (mode == FM_FS0) return dp ? launch_sweep_m<NF, FM_FS0, true>(h, P, grid, mlo, R, pass)
+                                  : launch_sweep_m<NF, FM_FS0, false>(h, P, grid, mlo, R, pass);
+    if (mode == FM_FX0) return dp ? launch_sweep_m<NF, FM_FX0, true>(h, P, grid, mlo, R, pass)
+                                  : launch_sweep_m<NF, FM_FX0, false>(h, P, grid, mlo, R, pass);
+    return launch_sweep_m<NF, FM_FX1, true>(h, P, grid, mlo, R, pass);
 }
 
-int launch_sweep(fzb_context* h, const SweepParams& P, dim3 grid, int nf, int mode, bool dp, int R, int pass) {
+int launch_sweep(fzb_context* h, const SweepParams& P, dim3 grid, int nf, int mode, bool dp, bool mlo, int R,
+                 int pass) {
     switch (nf) {
-        case 4: return launch_sweep_nf<4>(h, P, grid, mode, dp, R, pass);
-        case 5: return launch_sweep_nf<5>(h, P, grid, mode, dp, R, pass);
-        case 6: return launch_sweep_nf<6>(h, P, grid, mode, dp, R, pass);
+        case 4: return launch_sweep_nf<4>(h, P, grid, mode, dp, mlo, R, pass);
+        case 5: return launch_sweep_nf<5>(h, P, grid, mode, dp, mlo, R, pass);
+        case 6: return launch_sweep_nf<6>(h, P, grid, mode, dp, mlo, R, pass);
         default: break;
     }
     fzb_set_error("fp32 path: unsupported filter count %d", nf);
@@ -670,10 +637,9 @@ static int fast_prepare_mode(fzb_context* h, int mode) {
     }
     F.nf = nf;
     F.nm = nm;
-    F.rec = rec_floats(nf, mode);
-    if (F.recs.reserve((size_t)nm * F.rec * sizeof(float) + 64) || F.perm.reserve((size_t)nm * 4 + 16) ||
-        h->misc[6].reserve((size_t)nm * nf * sizeof(float) + 16))
-        return 1;
+    const bool mlo = !h->models_f32_exact;
+    F.rec = rec_floats(nf, mode, mlo);
+    if (F.recs.reserve((size_t)nm * F.rec * sizeof(float) + 64) || F.perm.reserve((size_t)nm * 4 + 16)) return 1;
     FZB_CUDA(cudaMemcpyAsync(F.perm.p, perm.data(), (size_t)nm * 4, cudaMemcpyHostToDevice, h->stream));
     if (kde) {
         if (F.bins.reserve((size_t)nm * 4 + 16) || F.invnorm.reserve((size_t)nm * 4 + 16) ||
@@ -691,9 +657,8 @@ static int fast_prepare_mode(fzb_context* h, int mode) {
     R.perm = F.perm.as<int32_t>();
     R.bins = kde ? F.bins.as<int32_t>() : nullptr;
     R.invnorm = kde ? F.invnorm.as<float>() : nullptr;
-    R.nm = nm; R.Nf = nf; R.mode = mode; R.rec = F.rec;
+    R.nm = nm; R.Nf = nf; R.mode = mode; R.rec = F.rec; R.mlo = mlo ? 1 : 0;
     R.recs = F.recs.as<float>();
-    R.mlo = h->misc[6].as<float>();
     k_build_records<<<(unsigned)((nm + 255) / 256), 256, 0, h->stream>>>(R);
     fzb_count_launch(h);
     FZB_CUDA(cudaGetLastError());
@@ -732,7 +697,8 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         if (chunk > fit) chunk = fit;
     }
     const int64_t chunk_pad = (chunk + 1023) / 1024 * 1024;
-    const int R = (chunk >= 64 * 1024) ? 4 : 1;
+    const int R = (chunk >= 64 * 1024) ? RBIG : 1;
+    const bool mlo = !h->models_f32_exact;
     const int64_t obj_tiles = (chunk_pad + (int64_t)FT * R - 1) / ((int64_t)FT * R);
     const int64_t ntiles = (nm + TM - 1) / TM;
     int64_t want_ctas = (int64_t)h->sm_count * 8;
@@ -746,15 +712,14 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     // scratch: object SoA (4 x nf + 3 planes), partials, routing
     DevBuf& so = h->misc[0];
     size_t plane = (size_t)chunk_pad * sizeof(float);
-    if (so.reserve(plane * (4 * nf + 3 + 2) + 256)) return 1;
+    if (so.reserve(plane * (4 * nf + 2 + 2) + 256)) return 1;
     float* base = so.as<float>();
     float* od = base;
     float* ow = od + (size_t)nf * chunk_pad;
     float* ox = ow + (size_t)nf * chunk_pad;
-    float* olo = ox + (size_t)nf * chunk_pad;
-    float* oA = olo + (size_t)nf * chunk_pad;
-    float* ocut = oA + chunk_pad;
-    float* osnr = ocut + chunk_pad;
+    float* odl = ox + (size_t)nf * chunk_pad;
+    float* oA = odl + (size_t)nf * chunk_pad;
+    float* osnr = oA + chunk_pad;
     float* M2 = osnr + chunk_pad;
     float* thr2 = M2 + chunk_pad;
     if (h->misc[1].reserve((size_t)nsplit * chunk_pad * 12 + 256)) return 1;
@@ -770,8 +735,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     float* hist = kde ? h->misc[4].as<float>() : nullptr;
 
     const double chi2_max = env_double("FZB_FAST_CHI2_MAX", 24.0);
-    const double snr_max = env_double("FZB_FAST_SNR_MAX", 5000.0);
-    const double lo_snr = env_double("FZB_FAST_LO_SNR", 8.0);
+    const double snr_max = env_double("FZB_FAST_SNR_MAX", 20000.0);
 
     float ms;
     for (int64_t o0 = 0; o0 < No; o0 += chunk) {
@@ -781,21 +745,20 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         PP.x = d_x + o0 * nf; PP.xe = d_xe + o0 * nf; PP.xm = d_xm + o0 * nf;
         PP.No = nc; PP.No_pad = nc_pad; PP.Nf = nf; PP.mode = mode;
         PP.free_scale = cfg.free_scale; PP.dim_prior = cfg.dim_prior;
-        PP.od = od; PP.ow = ow; PP.ox = ox; PP.olo = olo; PP.oA = oA; PP.ocut = ocut; PP.osnr = osnr;
-        PP.lo_snr = (float)lo_snr;
+        PP.od = od; PP.ow = ow; PP.ox = ox; PP.odl = odl; PP.oA = oA; PP.osnr = osnr;
         k_prep_objects<<<(unsigned)((nc_pad + 255) / 256), 256, 0, h->stream>>>(PP);
         fzb_count_launch(h);
         FZB_CUDA(cudaGetLastError());
 
         SweepParams SP = {};
-        SP.od = od; SP.ow = ow; SP.ox = ox; SP.olo = olo; SP.oA = oA; SP.ocut = ocut;
+        SP.od = od; SP.ow = ow; SP.ox = ox; SP.odl = odl; SP.oA = oA;
         SP.No_pad = nc_pad; SP.No = nc;
-        SP.recs = F.recs.as<float>(); SP.mlo = h->misc[6].as<float>(); SP.nm = nm;
+        SP.recs = F.recs.as<float>(); SP.nm = nm;
         SP.tiles_per_split = tiles_per_split;
         SP.pM = pM; SP.pS = pS; SP.pbest = pbest;
         const int64_t tiles1 = (nc + (int64_t)FT * R - 1) / ((int64_t)FT * R);
         FZB_CUDA(cudaEventRecord(h->ev[2], h->stream));
-        if (launch_sweep(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, R, 1)) return 1;
+        if (launch_sweep(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 1)) return 1;
         FZB_CUDA(cudaEventRecord(h->ev[3], h->stream));
         h->stats.pairs_fp32 += nc * nm;
 
@@ -838,7 +801,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             SP.No = nsafe; SP.objlist = safe_list; SP.M2 = M2; SP.thr2 = thr2; SP.hist = hist;
             SP.hist_stride = hist_stride;
             const int64_t tiles2 = (nsafe + (int64_t)FT * R - 1) / ((int64_t)FT * R);
-            if (launch_sweep(h, SP, dim3((unsigned)tiles2, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, R, 2))
+            if (launch_sweep(h, SP, dim3((unsigned)tiles2, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 2))
                 return 1;
             h->stats.pairs_fp32 += nsafe * nm;
             FZB_CUDA(cudaEventRecord(h->ev[5], h->stream));
