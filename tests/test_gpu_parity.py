@@ -218,3 +218,55 @@ def test_knn_query_matches_oracle(fz):
         for i in range(len(q)):
             oi, od = fo.knn_query_exact(feats, q[i], 9, p)
             assert np.array_equal(idx[i], oi) and np.allclose(dist[i], od, rtol=1e-14)
+
+
+def test_model_sharded_single_rank(fz):
+    """fzb_shard_pass1/2_dev + the merge arithmetic (world size 1 degenerates to identity collectives)."""
+    from frankenz_b200.distributed import fit_predict_model_sharded
+    g = golden("bruteforce_c1small.npz")
+    _, rdict = _dict(fz)
+    p, (lm, le), best = fit_predict_model_sharded(g["models"], g["models_err"], g["models_mask"], g["data"].copy(),
+                                                  g["data_err"].copy(), g["data_mask"].copy(), g["labels"],
+                                                  g["label_errs"], label_dict=rdict, return_best=True)
+    assert l1(p, g["pdf_dict"]) <= 1e-9
+    close_gof(lm, g["lmap"], 1e-9)
+    close_gof(le, g["levid"], 1e-9)
+    assert np.array_equal(best, g["fit_lnprob"].argmax(axis=1))
+
+
+def test_model_sharded_two_shards_one_gpu(fz):
+    """Two model shards evaluated one after the other on one GPU, merged with the same arithmetic the
+    NCCL path uses (the collectives replaced by their definitions)."""
+    import ctypes as C
+    import torch
+    from frankenz_b200 import _lib
+    from frankenz_b200._engine import Engine, make_config
+    g = golden("bruteforce_c1small.npz")
+    _, rdict = _dict(fz)
+    m, me, mm = g["models"], g["models_err"], g["models_mask"]
+    x = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (g["data"], g["data_err"], g["data_mask"])]
+    no, cut = len(g["data"]), 500
+    cfg = make_config(None, None)
+    engs, parts = [], []
+    for lo, hi in ((0, cut), (cut, len(m))):
+        e = Engine(m[lo:hi], me[lo:hi], mm[lo:hi])
+        e.set_kde(g["labels"][lo:hi], g["label_errs"][lo:hi], label_dict=rdict)
+        pm, ps = torch.empty(no, dtype=torch.float64).cuda(), torch.empty(no, dtype=torch.float64).cuda()
+        pb = torch.empty(no, dtype=torch.int64).cuda()
+        _lib.check(e.lib.fzb_shard_pass1_dev(e.h, x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr(), no, C.byref(cfg),
+                                             pm.data_ptr(), ps.data_ptr(), pb.data_ptr()))
+        engs.append(e)
+        parts.append((pm, ps, pb))
+    gmax = torch.maximum(parts[0][0], parts[1][0])
+    s = sum(ps * torch.exp(pm - gmax) for pm, ps, _ in parts)
+    levid = gmax + torch.log(s)
+    close_gof(gmax.cpu().numpy(), g["lmap"], 1e-9)
+    close_gof(levid.cpu().numpy(), g["levid"], 1e-9)
+    tot = torch.zeros((no, rdict.Ngrid), dtype=torch.float64).cuda()
+    for e in engs:
+        part = torch.empty((no, rdict.Ngrid), dtype=torch.float64).cuda()
+        _lib.check(e.lib.fzb_shard_pass2_dev(e.h, x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr(), no, C.byref(cfg),
+                                             gmax.data_ptr(), levid.data_ptr(), part.data_ptr()))
+        tot += part
+    p = (tot / tot.sum(dim=1, keepdim=True)).cpu().numpy()
+    assert l1(p, g["pdf_dict"]) <= 1e-9
