@@ -135,7 +135,11 @@ def main():
     ap.add_argument("--cpu-objects-per-core", type=int, default=6)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--lprob", default="", help="JSON overriding the likelihood flags (experiments only)")
     args = ap.parse_args()
+    if args.lprob:
+        LPROB.clear()
+        LPROB.update(json.loads(args.lprob))
     rank, world, local = dist_env()
     if world != max(1, args.gpus) and world > 1:
         args.gpus = world

@@ -1,8 +1,12 @@
 // C-ABI entry points of libfzb200 (see include/frankenz_b200.h): handle management, host<->device
 // staging, and dispatch between the fp32 register-tiled path (fzb_fast.cu) and the generic
 // float64 path (fzb_generic.cu).
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdarg>
+#include <mutex>
+#include <thread>
 
 #include "fzb_common.cuh"
 
@@ -173,6 +177,13 @@ int fzb_destroy(fzb_handle h) {
     for (auto& b : h->out_i64) b.release();
     for (auto& b : h->misc) b.release();
     for (auto& ev : h->ev) cudaEventDestroy(ev);
+    for (int b = 0; b < 2; ++b) {
+        h->pdf_dev[b].release();
+        if (h->pinned[b]) cudaFreeHost(h->pinned[b]);
+        if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
+        if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
+    }
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -364,6 +375,17 @@ int fzb_fit(fzb_handle h, const double* data, const double* data_err, const doub
     return t.stop();
 }
 
+static int fit_predict_dev_impl(fzb_context* h, const double* d_data, const double* d_err, const double* d_mask,
+                                int64_t No, const FzbConfig* cfg, double* d_pdfs, double* d_lmap, double* d_levid,
+                                int64_t* d_best_idx, double* d_best_chi2, double* d_best_scale) {
+    if (cfg->precision != FZB_PREC_FP64 && fzb_fast_supported(h, *cfg))
+        return fzb_fast_fit_predict_dev(h, d_data, d_err, d_mask, No, *cfg, d_pdfs, d_lmap, d_levid, d_best_idx,
+                                        d_best_chi2, d_best_scale);
+    FZB_CHECK(cfg->precision != FZB_PREC_FP32, "the fp32 path does not support this configuration");
+    return fzb_generic_fit_predict_dev(h, d_data, d_err, d_mask, No, nullptr, 0, *cfg, d_pdfs, d_lmap, d_levid,
+                                       d_best_idx, d_best_chi2, d_best_scale);
+}
+
 int fzb_fit_predict_dev(fzb_handle h, const double* d_data, const double* d_err, const double* d_mask, int64_t No,
                         const FzbConfig* cfg, double* d_pdfs, double* d_lmap, double* d_levid, int64_t* d_best_idx,
                         double* d_best_chi2, double* d_best_scale) {
@@ -372,18 +394,32 @@ int fzb_fit_predict_dev(fzb_handle h, const double* d_data, const double* d_err,
     reset_stats(h);
     if (No == 0) return 0;
     Timer t(h);
-    int rc;
-    if (cfg->precision != FZB_PREC_FP64 && fzb_fast_supported(h, *cfg)) {
-        rc = fzb_fast_fit_predict_dev(h, d_data, d_err, d_mask, No, *cfg, d_pdfs, d_lmap, d_levid, d_best_idx,
-                                      d_best_chi2, d_best_scale);
-    } else {
-        FZB_CHECK(cfg->precision != FZB_PREC_FP32, "the fp32 path does not support this configuration");
-        rc = fzb_generic_fit_predict_dev(h, d_data, d_err, d_mask, No, nullptr, 0, *cfg, d_pdfs, d_lmap, d_levid,
-                                         d_best_idx, d_best_chi2, d_best_scale);
-    }
+    int rc = fit_predict_dev_impl(h, d_data, d_err, d_mask, No, cfg, d_pdfs, d_lmap, d_levid, d_best_idx, d_best_chi2,
+                                  d_best_scale);
     if (rc) return rc;
     return t.stop();
 }
+
+// Host-pointer form.  The objects are processed in chunks; the PDFs of chunk c travel device -> pinned staging
+// buffer on a second stream (copy engine) and from there into the caller's array by a pool of host threads, while
+// the kernels of chunk c+1 run: PCIe and the host memcpy are hidden behind the compute.
+namespace {
+void parallel_memcpy(char* dst, const char* src, size_t bytes, int nthreads) {
+    if (bytes < ((size_t)8 << 20) || nthreads <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> pool;
+    size_t per = (bytes / nthreads + 4095) & ~(size_t)4095;
+    for (int t = 0; t < nthreads; ++t) {
+        size_t lo = (size_t)t * per;
+        if (lo >= bytes) break;
+        size_t n = std::min(per, bytes - lo);
+        pool.emplace_back([=] { memcpy(dst + lo, src + lo, n); });
+    }
+    for (auto& th : pool) th.join();
+}
+}  // namespace
 
 int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, const double* data_mask, int64_t No,
                     const FzbConfig* cfg, double* pdfs, double* lmap, double* levid, int64_t* best_idx,
@@ -391,28 +427,132 @@ int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, co
     if (use_device(h) || check_models(h)) return 2;
     FZB_CHECK(cfg != nullptr, "null config");
     FZB_CHECK(No >= 0, "negative object count");
-    if (No == 0) { reset_stats(h); return 0; }
+    reset_stats(h);
+    if (No == 0) return 0;
     const int Nf = h->Nf;
     const int Ng = h->Ng;
     size_t nin = (size_t)No * Nf;
     if (upload(h, h->obj_in[0], data, nin) || upload(h, h->obj_in[1], data_err, nin) ||
         upload(h, h->obj_in[2], data_mask, nin))
         return 1;
-    if (pdfs && h->out_f64[0].reserve((size_t)No * Ng * 8)) return 1;
     if (h->out_f64[1].reserve((size_t)No * 8) || h->out_f64[2].reserve((size_t)No * 8) ||
         h->out_f64[3].reserve((size_t)No * 8) || h->out_f64[4].reserve((size_t)No * 8) ||
         h->out_i64[0].reserve((size_t)No * 8))
         return 1;
-    int rc = fzb_fit_predict_dev(h, h->obj_in[0].as<double>(), h->obj_in[1].as<double>(), h->obj_in[2].as<double>(),
-                                 No, cfg, pdfs ? h->out_f64[0].as<double>() : nullptr, h->out_f64[1].as<double>(),
-                                 h->out_f64[2].as<double>(), h->out_i64[0].as<int64_t>(), h->out_f64[3].as<double>(),
-                                 h->out_f64[4].as<double>());
-    if (rc) return rc;
-    if (download(h, pdfs, h->out_f64[0].p, (size_t)No * Ng) || download(h, lmap, h->out_f64[1].p, (size_t)No) ||
-        download(h, levid, h->out_f64[2].p, (size_t)No) || download(h, best_idx, h->out_i64[0].p, (size_t)No) ||
-        download(h, best_chi2, h->out_f64[3].p, (size_t)No) || download(h, best_scale, h->out_f64[4].p, (size_t)No))
+    const double* d_x = h->obj_in[0].as<double>();
+    const double* d_xe = h->obj_in[1].as<double>();
+    const double* d_xm = h->obj_in[2].as<double>();
+    double* d_lmap = h->out_f64[1].as<double>();
+    double* d_levid = h->out_f64[2].as<double>();
+    double* d_bc = h->out_f64[3].as<double>();
+    double* d_bs = h->out_f64[4].as<double>();
+    int64_t* d_bi = h->out_i64[0].as<int64_t>();
+
+    // chunk size: large enough for full waves of the sweep kernels, small enough to pipeline
+    int64_t chunk = 98304;
+    if (const char* e = getenv("FZB_E2E_CHUNK")) chunk = std::max<int64_t>(1024, atoll(e));
+    if (!pdfs || No <= chunk + chunk / 2) chunk = No;
+    const size_t chunk_bytes = (size_t)chunk * Ng * sizeof(double);
+    const bool pipelined = pdfs && chunk < No;
+    int rc = 0;
+    if (!pipelined) {
+        if (pdfs && h->out_f64[0].reserve((size_t)No * Ng * 8)) return 1;
+        FZB_CUDA(cudaEventRecord(h->ev[0], h->stream));
+        rc = fit_predict_dev_impl(h, d_x, d_xe, d_xm, No, cfg, pdfs ? h->out_f64[0].as<double>() : nullptr, d_lmap,
+                                  d_levid, d_bi, d_bc, d_bs);
+        if (rc) return rc;
+        FZB_CUDA(cudaEventRecord(h->ev[1], h->stream));
+        if (download(h, pdfs, h->out_f64[0].p, (size_t)No * Ng)) return 1;
+    } else {
+        if (!h->stream2) FZB_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            if (h->pdf_dev[b].reserve(chunk_bytes)) return 1;
+            if (h->pinned_cap[b] < chunk_bytes) {
+                if (h->pinned[b]) cudaFreeHost(h->pinned[b]);
+                h->pinned[b] = nullptr;
+                h->pinned_cap[b] = 0;
+                FZB_CUDA(cudaHostAlloc(&h->pinned[b], chunk_bytes, cudaHostAllocDefault));
+                h->pinned_cap[b] = chunk_bytes;
+            }
+            if (!h->ev_done[b]) {
+                FZB_CUDA(cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming));
+                FZB_CUDA(cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
+            }
+        }
+        const int64_t nchunks = (No + chunk - 1) / chunk;
+        int nthreads = (int)std::min<unsigned>(12, std::max(1u, std::thread::hardware_concurrency() / 2));
+        // drainer: waits for the D2H of chunk c, spreads it into the caller's array, frees the staging buffer
+        std::mutex mu;
+        std::condition_variable cv;
+        int64_t copied_enqueued = 0;          // chunks whose D2H has been enqueued
+        int64_t drained = 0;                  // chunks fully delivered to the caller
+        std::atomic<int> drain_err{0};
+        bool abort_flag = false;
+        std::thread drainer([&] {
+            cudaSetDevice(h->device);
+            for (int64_t c = 0; c < nchunks; ++c) {
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return copied_enqueued > c || abort_flag; });
+                    if (abort_flag) return;
+                }
+                if (cudaEventSynchronize(h->ev_copied[c & 1]) != cudaSuccess) drain_err = 1;
+                int64_t o0 = c * chunk, nc = std::min(chunk, No - o0);
+                parallel_memcpy(reinterpret_cast<char*>(pdfs + (size_t)o0 * Ng),
+                                reinterpret_cast<const char*>(h->pinned[c & 1]), (size_t)nc * Ng * sizeof(double),
+                                nthreads);
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    drained = c + 1;
+                }
+                cv.notify_all();
+            }
+        });
+        FZB_CUDA(cudaEventRecord(h->ev[0], h->stream));
+        for (int64_t c = 0; c < nchunks && rc == 0; ++c) {
+            int64_t o0 = c * chunk, nc = std::min(chunk, No - o0);
+            int b = (int)(c & 1);
+            if (c >= 2) {   // device buffer b is free once its D2H finished; staging buffer once drained
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return drained >= c - 1; });
+            }
+            rc = fit_predict_dev_impl(h, d_x + o0 * Nf, d_xe + o0 * Nf, d_xm + o0 * Nf, nc, cfg,
+                                      h->pdf_dev[b].as<double>(), d_lmap + o0, d_levid + o0, d_bi + o0, d_bc + o0,
+                                      d_bs + o0);
+            if (rc) break;
+            if (cudaEventRecord(h->ev_done[b], h->stream) != cudaSuccess ||
+                cudaStreamWaitEvent(h->stream2, h->ev_done[b], 0) != cudaSuccess ||
+                cudaMemcpyAsync(h->pinned[b], h->pdf_dev[b].p, (size_t)nc * Ng * sizeof(double),
+                                cudaMemcpyDeviceToHost, h->stream2) != cudaSuccess ||
+                cudaEventRecord(h->ev_copied[b], h->stream2) != cudaSuccess) {
+                fzb_set_error("pipelined D2H failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = 1;
+                break;
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                copied_enqueued = c + 1;
+            }
+            cv.notify_all();
+        }
+        if (rc) {
+            std::lock_guard<std::mutex> lk(mu);
+            abort_flag = true;
+        }
+        cv.notify_all();
+        cudaEventRecord(h->ev[1], h->stream);
+        drainer.join();
+        if (rc) return rc;
+        FZB_CHECK(drain_err == 0, "device-to-host copy of the PDFs failed");
+    }
+    if (download(h, lmap, d_lmap, (size_t)No) || download(h, levid, d_levid, (size_t)No) ||
+        download(h, best_idx, d_bi, (size_t)No) || download(h, best_chi2, d_bc, (size_t)No) ||
+        download(h, best_scale, d_bs, (size_t)No))
         return 1;
     FZB_CUDA(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    h->stats.ms_total = ms;
     return 0;
 }
 

@@ -82,6 +82,13 @@ struct fzb_context {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    // pipelined host API: second stream (copy engine), double-buffered device + pinned staging for the PDFs
+    cudaStream_t stream2 = nullptr;
+    DevBuf pdf_dev[2];
+    void* pinned[2] = {nullptr, nullptr};
+    size_t pinned_cap[2] = {0, 0};
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};
 
     // model set (fp64 originals, row-major Nm x Nf)
     int64_t Nm = 0;
@@ -116,6 +123,7 @@ struct fzb_context {
     FastModels fast;
     bool fast_dirty = true;
     int fast_mode = -1;
+    bool fast_packed = true;
     int fast_wmax = 0;
     int fast_Ngpad = 0;
 

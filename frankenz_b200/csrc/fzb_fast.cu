@@ -310,6 +310,264 @@ __global__ void __launch_bounds__(FT, (R >= 8) ? 1 : 2) k_sweep(SweepParams P) {
     }
 }
 
+
+// =====================================================================================================
+// Packed-FP32 sweep (FFMA2 / FMUL2 / FADD2): two objects per 64-bit register pair.
+// `fma.rn.f32x2` issues at half the instruction rate of FFMA (tools/peak_ffma2.cu) but does two lanes'
+// worth of work, so the 30 FMA-class operations of a pair cost 15 issue slots instead of 30; the freed
+// slots go to the MUFU / select / shared-memory instructions that otherwise compete with the FMAs.
+// Model values are stored duplicated (m, m) in the shared-memory record so one LDS.128 yields two
+// ready-made packed operands.
+// =====================================================================================================
+// threads per CTA / CTAs per SM of the packed kernel: R=4 -> 384 threads x 1 (<= 168 registers), R=2 -> 256 threads x 3 (<= 85)
+__host__ __device__ constexpr int ft2_of(int R) { return R >= 4 ? 384 : 256; }
+__host__ __device__ constexpr int minb2_of(int R) { return R >= 4 ? 1 : 3; }
+
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pack2(float a, float b) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float lo2(f2 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a;
+}
+__device__ __forceinline__ float hi2(f2 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return b;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    f2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    f2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+__host__ __device__ constexpr int rec2_floats(int nf, int mode, bool mlo) {
+    // pairs (v, v): m[nf], aux[nf] (FS0: m^2, FX1: err^2), ml[nf] (MLO); tail: prior2 x2, invnorm x2, bin
+    int n = 2 * nf * (1 + ((mode == FM_FX0) ? 0 : 1) + (mlo ? 1 : 0)) + 5;
+    return (n + 3) / 4 * 4;
+}
+
+template <int NF, int MODE>
+struct ObjPack {     // two objects (lo half, hi half)
+    f2 d[NF];
+    f2 w[NF];        // FS0/FX0: weights; FX1: err^2 (+inf where masked)
+    f2 x[(MODE == FM_FS0) ? NF : 1];
+    f2 dl[NF];       // 2 * d_lo
+    f2 A;
+};
+
+template <int NF, int MODE, bool MLO>
+__device__ __forceinline__ f2 pack_chi2(const ObjPack<NF, MODE>& o, const f2* __restrict__ m,
+                                        const f2* __restrict__ aux, const f2* __restrict__ ml) {
+    f2 ns = 0;   // minus the optimal scale (FS0)
+    if (MODE == FM_FS0) {
+        f2 inter = mul2(o.x[0], m[0]);
+        f2 shape = mul2(o.w[0], aux[0]);
+#pragma unroll
+        for (int b = 1; b < NF; ++b) {
+            inter = fma2(o.x[b], m[b], inter);
+            shape = fma2(o.w[b], aux[b], shape);
+        }
+        float n0 = __fmul_rn(-lo2(inter), fast_rcp(lo2(shape)));
+        float n1 = __fmul_rn(-hi2(inter), fast_rcp(hi2(shape)));
+        ns = pack2(n0, n1);
+    }
+    f2 chi2 = 0, cm = 0;
+#pragma unroll
+    for (int b = 0; b < NF; ++b) {
+        f2 r, w;
+        if (MODE == FM_FS0) r = fma2(ns, m[b], o.d[b]);
+        else r = add2(o.d[b], m[b]);            // fixed scale: the record stores -m
+        if (MODE == FM_FX1) {
+            f2 var = add2(o.w[b], aux[b]);
+            w = pack2(fast_rcp(lo2(var)), fast_rcp(hi2(var)));
+        } else {
+            w = o.w[b];
+        }
+        f2 t = mul2(r, w);
+        f2 u = add2(r, o.dl[b]);                // chi2 + first-order lo correction: sum t * (r + 2 d_lo)
+        if (b == 0) {
+            chi2 = mul2(t, u);
+            if (MLO) cm = mul2(t, ml[0]);
+        } else {
+            chi2 = fma2(t, u, chi2);
+            if (MLO) cm = fma2(t, ml[b], cm);
+        }
+    }
+    if (MLO) chi2 = (MODE == FM_FS0) ? fma2(ns, cm, chi2) : add2(chi2, cm);   // FX: record stores -2*m_lo
+    return chi2;
+}
+
+template <int NF, int MODE, bool DP, bool MLO, int R, int PASS>
+__global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P) {
+    static_assert(R % 2 == 0, "objects come in packed pairs");
+    constexpr int FT2 = ft2_of(R);
+    constexpr int NP = R / 2;
+    constexpr int REC = rec2_floats(NF, MODE, MLO);
+    constexpr int AUXOFF = 2 * NF;
+    constexpr int MLOFF = 2 * NF * (1 + ((MODE == FM_FX0) ? 0 : 1));
+    constexpr int TAILOFF = MLOFF + (MLO ? 2 * NF : 0);   // prior2 x2, invnorm x2, bin
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * TM * REC * sizeof(float));
+    const int tid = threadIdx.x;
+
+    ObjPack<NF, MODE> ob[NP];
+    int oidx[R];
+    f2 negM[NP];          // minus the running / final max
+    f2 S[NP];             // pass 1: running sum.  pass 2: unused
+    float thr[R];         // pass 2: selection cut
+    int best[R];
+    f2 acc[NP];
+    const int64_t tile_base = (int64_t)blockIdx.x * (FT2 * R);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+        int64_t oo[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int r = 2 * p + h;
+            int64_t slot = tile_base + (int64_t)r * FT2 + tid;
+            int64_t o;
+            if (PASS == 1) o = slot < P.No_pad ? slot : P.No_pad - 1;
+            else o = slot < P.No ? P.objlist[slot] : -1;
+            oidx[r] = (int)o;
+            oo[h] = o < 0 ? 0 : o;
+            best[r] = 0;
+            thr[r] = (PASS == 2) ? P.thr2[oo[h]] : 0.f;
+        }
+#pragma unroll
+        for (int b = 0; b < NF; ++b) {
+            ob[p].d[b] = pack2(P.od[b * P.No_pad + oo[0]], P.od[b * P.No_pad + oo[1]]);
+            ob[p].w[b] = pack2(P.ow[b * P.No_pad + oo[0]], P.ow[b * P.No_pad + oo[1]]);
+            ob[p].dl[b] = pack2(P.odl[b * P.No_pad + oo[0]], P.odl[b * P.No_pad + oo[1]]);
+            if (MODE == FM_FS0) ob[p].x[b] = pack2(P.ox[b * P.No_pad + oo[0]], P.ox[b * P.No_pad + oo[1]]);
+        }
+        ob[p].A = pack2(P.oA[oo[0]], P.oA[oo[1]]);
+        if (PASS == 1) { negM[p] = pack2(FLT_MAX, FLT_MAX); S[p] = pack2(0.f, 0.f); }
+        else { negM[p] = pack2(-P.M2[oo[0]], -P.M2[oo[1]]); acc[p] = pack2(0.f, 0.f); }
+    }
+
+    const int64_t ntiles_all = (P.nm + TM - 1) / TM;
+    const int64_t t0 = (int64_t)blockIdx.y * P.tiles_per_split;
+    int64_t t1 = t0 + P.tiles_per_split;
+    if (t1 > ntiles_all) t1 = ntiles_all;
+    const int nt = (int)(t1 - t0);
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int it) {
+        int64_t first = (t0 + it) * TM;
+        int cnt = (int)((P.nm - first) < TM ? (P.nm - first) : TM);
+        uint32_t bytes = (uint32_t)cnt * REC * sizeof(float);
+        uint64_t* bar = &bars[it % NSTAGE];
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(stage + (size_t)(it % NSTAGE) * TM * REC, P.recs + first * REC, bytes, bar);
+    };
+    if (tid == 0) {
+        for (int it = 0; it < NSTAGE && it < nt; ++it) issue(it);
+    }
+    const f2 kNegHalfLog2e = pack2(-kHalfLog2e, -kHalfLog2e);
+    int cur_bin = -1;
+    for (int it = 0; it < nt; ++it) {
+        const int st = it % NSTAGE;
+        mbar_wait(&bars[st], (uint32_t)((it / NSTAGE) & 1));
+        const float* tile = stage + (size_t)st * TM * REC;
+        const int64_t first = (t0 + it) * TM;
+        const int cnt = (int)((P.nm - first) < TM ? (P.nm - first) : TM);
+#pragma unroll 2
+        for (int jj = 0; jj < cnt; ++jj) {
+            const float* rec = tile + jj * REC;       // same record for every thread: shared-memory broadcast
+            const f2* rec2 = reinterpret_cast<const f2*>(rec);
+            const f2 prior2 = rec2[TAILOFF / 2];
+            f2 invnorm = 0;
+            if (PASS == 2) {
+                invnorm = rec2[TAILOFF / 2 + 1];
+                const int bin = __float_as_int(rec[TAILOFF + 4]);
+                if (bin != cur_bin) {                  // warp-uniform
+                    if (cur_bin >= 0) {
+#pragma unroll
+                        for (int p = 0; p < NP; ++p) {
+                            float a0 = lo2(acc[p]), a1 = hi2(acc[p]);
+                            if (a0 != 0.f && oidx[2 * p] >= 0)
+                                atomicAdd(P.hist + (int64_t)oidx[2 * p] * P.hist_stride + cur_bin, a0);
+                            if (a1 != 0.f && oidx[2 * p + 1] >= 0)
+                                atomicAdd(P.hist + (int64_t)oidx[2 * p + 1] * P.hist_stride + cur_bin, a1);
+                            acc[p] = pack2(0.f, 0.f);
+                        }
+                    }
+                    cur_bin = bin;
+                }
+            }
+            f2 m[NF], aux[NF], ml[NF];
+#pragma unroll
+            for (int b = 0; b < NF; ++b) {
+                m[b] = rec2[b];
+                aux[b] = (MODE == FM_FX0) ? 0 : rec2[AUXOFF / 2 + b];
+                ml[b] = MLO ? rec2[MLOFF / 2 + b] : 0;
+            }
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                f2 chi2 = pack_chi2<NF, MODE, MLO>(ob[p], m, aux, ml);
+                f2 l = fma2(chi2, kNegHalfLog2e, prior2);
+                if (DP) l = fma2(ob[p].A, pack2(fast_lg2(lo2(chi2)), fast_lg2(hi2(chi2))), l);
+                f2 delta = add2(l, negM[p]);
+                float d0 = lo2(delta), d1 = hi2(delta);
+                if (PASS == 1) {
+                    float e0 = fast_ex2(-fabsf(d0)), e1 = fast_ex2(-fabsf(d1));
+                    bool g0 = d0 > 0.f, g1 = d1 > 0.f;
+                    S[p] = fma2(S[p], pack2(g0 ? e0 : 1.f, g1 ? e1 : 1.f), pack2(g0 ? 1.f : e0, g1 ? 1.f : e1));
+                    negM[p] = pack2(g0 ? -lo2(l) : lo2(negM[p]), g1 ? -hi2(l) : hi2(negM[p]));
+                    best[2 * p] = g0 ? (int)(first + jj) : best[2 * p];
+                    best[2 * p + 1] = g1 ? (int)(first + jj) : best[2 * p + 1];
+                } else {
+                    float u0 = fast_ex2(d0), u1 = fast_ex2(d1);
+                    u0 = (lo2(l) > thr[2 * p]) ? u0 : 0.f;
+                    u1 = (hi2(l) > thr[2 * p + 1]) ? u1 : 0.f;
+                    acc[p] = fma2(pack2(u0, u1), invnorm, acc[p]);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && it + NSTAGE < nt) issue(it + NSTAGE);
+    }
+    if (PASS == 1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            int64_t slot = tile_base + (int64_t)r * FT2 + tid;
+            if (slot < P.No_pad) {
+                size_t q = (size_t)blockIdx.y * P.No_pad + slot;
+                P.pM[q] = -((r & 1) ? hi2(negM[r / 2]) : lo2(negM[r / 2]));
+                P.pS[q] = (r & 1) ? hi2(S[r / 2]) : lo2(S[r / 2]);
+                P.pbest[q] = best[r];
+            }
+        }
+    } else if (cur_bin >= 0) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            float a0 = lo2(acc[p]), a1 = hi2(acc[p]);
+            if (a0 != 0.f && oidx[2 * p] >= 0) atomicAdd(P.hist + (int64_t)oidx[2 * p] * P.hist_stride + cur_bin, a0);
+            if (a1 != 0.f && oidx[2 * p + 1] >= 0)
+                atomicAdd(P.hist + (int64_t)oidx[2 * p + 1] * P.hist_stride + cur_bin, a1);
+        }
+    }
+}
+
 // ---- object preparation ------------------------------------------------------------------------
 struct PrepParams {
     const double *x, *xe, *xm;   // (No x Nf) raw inputs of this chunk
@@ -481,7 +739,7 @@ struct RecParams {
     const int32_t* bins;
     const float* invnorm;
     int64_t nm;
-    int Nf, mode, rec, mlo;
+    int Nf, mode, rec, mlo, packed;
     float* recs;
 };
 
@@ -490,6 +748,29 @@ __global__ void k_build_records(RecParams P) {
     if (p >= P.nm) return;
     int64_t j = P.perm[p];
     float* r = P.recs + p * P.rec;
+    if (P.packed) {
+        // packed layout (k_sweep2): every model value duplicated (v, v); fixed-scale modes store -m and -2*m_lo
+        const int nf = P.Nf;
+        const int auxoff = 2 * nf, mloff = 2 * nf * (1 + ((P.mode == FM_FX0) ? 0 : 1));
+        const float sgn = (P.mode == FM_FS0) ? 1.f : -1.f;
+        for (int b = 0; b < nf; ++b) {
+            double v = P.m[j * nf + b];
+            float hi = (float)v;
+            r[2 * b] = r[2 * b + 1] = sgn * hi;
+            if (P.mlo) r[mloff + 2 * b] = r[mloff + 2 * b + 1] = sgn * 2.f * (float)(v - (double)hi);
+            if (P.mode == FM_FS0) r[auxoff + 2 * b] = r[auxoff + 2 * b + 1] = (float)(v * v);
+            else if (P.mode == FM_FX1) {
+                double e = P.me[j * nf + b];
+                r[auxoff + 2 * b] = r[auxoff + 2 * b + 1] = (float)(e * e);
+            }
+        }
+        int tail = mloff + (P.mlo ? 2 * nf : 0);
+        r[tail] = r[tail + 1] = P.lnprior ? (float)(P.lnprior[j] * 1.4426950408889634) : 0.f;
+        r[tail + 2] = r[tail + 3] = P.invnorm ? P.invnorm[p] : 0.f;
+        r[tail + 4] = __int_as_float(P.bins ? P.bins[p] : -1);
+        for (int i = tail + 5; i < P.rec; ++i) r[i] = 0.f;
+        return;
+    }
     const int mloff = P.Nf + ((P.mode == FM_FX0) ? 0 : P.Nf);
     for (int b = 0; b < P.Nf; ++b) {
         double v = P.m[j * P.Nf + b];
@@ -532,8 +813,28 @@ int launch_sweep_t(fzb_context* h, const SweepParams& P, dim3 grid) {
     return 0;
 }
 
+template <int NF, int MODE, bool DP, bool MLO, int R, int PASS>
+int launch_sweep2_t(fzb_context* h, const SweepParams& P, dim3 grid) {
+    constexpr int REC = rec2_floats(NF, MODE, MLO);
+    size_t smem = (size_t)NSTAGE * TM * REC * sizeof(float) + NSTAGE * sizeof(uint64_t);
+    auto kern = k_sweep2<NF, MODE, DP, MLO, R, PASS>;
+    FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, ft2_of(R), smem, h->stream>>>(P);
+    fzb_count_launch(h);
+    FZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <int NF, int MODE, bool DP, bool MLO>
 int launch_sweep_r(fzb_context* h, const SweepParams& P, dim3 grid, int R, int pass) {
+    if (R < 0) {   // packed kernels: R = -objects per thread
+        if (pass == 1) {
+            if (R == -4) return launch_sweep2_t<NF, MODE, DP, MLO, 4, 1>(h, P, grid);
+            return launch_sweep2_t<NF, MODE, DP, MLO, 2, 1>(h, P, grid);
+        }
+        if (R == -4) return launch_sweep2_t<NF, MODE, DP, MLO, 4, 2>(h, P, grid);
+        return launch_sweep2_t<NF, MODE, DP, MLO, 2, 2>(h, P, grid);
+    }
     if (pass == 1) {
         if (R == RBIG) return launch_sweep_t<NF, MODE, DP, MLO, RBIG, 1>(h, P, grid);
         return launch_sweep_t<NF, MODE, DP, MLO, 1, 1>(h, P, grid);
@@ -638,7 +939,9 @@ static int fast_prepare_mode(fzb_context* h, int mode) {
     F.nf = nf;
     F.nm = nm;
     const bool mlo = !h->models_f32_exact;
-    F.rec = rec_floats(nf, mode, mlo);
+    const bool packed = getenv("FZB_FAST_SCALAR") == nullptr;
+    F.rec = packed ? rec2_floats(nf, mode, mlo) : rec_floats(nf, mode, mlo);
+    h->fast_packed = packed;
     if (F.recs.reserve((size_t)nm * F.rec * sizeof(float) + 64) || F.perm.reserve((size_t)nm * 4 + 16)) return 1;
     FZB_CUDA(cudaMemcpyAsync(F.perm.p, perm.data(), (size_t)nm * 4, cudaMemcpyHostToDevice, h->stream));
     if (kde) {
@@ -657,7 +960,7 @@ static int fast_prepare_mode(fzb_context* h, int mode) {
     R.perm = F.perm.as<int32_t>();
     R.bins = kde ? F.bins.as<int32_t>() : nullptr;
     R.invnorm = kde ? F.invnorm.as<float>() : nullptr;
-    R.nm = nm; R.Nf = nf; R.mode = mode; R.rec = F.rec; R.mlo = mlo ? 1 : 0;
+    R.nm = nm; R.Nf = nf; R.mode = mode; R.rec = F.rec; R.mlo = mlo ? 1 : 0; R.packed = packed ? 1 : 0;
     R.recs = F.recs.as<float>();
     k_build_records<<<(unsigned)((nm + 255) / 256), 256, 0, h->stream>>>(R);
     fzb_count_launch(h);
@@ -696,12 +999,18 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         if (fit < 1024) fit = 1024;
         if (chunk > fit) chunk = fit;
     }
-    const int64_t chunk_pad = (chunk + 1023) / 1024 * 1024;
-    const int R = (chunk >= 64 * 1024) ? RBIG : 1;
+    const int64_t chunk_pad = (chunk + 6143) / 6144 * 6144;
+    const bool packed = h->fast_packed;
+    // objects per thread: 4 for large batches; small batches use fewer so that more CTAs exist.
+    // (negative R selects the packed kernel in launch_sweep_r)
+    int Robj = packed ? ((chunk >= 48 * 1024) ? 4 : 2) : ((chunk >= 64 * 1024) ? RBIG : 1);
+    if (packed && getenv("FZB_FAST_R")) Robj = atoi(getenv("FZB_FAST_R")) >= 4 ? 4 : 2;
+    const int R = packed ? -Robj : Robj;
+    const int64_t tile_objs = (int64_t)(packed ? ft2_of(Robj) : FT) * Robj;
     const bool mlo = !h->models_f32_exact;
-    const int64_t obj_tiles = (chunk_pad + (int64_t)FT * R - 1) / ((int64_t)FT * R);
+    const int64_t obj_tiles = (chunk_pad + tile_objs - 1) / tile_objs;
     const int64_t ntiles = (nm + TM - 1) / TM;
-    int64_t want_ctas = (int64_t)h->sm_count * 8;
+    int64_t want_ctas = (int64_t)h->sm_count * ((packed && Robj >= 4) ? 24 : 48);   // many short waves: small tail
     int64_t nsplit = (want_ctas + obj_tiles - 1) / obj_tiles;
     if (nsplit > ntiles) nsplit = ntiles;
     if (nsplit > 256) nsplit = 256;
@@ -756,7 +1065,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         SP.recs = F.recs.as<float>(); SP.nm = nm;
         SP.tiles_per_split = tiles_per_split;
         SP.pM = pM; SP.pS = pS; SP.pbest = pbest;
-        const int64_t tiles1 = (nc + (int64_t)FT * R - 1) / ((int64_t)FT * R);
+        const int64_t tiles1 = (nc + tile_objs - 1) / tile_objs;
         FZB_CUDA(cudaEventRecord(h->ev[2], h->stream));
         if (launch_sweep(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 1)) return 1;
         FZB_CUDA(cudaEventRecord(h->ev[3], h->stream));
@@ -800,7 +1109,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             FZB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nc_pad * hist_stride * 4, h->stream));
             SP.No = nsafe; SP.objlist = safe_list; SP.M2 = M2; SP.thr2 = thr2; SP.hist = hist;
             SP.hist_stride = hist_stride;
-            const int64_t tiles2 = (nsafe + (int64_t)FT * R - 1) / ((int64_t)FT * R);
+            const int64_t tiles2 = (nsafe + tile_objs - 1) / tile_objs;
             if (launch_sweep(h, SP, dim3((unsigned)tiles2, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 2))
                 return 1;
             h->stats.pairs_fp32 += nsafe * nm;
