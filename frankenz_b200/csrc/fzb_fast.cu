@@ -36,19 +36,11 @@
 
 namespace {
 
-constexpr int FT = 256;          // threads per CTA
 constexpr int TM = 256;          // models per shared-memory tile
 constexpr int NSTAGE = 2;
-constexpr int RBIG = 4;           // objects per thread of the large-shape kernels
 constexpr float kHalfLog2e = 0.7213475204444817f;
 
 enum FastMode { FM_FS0 = 0, FM_FX0 = 1, FM_FX1 = 2 };
-
-__host__ __device__ constexpr int rec_floats(int nf, int mode, bool mlo) {
-    // m[nf] (+ q[nf] = m^2 for FS0, me2[nf] for FX1) (+ ml2[nf] = 2*m_lo) + prior2 + bin + invnorm, padded to 4
-    int n = nf + ((mode == FM_FX0) ? 0 : nf) + (mlo ? nf : 0) + 3;
-    return (n + 3) / 4 * 4;
-}
 
 // ---- PTX helpers: mbarrier + TMA bulk copy ----------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -109,7 +101,7 @@ struct SweepParams {
     int tiles_per_split;
     // pass 1 outputs: [nsplit][No_pad]
     float* pM;
-    float* pS;
+    double* pS;
     int32_t* pbest;
     // pass 2
     const int32_t* objlist;
@@ -118,197 +110,6 @@ struct SweepParams {
     float* hist;          // [No_pad][hist_stride]
     int64_t hist_stride;
 };
-
-template <int NF, int MODE>
-struct ObjRegs {
-    float d[NF];
-    float w[NF];    // FS0/FX0: weights; FX1: err^2 (+inf where masked)
-    float x[(MODE == FM_FS0) ? NF : 1];   // FS0 only: d*w
-    float dl[NF];   // 2 * d_lo
-    float A;
-};
-
-// chi2 of one pair: hi parts + first-order lo correction.  m / aux / ml point into the shared-memory record.
-template <int NF, int MODE, bool MLO>
-__device__ __forceinline__ float pair_chi2(const ObjRegs<NF, MODE>& o, const float* __restrict__ m,
-                                           const float* __restrict__ aux, const float* __restrict__ ml) {
-    float chi2, corr, cm = 0.f, s = 1.f;
-    if (MODE == FM_FS0) {
-        float inter = __fmul_rn(o.x[0], m[0]);
-        float shape = __fmul_rn(o.w[0], aux[0]);
-#pragma unroll
-        for (int b = 1; b < NF; ++b) {
-            inter = __fmaf_rn(o.x[b], m[b], inter);
-            shape = __fmaf_rn(o.w[b], aux[b], shape);
-        }
-        s = __fmul_rn(inter, fast_rcp(shape));
-    }
-#pragma unroll
-    for (int b = 0; b < NF; ++b) {
-        float r = (MODE == FM_FS0) ? __fmaf_rn(-s, m[b], o.d[b]) : __fsub_rn(o.d[b], m[b]);
-        float w = (MODE == FM_FX1) ? fast_rcp(__fadd_rn(o.w[b], aux[b])) : o.w[b];
-        float t = __fmul_rn(r, w);
-        if (b == 0) {
-            chi2 = __fmul_rn(t, r);
-            corr = __fmul_rn(t, o.dl[0]);
-            if (MLO) cm = __fmul_rn(t, ml[0]);
-        } else {
-            chi2 = __fmaf_rn(t, r, chi2);
-            corr = __fmaf_rn(t, o.dl[b], corr);
-            if (MLO) cm = __fmaf_rn(t, ml[b], cm);
-        }
-    }
-    chi2 = __fadd_rn(chi2, corr);
-    if (MLO) chi2 = __fmaf_rn(-s, cm, chi2);
-    return chi2;
-}
-
-template <bool DP>
-__device__ __forceinline__ float chi2_to_l2(float chi2, float A, float prior2) {
-    // ln-likelihood in log2 units without the per-object constant:
-    //   DP: (dof/2 - 1) * log2(chi2) - chi2 * log2(e)/2        (pdf.py:93 / :229)
-    //  !DP: - chi2 * log2(e)/2                                   (pdf.py:96, :192)
-    // xlogy's 0*log(0) = 0 case (A == 0, chi2 == 0) yields NaN here; the NaN poisons the object's sum and the
-    // object is then routed to the float64 path, which has the exact semantics.
-    float l = __fmaf_rn(chi2, -kHalfLog2e, prior2);
-    if (DP) l = __fmaf_rn(A, fast_lg2(chi2), l);
-    return l;
-}
-
-template <int NF, int MODE, bool DP, bool MLO, int R, int PASS>
-__global__ void __launch_bounds__(FT, (R >= 8) ? 1 : 2) k_sweep(SweepParams P) {
-    constexpr int REC = rec_floats(NF, MODE, MLO);
-    constexpr int AUXOFF = NF;                                  // q / me2
-    constexpr int MLOFF = NF + ((MODE == FM_FX0) ? 0 : NF);     // 2*m_lo (MLO only)
-    constexpr int TAILOFF = MLOFF + (MLO ? NF : 0);             // prior2, bin, invnorm
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* stage = reinterpret_cast<float*>(smem_raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * TM * REC * sizeof(float));
-    const int tid = threadIdx.x;
-
-    // ---- this thread's objects -----------------------------------------------------------------
-    ObjRegs<NF, MODE> ob[R];
-    int oidx[R];
-    float M[R], S[R];     // pass 1: running max / sum.  pass 2: final max / selection cut
-    int best[R];
-    float acc[R];
-    const int64_t tile_base = (int64_t)blockIdx.x * (FT * R);
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        int64_t slot = tile_base + (int64_t)r * FT + tid;
-        int64_t o;
-        if (PASS == 1) o = slot < P.No_pad ? slot : P.No_pad - 1;
-        else o = slot < P.No ? P.objlist[slot] : -1;
-        oidx[r] = (int)o;
-        int64_t oo = o < 0 ? 0 : o;
-#pragma unroll
-        for (int b = 0; b < NF; ++b) {
-            ob[r].d[b] = P.od[b * P.No_pad + oo];
-            ob[r].w[b] = P.ow[b * P.No_pad + oo];
-            ob[r].dl[b] = P.odl[b * P.No_pad + oo];
-            if (MODE == FM_FS0) ob[r].x[b] = P.ox[b * P.No_pad + oo];
-        }
-        ob[r].A = P.oA[oo];
-        if (PASS == 1) { M[r] = -FLT_MAX; S[r] = 0.f; best[r] = 0; }
-        else { M[r] = P.M2[oo]; S[r] = P.thr2[oo]; acc[r] = 0.f; }
-    }
-
-    // ---- model tiles of this split ---------------------------------------------------------------
-    const int64_t ntiles_all = (P.nm + TM - 1) / TM;
-    const int64_t t0 = (int64_t)blockIdx.y * P.tiles_per_split;
-    int64_t t1 = t0 + P.tiles_per_split;
-    if (t1 > ntiles_all) t1 = ntiles_all;
-    const int nt = (int)(t1 - t0);
-    if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    auto issue = [&](int it) {
-        int64_t tile = t0 + it;
-        int64_t first = tile * TM;
-        int cnt = (int)((P.nm - first) < TM ? (P.nm - first) : TM);
-        uint32_t bytes = (uint32_t)cnt * REC * sizeof(float);
-        uint64_t* bar = &bars[it % NSTAGE];
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(stage + (size_t)(it % NSTAGE) * TM * REC, P.recs + first * REC, bytes, bar);
-    };
-    if (tid == 0) {
-        for (int it = 0; it < NSTAGE && it < nt; ++it) issue(it);
-    }
-    int cur_bin = -1;
-    for (int it = 0; it < nt; ++it) {
-        const int st = it % NSTAGE;
-        mbar_wait(&bars[st], (uint32_t)((it / NSTAGE) & 1));
-        const float* tile = stage + (size_t)st * TM * REC;
-        const int64_t first = (t0 + it) * TM;
-        const int cnt = (int)((P.nm - first) < TM ? (P.nm - first) : TM);
-#pragma unroll 1
-        for (int jj = 0; jj < cnt; ++jj) {
-            const float* rec = tile + jj * REC;   // every thread reads the same record: shared-memory broadcast
-            const float prior2 = rec[TAILOFF];
-            float invnorm = 0.f;
-            if (PASS == 2) {
-                const int bin = __float_as_int(rec[TAILOFF + 1]);
-                invnorm = rec[TAILOFF + 2];
-                if (bin != cur_bin) {       // warp-uniform: every thread walks the same model
-                    if (cur_bin >= 0) {
-#pragma unroll
-                        for (int r = 0; r < R; ++r) {
-                            if (acc[r] != 0.f && oidx[r] >= 0)
-                                atomicAdd(P.hist + (int64_t)oidx[r] * P.hist_stride + cur_bin, acc[r]);
-                            acc[r] = 0.f;
-                        }
-                    }
-                    cur_bin = bin;
-                }
-            }
-            float m[NF], aux[NF], ml[NF];
-#pragma unroll
-            for (int b = 0; b < NF; ++b) {
-                m[b] = rec[b];
-                aux[b] = (MODE == FM_FX0) ? 0.f : rec[AUXOFF + b];
-                ml[b] = MLO ? rec[MLOFF + b] : 0.f;
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                float chi2 = pair_chi2<NF, MODE, MLO>(ob[r], m, aux, ml);
-                float l2 = chi2_to_l2<DP>(chi2, ob[r].A, prior2);
-                float delta = __fsub_rn(l2, M[r]);
-                if (PASS == 1) {
-                    float e = fast_ex2(-fabsf(delta));
-                    bool gt = delta > 0.f;
-                    S[r] = __fmaf_rn(S[r], gt ? e : 1.f, gt ? 1.f : e);
-                    M[r] = gt ? l2 : M[r];
-                    best[r] = gt ? (int)(first + jj) : best[r];
-                } else {
-                    float u = fast_ex2(delta);
-                    u = (l2 > S[r]) ? u : 0.f;      // S[r] holds the selection cut in pass 2
-                    acc[r] = __fmaf_rn(u, invnorm, acc[r]);
-                }
-            }
-        }
-        __syncthreads();   // everyone is done with this stage
-        if (tid == 0 && it + NSTAGE < nt) issue(it + NSTAGE);
-    }
-    if (PASS == 1) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            int64_t slot = tile_base + (int64_t)r * FT + tid;
-            if (slot < P.No_pad) {
-                size_t q = (size_t)blockIdx.y * P.No_pad + slot;
-                P.pM[q] = M[r];
-                P.pS[q] = S[r];
-                P.pbest[q] = best[r];
-            }
-        }
-    } else if (cur_bin >= 0) {
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-            if (acc[r] != 0.f && oidx[r] >= 0)
-                atomicAdd(P.hist + (int64_t)oidx[r] * P.hist_stride + cur_bin, acc[r]);
-    }
-}
 
 
 // =====================================================================================================
@@ -433,6 +234,10 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
     float thr[R];         // pass 2: selection cut
     int best[R];
     f2 acc[NP];
+    // pass 1 sums 2^(l - max) in fp32 only within one model tile; tiles are combined in float64 so that the
+    // rounding error of the evidence does not grow with the number of models
+    double Sd[R];
+    float Mfl[R];
     const int64_t tile_base = (int64_t)blockIdx.x * (FT2 * R);
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
@@ -447,6 +252,8 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
             oidx[r] = (int)o;
             oo[h] = o < 0 ? 0 : o;
             best[r] = 0;
+            Sd[r] = 0.0;
+            Mfl[r] = -FLT_MAX;
             thr[r] = (PASS == 2) ? P.thr2[oo[h]] : 0.f;
         }
 #pragma unroll
@@ -543,6 +350,17 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
                 }
             }
         }
+        if (PASS == 1) {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                float m0 = -lo2(negM[p]), m1 = -hi2(negM[p]);
+                Sd[2 * p] = Sd[2 * p] * (double)fast_ex2(Mfl[2 * p] - m0) + (double)lo2(S[p]);
+                Sd[2 * p + 1] = Sd[2 * p + 1] * (double)fast_ex2(Mfl[2 * p + 1] - m1) + (double)hi2(S[p]);
+                Mfl[2 * p] = m0;
+                Mfl[2 * p + 1] = m1;
+                S[p] = pack2(0.f, 0.f);
+            }
+        }
         __syncthreads();
         if (tid == 0 && it + NSTAGE < nt) issue(it + NSTAGE);
     }
@@ -552,8 +370,8 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
             int64_t slot = tile_base + (int64_t)r * FT2 + tid;
             if (slot < P.No_pad) {
                 size_t q = (size_t)blockIdx.y * P.No_pad + slot;
-                P.pM[q] = -((r & 1) ? hi2(negM[r / 2]) : lo2(negM[r / 2]));
-                P.pS[q] = (r & 1) ? hi2(S[r / 2]) : lo2(S[r / 2]);
+                P.pM[q] = Mfl[r];
+                P.pS[q] = Sd[r];
                 P.pbest[q] = best[r];
             }
         }
@@ -619,7 +437,8 @@ struct MergeParams {
     const int32_t* perm;                // sorted position -> original model
     int64_t No, No_pad, o_base;
     int Nf, nsplit, free_scale, ime, dim_prior;
-    const float *pM, *pS;
+    const float* pM;
+    const double* pS;
     const int32_t* pbest;
     const float* osnr;
     double log2_wt_thresh;              // log2(wt_thresh) or -inf
@@ -644,9 +463,10 @@ __global__ void k_merge(MergeParams P) {
     double S = 0.0;
     bool bad = false;
     for (int s = 0; s < P.nsplit; ++s) {
-        float v = P.pM[(size_t)s * P.No_pad + o], ss = P.pS[(size_t)s * P.No_pad + o];
+        float v = P.pM[(size_t)s * P.No_pad + o];
+        double ss = P.pS[(size_t)s * P.No_pad + o];
         if (!(ss == ss) || isinf(ss)) bad = true;
-        if (v > -FLT_MAX) S += (double)ss * exp2((double)v - (double)M);
+        if (v > -FLT_MAX) S += ss * exp2((double)v - (double)M);
     }
     int64_t sorted_best = P.pbest[(size_t)bs * P.No_pad + o];
     int64_t j = P.perm[sorted_best];
@@ -748,7 +568,7 @@ __global__ void k_build_records(RecParams P) {
     if (p >= P.nm) return;
     int64_t j = P.perm[p];
     float* r = P.recs + p * P.rec;
-    if (P.packed) {
+    {
         // packed layout (k_sweep2): every model value duplicated (v, v); fixed-scale modes store -m and -2*m_lo
         const int nf = P.Nf;
         const int auxoff = 2 * nf, mloff = 2 * nf * (1 + ((P.mode == FM_FX0) ? 0 : 1));
@@ -771,23 +591,6 @@ __global__ void k_build_records(RecParams P) {
         for (int i = tail + 5; i < P.rec; ++i) r[i] = 0.f;
         return;
     }
-    const int mloff = P.Nf + ((P.mode == FM_FX0) ? 0 : P.Nf);
-    for (int b = 0; b < P.Nf; ++b) {
-        double v = P.m[j * P.Nf + b];
-        float hi = (float)v;
-        r[b] = hi;
-        if (P.mlo) r[mloff + b] = 2.f * (float)(v - (double)hi);
-        if (P.mode == FM_FS0) r[P.Nf + b] = (float)(v * v);
-        else if (P.mode == FM_FX1) {
-            double e = P.me[j * P.Nf + b];
-            r[P.Nf + b] = (float)(e * e);
-        }
-    }
-    int tail = mloff + (P.mlo ? P.Nf : 0);
-    r[tail] = P.lnprior ? (float)(P.lnprior[j] * 1.4426950408889634) : 0.f;
-    r[tail + 1] = __int_as_float(P.bins ? P.bins[p] : -1);
-    r[tail + 2] = P.invnorm ? P.invnorm[p] : 0.f;
-    for (int i = tail + 3; i < P.rec; ++i) r[i] = 0.f;
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -799,18 +602,6 @@ int mode_of(const FzbConfig& cfg) {
 double env_double(const char* name, double dflt) {
     const char* v = getenv(name);
     return v ? atof(v) : dflt;
-}
-
-template <int NF, int MODE, bool DP, bool MLO, int R, int PASS>
-int launch_sweep_t(fzb_context* h, const SweepParams& P, dim3 grid) {
-    constexpr int REC = rec_floats(NF, MODE, MLO);
-    size_t smem = (size_t)NSTAGE * TM * REC * sizeof(float) + NSTAGE * sizeof(uint64_t);
-    auto kern = k_sweep<NF, MODE, DP, MLO, R, PASS>;
-    FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, FT, smem, h->stream>>>(P);
-    fzb_count_launch(h);
-    FZB_CUDA(cudaGetLastError());
-    return 0;
 }
 
 template <int NF, int MODE, bool DP, bool MLO, int R, int PASS>
@@ -835,12 +626,8 @@ int launch_sweep_r(fzb_context* h, const SweepParams& P, dim3 grid, int R, int p
         if (R == -4) return launch_sweep2_t<NF, MODE, DP, MLO, 4, 2>(h, P, grid);
         return launch_sweep2_t<NF, MODE, DP, MLO, 2, 2>(h, P, grid);
     }
-    if (pass == 1) {
-        if (R == RBIG) return launch_sweep_t<NF, MODE, DP, MLO, RBIG, 1>(h, P, grid);
-        return launch_sweep_t<NF, MODE, DP, MLO, 1, 1>(h, P, grid);
-    }
-    if (R == RBIG) return launch_sweep_t<NF, MODE, DP, MLO, RBIG, 2>(h, P, grid);
-    return launch_sweep_t<NF, MODE, DP, MLO, 1, 2>(h, P, grid);
+    fzb_set_error("fp32 path: bad kernel selector");
+    return 2;
 }
 
 template <int NF, int MODE, bool DP>
@@ -939,8 +726,8 @@ static int fast_prepare_mode(fzb_context* h, int mode) {
     F.nf = nf;
     F.nm = nm;
     const bool mlo = !h->models_f32_exact;
-    const bool packed = getenv("FZB_FAST_SCALAR") == nullptr;
-    F.rec = packed ? rec2_floats(nf, mode, mlo) : rec_floats(nf, mode, mlo);
+    const bool packed = true;
+    F.rec = rec2_floats(nf, mode, mlo);
     h->fast_packed = packed;
     if (F.recs.reserve((size_t)nm * F.rec * sizeof(float) + 64) || F.perm.reserve((size_t)nm * 4 + 16)) return 1;
     FZB_CUDA(cudaMemcpyAsync(F.perm.p, perm.data(), (size_t)nm * 4, cudaMemcpyHostToDevice, h->stream));
@@ -1003,10 +790,10 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     const bool packed = h->fast_packed;
     // objects per thread: 4 for large batches; small batches use fewer so that more CTAs exist.
     // (negative R selects the packed kernel in launch_sweep_r)
-    int Robj = packed ? ((chunk >= 48 * 1024) ? 4 : 2) : ((chunk >= 64 * 1024) ? RBIG : 1);
+    int Robj = (chunk >= 48 * 1024) ? 4 : 2;
     if (packed && getenv("FZB_FAST_R")) Robj = atoi(getenv("FZB_FAST_R")) >= 4 ? 4 : 2;
     const int R = packed ? -Robj : Robj;
-    const int64_t tile_objs = (int64_t)(packed ? ft2_of(Robj) : FT) * Robj;
+    const int64_t tile_objs = (int64_t)ft2_of(Robj) * Robj;
     const bool mlo = !h->models_f32_exact;
     const int64_t obj_tiles = (chunk_pad + tile_objs - 1) / tile_objs;
     const int64_t ntiles = (nm + TM - 1) / TM;
@@ -1031,10 +818,10 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     float* osnr = oA + chunk_pad;
     float* M2 = osnr + chunk_pad;
     float* thr2 = M2 + chunk_pad;
-    if (h->misc[1].reserve((size_t)nsplit * chunk_pad * 12 + 256)) return 1;
-    float* pM = h->misc[1].as<float>();
-    float* pS = pM + (size_t)nsplit * chunk_pad;
-    int32_t* pbest = reinterpret_cast<int32_t*>(pS + (size_t)nsplit * chunk_pad);
+    if (h->misc[1].reserve((size_t)nsplit * chunk_pad * 16 + 256)) return 1;
+    double* pS = h->misc[1].as<double>();
+    float* pM = reinterpret_cast<float*>(pS + (size_t)nsplit * chunk_pad);
+    int32_t* pbest = reinterpret_cast<int32_t*>(pM + (size_t)nsplit * chunk_pad);
     if (h->misc[2].reserve((size_t)chunk_pad * 8 + 64)) return 1;
     int32_t* safe_list = h->misc[2].as<int32_t>();
     int32_t* unsafe_list = safe_list + chunk_pad;
