@@ -169,7 +169,7 @@ int fzb_destroy(fzb_handle h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->models, &h->models_err, &h->models_mask, &h->lnprior, &h->widths, &h->koff, &h->kernels,
                       &h->kcdf, &h->yidx, &h->ysidx, &h->grid, &h->y, &h->ystd, &h->lowers, &h->uppers, &h->rows,
-                      &h->knn_feats, &h->fast.recs, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
+                      &h->knn_feats, &h->knn_cand, &h->knn_redo, &h->fast.recs, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
                       &h->fast.d_slot_sidx};
     for (auto* b : bufs) b->release();
     for (auto& b : h->obj_in) b.release();
@@ -623,8 +623,15 @@ int fzb_knn_build(fzb_handle h, const float* feats, int32_t K, int64_t Nm, int32
     if (use_device(h)) return 2;
     FZB_CHECK(feats && K > 0 && Nm > 0 && Nf > 0, "bad kNN build arguments");
     FZB_CHECK(Nf <= FZB_MAXF, "Nf=%d exceeds the supported maximum %d", Nf, FZB_MAXF);
-    if (upload(h, h->knn_feats, feats, (size_t)K * Nm * Nf)) return 1;
+    // per-tree stride padded to 16 bytes so that every tile of every tree is a legal TMA bulk-copy source
+    const int64_t stride = ((int64_t)Nm * Nf + 3 + 3) / 4 * 4;
+    if (h->knn_feats.reserve((size_t)K * stride * sizeof(float) + 64)) return 1;
+    FZB_CUDA(cudaMemsetAsync(h->knn_feats.p, 0, (size_t)K * stride * sizeof(float) + 64, h->stream));
+    for (int t = 0; t < K; ++t)
+        FZB_CUDA(cudaMemcpyAsync(h->knn_feats.as<float>() + (size_t)t * stride, feats + (size_t)t * Nm * Nf,
+                                 (size_t)Nm * Nf * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     FZB_CUDA(cudaStreamSynchronize(h->stream));
+    h->knn_stride = stride;
     h->knn_K = K;
     h->knn_Nm = Nm;
     h->knn_Nf = Nf;

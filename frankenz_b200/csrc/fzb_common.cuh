@@ -128,8 +128,10 @@ struct fzb_context {
     int fast_Ngpad = 0;
 
     // kNN
-    DevBuf knn_feats;       // float32 K x Nm x Nf
+    DevBuf knn_feats;       // float32 K x Nm x Nf (+ 64 B pad)
+    DevBuf knn_cand, knn_redo;
     int knn_K = 0;
+    int64_t knn_stride = 0;  // floats between consecutive trees (16-byte aligned, >= Nm*Nf + 3)
     int64_t knn_Nm = 0;
     int knn_Nf = 0;
 

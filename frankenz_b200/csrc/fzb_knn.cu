@@ -18,9 +18,10 @@ __device__ __forceinline__ bool lex_less(double da, long long ia, double db, lon
 }
 
 // one CTA per (query, tree); each warp keeps a sorted top-k list in shared memory
-__global__ void __launch_bounds__(KT) k_knn_exact(const float* __restrict__ feats, int K, int64_t Nm, int Nf,
+__global__ void __launch_bounds__(KT) k_knn_exact(const float* __restrict__ feats, int64_t tstride, int K, int64_t Nm, int Nf,
                                                   const double* __restrict__ q, int64_t No, int k, double p, int pmode,
-                                                  int64_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+                                                  int64_t* __restrict__ out_idx, double* __restrict__ out_dist,
+                                                  const int64_t* __restrict__ items, const int* __restrict__ n_items) {
     extern __shared__ double sm[];
     const int nw = KT / 32;
     double* s_q = sm;                                  // Nf
@@ -30,13 +31,15 @@ __global__ void __launch_bounds__(KT) k_knn_exact(const float* __restrict__ feat
     double* my_d = l_d + (size_t)warp * k;
     long long* my_i = l_i + (size_t)warp * k;
 
-    for (int64_t item = blockIdx.x; item < No * K; item += gridDim.x) {
+    const int64_t total = items ? (int64_t)*n_items : No * K;
+    for (int64_t it_ = blockIdx.x; it_ < total; it_ += gridDim.x) {
+        const int64_t item = items ? items[it_] : it_;
         const int64_t o = item / K;
         const int t = (int)(item % K);
         __syncthreads();
         if (tid < Nf) s_q[tid] = q[o * Nf + tid];
         __syncthreads();
-        const float* F = feats + (size_t)t * Nm * Nf;
+        const float* F = feats + (size_t)t * tstride;
         int cnt = 0;                        // warp-uniform
         double worst_d = CUDART_INF;
         long long worst_i = 0x7fffffffffffffffll;
@@ -112,6 +115,195 @@ __global__ void __launch_bounds__(KT) k_knn_exact(const float* __restrict__ feat
     }
 }
 
+
+// ---- fp32 scan + float64 re-rank ---------------------------------------------------------------------
+// Scan: one thread owns R queries (features in registers) and keeps, per query, the KC = k + 8 smallest fp32
+// squared distances seen so far in a small local-memory list; the training rows are staged tile by tile into
+// shared memory with TMA bulk copies and broadcast to all threads, so each row costs one compare per query in the
+// common case.  Re-rank: the candidates are re-evaluated in float64 (numpy's bits) and ordered by (distance,
+// index).  The result is accepted only if the k-th exact distance is strictly below the smallest distance any
+// EXCLUDED row can have, d >= sqrt(tau (1 - 5e-7)) - 2^-24 |q|, where tau is the fp32 list threshold (fp32
+// evaluation error and float rounding of the query, triangle inequality).  Otherwise the (query, tree) pair is
+// appended to a list that k_knn_exact re-does from scratch.
+constexpr int KS_T = 256;       // threads per CTA
+constexpr int KS_R = 4;         // queries per thread
+constexpr int KS_TM = 1024;     // rows per shared-memory tile
+constexpr int KS_KCMAX = 64;    // candidate list capacity
+
+__device__ __forceinline__ uint32_t ks_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ks_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nKW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra KD_%=;\nbra KW_%=;\nKD_%=:\n}\n" ::"r"(
+            ks_smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int NF>
+__global__ void __launch_bounds__(KS_T, 2) k_knn_scan(const float* __restrict__ feats, int64_t tstride, int64_t Nm,
+                                                      const double* __restrict__ q, int64_t No, int KC,
+                                                      int64_t rows_per_split, float* __restrict__ cand_d,
+                                                      int* __restrict__ cand_i) {
+    extern __shared__ __align__(128) unsigned char ks_raw[];
+    float* stage = reinterpret_cast<float*>(ks_raw);                                   // 2 x KS_TM x NF
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ks_raw + (size_t)2 * KS_TM * NF * sizeof(float));
+    const int tid = threadIdx.x;
+    const int t = blockIdx.y, sp = blockIdx.z, nsp = gridDim.z, K = gridDim.y;
+    const float* F = feats + (size_t)t * tstride;
+    float qf[KS_R][NF];
+    float ld[KS_R][KS_KCMAX];
+    int li[KS_R][KS_KCMAX];
+    float tau[KS_R];
+    int pmax[KS_R];
+    int64_t oq[KS_R];
+#pragma unroll
+    for (int r = 0; r < KS_R; ++r) {
+        int64_t o = (int64_t)blockIdx.x * (KS_T * KS_R) + (int64_t)r * KS_T + tid;
+        oq[r] = o;
+        int64_t oo = o < No ? o : No - 1;
+#pragma unroll
+        for (int b = 0; b < NF; ++b) qf[r][b] = (float)q[oo * NF + b];
+        for (int c = 0; c < KC; ++c) { ld[r][c] = CUDART_INF_F; li[r][c] = -1; }
+        tau[r] = CUDART_INF_F;
+        pmax[r] = 0;
+    }
+    const int64_t row0 = (int64_t)sp * rows_per_split;
+    int64_t row1 = row0 + rows_per_split;
+    if (row1 > Nm) row1 = Nm;
+    const int nt = (int)((row1 - row0 + KS_TM - 1) / KS_TM);
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ks_smem_u32(&bars[s])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int it) {
+        int64_t first = row0 + (int64_t)it * KS_TM;
+        int cnt = (int)((row1 - first) < KS_TM ? (row1 - first) : KS_TM);
+        uint32_t bytes = ((uint32_t)cnt * NF * sizeof(float) + 15u) & ~15u;   // tail reads stay inside the K x Nm x NF array + pad
+        uint64_t* bar = &bars[it & 1];
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ks_smem_u32(bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         ks_smem_u32(stage + (size_t)(it & 1) * KS_TM * NF)),
+                     "l"(F + first * NF), "r"(bytes), "r"(ks_smem_u32(bar))
+                     : "memory");
+    };
+    if (tid == 0) {
+        for (int it = 0; it < 2 && it < nt; ++it) issue(it);
+    }
+    for (int it = 0; it < nt; ++it) {
+        ks_mbar_wait(&bars[it & 1], (uint32_t)((it >> 1) & 1));
+        const float* tile = stage + (size_t)(it & 1) * KS_TM * NF;
+        const int64_t first = row0 + (int64_t)it * KS_TM;
+        const int cnt = (int)((row1 - first) < KS_TM ? (row1 - first) : KS_TM);
+#pragma unroll 2
+        for (int jj = 0; jj < cnt; ++jj) {
+            float f[NF];
+#pragma unroll
+            for (int b = 0; b < NF; ++b) f[b] = tile[jj * NF + b];
+#pragma unroll
+            for (int r = 0; r < KS_R; ++r) {
+                float d = __fsub_rn(f[0], qf[r][0]);
+                float d2 = __fmul_rn(d, d);
+#pragma unroll
+                for (int b = 1; b < NF; ++b) {
+                    d = __fsub_rn(f[b], qf[r][b]);
+                    d2 = __fmaf_rn(d, d, d2);
+                }
+                if (d2 < tau[r]) {            // rare after warm-up: replace the current maximum of the list
+                    ld[r][pmax[r]] = d2;
+                    li[r][pmax[r]] = (int)(first + jj);
+                    float mx = -1.f;
+                    int pm = 0;
+                    for (int c = 0; c < KC; ++c) {
+                        float v = ld[r][c];
+                        if (v > mx) { mx = v; pm = c; }
+                    }
+                    tau[r] = mx;
+                    pmax[r] = pm;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && it + 2 < nt) issue(it + 2);
+    }
+#pragma unroll
+    for (int r = 0; r < KS_R; ++r) {
+        if (oq[r] < No) {
+            size_t base = (((size_t)oq[r] * K + t) * nsp + sp) * KC;
+            for (int c = 0; c < KC; ++c) { cand_d[base + c] = ld[r][c]; cand_i[base + c] = li[r][c]; }
+        }
+    }
+}
+
+// one warp per (query, tree): exact float64 distances of the candidates, order by (distance, index), verify
+__global__ void k_knn_rerank(const float* __restrict__ feats, int64_t tstride, int K, int64_t Nm, int NF, const double* __restrict__ q,
+                             int64_t No, int k, int KC, int nsp, const float* __restrict__ cand_d,
+                             const int* __restrict__ cand_i, int64_t* __restrict__ out_idx,
+                             double* __restrict__ out_dist, int64_t* __restrict__ redo, int* __restrict__ n_redo) {
+    extern __shared__ double rs[];
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, w = threadIdx.x >> 5;
+    const int C = KC * nsp;
+    double* sd = rs + (size_t)w * C * 2;
+    long long* si = reinterpret_cast<long long*>(sd + C);
+    const int64_t item = (int64_t)blockIdx.x * wpb + w;
+    if (item >= No * K) return;
+    const int64_t o = item / K;
+    const int t = (int)(item % K);
+    const float* F = feats + (size_t)t * tstride;
+    const size_t base = (size_t)item * C;
+    double qn = 0.0;
+    for (int b = 0; b < NF; ++b) qn += q[o * NF + b] * q[o * NF + b];
+    const double eq = sqrt(qn) * 5.9604644775390625e-08;     // 2^-24 |q|
+    float tau = CUDART_INF_F;          // smallest per-split threshold = smallest fp32 distance of any excluded row
+    for (int s = 0; s < nsp; ++s) {
+        float mx = 0.f;
+        for (int c = lane; c < KC; c += 32) mx = fmaxf(mx, cand_d[base + (size_t)s * KC + c]);
+        for (int sh = 16; sh > 0; sh >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
+        tau = fminf(tau, mx);
+    }
+    int nvalid = 0;
+    for (int c = lane; c < C; c += 32) {
+        int r = cand_i[base + c];
+        double acc = CUDART_INF;
+        if (r >= 0) {
+            acc = 0.0;
+            for (int b = 0; b < NF; ++b) {
+                double df = __dsub_rn((double)F[(size_t)r * NF + b], q[o * NF + b]);
+                acc = __dadd_rn(acc, __dmul_rn(df, df));
+            }
+            if (isnan(acc)) acc = CUDART_INF;
+            ++nvalid;
+        }
+        sd[c] = acc;
+        si[c] = r >= 0 ? r : 0x7fffffffffffffffll;
+    }
+    for (int sh = 16; sh > 0; sh >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, sh);
+    __syncwarp();
+    double dk = CUDART_INF;
+    for (int c = lane; c < C; c += 32) {
+        double de = sd[c];
+        long long ie = si[c];
+        if (ie == 0x7fffffffffffffffll) continue;
+        int rank = 0;
+        for (int j = 0; j < C; ++j) rank += lex_less(sd[j], si[j], de, ie) ? 1 : 0;
+        if (rank < k) {
+            size_t wout = (size_t)item * k + rank;
+            out_idx[wout] = ie;
+            if (out_dist) out_dist[wout] = sqrt(de);
+            if (rank == k - 1) dk = de;
+        }
+    }
+    for (int sh = 16; sh > 0; sh >>= 1) dk = fmin(dk, __shfl_xor_sync(0xffffffffu, dk, sh));
+    // accept only if no excluded row can belong to the top k
+    bool ok = nvalid >= k && isfinite(dk);
+    if (ok && !isinf(tau)) {
+        double dmin_excl = sqrt((double)tau * (1.0 - 5e-7)) - eq;
+        ok = sqrt(dk) < dmin_excl;
+    }
+    if (!ok && lane == 0) redo[atomicAdd(n_redo, 1)] = item;
+}
+
 // ordered union: one warp per object
 __global__ void k_union(const int64_t* __restrict__ idx, int64_t No, int W, int64_t* __restrict__ nbr,
                         int64_t* __restrict__ nnbr) {
@@ -141,17 +333,86 @@ __global__ void k_union(const int64_t* __restrict__ idx, int64_t No, int W, int6
 
 }  // namespace
 
-int fzb_knn_query_dev(fzb_context* h, const double* d_q, int64_t No, int k, double p, int64_t* d_idx, double* d_dist) {
-    int pmode = (p == 2.0) ? 2 : (p == 1.0) ? 1 : (!(p > 0) || std::isinf(p)) ? 0 : 3;
+static int knn_exact_launch(fzb_context* h, const double* d_q, int64_t No, int k, double p, int pmode, int64_t* d_idx,
+                            double* d_dist, const int64_t* items, const int* n_items, int64_t max_items) {
     size_t smem = sizeof(double) * FZB_MAXF + (size_t)(KT / 32) * k * 16;
     FZB_CHECK(smem <= 200 * 1024, "k=%d too large for the kNN kernel", k);
     FZB_CUDA(cudaFuncSetAttribute(k_knn_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int64_t items = No * h->knn_K;
-    int64_t grid = items < (int64_t)h->sm_count * 8 ? items : (int64_t)h->sm_count * 8;
-    k_knn_exact<<<(unsigned)grid, KT, smem, h->stream>>>(h->knn_feats.as<float>(), h->knn_K, h->knn_Nm, h->knn_Nf, d_q,
-                                                         No, k, p, pmode, d_idx, d_dist);
+    int64_t grid = max_items < (int64_t)h->sm_count * 8 ? max_items : (int64_t)h->sm_count * 8;
+    if (grid < 1) grid = 1;
+    k_knn_exact<<<(unsigned)grid, KT, smem, h->stream>>>(h->knn_feats.as<float>(), h->knn_stride, h->knn_K, h->knn_Nm, h->knn_Nf, d_q,
+                                                         No, k, p, pmode, d_idx, d_dist, items, n_items);
     fzb_count_launch(h);
     FZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int NF>
+static int knn_scan_launch(fzb_context* h, const double* d_q, int64_t No, int KC, int nsp, int64_t rows_per_split,
+                           float* cand_d, int* cand_i) {
+    size_t smem = (size_t)2 * KS_TM * NF * sizeof(float) + 2 * sizeof(uint64_t);
+    FZB_CUDA(cudaFuncSetAttribute(k_knn_scan<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((No + KS_T * KS_R - 1) / (KS_T * KS_R)), (unsigned)h->knn_K, (unsigned)nsp);
+    k_knn_scan<NF><<<grid, KS_T, smem, h->stream>>>(h->knn_feats.as<float>(), h->knn_stride, h->knn_Nm, d_q, No, KC, rows_per_split,
+                                                    cand_d, cand_i);
+    fzb_count_launch(h);
+    FZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int fzb_knn_query_dev(fzb_context* h, const double* d_q, int64_t No, int k, double p, int64_t* d_idx, double* d_dist) {
+    int pmode = (p == 2.0) ? 2 : (p == 1.0) ? 1 : (!(p > 0) || std::isinf(p)) ? 0 : 3;
+    const int nf = h->knn_Nf;
+    const int K = h->knn_K;
+    const int64_t Nm = h->knn_Nm;
+    const int KC = k + 8;
+    const bool fast = pmode == 2 && nf >= 4 && nf <= 6 && KC <= KS_KCMAX && Nm >= 4096 && Nm < ((int64_t)1 << 31) &&
+                      getenv("FZB_KNN_EXACT_ONLY") == nullptr;
+    if (!fast) return knn_exact_launch(h, d_q, No, k, p, pmode, d_idx, d_dist, nullptr, nullptr, No * K);
+
+    // row splits so that small query batches still fill the GPU
+    int64_t qtiles = (No + KS_T * KS_R - 1) / (KS_T * KS_R);
+    int64_t want = (int64_t)h->sm_count * 8;
+    int64_t nsp = (want + qtiles * K - 1) / (qtiles * K);
+    int64_t max_sp = (Nm + 4 * KS_TM - 1) / (4 * KS_TM);
+    if (nsp > max_sp) nsp = max_sp;
+    if (nsp > 32) nsp = 32;
+    if (nsp < 1) nsp = 1;
+    int64_t rows_per_split = ((Nm + nsp - 1) / nsp + KS_TM - 1) / KS_TM * KS_TM;
+    nsp = (Nm + rows_per_split - 1) / rows_per_split;
+    // process the queries in chunks that bound the candidate buffers (~2 GB)
+    size_t per_q = (size_t)K * nsp * KC * 8;
+    int64_t chunk = (int64_t)(((size_t)2 << 30) / per_q);
+    if (chunk < KS_T * KS_R) chunk = KS_T * KS_R;
+    if (chunk > No) chunk = No;
+    if (h->knn_cand.reserve((size_t)chunk * per_q + 256) || h->knn_redo.reserve((size_t)chunk * K * 8 + 64)) return 1;
+    float* cand_d = h->knn_cand.as<float>();
+    int* cand_i = reinterpret_cast<int*>(cand_d + (size_t)chunk * K * nsp * KC);
+    int* n_redo = h->knn_redo.as<int>();
+    int64_t* redo = reinterpret_cast<int64_t*>(n_redo + 4);
+    for (int64_t o0 = 0; o0 < No; o0 += chunk) {
+        int64_t nc = No - o0 < chunk ? No - o0 : chunk;
+        const double* qq = d_q + o0 * nf;
+        int rc = nf == 4 ? knn_scan_launch<4>(h, qq, nc, KC, (int)nsp, rows_per_split, cand_d, cand_i)
+               : nf == 5 ? knn_scan_launch<5>(h, qq, nc, KC, (int)nsp, rows_per_split, cand_d, cand_i)
+                         : knn_scan_launch<6>(h, qq, nc, KC, (int)nsp, rows_per_split, cand_d, cand_i);
+        if (rc) return rc;
+        FZB_CUDA(cudaMemsetAsync(n_redo, 0, 16, h->stream));
+        const int wpb = 4;
+        size_t smem = (size_t)wpb * KC * nsp * 16;
+        FZB_CHECK(smem <= 200 * 1024, "kNN re-rank: too many candidates");
+        FZB_CUDA(cudaFuncSetAttribute(k_knn_rerank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int64_t items = nc * K;
+        k_knn_rerank<<<(unsigned)((items + wpb - 1) / wpb), wpb * 32, smem, h->stream>>>(
+            h->knn_feats.as<float>(), h->knn_stride, K, Nm, nf, qq, nc, k, KC, (int)nsp, cand_d, cand_i, d_idx + (size_t)o0 * K * k,
+            d_dist ? d_dist + (size_t)o0 * K * k : nullptr, redo, n_redo);
+        fzb_count_launch(h);
+        FZB_CUDA(cudaGetLastError());
+        // the rare (query, tree) pairs that failed the exactness test are re-done by the float64 kernel
+        if (knn_exact_launch(h, qq, nc, k, p, pmode, d_idx + (size_t)o0 * K * k,
+                             d_dist ? d_dist + (size_t)o0 * K * k : nullptr, redo, n_redo, 4096))
+            return 1;
+    }
     return 0;
 }
 

@@ -108,3 +108,37 @@ def test_default_likelihood_c1_shape():
     po, lmo, leo = fo.bruteforce_fit_predict(m, me, mm, x[:8].copy(), xe[:8].copy(), xm[:8].copy(), z, labe,
                                              label_dict=kd)
     assert np.max(np.sum(np.abs(p1[:8] - po), axis=1)) <= 1e-9 and np.allclose(lm1[:8], lmo, rtol=1e-10)
+
+
+def test_knn_fast_scan_matches_exact_kernel_and_oracle(monkeypatch):
+    """fp32 scan + float64 re-rank (large training sets) against the all-float64 kernel and the oracle,
+    including duplicated training rows (exact-distance ties) and queries that coincide with training rows."""
+    import frankenz_b200 as fz
+    from frankenz_b200._engine import Engine
+    m, me, mm, z, x, xe, xm, _ = bench_data.c1_dataset(20000, 700)
+    depth = np.load(bench_data.GOLDEN + "/sdss_cww_mock.npz")["depth_flux1sig"]
+    kw = dict(skynoise=depth, zeropoints=10 ** (-0.4 * -23.9))
+    feats = fo.knn_train_features(m, me, 3, feature_map="luptitude", fmap_kwargs=kw, rstate=np.random.RandomState(5))
+    feats[1, 5000:5040] = feats[1, 100:140]          # duplicated rows -> exact ties
+    q, _ = fo.luptitude(np.random.RandomState(6).normal(x, xe), xe, **kw)
+    q[:10] = feats[0, 200:210].astype(np.float64)    # zero-distance hits in tree 0
+    q[10:20] = feats[1, 100:110].astype(np.float64)  # zero-distance ties in tree 1
+    eng = Engine(m, me, mm)
+    eng.knn_build(feats)
+    idx_fast, dist_fast = eng.knn_query(q, 25, p=2)
+    monkeypatch.setenv("FZB_KNN_EXACT_ONLY", "1")
+    idx_exact, dist_exact = eng.knn_query(q, 25, p=2)
+    monkeypatch.delenv("FZB_KNN_EXACT_ONLY")
+    assert np.array_equal(idx_fast, idx_exact)        # bit-exact indices, ties included
+    assert np.array_equal(dist_fast, dist_exact)
+    for i in (0, 3, 12, 15, 100, 699):
+        oi, od = fo.knn_query_exact(feats, q[i], 25, 2)
+        assert np.array_equal(idx_fast[i], oi) and np.allclose(dist_fast[i], od, rtol=1e-14, atol=0)
+    # through the estimator: neighbours / fits identical between the two search kernels
+    nn = fz.NearestNeighbors(m, me, mm, K=3, fmap_kwargs=kw, rstate=np.random.RandomState(5), verbose=False)
+    nn.fit(x.copy(), xe.copy(), xm.copy(), k=25, eps=0, rstate=np.random.RandomState(6), verbose=False)
+    nb, nnb, lp = nn.neighbors.copy(), nn.Nneighbors.copy(), nn.fit_lnprob.copy()
+    monkeypatch.setenv("FZB_KNN_EXACT_ONLY", "1")
+    nn.fit(x.copy(), xe.copy(), xm.copy(), k=25, eps=0, rstate=np.random.RandomState(6), verbose=False)
+    assert np.array_equal(nb, nn.neighbors) and np.array_equal(nnb, nn.Nneighbors)
+    assert np.array_equal(lp, nn.fit_lnprob)
