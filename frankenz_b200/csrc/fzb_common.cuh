@@ -69,6 +69,8 @@ struct FastModels {
     int64_t nm_pad = 0;    // padded to a multiple of the tile
     int rec = 0;           // floats per model record
     DevBuf recs;           // [nm_pad][rec] float: see fzb_fast.cu for the record layout
+    DevBuf recs64;         // [nm][rec64] double records of the float64 sweep
+    DevBuf aux64;          // per-object float64 pass-2 inputs
     DevBuf perm;           // int32 [nm_pad]: sorted position -> original model index (-1 = padding)
     DevBuf bins;           // int32 [nm_pad]: KDE histogram bin (slot*Ng + pos) of each sorted model, -1 = none
     DevBuf invnorm;        // float [nm_pad]: 1 / kernel normalisation of each sorted model

@@ -28,6 +28,7 @@
 // exactly representable in fp32).
 #include <algorithm>
 #include <cfloat>
+#include <float.h>
 #include <cstdlib>
 #include <numeric>
 
@@ -100,7 +101,7 @@ struct SweepParams {
     int64_t nm;
     int tiles_per_split;
     // pass 1 outputs: [nsplit][No_pad]
-    float* pM;
+    double* pM;
     double* pS;
     int32_t* pbest;
     // pass 2
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
             int64_t slot = tile_base + (int64_t)r * FT2 + tid;
             if (slot < P.No_pad) {
                 size_t q = (size_t)blockIdx.y * P.No_pad + slot;
-                P.pM[q] = Mfl[r];
+                P.pM[q] = (double)Mfl[r];
                 P.pS[q] = Sd[r];
                 P.pbest[q] = best[r];
             }
@@ -384,6 +385,226 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
                 atomicAdd(P.hist + (int64_t)oidx[2 * p + 1] * P.hist_stride + cur_bin, a1);
         }
     }
+}
+
+
+// =====================================================================================================
+// Float64 register-tiled sweep: same structure as k_sweep2 (objects in registers, model tiles staged by
+// TMA bulk copies, online reductions) with chi2 evaluated in double precision, for the objects whose
+// best-fit chi2 is too large for fp32 (template mismatch, very bright objects).  Only log2 / exp2 go
+// through the fp32 special-function unit: their absolute error (~1e-7) does not scale with chi2.
+// B200 issues DFMA at half the FP32 rate, so this path runs at a sizeable fraction of the fp32 sweep
+// instead of the L2-bound generic kernel.
+// =====================================================================================================
+constexpr int FT64 = 256;
+constexpr int R64 = 2;
+
+__host__ __device__ constexpr int rec64_doubles(int nf, int mode) {
+    int n = nf * ((mode == FM_FX0) ? 1 : 2) + 2;      // m, aux, prior2, {bin, invnorm}
+    return (n + 1) / 2 * 2;
+}
+
+struct Sweep64Params {
+    const double *x, *xe, *xm;      // raw objects of this chunk (No x Nf)
+    int64_t No, No_pad;
+    const int32_t* objlist;         // chunk-local object indices
+    int64_t nlist;
+    int free_scale, dim_prior;
+    const double* recs;             // [nm][REC64]
+    int64_t nm;
+    int tiles_per_split;
+    double* pM;                     // [nsplit][No_pad]  pass 1 out
+    double* pS;
+    int32_t* pbest;
+    const double* M2;               // [No_pad]  pass 2 in
+    const double* thr2;
+    float* hist;
+    int64_t hist_stride;
+};
+
+template <int NF, int MODE, bool DP, int PASS>
+__global__ void __launch_bounds__(FT64, 2) k_sweep64(Sweep64Params P) {
+    constexpr int REC = rec64_doubles(NF, MODE);
+    constexpr int AUXOFF = NF;
+    constexpr int TAILOFF = NF * ((MODE == FM_FX0) ? 1 : 2);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stage = reinterpret_cast<double*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * TM * REC * sizeof(double));
+    const int tid = threadIdx.x;
+    double d[R64][NF], w[R64][NF], xw[R64][NF], A[R64], M[R64], Sd[R64], Mfl[R64], thr[R64];
+    float S[R64], acc[R64];
+    int oidx[R64], best[R64];
+#pragma unroll
+    for (int r = 0; r < R64; ++r) {
+        int64_t slot = (int64_t)blockIdx.x * (FT64 * R64) + (int64_t)r * FT64 + tid;
+        int o = slot < P.nlist ? P.objlist[slot] : -1;
+        oidx[r] = o;
+        int64_t oo = o < 0 ? 0 : o;
+        double ndim = 0.0;
+#pragma unroll
+        for (int b = 0; b < NF; ++b) {
+            double v = P.x[oo * NF + b], e = P.xe[oo * NF + b], k = P.xm[oo * NF + b];
+            bool clean = isfinite(v) && isfinite(e) && (e > 0.0);
+            if (!clean) { v = 0.0; e = 1.0; k = 0.0; }
+            d[r][b] = v;
+            if (MODE == FM_FX1) w[r][b] = (k != 0.0) ? e * e : CUDART_INF;
+            else w[r][b] = k / (e * e);
+            xw[r][b] = v * w[r][b];
+            ndim += k;
+        }
+        double a = P.free_scale ? 0.5 * (ndim - 1.0) : 0.5 * ndim;
+        A[r] = P.dim_prior ? a - 1.0 : 0.0;
+        S[r] = 0.f; Sd[r] = 0.0; Mfl[r] = -DBL_MAX; best[r] = 0; acc[r] = 0.f;
+        if (PASS == 1) { M[r] = -DBL_MAX; thr[r] = 0.0; }
+        else { M[r] = P.M2[oo]; thr[r] = P.thr2[oo]; }
+    }
+    const int64_t ntiles_all = (P.nm + TM - 1) / TM;
+    const int64_t t0 = (int64_t)blockIdx.y * P.tiles_per_split;
+    int64_t t1 = t0 + P.tiles_per_split;
+    if (t1 > ntiles_all) t1 = ntiles_all;
+    const int nt = (int)(t1 - t0);
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int it) {
+        int64_t first = (t0 + it) * TM;
+        int cnt = (int)((P.nm - first) < TM ? (P.nm - first) : TM);
+        uint32_t bytes = (uint32_t)cnt * REC * sizeof(double);
+        uint64_t* bar = &bars[it % NSTAGE];
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(stage + (size_t)(it % NSTAGE) * TM * REC, P.recs + first * REC, bytes, bar);
+    };
+    if (tid == 0) {
+        for (int it = 0; it < NSTAGE && it < nt; ++it) issue(it);
+    }
+    int cur_bin = -1;
+    for (int it = 0; it < nt; ++it) {
+        const int st = it % NSTAGE;
+        mbar_wait(&bars[st], (uint32_t)((it / NSTAGE) & 1));
+        const double* tile = stage + (size_t)st * TM * REC;
+        const int64_t first = (t0 + it) * TM;
+        const int cnt = (int)((P.nm - first) < TM ? (P.nm - first) : TM);
+#pragma unroll 1
+        for (int jj = 0; jj < cnt; ++jj) {
+            const double* rec = tile + jj * REC;
+            const double prior2 = rec[TAILOFF];
+            float invnorm = 0.f;
+            if (PASS == 2) {
+                const int2 tl = *reinterpret_cast<const int2*>(rec + TAILOFF + 1);
+                invnorm = __int_as_float(tl.y);
+                if (tl.x != cur_bin) {
+                    if (cur_bin >= 0) {
+#pragma unroll
+                        for (int r = 0; r < R64; ++r) {
+                            if (acc[r] != 0.f && oidx[r] >= 0)
+                                atomicAdd(P.hist + (int64_t)oidx[r] * P.hist_stride + cur_bin, acc[r]);
+                            acc[r] = 0.f;
+                        }
+                    }
+                    cur_bin = tl.x;
+                }
+            }
+            double m[NF], aux[NF];
+#pragma unroll
+            for (int b = 0; b < NF; ++b) {
+                m[b] = rec[b];
+                aux[b] = (MODE == FM_FX0) ? 0.0 : rec[AUXOFF + b];
+            }
+#pragma unroll
+            for (int r = 0; r < R64; ++r) {
+                double s = 1.0;
+                if (MODE == FM_FS0) {
+                    double inter = 0.0, shape = 0.0;
+#pragma unroll
+                    for (int b = 0; b < NF; ++b) {
+                        inter = fma(xw[r][b], m[b], inter);
+                        shape = fma(w[r][b], aux[b], shape);
+                    }
+                    s = inter / shape;
+                }
+                double chi2 = 0.0;
+#pragma unroll
+                for (int b = 0; b < NF; ++b) {
+                    double res = fma(-s, m[b], d[r][b]);
+                    double wb = (MODE == FM_FX1) ? 1.0 / (w[r][b] + aux[b]) : w[r][b];
+                    chi2 = fma(res * wb, res, chi2);
+                }
+                double l = fma(chi2, -0.72134752044448170368, prior2);
+                if (DP) l = fma(A[r], (double)fast_lg2((float)chi2), l);
+                double delta = l - M[r];
+                if (PASS == 1) {
+                    float e = fast_ex2(-fabsf((float)delta));
+                    bool gt = delta > 0.0;
+                    S[r] = __fmaf_rn(S[r], gt ? e : 1.f, gt ? 1.f : e);
+                    M[r] = gt ? l : M[r];
+                    best[r] = gt ? (int)(first + jj) : best[r];
+                } else {
+                    float u = fast_ex2((float)delta);
+                    u = (l > thr[r]) ? u : 0.f;
+                    acc[r] = __fmaf_rn(u, invnorm, acc[r]);
+                }
+            }
+        }
+        if (PASS == 1) {
+#pragma unroll
+            for (int r = 0; r < R64; ++r) {
+                Sd[r] = Sd[r] * exp2(Mfl[r] - M[r]) + (double)S[r];
+                Mfl[r] = M[r];
+                S[r] = 0.f;
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && it + NSTAGE < nt) issue(it + NSTAGE);
+    }
+    if (PASS == 1) {
+#pragma unroll
+        for (int r = 0; r < R64; ++r)
+            if (oidx[r] >= 0) {
+                size_t q = (size_t)blockIdx.y * P.No_pad + oidx[r];
+                P.pM[q] = Mfl[r];
+                P.pS[q] = Sd[r];
+                P.pbest[q] = best[r];
+            }
+    } else if (cur_bin >= 0) {
+#pragma unroll
+        for (int r = 0; r < R64; ++r)
+            if (acc[r] != 0.f && oidx[r] >= 0) atomicAdd(P.hist + (int64_t)oidx[r] * P.hist_stride + cur_bin, acc[r]);
+    }
+}
+
+struct Rec64Params {
+    const double *m, *me, *lnprior;
+    const int32_t* perm;
+    const int32_t* bins;
+    const float* invnorm;
+    int64_t nm;
+    int Nf, mode, rec;
+    double* recs;
+};
+
+__global__ void k_build_records64(Rec64Params P) {
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.nm) return;
+    int64_t j = P.perm[p];
+    double* r = P.recs + p * P.rec;
+    for (int b = 0; b < P.Nf; ++b) {
+        double v = P.m[j * P.Nf + b];
+        r[b] = v;
+        if (P.mode == FM_FS0) r[P.Nf + b] = v * v;
+        else if (P.mode == FM_FX1) {
+            double e = P.me[j * P.Nf + b];
+            r[P.Nf + b] = e * e;
+        }
+    }
+    int tail = P.Nf * ((P.mode == FM_FX0) ? 1 : 2);
+    r[tail] = P.lnprior ? P.lnprior[j] * 1.4426950408889634 : 0.0;
+    int2 tl;
+    tl.x = P.bins ? P.bins[p] : -1;
+    tl.y = __float_as_int(P.invnorm ? P.invnorm[p] : 0.f);
+    *reinterpret_cast<int2*>(r + tail + 1) = tl;
+    for (int i = tail + 2; i < P.rec; ++i) r[i] = 0.0;
 }
 
 // ---- object preparation ------------------------------------------------------------------------
@@ -437,36 +658,49 @@ struct MergeParams {
     const int32_t* perm;                // sorted position -> original model
     int64_t No, No_pad, o_base;
     int Nf, nsplit, free_scale, ime, dim_prior;
-    const float* pM;
+    const double* pM;
     const double* pS;
     const int32_t* pbest;
     const float* osnr;
     double log2_wt_thresh;              // log2(wt_thresh) or -inf
     double chi2_max, snr_max, consist_tol;
     int force_fp32;
+    int stage;                          // 0: after the fp32 sweep (all objects); 1: after the float64 sweep (in_list)
+    const int32_t* in_list;
+    int64_t n_in;
     // outputs
     double *lmap, *levid, *best_chi2, *best_scale;   // absolute object index
     int64_t* best_idx;
-    float *M2, *thr2;                   // chunk-local
-    int32_t *safe_list, *unsafe_list, *counts;   // counts[0]=safe, counts[1]=unsafe
+    float *M2, *thr2;                   // chunk-local, for the fp32 pass 2
+    double *M2d, *thr2d;                // chunk-local, for the float64 pass 2
+    // routing: counts[0] fp32-safe (chunk-local), counts[1] degenerate -> generic kernel (absolute),
+    //          counts[2] needs the float64 sweep (chunk-local), counts[3] float64-sweep objects ready for pass 2
+    int32_t *safe_list, *unsafe_list, *prec_list, *safe64_list, *counts;
 };
 
 __global__ void k_merge(MergeParams P) {
-    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= P.No) return;
-    float M = -FLT_MAX;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t o;
+    if (P.stage == 0) {
+        if (i >= P.No) return;
+        o = i;
+    } else {
+        if (i >= P.n_in) return;
+        o = P.in_list[i];
+    }
+    double M = -DBL_MAX;
     int bs = 0;
     for (int s = 0; s < P.nsplit; ++s) {
-        float v = P.pM[(size_t)s * P.No_pad + o];
+        double v = P.pM[(size_t)s * P.No_pad + o];
         if (v > M) { M = v; bs = s; }
     }
     double S = 0.0;
     bool bad = false;
     for (int s = 0; s < P.nsplit; ++s) {
-        float v = P.pM[(size_t)s * P.No_pad + o];
+        double v = P.pM[(size_t)s * P.No_pad + o];
         double ss = P.pS[(size_t)s * P.No_pad + o];
         if (!(ss == ss) || isinf(ss)) bad = true;
-        if (v > -FLT_MAX) S += ss * exp2((double)v - (double)M);
+        if (v > -1e300) S += ss * exp2(v - M);
     }
     int64_t sorted_best = P.pbest[(size_t)bs * P.No_pad + o];
     int64_t j = P.perm[sorted_best];
@@ -485,22 +719,31 @@ __global__ void k_merge(MergeParams P) {
     double lnl = P.dim_prior ? fzb64::chi2_logpdf(st.chi2, a) : st.lnl;
     double lp = P.lnprior ? P.lnprior[j] : 0.0;
     double lmap = P.lnprior ? lnl + lp : lnl;
-    // the same "varying part" the fp32 sweep tracks, in float64, for a consistency check
+    // the same "varying part" the sweeps track, in float64, for a consistency check
     double vary = -0.5 * st.chi2 * 1.4426950408889634 + lp * 1.4426950408889634;
     if (P.dim_prior && (a - 1.0) != 0.0) vary += (a - 1.0) * log2(st.chi2);
-    bool safe = !bad && isfinite((double)M) && M > -FLT_MAX && isfinite(S) && S >= 0.5 && isfinite(lmap) &&
-                fabs(vary - (double)M) <= P.consist_tol * fmax(1.0, fabs(vary));
-    if (!P.force_fp32) safe = safe && (st.chi2 <= P.chi2_max) && ((double)P.osnr[o] <= P.snr_max);
+    const bool finite = !bad && isfinite(M) && M > -1e300 && isfinite(S) && S >= 0.5 && isfinite(lmap);
+    const bool consistent = fabs(vary - M) <= P.consist_tol * fmax(1.0, fabs(vary));
+    bool precise = consistent;
+    if (P.stage == 0 && !P.force_fp32) precise = precise && (st.chi2 <= P.chi2_max) && ((double)P.osnr[o] <= P.snr_max);
     int64_t og = P.o_base + o;
     if (P.lmap) P.lmap[og] = lmap;
     if (P.levid) P.levid[og] = lmap + log(S);
     if (P.best_idx) P.best_idx[og] = j;
     if (P.best_chi2) P.best_chi2[og] = st.chi2;
     if (P.best_scale) P.best_scale[og] = st.scale;
-    P.M2[o] = M;
-    P.thr2[o] = (float)((double)M + P.log2_wt_thresh);
-    if (safe) P.safe_list[atomicAdd(&P.counts[0], 1)] = (int32_t)o;
-    else P.unsafe_list[atomicAdd(&P.counts[1], 1)] = (int32_t)og;
+    if (P.stage == 0) {
+        P.M2[o] = (float)M;
+        P.thr2[o] = (float)(M + P.log2_wt_thresh);
+        if (finite && precise) P.safe_list[atomicAdd(&P.counts[0], 1)] = (int32_t)o;
+        else if (finite && P.prec_list) P.prec_list[atomicAdd(&P.counts[2], 1)] = (int32_t)o;
+        else P.unsafe_list[atomicAdd(&P.counts[1], 1)] = (int32_t)og;
+    } else {
+        P.M2d[o] = M;
+        P.thr2d[o] = M + P.log2_wt_thresh;
+        if (finite && precise) P.safe64_list[atomicAdd(&P.counts[3], 1)] = (int32_t)o;
+        else P.unsafe_list[atomicAdd(&P.counts[1], 1)] = (int32_t)og;
+    }
 }
 
 // ---- histogram (*) kernel, normalise, write -------------------------------------------------------
@@ -645,6 +888,44 @@ int launch_sweep_nf(fzb_context* h, const SweepParams& P, dim3 grid, int mode, b
     return launch_sweep_m<NF, FM_FX1, true>(h, P, grid, mlo, R, pass);
 }
 
+template <int NF, int MODE, bool DP>
+int launch_sweep64_t(fzb_context* h, const Sweep64Params& P, dim3 grid, int pass) {
+    constexpr int REC = rec64_doubles(NF, MODE);
+    size_t smem = (size_t)NSTAGE * TM * REC * sizeof(double) + NSTAGE * sizeof(uint64_t);
+    if (pass == 1) {
+        auto kern = k_sweep64<NF, MODE, DP, 1>;
+        FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, FT64, smem, h->stream>>>(P);
+    } else {
+        auto kern = k_sweep64<NF, MODE, DP, 2>;
+        FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, FT64, smem, h->stream>>>(P);
+    }
+    fzb_count_launch(h);
+    FZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int NF>
+int launch_sweep64_nf(fzb_context* h, const Sweep64Params& P, dim3 grid, int mode, bool dp, int pass) {
+    if (mode == FM_FS0) return dp ? launch_sweep64_t<NF, FM_FS0, true>(h, P, grid, pass)
+                                  : launch_sweep64_t<NF, FM_FS0, false>(h, P, grid, pass);
+    if (mode == FM_FX0) return dp ? launch_sweep64_t<NF, FM_FX0, true>(h, P, grid, pass)
+                                  : launch_sweep64_t<NF, FM_FX0, false>(h, P, grid, pass);
+    return launch_sweep64_t<NF, FM_FX1, true>(h, P, grid, pass);
+}
+
+int launch_sweep64(fzb_context* h, const Sweep64Params& P, dim3 grid, int nf, int mode, bool dp, int pass) {
+    switch (nf) {
+        case 4: return launch_sweep64_nf<4>(h, P, grid, mode, dp, pass);
+        case 5: return launch_sweep64_nf<5>(h, P, grid, mode, dp, pass);
+        case 6: return launch_sweep64_nf<6>(h, P, grid, mode, dp, pass);
+        default: break;
+    }
+    fzb_set_error("float64 sweep: unsupported filter count %d", nf);
+    return 2;
+}
+
 int launch_sweep(fzb_context* h, const SweepParams& P, dim3 grid, int nf, int mode, bool dp, bool mlo, int R,
                  int pass) {
     switch (nf) {
@@ -752,6 +1033,16 @@ static int fast_prepare_mode(fzb_context* h, int mode) {
     k_build_records<<<(unsigned)((nm + 255) / 256), 256, 0, h->stream>>>(R);
     fzb_count_launch(h);
     FZB_CUDA(cudaGetLastError());
+    {
+        Rec64Params R6 = {};
+        R6.m = R.m; R6.me = R.me; R6.lnprior = R.lnprior; R6.perm = R.perm; R6.bins = R.bins; R6.invnorm = R.invnorm;
+        R6.nm = nm; R6.Nf = nf; R6.mode = mode; R6.rec = rec64_doubles(nf, mode);
+        if (F.recs64.reserve((size_t)nm * R6.rec * sizeof(double) + 64)) return 1;
+        R6.recs = F.recs64.as<double>();
+        k_build_records64<<<(unsigned)((nm + 255) / 256), 256, 0, h->stream>>>(R6);
+        fzb_count_launch(h);
+        FZB_CUDA(cudaGetLastError());
+    }
     FZB_CUDA(cudaStreamSynchronize(h->stream));
     F.valid = true;
     h->fast_dirty = false;
@@ -805,7 +1096,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     const int tiles_per_split = (int)((ntiles + nsplit - 1) / nsplit);
     nsplit = (ntiles + tiles_per_split - 1) / tiles_per_split;
 
-    // scratch: object SoA (4 x nf + 3 planes), partials, routing
+    // scratch: object SoA (4 x nf + 2 planes), partials, routing
     DevBuf& so = h->misc[0];
     size_t plane = (size_t)chunk_pad * sizeof(float);
     if (so.reserve(plane * (4 * nf + 2 + 2) + 256)) return 1;
@@ -818,20 +1109,26 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     float* osnr = oA + chunk_pad;
     float* M2 = osnr + chunk_pad;
     float* thr2 = M2 + chunk_pad;
-    if (h->misc[1].reserve((size_t)nsplit * chunk_pad * 16 + 256)) return 1;
+    if (h->misc[1].reserve((size_t)nsplit * chunk_pad * 20 + 256)) return 1;
     double* pS = h->misc[1].as<double>();
-    float* pM = reinterpret_cast<float*>(pS + (size_t)nsplit * chunk_pad);
+    double* pM = pS + (size_t)nsplit * chunk_pad;
     int32_t* pbest = reinterpret_cast<int32_t*>(pM + (size_t)nsplit * chunk_pad);
-    if (h->misc[2].reserve((size_t)chunk_pad * 8 + 64)) return 1;
+    if (h->misc[2].reserve((size_t)chunk_pad * 16 + 64)) return 1;
     int32_t* safe_list = h->misc[2].as<int32_t>();
     int32_t* unsafe_list = safe_list + chunk_pad;
+    int32_t* prec_list = unsafe_list + chunk_pad;
+    int32_t* safe64_list = prec_list + chunk_pad;
     if (h->misc[3].reserve(64)) return 1;
     int32_t* counts = h->misc[3].as<int32_t>();
     if (kde && h->misc[4].reserve((size_t)chunk_pad * hist_stride * 4 + 256)) return 1;
     float* hist = kde ? h->misc[4].as<float>() : nullptr;
+    if (F.aux64.reserve((size_t)chunk_pad * 16 + 64)) return 1;
+    double* M2d = F.aux64.as<double>();
+    double* thr2d = M2d + chunk_pad;
 
     const double chi2_max = env_double("FZB_FAST_CHI2_MAX", 24.0);
     const double snr_max = env_double("FZB_FAST_SNR_MAX", 20000.0);
+    const bool use_sweep64 = getenv("FZB_NO_SWEEP64") == nullptr;
 
     float ms;
     for (int64_t o0 = 0; o0 < No; o0 += chunk) {
@@ -846,6 +1143,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         fzb_count_launch(h);
         FZB_CUDA(cudaGetLastError());
 
+        // ---- pass 1 (fp32, every object) ------------------------------------------------------------
         SweepParams SP = {};
         SP.od = od; SP.ow = ow; SP.ox = ox; SP.odl = odl; SP.oA = oA;
         SP.No_pad = nc_pad; SP.No = nc;
@@ -871,9 +1169,12 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         MP.log2_wt_thresh = cfg.use_wt_thresh ? std::log2(cfg.wt_thresh) : -INFINITY;
         MP.chi2_max = chi2_max; MP.snr_max = snr_max; MP.consist_tol = 1e-4;
         MP.force_fp32 = (cfg.precision == FZB_PREC_FP32);
+        MP.stage = 0;
         MP.lmap = d_lmap; MP.levid = d_levid; MP.best_chi2 = d_best_chi2; MP.best_scale = d_best_scale;
         MP.best_idx = d_best_idx;
-        MP.M2 = M2; MP.thr2 = thr2; MP.safe_list = safe_list; MP.unsafe_list = unsafe_list; MP.counts = counts;
+        MP.M2 = M2; MP.thr2 = thr2; MP.M2d = M2d; MP.thr2d = thr2d;
+        MP.safe_list = safe_list; MP.unsafe_list = unsafe_list; MP.prec_list = use_sweep64 ? prec_list : nullptr;
+        MP.safe64_list = safe64_list; MP.counts = counts;
         k_merge<<<(unsigned)((nc + 255) / 256), 256, 0, h->stream>>>(MP);
         fzb_count_launch(h);
         FZB_CUDA(cudaGetLastError());
@@ -882,34 +1183,74 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         FZB_CUDA(cudaStreamSynchronize(h->stream));
         FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
         h->stats.ms_scan += ms;
-        const int64_t nsafe = hc[0], nunsafe = hc[1];
-        h->stats.objects_fp64 += nunsafe;
+        const int64_t nsafe = hc[0], nprec = hc[2];
+
+        // ---- objects whose fp32 result is not trusted: float64 sweep, pass 1 ---------------------------
+        Sweep64Params S6 = {};
+        int64_t nsafe64 = 0;
+        if (nprec > 0) {
+            S6.x = PP.x; S6.xe = PP.xe; S6.xm = PP.xm; S6.No = nc; S6.No_pad = nc_pad;
+            S6.objlist = prec_list; S6.nlist = nprec;
+            S6.free_scale = cfg.free_scale; S6.dim_prior = cfg.dim_prior;
+            S6.recs = F.recs64.as<double>(); S6.nm = nm; S6.tiles_per_split = tiles_per_split;
+            S6.pM = pM; S6.pS = pS; S6.pbest = pbest;
+            const int64_t t64 = (nprec + FT64 * R64 - 1) / (FT64 * R64);
+            if (launch_sweep64(h, S6, dim3((unsigned)t64, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, 1)) return 1;
+            h->stats.pairs_fp64 += nprec * nm;
+            MP.stage = 1; MP.in_list = prec_list; MP.n_in = nprec; MP.consist_tol = 1e-6;
+            k_merge<<<(unsigned)((nprec + 255) / 256), 256, 0, h->stream>>>(MP);
+            fzb_count_launch(h);
+            FZB_CUDA(cudaGetLastError());
+            FZB_CUDA(cudaMemcpyAsync(hc, counts, 16, cudaMemcpyDeviceToHost, h->stream));
+            FZB_CUDA(cudaStreamSynchronize(h->stream));
+            nsafe64 = hc[3];
+        }
+        const int64_t nunsafe = hc[1];
+        h->stats.objects_fp64 += nunsafe + nprec;
 
         if (nunsafe > 0) {
-            // float64 route; objsel holds absolute object indices
+            // degenerate rows (non-finite sums, NaN-producing models, ...): generic float64 kernel with the
+            // reference's exact semantics; objsel holds absolute object indices
             if (fzb_generic_fit_predict_dev(h, d_x, d_xe, d_xm, No, unsafe_list, nunsafe, cfg, d_pdfs, d_lmap, d_levid,
                                             d_best_idx, d_best_chi2, d_best_scale))
                 return 1;
         }
-        if (kde && nsafe > 0) {
+        if (kde && (nsafe > 0 || nsafe64 > 0)) {
             FZB_CUDA(cudaEventRecord(h->ev[4], h->stream));
             FZB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nc_pad * hist_stride * 4, h->stream));
-            SP.No = nsafe; SP.objlist = safe_list; SP.M2 = M2; SP.thr2 = thr2; SP.hist = hist;
-            SP.hist_stride = hist_stride;
-            const int64_t tiles2 = (nsafe + tile_objs - 1) / tile_objs;
-            if (launch_sweep(h, SP, dim3((unsigned)tiles2, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 2))
-                return 1;
-            h->stats.pairs_fp32 += nsafe * nm;
+            if (nsafe > 0) {
+                SP.No = nsafe; SP.objlist = safe_list; SP.M2 = M2; SP.thr2 = thr2; SP.hist = hist;
+                SP.hist_stride = hist_stride;
+                const int64_t tiles2 = (nsafe + tile_objs - 1) / tile_objs;
+                if (launch_sweep(h, SP, dim3((unsigned)tiles2, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 2))
+                    return 1;
+                h->stats.pairs_fp32 += nsafe * nm;
+            }
+            if (nsafe64 > 0) {
+                S6.objlist = safe64_list; S6.nlist = nsafe64; S6.M2 = M2d; S6.thr2 = thr2d; S6.hist = hist;
+                S6.hist_stride = hist_stride;
+                const int64_t t64 = (nsafe64 + FT64 * R64 - 1) / (FT64 * R64);
+                if (launch_sweep64(h, S6, dim3((unsigned)t64, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, 2)) return 1;
+                h->stats.pairs_fp64 += nsafe64 * nm;
+            }
             FZB_CUDA(cudaEventRecord(h->ev[5], h->stream));
             FinishParams FP = {};
-            FP.hist = hist; FP.hist_stride = hist_stride; FP.objlist = safe_list; FP.o_base = o0;
+            FP.hist = hist; FP.hist_stride = hist_stride; FP.o_base = o0;
             FP.Ng = h->Ng; FP.Ngpad = h->fast_Ngpad; FP.wmax = h->fast_wmax; FP.nslot = F.nslot;
             FP.slot_sidx = F.d_slot_sidx.as<int32_t>(); FP.widths = h->widths.as<int32_t>();
             FP.koff = h->koff.as<int64_t>(); FP.kernels = h->kernels.as<double>(); FP.pdfs = d_pdfs;
             size_t smem = sizeof(double) * ((size_t)h->fast_Ngpad + h->Ng);
             FZB_CUDA(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_finish<<<(unsigned)nsafe, 256, smem, h->stream>>>(FP);
-            fzb_count_launch(h);
+            if (nsafe > 0) {
+                FP.objlist = safe_list;
+                k_finish<<<(unsigned)nsafe, 256, smem, h->stream>>>(FP);
+                fzb_count_launch(h);
+            }
+            if (nsafe64 > 0) {
+                FP.objlist = safe64_list;
+                k_finish<<<(unsigned)nsafe64, 256, smem, h->stream>>>(FP);
+                fzb_count_launch(h);
+            }
             FZB_CUDA(cudaGetLastError());
             FZB_CUDA(cudaEventRecord(h->ev[6], h->stream));
             FZB_CUDA(cudaStreamSynchronize(h->stream));

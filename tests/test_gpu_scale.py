@@ -142,3 +142,25 @@ def test_knn_fast_scan_matches_exact_kernel_and_oracle(monkeypatch):
     nn.fit(x.copy(), xe.copy(), xm.copy(), k=25, eps=0, rstate=np.random.RandomState(6), verbose=False)
     assert np.array_equal(nb, nn.neighbors) and np.array_equal(nnb, nn.Nneighbors)
     assert np.array_equal(lp, nn.fit_lnprob)
+
+
+def test_float64_sweep_route_matches_generic(c3):
+    """Fixed-scale fits of the C3 objects: most best-fit chi2 are far above the fp32 bound, so the objects take the
+    register-tiled float64 sweep (k_sweep64).  Its PDFs must agree with the reference-order float64 kernel."""
+    fz = c3["fz"]
+    sel = np.arange(0, 60000, 7)[:6000]
+    for kw in (dict(free_scale=False, ignore_model_err=True), dict()):
+        bf = fz.BruteForce(c3["models"], np.zeros_like(c3["models"]), np.ones_like(c3["models"]))
+        p, (lm, le) = bf.fit_predict(c3["x"][sel].copy(), c3["xe"][sel].copy(), c3["xm"][sel].copy(), c3["labels"],
+                                     c3["labe"], label_dict=c3["rdict"], return_gof=True, verbose=False,
+                                     save_fits=False, lprob_kwargs=kw)
+        st = bf._eng().stats()
+        assert st["objects_fp64"] > 500 and st["pairs_fp64"] > 0, st      # the float64 sweep really ran
+        sub = np.arange(0, len(sel), 13)
+        p64, (lm64, le64) = bf.fit_predict(c3["x"][sel][sub].copy(), c3["xe"][sel][sub].copy(),
+                                           c3["xm"][sel][sub].copy(), c3["labels"], c3["labe"],
+                                           label_dict=c3["rdict"], return_gof=True, verbose=False, save_fits=False,
+                                           lprob_kwargs=dict(kw, precision="fp64"))
+        assert np.max(np.sum(np.abs(p[sub] - p64), axis=1)) <= 1e-5
+        assert np.all(np.abs(lm[sub] - lm64) <= 1e-5 * np.maximum(1, np.abs(lm64)))
+        assert np.all(np.abs(le[sub] - le64) <= 1e-5 * np.maximum(1, np.abs(le64)))
