@@ -33,6 +33,9 @@ import bench_data  # noqa: E402
 
 FLOPS_PER_PAIR = 54.0   # FS0 at Nf=5, 9*Nf+9 (FMA = 2 flops), + 3 MUFU per pair
 MUFU_PER_PAIR = 3.0
+# DRAM traffic of one k_sweep2 launch from the `ncu --set full` capture in profiles/r1_sweep_ncu.md
+# (dram__bytes_read.sum + dram__bytes_write.sum = 85.9 MB for 196,608 objects): bytes per object of the launch
+NCU_DRAM_BYTES_PER_OBJECT = 85.9e6 / 196608
 LPROB = dict(free_scale=True, ignore_model_err=True, dim_prior=True)
 
 
@@ -292,8 +295,13 @@ def main():
                 "peak_source": "fzb_measure_peaks (dependency-free FFMA loop, this run; MEASURED_PEAKS.json has no "
                                "fp32 entry)",
                 "mufu": {"achieved_gops": MUFU_PER_PAIR * dom_pairs / (dom_ms * 1e-3) / 1e9, "peak_gops": mufu_peak},
-                "traffic": None, "algorithmic_flops_per_pair": FLOPS_PER_PAIR,
+                "traffic": NCU_DRAM_BYTES_PER_OBJECT * float(no),
+                "traffic_note": "bytes per launch scaled from the ncu --set full capture in profiles/r1_sweep_ncu.md "
+                                "(437 B/object: photometry planes in, per-split partials out); the kernel is "
+                                "compute-bound, HBM carries ~0.002 B per pair",
+                "algorithmic_flops_per_pair": FLOPS_PER_PAIR,
                 "pairs_per_s_kernel": dom_pairs / (dom_ms * 1e-3),
+                "fit_only_pairs_per_s": float(no) * nm / (ms_scan * 1e-3),
                 "ms": {"pass1_scan": ms_scan, "pass2_accumulate": ms_acc, "finish": ms_fin,
                        "step_total": float(np.mean(ms_steps))},
                 "objects_routed_to_fp64": n64}

@@ -100,6 +100,7 @@ struct SweepParams {
     const float* recs;    // [nm][REC]
     int64_t nm;
     int tiles_per_split;
+    int has_prior;
     // pass 1 outputs: [nsplit][No_pad]
     double* pM;
     double* pS;
@@ -214,7 +215,7 @@ __device__ __forceinline__ f2 pack_chi2(const ObjPack<NF, MODE>& o, const f2* __
     return chi2;
 }
 
-template <int NF, int MODE, bool DP, bool MLO, int R, int PASS>
+template <int NF, int MODE, bool DP, bool MLO, bool PRIOR, int R, int PASS>
 __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P) {
     static_assert(R % 2 == 0, "objects come in packed pairs");
     constexpr int FT2 = ft2_of(R);
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
 
     ObjPack<NF, MODE> ob[NP];
     int oidx[R];
-    f2 negM[NP];          // minus the running / final max
+    f2 M[NP];             // running (pass 1) / final (pass 2) maximum
     f2 S[NP];             // pass 1: running sum.  pass 2: unused
     float thr[R];         // pass 2: selection cut
     int best[R];
@@ -265,8 +266,8 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
             if (MODE == FM_FS0) ob[p].x[b] = pack2(P.ox[b * P.No_pad + oo[0]], P.ox[b * P.No_pad + oo[1]]);
         }
         ob[p].A = pack2(P.oA[oo[0]], P.oA[oo[1]]);
-        if (PASS == 1) { negM[p] = pack2(FLT_MAX, FLT_MAX); S[p] = pack2(0.f, 0.f); }
-        else { negM[p] = pack2(-P.M2[oo[0]], -P.M2[oo[1]]); acc[p] = pack2(0.f, 0.f); }
+        if (PASS == 1) { M[p] = pack2(-FLT_MAX, -FLT_MAX); S[p] = pack2(0.f, 0.f); }
+        else { M[p] = pack2(P.M2[oo[0]], P.M2[oo[1]]); acc[p] = pack2(0.f, 0.f); }
     }
 
     const int64_t ntiles_all = (P.nm + TM - 1) / TM;
@@ -291,6 +292,7 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
         for (int it = 0; it < NSTAGE && it < nt; ++it) issue(it);
     }
     const f2 kNegHalfLog2e = pack2(-kHalfLog2e, -kHalfLog2e);
+    const f2 kMinusOne = pack2(-1.f, -1.f);
     int cur_bin = -1;
     for (int it = 0; it < nt; ++it) {
         const int st = it % NSTAGE;
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
         for (int jj = 0; jj < cnt; ++jj) {
             const float* rec = tile + jj * REC;       // same record for every thread: shared-memory broadcast
             const f2* rec2 = reinterpret_cast<const f2*>(rec);
-            const f2 prior2 = rec2[TAILOFF / 2];
+            const f2 prior2 = PRIOR ? rec2[TAILOFF / 2] : 0;
             f2 invnorm = 0;
             if (PASS == 2) {
                 invnorm = rec2[TAILOFF / 2 + 1];
@@ -332,15 +334,23 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
                 f2 chi2 = pack_chi2<NF, MODE, MLO>(ob[p], m, aux, ml);
-                f2 l = fma2(chi2, kNegHalfLog2e, prior2);
-                if (DP) l = fma2(ob[p].A, pack2(fast_lg2(lo2(chi2)), fast_lg2(hi2(chi2))), l);
-                f2 delta = add2(l, negM[p]);
+                // ln-likelihood in log2 units up to a per-object constant.  For FS0 / FX0 the factor -log2(e)/2 is
+                // folded into the object weights (k_prep_objects), so `chi2` already holds c = -chi2*log2(e)/2 and
+                // l = (dof/2-1) log2|c| + c (+ prior): one packed FMA.  FX1 weights are per pair, so c is formed here.
+                f2 c = (MODE == FM_FX1) ? mul2(chi2, kNegHalfLog2e) : chi2;
+                if (PRIOR) c = add2(c, prior2);
+                f2 l = c;
+                if (DP) {
+                    f2 cc = (MODE == FM_FX1 || PRIOR) ? ((MODE == FM_FX1) ? mul2(chi2, kNegHalfLog2e) : chi2) : c;
+                    l = fma2(ob[p].A, pack2(fast_lg2(fabsf(lo2(cc))), fast_lg2(fabsf(hi2(cc)))), c);
+                }
+                f2 delta = fma2(M[p], kMinusOne, l);
                 float d0 = lo2(delta), d1 = hi2(delta);
                 if (PASS == 1) {
                     float e0 = fast_ex2(-fabsf(d0)), e1 = fast_ex2(-fabsf(d1));
                     bool g0 = d0 > 0.f, g1 = d1 > 0.f;
                     S[p] = fma2(S[p], pack2(g0 ? e0 : 1.f, g1 ? e1 : 1.f), pack2(g0 ? 1.f : e0, g1 ? 1.f : e1));
-                    negM[p] = pack2(g0 ? -lo2(l) : lo2(negM[p]), g1 ? -hi2(l) : hi2(negM[p]));
+                    M[p] = pack2(g0 ? lo2(l) : lo2(M[p]), g1 ? hi2(l) : hi2(M[p]));
                     best[2 * p] = g0 ? (int)(first + jj) : best[2 * p];
                     best[2 * p + 1] = g1 ? (int)(first + jj) : best[2 * p + 1];
                 } else {
@@ -354,7 +364,7 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
         if (PASS == 1) {
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
-                float m0 = -lo2(negM[p]), m1 = -hi2(negM[p]);
+                float m0 = lo2(M[p]), m1 = hi2(M[p]);
                 Sd[2 * p] = Sd[2 * p] * (double)fast_ex2(Mfl[2 * p] - m0) + (double)lo2(S[p]);
                 Sd[2 * p + 1] = Sd[2 * p + 1] * (double)fast_ex2(Mfl[2 * p + 1] - m1) + (double)hi2(S[p]);
                 Mfl[2 * p] = m0;
@@ -531,8 +541,9 @@ __global__ void __launch_bounds__(FT64, 2) k_sweep64(Sweep64Params P) {
                     double wb = (MODE == FM_FX1) ? 1.0 / (w[r][b] + aux[b]) : w[r][b];
                     chi2 = fma(res * wb, res, chi2);
                 }
-                double l = fma(chi2, -0.72134752044448170368, prior2);
-                if (DP) l = fma(A[r], (double)fast_lg2((float)chi2), l);
+                const double cc = chi2 * 0.72134752044448170368;
+                double l = prior2 - cc;
+                if (DP) l = fma(A[r], (double)fast_lg2((float)cc), l);
                 double delta = l - M[r];
                 if (PASS == 1) {
                     float e = fast_ex2(-fabsf((float)delta));
@@ -638,8 +649,10 @@ __global__ void k_prep_objects(PrepParams P) {
             P.ow[q] = (k != 0.0) ? (float)(e * e) : CUDART_INF_F;
             P.ox[q] = 0.f;
         } else {
-            P.ow[q] = (float)w;
-            P.ox[q] = (float)(d * w);
+            // weights carry the factor -log2(e)/2 so that the sweep accumulates c = -chi2*log2(e)/2 directly
+            const double wk = -0.72134752044448170368 * w;
+            P.ow[q] = (float)wk;
+            P.ox[q] = (float)(d * wk);
         }
         ndim += k;
         double sn = (k != 0.0) ? fabs(d) / e : 0.0;
@@ -720,8 +733,9 @@ __global__ void k_merge(MergeParams P) {
     double lp = P.lnprior ? P.lnprior[j] : 0.0;
     double lmap = P.lnprior ? lnl + lp : lnl;
     // the same "varying part" the sweeps track, in float64, for a consistency check
-    double vary = -0.5 * st.chi2 * 1.4426950408889634 + lp * 1.4426950408889634;
-    if (P.dim_prior && (a - 1.0) != 0.0) vary += (a - 1.0) * log2(st.chi2);
+    const double cc = 0.72134752044448170368 * st.chi2;
+    double vary = -cc + lp * 1.4426950408889634;
+    if (P.dim_prior && (a - 1.0) != 0.0) vary += (a - 1.0) * log2(cc);
     const bool finite = !bad && isfinite(M) && M > -1e300 && isfinite(S) && S >= 0.5 && isfinite(lmap);
     const bool consistent = fabs(vary - M) <= P.consist_tol * fmax(1.0, fabs(vary));
     bool precise = consistent;
@@ -848,12 +862,18 @@ double env_double(const char* name, double dflt) {
 }
 
 template <int NF, int MODE, bool DP, bool MLO, int R, int PASS>
-int launch_sweep2_t(fzb_context* h, const SweepParams& P, dim3 grid) {
+int launch_sweep2_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prior) {
     constexpr int REC = rec2_floats(NF, MODE, MLO);
     size_t smem = (size_t)NSTAGE * TM * REC * sizeof(float) + NSTAGE * sizeof(uint64_t);
-    auto kern = k_sweep2<NF, MODE, DP, MLO, R, PASS>;
-    FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, ft2_of(R), smem, h->stream>>>(P);
+    if (prior) {
+        auto kern = k_sweep2<NF, MODE, DP, MLO, true, R, PASS>;
+        FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, ft2_of(R), smem, h->stream>>>(P);
+    } else {
+        auto kern = k_sweep2<NF, MODE, DP, MLO, false, R, PASS>;
+        FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, ft2_of(R), smem, h->stream>>>(P);
+    }
     fzb_count_launch(h);
     FZB_CUDA(cudaGetLastError());
     return 0;
@@ -863,11 +883,11 @@ template <int NF, int MODE, bool DP, bool MLO>
 int launch_sweep_r(fzb_context* h, const SweepParams& P, dim3 grid, int R, int pass) {
     if (R < 0) {   // packed kernels: R = -objects per thread
         if (pass == 1) {
-            if (R == -4) return launch_sweep2_t<NF, MODE, DP, MLO, 4, 1>(h, P, grid);
-            return launch_sweep2_t<NF, MODE, DP, MLO, 2, 1>(h, P, grid);
+            if (R == -4) return launch_sweep2_t<NF, MODE, DP, MLO, 4, 1>(h, P, grid, P.has_prior != 0);
+            return launch_sweep2_t<NF, MODE, DP, MLO, 2, 1>(h, P, grid, P.has_prior != 0);
         }
-        if (R == -4) return launch_sweep2_t<NF, MODE, DP, MLO, 4, 2>(h, P, grid);
-        return launch_sweep2_t<NF, MODE, DP, MLO, 2, 2>(h, P, grid);
+        if (R == -4) return launch_sweep2_t<NF, MODE, DP, MLO, 4, 2>(h, P, grid, P.has_prior != 0);
+        return launch_sweep2_t<NF, MODE, DP, MLO, 2, 2>(h, P, grid, P.has_prior != 0);
     }
     fzb_set_error("fp32 path: bad kernel selector");
     return 2;
@@ -1147,7 +1167,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         SweepParams SP = {};
         SP.od = od; SP.ow = ow; SP.ox = ox; SP.odl = odl; SP.oA = oA;
         SP.No_pad = nc_pad; SP.No = nc;
-        SP.recs = F.recs.as<float>(); SP.nm = nm;
+        SP.recs = F.recs.as<float>(); SP.nm = nm; SP.has_prior = h->has_lnprior ? 1 : 0;
         SP.tiles_per_split = tiles_per_split;
         SP.pM = pM; SP.pS = pS; SP.pbest = pbest;
         const int64_t tiles1 = (nc + tile_objs - 1) / tile_objs;
