@@ -135,7 +135,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--objects", type=int, default=int(os.environ.get("FZB_BENCH_OBJECTS", 1000000)))
     ap.add_argument("--e2e-objects", type=int, default=0, help="objects per e2e step (default: same as --objects)")
-    ap.add_argument("--cpu-objects-per-core", type=int, default=6)
+    ap.add_argument("--cpu-objects-per-core", type=int, default=24)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--lprob", default="", help="JSON overriding the likelihood flags (experiments only)")

@@ -1,6 +1,7 @@
 // C-ABI entry points of libfzb200 (see include/frankenz_b200.h): handle management, host<->device
 // staging, and dispatch between the fp32 register-tiled path (fzb_fast.cu) and the generic
 // float64 path (fzb_generic.cu).
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <condition_variable>
@@ -60,6 +61,163 @@ int check_models(fzb_context* h) {
     FZB_CHECK(h->Nm > 0 && h->Nf > 0, "no models loaded: call fzb_set_models first");
     return 0;
 }
+
+
+// ---- staged device -> host download ------------------------------------------------------------------
+// Large results (PDFs, full fit arrays) go device -> pinned staging (copy engine, second stream) -> caller's
+// pageable array (a pool of host threads), in pieces, double buffered, so that PCIe and the host memcpy (incl. the
+// first-touch page faults of a freshly allocated numpy array) overlap with each other and with the kernels.
+void parallel_memcpy(char* dst, const char* src, size_t bytes, int nthreads) {
+    if (bytes < ((size_t)4 << 20) || nthreads <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> pool;
+    size_t per = (bytes / nthreads + 4095) & ~(size_t)4095;
+    for (int t = 0; t < nthreads; ++t) {
+        size_t lo = (size_t)t * per;
+        if (lo >= bytes) break;
+        size_t n = std::min(per, bytes - lo);
+        pool.emplace_back([=] { memcpy(dst + lo, src + lo, n); });
+    }
+    for (auto& th : pool) th.join();
+}
+
+class StagedDownloader {
+  public:
+    explicit StagedDownloader(fzb_context* h) : h_(h) {}
+    ~StagedDownloader() { finish(); }
+    int init(size_t piece_bytes = (size_t)64 << 20) {
+        piece_ = piece_bytes;
+        if (!h_->stream2) FZB_CUDA(cudaStreamCreateWithFlags(&h_->stream2, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            if (h_->pinned_cap[b] < piece_) {
+                if (h_->pinned[b]) cudaFreeHost(h_->pinned[b]);
+                h_->pinned[b] = nullptr;
+                h_->pinned_cap[b] = 0;
+                FZB_CUDA(cudaHostAlloc(&h_->pinned[b], piece_, cudaHostAllocDefault));
+                h_->pinned_cap[b] = piece_;
+            }
+            if (!h_->ev_copied[b]) FZB_CUDA(cudaEventCreateWithFlags(&h_->ev_copied[b], cudaEventDisableTiming));
+        }
+        nthreads_ = (int)std::min<unsigned>(12, std::max(1u, std::thread::hardware_concurrency() / 2));
+        started_ = true;
+        worker_ = std::thread([this] { work_loop(); });
+        return 0;
+    }
+    // Non-blocking: copy `bytes` from device `src` to host `dst` once everything enqueued so far on the compute
+    // stream is done.  Returns the id of the request (for fence_compute) in *id.
+    int push(void* dst, const void* src, size_t bytes, int64_t* id = nullptr) {
+        if (bytes == 0) return 0;
+        Request r;
+        r.dst = static_cast<char*>(dst);
+        r.src = static_cast<const char*>(src);
+        r.bytes = bytes;
+        FZB_CUDA(cudaEventCreateWithFlags(&r.ready, cudaEventDisableTiming));
+        FZB_CUDA(cudaEventCreateWithFlags(&r.left_device, cudaEventDisableTiming));
+        FZB_CUDA(cudaEventRecord(r.ready, h_->stream));
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            reqs_.push_back(r);
+            if (id) *id = (int64_t)reqs_.size() - 1;
+        }
+        cv_.notify_all();
+        return 0;
+    }
+    // Later work on the compute stream may overwrite the device buffers of requests 0..id.
+    int fence_compute(int64_t id) {
+        if (id < 0) return 0;
+        cudaEvent_t ev;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return issued_ > id; });     // its last device->pinned copy has been enqueued
+            ev = reqs_[(size_t)id].left_device;
+        }
+        FZB_CUDA(cudaStreamWaitEvent(h_->stream, ev, 0));
+        return 0;
+    }
+    int finish() {
+        if (!started_) return err_;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            closing_ = true;
+        }
+        cv_.notify_all();
+        if (worker_.joinable()) worker_.join();
+        started_ = false;
+        for (auto& r : reqs_) {
+            cudaEventDestroy(r.ready);
+            cudaEventDestroy(r.left_device);
+        }
+        reqs_.clear();
+        return err_;
+    }
+
+  private:
+    struct Request {
+        char* dst;
+        const char* src;
+        size_t bytes;
+        cudaEvent_t ready, left_device;
+    };
+    // one worker: enqueue the device->pinned copy of piece p, then spread piece p-1 into the caller's array while
+    // the copy engine moves piece p
+    void work_loop() {
+        cudaSetDevice(h_->device);
+        int64_t piece = 0;
+        char* prev_dst = nullptr;
+        size_t prev_bytes = 0;
+        auto drain_prev = [&] {
+            if (!prev_dst) return;
+            if (cudaEventSynchronize(h_->ev_copied[(piece - 1) & 1]) != cudaSuccess) err_ = 1;
+            parallel_memcpy(prev_dst, static_cast<const char*>(h_->pinned[(piece - 1) & 1]), prev_bytes, nthreads_);
+            prev_dst = nullptr;
+        };
+        for (int64_t q = 0;; ++q) {
+            Request r;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return (int64_t)reqs_.size() > q || closing_; });
+                if ((int64_t)reqs_.size() <= q) break;
+                r = reqs_[(size_t)q];
+            }
+            if (cudaStreamWaitEvent(h_->stream2, r.ready, 0) != cudaSuccess) err_ = 1;
+            for (size_t off = 0; off < r.bytes; off += piece_) {
+                size_t n = std::min(piece_, r.bytes - off);
+                int b = (int)(piece & 1);
+                // staging buffer b was drained two pieces ago (this thread did it)
+                if (cudaMemcpyAsync(h_->pinned[b], r.src + off, n, cudaMemcpyDeviceToHost, h_->stream2) != cudaSuccess)
+                    err_ = 1;
+                if (cudaEventRecord(h_->ev_copied[b], h_->stream2) != cudaSuccess) err_ = 1;
+                ++piece;
+                // while that copy runs, deliver the previous piece
+                if (prev_dst) {
+                    if (cudaEventSynchronize(h_->ev_copied[(piece - 2) & 1]) != cudaSuccess) err_ = 1;
+                    parallel_memcpy(prev_dst, static_cast<const char*>(h_->pinned[(piece - 2) & 1]), prev_bytes, nthreads_);
+                }
+                prev_dst = r.dst + off;
+                prev_bytes = n;
+            }
+            if (cudaEventRecord(r.left_device, h_->stream2) != cudaSuccess) err_ = 1;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                issued_ = q + 1;
+            }
+            cv_.notify_all();
+        }
+        drain_prev();
+    }
+    fzb_context* h_;
+    size_t piece_ = 0;
+    int nthreads_ = 1;
+    bool started_ = false, closing_ = false;
+    int err_ = 0;
+    int64_t issued_ = 0;
+    std::vector<Request> reqs_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::thread worker_;
+};
 
 // dependency-free FFMA / MUFU loops: 8 independent chains per thread, 2048 resident threads per SM
 __global__ void __launch_bounds__(256) k_peak_ffma(float* out, int iters) {
@@ -182,6 +340,7 @@ int fzb_destroy(fzb_handle h) {
         if (h->pinned[b]) cudaFreeHost(h->pinned[b]);
         if (h->ev_done[b]) cudaEventDestroy(h->ev_done[b]);
         if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
+        if (h->ev_chunk[b]) cudaEventDestroy(h->ev_chunk[b]);
     }
     if (h->stream2) cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->stream);
@@ -356,6 +515,9 @@ int fzb_fit(fzb_handle h, const double* data, const double* data_err, const doub
         if (h->out_i64[0].reserve(cn * 8)) return 1;
         d_nd = h->out_i64[0].as<int64_t>();
     }
+    StagedDownloader dl(h);
+    if (dl.init()) return 1;
+    int64_t last_push = -1;
     Timer t(h);
     for (int64_t o0 = 0; o0 < No; o0 += chunk) {
         int64_t nc = No - o0 < chunk ? No - o0 : chunk;
@@ -363,16 +525,18 @@ int fzb_fit(fzb_handle h, const double* data, const double* data_err, const doub
         if (upload(h, h->obj_in[0], data + o0 * Nf, nin) || upload(h, h->obj_in[1], data_err + o0 * Nf, nin) ||
             upload(h, h->obj_in[2], data_mask + o0 * Nf, nin))
             return 1;
+        if (dl.fence_compute(last_push)) return 1;     // the previous chunk's outputs have left the device buffers
         if (fzb_generic_fit_dev(h, h->obj_in[0].as<double>(), h->obj_in[1].as<double>(), h->obj_in[2].as<double>(), nc,
                                 *cfg, d_o[0], d_o[1], d_o[2], d_nd, d_o[3], d_o[4], d_o[5]))
             return 1;
         size_t no = (size_t)nc * Nm;
         for (int i = 0; i < 6; ++i)
-            if (download(h, hostp[i] ? hostp[i] + (size_t)o0 * Nm : nullptr, d_o[i], no)) return 1;
-        if (download(h, out->Ndim ? out->Ndim + (size_t)o0 * Nm : nullptr, d_nd, no)) return 1;
-        FZB_CUDA(cudaStreamSynchronize(h->stream));
+            if (hostp[i] && dl.push(hostp[i] + (size_t)o0 * Nm, d_o[i], no * sizeof(double), &last_push)) return 1;
+        if (out->Ndim && dl.push(out->Ndim + (size_t)o0 * Nm, d_nd, no * sizeof(int64_t), &last_push)) return 1;
     }
-    return t.stop();
+    int rc = t.stop();
+    FZB_CHECK(dl.finish() == 0, "device-to-host copy of the fit arrays failed");
+    return rc;
 }
 
 static int fit_predict_dev_impl(fzb_context* h, const double* d_data, const double* d_err, const double* d_mask,
@@ -400,27 +564,8 @@ int fzb_fit_predict_dev(fzb_handle h, const double* d_data, const double* d_err,
     return t.stop();
 }
 
-// Host-pointer form.  The objects are processed in chunks; the PDFs of chunk c travel device -> pinned staging
-// buffer on a second stream (copy engine) and from there into the caller's array by a pool of host threads, while
-// the kernels of chunk c+1 run: PCIe and the host memcpy are hidden behind the compute.
-namespace {
-void parallel_memcpy(char* dst, const char* src, size_t bytes, int nthreads) {
-    if (bytes < ((size_t)8 << 20) || nthreads <= 1) {
-        memcpy(dst, src, bytes);
-        return;
-    }
-    std::vector<std::thread> pool;
-    size_t per = (bytes / nthreads + 4095) & ~(size_t)4095;
-    for (int t = 0; t < nthreads; ++t) {
-        size_t lo = (size_t)t * per;
-        if (lo >= bytes) break;
-        size_t n = std::min(per, bytes - lo);
-        pool.emplace_back([=] { memcpy(dst + lo, src + lo, n); });
-    }
-    for (auto& th : pool) th.join();
-}
-}  // namespace
-
+// Host-pointer form.  The objects are processed in chunks; the PDFs of chunk c leave through the staged downloader
+// while the kernels of chunk c+1 run, so PCIe and the host memcpy are hidden behind the compute.
 int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, const double* data_mask, int64_t No,
                     const FzbConfig* cfg, double* pdfs, double* lmap, double* levid, int64_t* best_idx,
                     double* best_chi2, double* best_scale) {
@@ -453,103 +598,34 @@ int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, co
     if (const char* e = getenv("FZB_E2E_CHUNK")) chunk = std::max<int64_t>(1024, atoll(e));
     if (!pdfs || No <= chunk + chunk / 2) chunk = No;
     const size_t chunk_bytes = (size_t)chunk * Ng * sizeof(double);
-    const bool pipelined = pdfs && chunk < No;
-    int rc = 0;
-    if (!pipelined) {
-        if (pdfs && h->out_f64[0].reserve((size_t)No * Ng * 8)) return 1;
-        FZB_CUDA(cudaEventRecord(h->ev[0], h->stream));
-        rc = fit_predict_dev_impl(h, d_x, d_xe, d_xm, No, cfg, pdfs ? h->out_f64[0].as<double>() : nullptr, d_lmap,
-                                  d_levid, d_bi, d_bc, d_bs);
-        if (rc) return rc;
-        FZB_CUDA(cudaEventRecord(h->ev[1], h->stream));
-        if (download(h, pdfs, h->out_f64[0].p, (size_t)No * Ng)) return 1;
-    } else {
-        if (!h->stream2) FZB_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; ++b) {
+    StagedDownloader dl(h);
+    if (pdfs) {
+        if (dl.init()) return 1;
+        for (int b = 0; b < 2; ++b)
             if (h->pdf_dev[b].reserve(chunk_bytes)) return 1;
-            if (h->pinned_cap[b] < chunk_bytes) {
-                if (h->pinned[b]) cudaFreeHost(h->pinned[b]);
-                h->pinned[b] = nullptr;
-                h->pinned_cap[b] = 0;
-                FZB_CUDA(cudaHostAlloc(&h->pinned[b], chunk_bytes, cudaHostAllocDefault));
-                h->pinned_cap[b] = chunk_bytes;
-            }
-            if (!h->ev_done[b]) {
-                FZB_CUDA(cudaEventCreateWithFlags(&h->ev_done[b], cudaEventDisableTiming));
-                FZB_CUDA(cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
-            }
-        }
-        const int64_t nchunks = (No + chunk - 1) / chunk;
-        int nthreads = (int)std::min<unsigned>(12, std::max(1u, std::thread::hardware_concurrency() / 2));
-        // drainer: waits for the D2H of chunk c, spreads it into the caller's array, frees the staging buffer
-        std::mutex mu;
-        std::condition_variable cv;
-        int64_t copied_enqueued = 0;          // chunks whose D2H has been enqueued
-        int64_t drained = 0;                  // chunks fully delivered to the caller
-        std::atomic<int> drain_err{0};
-        bool abort_flag = false;
-        std::thread drainer([&] {
-            cudaSetDevice(h->device);
-            for (int64_t c = 0; c < nchunks; ++c) {
-                {
-                    std::unique_lock<std::mutex> lk(mu);
-                    cv.wait(lk, [&] { return copied_enqueued > c || abort_flag; });
-                    if (abort_flag) return;
-                }
-                if (cudaEventSynchronize(h->ev_copied[c & 1]) != cudaSuccess) drain_err = 1;
-                int64_t o0 = c * chunk, nc = std::min(chunk, No - o0);
-                parallel_memcpy(reinterpret_cast<char*>(pdfs + (size_t)o0 * Ng),
-                                reinterpret_cast<const char*>(h->pinned[c & 1]), (size_t)nc * Ng * sizeof(double),
-                                nthreads);
-                {
-                    std::lock_guard<std::mutex> lk(mu);
-                    drained = c + 1;
-                }
-                cv.notify_all();
-            }
-        });
-        FZB_CUDA(cudaEventRecord(h->ev[0], h->stream));
-        for (int64_t c = 0; c < nchunks && rc == 0; ++c) {
-            int64_t o0 = c * chunk, nc = std::min(chunk, No - o0);
-            int b = (int)(c & 1);
-            if (c >= 2) {   // device buffer b is free once its D2H finished; staging buffer once drained
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return drained >= c - 1; });
-            }
-            rc = fit_predict_dev_impl(h, d_x + o0 * Nf, d_xe + o0 * Nf, d_xm + o0 * Nf, nc, cfg,
-                                      h->pdf_dev[b].as<double>(), d_lmap + o0, d_levid + o0, d_bi + o0, d_bc + o0,
-                                      d_bs + o0);
-            if (rc) break;
-            if (cudaEventRecord(h->ev_done[b], h->stream) != cudaSuccess ||
-                cudaStreamWaitEvent(h->stream2, h->ev_done[b], 0) != cudaSuccess ||
-                cudaMemcpyAsync(h->pinned[b], h->pdf_dev[b].p, (size_t)nc * Ng * sizeof(double),
-                                cudaMemcpyDeviceToHost, h->stream2) != cudaSuccess ||
-                cudaEventRecord(h->ev_copied[b], h->stream2) != cudaSuccess) {
-                fzb_set_error("pipelined D2H failed: %s", cudaGetErrorString(cudaGetLastError()));
-                rc = 1;
-                break;
-            }
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                copied_enqueued = c + 1;
-            }
-            cv.notify_all();
-        }
-        if (rc) {
-            std::lock_guard<std::mutex> lk(mu);
-            abort_flag = true;
-        }
-        cv.notify_all();
-        cudaEventRecord(h->ev[1], h->stream);
-        drainer.join();
-        if (rc) return rc;
-        FZB_CHECK(drain_err == 0, "device-to-host copy of the PDFs failed");
     }
+    FZB_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    int64_t c = 0;
+    int64_t push_id[2] = {-1, -1};
+    for (int64_t o0 = 0; o0 < No; o0 += chunk, ++c) {
+        int64_t nc = std::min(chunk, No - o0);
+        int b = (int)(c & 1);
+        // device buffer b was last read by the download of chunk c-2 (issued before that of chunk c-1)
+        if (pdfs && c >= 2 && dl.fence_compute(push_id[b])) return 1;
+        int rc = fit_predict_dev_impl(h, d_x + o0 * Nf, d_xe + o0 * Nf, d_xm + o0 * Nf, nc, cfg,
+                                      pdfs ? h->pdf_dev[b].as<double>() : nullptr, d_lmap + o0, d_levid + o0, d_bi + o0,
+                                      d_bc + o0, d_bs + o0);
+        if (rc) return rc;
+        if (pdfs && dl.push(pdfs + (size_t)o0 * Ng, h->pdf_dev[b].p, (size_t)nc * Ng * sizeof(double), &push_id[b]))
+            return 1;
+    }
+    FZB_CUDA(cudaEventRecord(h->ev[1], h->stream));
     if (download(h, lmap, d_lmap, (size_t)No) || download(h, levid, d_levid, (size_t)No) ||
         download(h, best_idx, d_bi, (size_t)No) || download(h, best_chi2, d_bc, (size_t)No) ||
         download(h, best_scale, d_bs, (size_t)No))
         return 1;
     FZB_CUDA(cudaStreamSynchronize(h->stream));
+    FZB_CHECK(dl.finish() == 0, "device-to-host copy of the PDFs failed");
     float ms = 0.f;
     FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
     h->stats.ms_total = ms;

@@ -91,6 +91,7 @@ struct fzb_context {
     size_t pinned_cap[2] = {0, 0};
     cudaEvent_t ev_done[2] = {nullptr, nullptr};
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+    cudaEvent_t ev_chunk[2] = {nullptr, nullptr};   // all pieces of chunk c (c & 1) have reached pinned memory
 
     // model set (fp64 originals, row-major Nm x Nf)
     int64_t Nm = 0;
