@@ -680,7 +680,15 @@ int fzb_shard_pass1_dev(fzb_handle h, const double* d_data, const double* d_err,
     reset_stats(h);
     if (No == 0) return 0;
     Timer t(h);
-    if (fzb_generic_shard_pass1_dev(h, d_data, d_err, d_mask, No, *cfg, d_pmax, d_psum, d_pbest)) return 1;
+    if (cfg->precision != FZB_PREC_FP64 && fzb_fast_supported(h, *cfg)) {
+        if (fzb_fast_fit_predict_dev(h, d_data, d_err, d_mask, No, *cfg, nullptr, d_pmax, nullptr, d_pbest, nullptr,
+                                     nullptr, 1, d_psum, nullptr))
+            return 1;
+    } else {
+        h->shard_valid = false;
+        if (fzb_generic_shard_pass1_dev(h, d_data, d_err, d_mask, No, nullptr, 0, *cfg, d_pmax, d_psum, d_pbest))
+            return 1;
+    }
     return t.stop();
 }
 
@@ -691,7 +699,14 @@ int fzb_shard_pass2_dev(fzb_handle h, const double* d_data, const double* d_err,
     reset_stats(h);
     if (No == 0) return 0;
     Timer t(h);
-    if (fzb_generic_shard_pass2_dev(h, d_data, d_err, d_mask, No, *cfg, d_lmap, d_levid, d_pdf_partial)) return 1;
+    if (cfg->precision != FZB_PREC_FP64 && fzb_fast_supported(h, *cfg) && h->shard_valid && h->shard_No == No) {
+        if (fzb_fast_fit_predict_dev(h, d_data, d_err, d_mask, No, *cfg, d_pdf_partial, nullptr, nullptr, nullptr,
+                                     nullptr, nullptr, 2, nullptr, d_lmap))
+            return 1;
+    } else {
+        if (fzb_generic_shard_pass2_dev(h, d_data, d_err, d_mask, No, nullptr, 0, *cfg, d_lmap, d_levid, d_pdf_partial))
+            return 1;
+    }
     return t.stop();
 }
 

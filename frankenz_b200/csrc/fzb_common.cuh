@@ -129,6 +129,11 @@ struct fzb_context {
     bool fast_packed = true;
     int fast_wmax = 0;
     int fast_Ngpad = 0;
+    // state a model-sharded pass 1 leaves for pass 2
+    bool shard_valid = false;
+    int64_t shard_No = 0;
+    int shard_counts[4] = {0, 0, 0, 0};
+    int shard_cfg_key = 0;
 
     // kNN
     DevBuf knn_feats;       // float32 K x Nm x Nf (+ 64 B pad)
@@ -155,10 +160,11 @@ int fzb_generic_predict_logwt_dev(fzb_context* h, const double* d_logwt, int64_t
                                   const int64_t* d_neighbors, const int64_t* d_nneighbors, const FzbConfig& cfg,
                                   double* d_pdfs, double* d_lmap, double* d_levid);
 int fzb_generic_shard_pass1_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm,
-                                int64_t No, const FzbConfig& cfg, double* d_pmax, double* d_psum, int64_t* d_pbest);
+                                int64_t No, const int32_t* d_objsel, int64_t Nsel, const FzbConfig& cfg,
+                                double* d_pmax, double* d_psum, int64_t* d_pbest);
 int fzb_generic_shard_pass2_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm,
-                                int64_t No, const FzbConfig& cfg, const double* d_lmap, const double* d_levid,
-                                double* d_pdf_partial);
+                                int64_t No, const int32_t* d_objsel, int64_t Nsel, const FzbConfig& cfg,
+                                const double* d_lmap, const double* d_levid, double* d_pdf_partial);
 int fzb_generic_gather_fit_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm,
                                int64_t No, int64_t W, const int64_t* d_neighbors, const int64_t* d_nneighbors,
                                const FzbConfig& cfg, double* d_lnprior, double* d_lnlike, double* d_lnprob,
@@ -167,9 +173,13 @@ int fzb_generic_gather_fit_dev(fzb_context* h, const double* d_x, const double* 
 // ---- fp32 fast path (fzb_fast.cu) ------------------------------------------------------------
 bool fzb_fast_supported(const fzb_context* h, const FzbConfig& cfg);
 int fzb_fast_prepare(fzb_context* h);
+// shard_mode 0: whole fit_predict.  1: model-sharded pass 1 (d_lmap = partial max, d_psum = partial sum, d_best_idx =
+// partial arg-max; state for pass 2 stays in the context).  2: model-sharded pass 2 (d_glmap = global lmap in,
+// d_pdfs = un-normalised PDF partial out).
 int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm, int64_t No,
                              const FzbConfig& cfg, double* d_pdfs, double* d_lmap, double* d_levid,
-                             int64_t* d_best_idx, double* d_best_chi2, double* d_best_scale);
+                             int64_t* d_best_idx, double* d_best_chi2, double* d_best_scale, int shard_mode = 0,
+                             double* d_psum = nullptr, const double* d_glmap = nullptr);
 
 // ---- kNN (fzb_knn.cu) -------------------------------------------------------------------------
 int fzb_knn_query_dev(fzb_context* h, const double* d_q, int64_t No, int k, double p, int64_t* d_idx, double* d_dist);

@@ -683,6 +683,9 @@ struct MergeParams {
     int64_t n_in;
     // outputs
     double *lmap, *levid, *best_chi2, *best_scale;   // absolute object index
+    double* Sout;                       // nullable: sum exp(l - lmap) (model-sharded pass 1)
+    double* lmap_local;                 // chunk-local copy of lmap (model-sharded pass 2 needs it)
+    double* Mlocal;                     // chunk-local maximum in sweep units, float64
     int64_t* best_idx;
     float *M2, *thr2;                   // chunk-local, for the fp32 pass 2
     double *M2d, *thr2d;                // chunk-local, for the float64 pass 2
@@ -743,6 +746,9 @@ __global__ void k_merge(MergeParams P) {
     int64_t og = P.o_base + o;
     if (P.lmap) P.lmap[og] = lmap;
     if (P.levid) P.levid[og] = lmap + log(S);
+    if (P.Sout) P.Sout[og] = S;
+    if (P.lmap_local) P.lmap_local[o] = lmap;
+    if (P.Mlocal) P.Mlocal[o] = M;
     if (P.best_idx) P.best_idx[og] = j;
     if (P.best_chi2) P.best_chi2[og] = st.chi2;
     if (P.best_scale) P.best_scale[og] = st.scale;
@@ -760,6 +766,28 @@ __global__ void k_merge(MergeParams P) {
     }
 }
 
+// ---- model-sharded pass 2: express the GLOBAL lmap in this shard's sweep units ------------------------
+struct ShardThrParams {
+    int64_t No;
+    const double* g_lmap;        // global lmap (natural log, with all constants)
+    const double* lmap_local;    // this shard's lmap
+    const double* M2d_local;     // this shard's maximum in sweep units (float64 copy)
+    double log2_wt_thresh;
+    float *M2, *thr2;
+    double *M2d, *thr2d;
+};
+__global__ void k_shard_thr(ShardThrParams P) {
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= P.No) return;
+    // l_sweep = (lnprob - C_o) * log2(e) with the same per-object constant C_o for every model, so
+    // M_ref = M_local + (lmap_global - lmap_local) * log2(e) makes 2^(l_sweep - M_ref) = exp(lnprob - lmap_global)
+    double mref = P.M2d_local[o] + (P.g_lmap[o] - P.lmap_local[o]) * 1.4426950408889634;
+    P.M2[o] = (float)mref;
+    P.thr2[o] = (float)(mref + P.log2_wt_thresh);
+    P.M2d[o] = mref;
+    P.thr2d[o] = mref + P.log2_wt_thresh;
+}
+
 // ---- histogram (*) kernel, normalise, write -------------------------------------------------------
 struct FinishParams {
     const float* hist;          // [No_pad][hist_stride]
@@ -772,6 +800,7 @@ struct FinishParams {
     const int64_t* koff;
     const double* kernels;
     double* pdfs;               // absolute rows
+    int normalise;              // 0: write the un-normalised sum (model-sharded partial)
 };
 
 __global__ void __launch_bounds__(256) k_finish(FinishParams P) {
@@ -806,6 +835,7 @@ __global__ void __launch_bounds__(256) k_finish(FinishParams P) {
     double tot = 0.0;
     for (int i = 0; i < 8; ++i) tot += red[i];
     double* out = P.pdfs + (size_t)(P.o_base + o) * P.Ng;
+    if (!P.normalise) tot = 1.0;
     for (int g = tid; g < P.Ng; g += 256) out[g] = pdf[g] / tot;
 }
 
@@ -1076,11 +1106,13 @@ int fzb_fast_prepare(fzb_context* h) { return 0; }
 
 int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm, int64_t No,
                              const FzbConfig& cfg, double* d_pdfs, double* d_lmap, double* d_levid,
-                             int64_t* d_best_idx, double* d_best_chi2, double* d_best_scale) {
+                             int64_t* d_best_idx, double* d_best_chi2, double* d_best_scale, int shard_mode,
+                             double* d_psum, const double* d_glmap) {
     const int mode = mode_of(cfg);
     const int nf = h->Nf;
-    const bool want_pdf = d_pdfs != nullptr;
+    const bool want_pdf = d_pdfs != nullptr || shard_mode == 1;   // pass 1 of a sharded run prepares the KDE layout too
     if (want_pdf) FZB_CHECK(h->kde_mode == FZB_KDE_DICT && h->labels_dict_set, "dictionary KDE not configured");
+    if (shard_mode != 1) h->shard_valid = (shard_mode == 2) ? h->shard_valid : false;
     if (h->fast_dirty || !h->fast.valid || h->fast_mode != mode) {
         if (fast_prepare_mode(h, mode)) return 1;
     }
@@ -1097,6 +1129,9 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         if (fit < 1024) fit = 1024;
         if (chunk > fit) chunk = fit;
     }
+    FZB_CHECK(shard_mode == 0 || chunk == No,
+              "model-sharded passes keep per-object state on the device: call them with at most %lld objects at a time",
+              (long long)chunk);
     const int64_t chunk_pad = (chunk + 6143) / 6144 * 6144;
     const bool packed = h->fast_packed;
     // objects per thread: 4 for large batches; small batches use fewer so that more CTAs exist.
@@ -1142,9 +1177,11 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     int32_t* counts = h->misc[3].as<int32_t>();
     if (kde && h->misc[4].reserve((size_t)chunk_pad * hist_stride * 4 + 256)) return 1;
     float* hist = kde ? h->misc[4].as<float>() : nullptr;
-    if (F.aux64.reserve((size_t)chunk_pad * 16 + 64)) return 1;
+    if (F.aux64.reserve((size_t)chunk_pad * 32 + 64)) return 1;
     double* M2d = F.aux64.as<double>();
     double* thr2d = M2d + chunk_pad;
+    double* lmap_local = thr2d + chunk_pad;
+    double* M2d_local = lmap_local + chunk_pad;
 
     const double chi2_max = env_double("FZB_FAST_CHI2_MAX", 24.0);
     const double snr_max = env_double("FZB_FAST_SNR_MAX", 20000.0);
@@ -1164,6 +1201,12 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         FZB_CUDA(cudaGetLastError());
 
         // ---- pass 1 (fp32, every object) ------------------------------------------------------------
+        int32_t hc[4] = {0, 0, 0, 0};
+        Sweep64Params S6 = {};
+        S6.x = PP.x; S6.xe = PP.xe; S6.xm = PP.xm; S6.No = nc; S6.No_pad = nc_pad;
+        S6.free_scale = cfg.free_scale; S6.dim_prior = cfg.dim_prior;
+        S6.recs = F.recs64.as<double>(); S6.nm = nm; S6.tiles_per_split = tiles_per_split;
+        S6.pM = pM; S6.pS = pS; S6.pbest = pbest;
         SweepParams SP = {};
         SP.od = od; SP.ow = ow; SP.ox = ox; SP.odl = odl; SP.oA = oA;
         SP.No_pad = nc_pad; SP.No = nc;
@@ -1171,6 +1214,8 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         SP.tiles_per_split = tiles_per_split;
         SP.pM = pM; SP.pS = pS; SP.pbest = pbest;
         const int64_t tiles1 = (nc + tile_objs - 1) / tile_objs;
+        int64_t nsafe = 0, nsafe64 = 0, nunsafe = 0;
+        if (shard_mode != 2) {
         FZB_CUDA(cudaEventRecord(h->ev[2], h->stream));
         if (launch_sweep(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 1)) return 1;
         FZB_CUDA(cudaEventRecord(h->ev[3], h->stream));
@@ -1192,28 +1237,24 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         MP.stage = 0;
         MP.lmap = d_lmap; MP.levid = d_levid; MP.best_chi2 = d_best_chi2; MP.best_scale = d_best_scale;
         MP.best_idx = d_best_idx;
+        MP.Sout = (shard_mode == 1) ? d_psum : nullptr;
+        MP.lmap_local = lmap_local; MP.Mlocal = M2d_local;
         MP.M2 = M2; MP.thr2 = thr2; MP.M2d = M2d; MP.thr2d = thr2d;
         MP.safe_list = safe_list; MP.unsafe_list = unsafe_list; MP.prec_list = use_sweep64 ? prec_list : nullptr;
         MP.safe64_list = safe64_list; MP.counts = counts;
         k_merge<<<(unsigned)((nc + 255) / 256), 256, 0, h->stream>>>(MP);
         fzb_count_launch(h);
         FZB_CUDA(cudaGetLastError());
-        int32_t hc[4] = {0, 0, 0, 0};
         FZB_CUDA(cudaMemcpyAsync(hc, counts, 16, cudaMemcpyDeviceToHost, h->stream));
         FZB_CUDA(cudaStreamSynchronize(h->stream));
         FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
         h->stats.ms_scan += ms;
-        const int64_t nsafe = hc[0], nprec = hc[2];
+        nsafe = hc[0];
+        const int64_t nprec = hc[2];
 
         // ---- objects whose fp32 result is not trusted: float64 sweep, pass 1 ---------------------------
-        Sweep64Params S6 = {};
-        int64_t nsafe64 = 0;
         if (nprec > 0) {
-            S6.x = PP.x; S6.xe = PP.xe; S6.xm = PP.xm; S6.No = nc; S6.No_pad = nc_pad;
             S6.objlist = prec_list; S6.nlist = nprec;
-            S6.free_scale = cfg.free_scale; S6.dim_prior = cfg.dim_prior;
-            S6.recs = F.recs64.as<double>(); S6.nm = nm; S6.tiles_per_split = tiles_per_split;
-            S6.pM = pM; S6.pS = pS; S6.pbest = pbest;
             const int64_t t64 = (nprec + FT64 * R64 - 1) / (FT64 * R64);
             if (launch_sweep64(h, S6, dim3((unsigned)t64, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, 1)) return 1;
             h->stats.pairs_fp64 += nprec * nm;
@@ -1225,14 +1266,40 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             FZB_CUDA(cudaStreamSynchronize(h->stream));
             nsafe64 = hc[3];
         }
-        const int64_t nunsafe = hc[1];
+        nunsafe = hc[1];
         h->stats.objects_fp64 += nunsafe + nprec;
+        if (shard_mode == 1) {
+            // model-sharded pass 1: partials are out; remember the routing for pass 2
+            if (nunsafe > 0 && fzb_generic_shard_pass1_dev(h, d_x, d_xe, d_xm, No, unsafe_list, nunsafe, cfg, d_lmap,
+                                                           d_psum, d_best_idx))
+                return 1;
+            h->shard_valid = true;
+            h->shard_No = No;
+            h->shard_counts[0] = (int)nsafe; h->shard_counts[1] = (int)nunsafe; h->shard_counts[3] = (int)nsafe64;
+            continue;
+        }
+        } else {
+            // model-sharded pass 2: routing lists and local maxima are still in the context; move the reference
+            // of the weights and of the selection cut to the GLOBAL lmap
+            FZB_CHECK(h->shard_valid && h->shard_No == No, "fzb_shard_pass2_dev without a matching pass 1");
+            nsafe = h->shard_counts[0]; nunsafe = h->shard_counts[1]; nsafe64 = h->shard_counts[3];
+            ShardThrParams TP = {};
+            TP.No = nc; TP.g_lmap = d_glmap; TP.lmap_local = lmap_local; TP.M2d_local = M2d_local;
+            TP.log2_wt_thresh = cfg.use_wt_thresh ? std::log2(cfg.wt_thresh) : -INFINITY;
+            TP.M2 = M2; TP.thr2 = thr2; TP.M2d = M2d; TP.thr2d = thr2d;
+            k_shard_thr<<<(unsigned)((nc + 255) / 256), 256, 0, h->stream>>>(TP);
+            fzb_count_launch(h);
+            FZB_CUDA(cudaGetLastError());
+        }
 
         if (nunsafe > 0) {
             // degenerate rows (non-finite sums, NaN-producing models, ...): generic float64 kernel with the
             // reference's exact semantics; objsel holds absolute object indices
-            if (fzb_generic_fit_predict_dev(h, d_x, d_xe, d_xm, No, unsafe_list, nunsafe, cfg, d_pdfs, d_lmap, d_levid,
-                                            d_best_idx, d_best_chi2, d_best_scale))
+            if (shard_mode == 2) {
+                if (fzb_generic_shard_pass2_dev(h, d_x, d_xe, d_xm, No, unsafe_list, nunsafe, cfg, d_glmap, d_glmap, d_pdfs))
+                    return 1;
+            } else if (fzb_generic_fit_predict_dev(h, d_x, d_xe, d_xm, No, unsafe_list, nunsafe, cfg, d_pdfs, d_lmap,
+                                                   d_levid, d_best_idx, d_best_chi2, d_best_scale))
                 return 1;
         }
         if (kde && (nsafe > 0 || nsafe64 > 0)) {
@@ -1259,6 +1326,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             FP.Ng = h->Ng; FP.Ngpad = h->fast_Ngpad; FP.wmax = h->fast_wmax; FP.nslot = F.nslot;
             FP.slot_sidx = F.d_slot_sidx.as<int32_t>(); FP.widths = h->widths.as<int32_t>();
             FP.koff = h->koff.as<int64_t>(); FP.kernels = h->kernels.as<double>(); FP.pdfs = d_pdfs;
+            FP.normalise = (shard_mode == 2) ? 0 : 1;
             size_t smem = sizeof(double) * ((size_t)h->fast_Ngpad + h->Ng);
             FZB_CUDA(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (nsafe > 0) {

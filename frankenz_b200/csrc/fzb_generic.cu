@@ -211,8 +211,10 @@ __device__ void row_to_pdf(const double* row, int64_t n, const int64_t* map, con
             if (out_levid) *out_levid = levid;
         }
     } else {
+        // model-sharded pass 2: weights are exp(l - GLOBAL lmap) on every rank and in every kernel (the common
+        // factor cancels when the summed partials are normalised), selection is wt > wt_thresh
         lmap = *given_lmap;
-        levid = *given_levid;
+        levid = lmap;
         amax = lmap;
     }
     if (out_pdf == nullptr) return;
@@ -579,24 +581,30 @@ int fzb_generic_predict_logwt_dev(fzb_context* h, const double* d_logwt, int64_t
 }
 
 int fzb_generic_shard_pass1_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm, int64_t No,
-                                const FzbConfig& cfg, double* d_pmax, double* d_psum, int64_t* d_pbest) {
+                                const int32_t* d_objsel, int64_t Nsel, const FzbConfig& cfg, double* d_pmax,
+                                double* d_psum, int64_t* d_pbest) {
     GenParams P = {};
     fill_common(h, P, d_x, d_xe, d_xm, No, cfg);
     P.stage = ST_PASS1;
+    P.objsel = d_objsel; P.Nsel = Nsel;
     P.pmax = d_pmax; P.psum = d_psum; P.pbest = d_pbest;
-    h->stats.pairs_fp64 += No * h->Nm;
-    return launch_generic(h, P, No, true);
+    int64_t items = d_objsel ? Nsel : No;
+    h->stats.pairs_fp64 += items * h->Nm;
+    return launch_generic(h, P, items, true);
 }
 
 int fzb_generic_shard_pass2_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm, int64_t No,
-                                const FzbConfig& cfg, const double* d_lmap, const double* d_levid,
-                                double* d_pdf_partial) {
+                                const int32_t* d_objsel, int64_t Nsel, const FzbConfig& cfg, const double* d_lmap,
+                                const double* d_levid, double* d_pdf_partial) {
     if (check_kde(h)) return 2;
+    FZB_CHECK(cfg.use_wt_thresh || !cfg.use_cdf_thresh, "the CDF threshold rule needs all models on one device");
     GenParams P = {};
     fill_common(h, P, d_x, d_xe, d_xm, No, cfg);
     P.stage = ST_PASS2;
+    P.objsel = d_objsel; P.Nsel = Nsel;
     P.kde = make_kde(h, cfg);
     P.pdfs = d_pdf_partial; P.g_lmap = d_lmap; P.g_levid = d_levid;
-    h->stats.pairs_fp64 += No * h->Nm;
-    return launch_generic(h, P, No, true);
+    int64_t items = d_objsel ? Nsel : No;
+    h->stats.pairs_fp64 += items * h->Nm;
+    return launch_generic(h, P, items, true);
 }

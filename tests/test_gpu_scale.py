@@ -164,3 +164,44 @@ def test_float64_sweep_route_matches_generic(c3):
         assert np.max(np.sum(np.abs(p[sub] - p64), axis=1)) <= 1e-5
         assert np.all(np.abs(lm[sub] - lm64) <= 1e-5 * np.maximum(1, np.abs(lm64)))
         assert np.all(np.abs(le[sub] - le64) <= 1e-5 * np.maximum(1, np.abs(le64)))
+
+
+def test_model_sharded_fast_path_matches_unsharded(c3):
+    """Model-sharded passes on the fp32 sweep kernels: three model shards of the C3 grid on one GPU, merged with the
+    arithmetic of frankenz_b200.distributed (collectives replaced by their definitions), against the unsharded run."""
+    import ctypes as C
+    import torch
+    from frankenz_b200 import _lib
+    from frankenz_b200._engine import Engine, make_config
+    from frankenz_b200.distributed import shard_bounds
+    n = 4096
+    x = [torch.from_numpy(np.ascontiguousarray(a[:n])).cuda() for a in (c3["x"], c3["xe"], c3["xm"])]
+    cfg = make_config(LPROB, None)
+    nm = len(c3["models"])
+    engs, parts = [], []
+    for r in range(3):
+        lo, hi = shard_bounds(nm, 3, r)
+        e = Engine(c3["models"][lo:hi], np.zeros((hi - lo, 5)), np.ones((hi - lo, 5)))
+        e.set_kde(c3["labels"][lo:hi], c3["labe"][lo:hi], label_dict=c3["rdict"])
+        pm = torch.empty(n, dtype=torch.float64).cuda()
+        ps = torch.empty(n, dtype=torch.float64).cuda()
+        pb = torch.empty(n, dtype=torch.int64).cuda()
+        _lib.check(e.lib.fzb_shard_pass1_dev(e.h, x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr(), n, C.byref(cfg),
+                                             pm.data_ptr(), ps.data_ptr(), pb.data_ptr()))
+        assert e.stats()["pairs_fp32"] > 0          # the sweep kernels, not the generic path
+        engs.append(e)
+        parts.append((pm, ps, pb + lo))
+    gmax = torch.stack([p[0] for p in parts]).max(dim=0).values
+    s = sum(ps * torch.exp(pm - gmax) for pm, ps, _ in parts)
+    levid = gmax + torch.log(s)
+    assert np.allclose(gmax.cpu().numpy(), c3["lm"][:n], rtol=0, atol=1e-6)
+    assert np.allclose(levid.cpu().numpy(), c3["le"][:n], rtol=0, atol=3e-6)
+    tot = torch.zeros((n, 701), dtype=torch.float64).cuda()
+    for e in engs:
+        part = torch.empty((n, 701), dtype=torch.float64).cuda()
+        _lib.check(e.lib.fzb_shard_pass2_dev(e.h, x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr(), n, C.byref(cfg),
+                                             gmax.data_ptr(), levid.data_ptr(), part.data_ptr()))
+        assert e.stats()["pairs_fp32"] > 0
+        tot += part
+    p = (tot / tot.sum(dim=1, keepdim=True)).cpu().numpy()
+    assert np.max(np.sum(np.abs(p - c3["p"][:n]), axis=1)) <= 3e-6
