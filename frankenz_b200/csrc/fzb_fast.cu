@@ -775,17 +775,23 @@ struct ShardThrParams {
     double log2_wt_thresh;
     float *M2, *thr2;
     double *M2d, *thr2d;
+    double* scale;               // factor applied to the fp32-path histogram of each object by k_finish
 };
 __global__ void k_shard_thr(ShardThrParams P) {
     int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= P.No) return;
     // l_sweep = (lnprob - C_o) * log2(e) with the same per-object constant C_o for every model, so
-    // M_ref = M_local + (lmap_global - lmap_local) * log2(e) makes 2^(l_sweep - M_ref) = exp(lnprob - lmap_global)
-    double mref = P.M2d_local[o] + (P.g_lmap[o] - P.lmap_local[o]) * 1.4426950408889634;
-    P.M2[o] = (float)mref;
+    // M_ref = M_local + (lmap_global - lmap_local) * log2(e) makes 2^(l_sweep - M_ref) = exp(lnprob - lmap_global).
+    // The fp32 sweep keeps its own (exactly representable) local maximum as the reference of its weights and the
+    // factor 2^(M_local - M_ref) <= 1 is applied in float64 when the histogram is convolved; the float64 sweep uses
+    // M_ref directly.
+    const double mloc = P.M2d_local[o];
+    const double mref = mloc + (P.g_lmap[o] - P.lmap_local[o]) * 1.4426950408889634;
+    P.M2[o] = (float)mloc;
     P.thr2[o] = (float)(mref + P.log2_wt_thresh);
     P.M2d[o] = mref;
     P.thr2d[o] = mref + P.log2_wt_thresh;
+    P.scale[o] = exp2((double)(float)mloc - mref);
 }
 
 // ---- histogram (*) kernel, normalise, write -------------------------------------------------------
@@ -801,6 +807,7 @@ struct FinishParams {
     const double* kernels;
     double* pdfs;               // absolute rows
     int normalise;              // 0: write the un-normalised sum (model-sharded partial)
+    const double* scale;        // nullable per-object factor (chunk-local), only with normalise == 0
 };
 
 __global__ void __launch_bounds__(256) k_finish(FinishParams P) {
@@ -835,7 +842,7 @@ __global__ void __launch_bounds__(256) k_finish(FinishParams P) {
     double tot = 0.0;
     for (int i = 0; i < 8; ++i) tot += red[i];
     double* out = P.pdfs + (size_t)(P.o_base + o) * P.Ng;
-    if (!P.normalise) tot = 1.0;
+    if (!P.normalise) tot = P.scale ? 1.0 / P.scale[o] : 1.0;
     for (int g = tid; g < P.Ng; g += 256) out[g] = pdf[g] / tot;
 }
 
@@ -1177,11 +1184,12 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     int32_t* counts = h->misc[3].as<int32_t>();
     if (kde && h->misc[4].reserve((size_t)chunk_pad * hist_stride * 4 + 256)) return 1;
     float* hist = kde ? h->misc[4].as<float>() : nullptr;
-    if (F.aux64.reserve((size_t)chunk_pad * 32 + 64)) return 1;
+    if (F.aux64.reserve((size_t)chunk_pad * 40 + 64)) return 1;
     double* M2d = F.aux64.as<double>();
     double* thr2d = M2d + chunk_pad;
     double* lmap_local = thr2d + chunk_pad;
     double* M2d_local = lmap_local + chunk_pad;
+    double* shard_scale = M2d_local + chunk_pad;
 
     const double chi2_max = env_double("FZB_FAST_CHI2_MAX", 24.0);
     const double snr_max = env_double("FZB_FAST_SNR_MAX", 20000.0);
@@ -1286,7 +1294,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             ShardThrParams TP = {};
             TP.No = nc; TP.g_lmap = d_glmap; TP.lmap_local = lmap_local; TP.M2d_local = M2d_local;
             TP.log2_wt_thresh = cfg.use_wt_thresh ? std::log2(cfg.wt_thresh) : -INFINITY;
-            TP.M2 = M2; TP.thr2 = thr2; TP.M2d = M2d; TP.thr2d = thr2d;
+            TP.M2 = M2; TP.thr2 = thr2; TP.M2d = M2d; TP.thr2d = thr2d; TP.scale = shard_scale;
             k_shard_thr<<<(unsigned)((nc + 255) / 256), 256, 0, h->stream>>>(TP);
             fzb_count_launch(h);
             FZB_CUDA(cudaGetLastError());
@@ -1331,11 +1339,13 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             FZB_CUDA(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (nsafe > 0) {
                 FP.objlist = safe_list;
+                FP.scale = (shard_mode == 2) ? shard_scale : nullptr;
                 k_finish<<<(unsigned)nsafe, 256, smem, h->stream>>>(FP);
                 fzb_count_launch(h);
             }
             if (nsafe64 > 0) {
                 FP.objlist = safe64_list;
+                FP.scale = nullptr;
                 k_finish<<<(unsigned)nsafe64, 256, smem, h->stream>>>(FP);
                 fzb_count_launch(h);
             }
