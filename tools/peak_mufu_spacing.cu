@@ -1,0 +1,59 @@
+// Does the placement of MUFU instructions inside an FFMA2 stream matter?  34 FFMA2 + 6 MUFU per iteration (the
+// k_sweep2 mix per object pair), MUFUs either back to back or evenly spaced; asm volatile keeps program order.
+#include <cstdio>
+#include <cuda_runtime.h>
+typedef unsigned long long u64;
+#define FMA2(a, x, y) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a) : "l"(x), "l"(y))
+#define EX2(m) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(m))
+template <int MODE>
+__global__ void __launch_bounds__(384, 1) k(float* out, int iters) {
+    u64 a[6], x = 0x3f8000013f800001ull, y = 0x3089705f3089705full;
+    float m[6];
+    for (int i = 0; i < 6; ++i) { a[i] = 0x3dcccccd3dcccccdull + i + threadIdx.x; m[i] = -0.001f * (i + 1); }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 4; ++rep) {
+            if (MODE == 0) {            // clustered: 6 MUFU, then 34 FFMA2
+#pragma unroll
+                for (int i = 0; i < 6; ++i) EX2(m[i]);
+#pragma unroll
+                for (int i = 0; i < 34; ++i) FMA2(a[i % 6], x, y);
+            } else if (MODE == 1) {     // spaced: one MUFU every 5-6 FFMA2
+#pragma unroll
+                for (int i = 0; i < 34; ++i) {
+                    FMA2(a[i % 6], x, y);
+                    if (i % 6 == 2 && i / 6 < 6) EX2(m[i / 6]);
+                }
+            } else {                    // pairs: 2 MUFU every 11 FFMA2
+#pragma unroll
+                for (int i = 0; i < 34; ++i) {
+                    FMA2(a[i % 6], x, y);
+                    if (i % 11 == 5) { EX2(m[(i / 11) * 2]); EX2(m[(i / 11) * 2 + 1]); }
+                }
+            }
+        }
+    }
+    u64 s = 0; for (int i = 0; i < 6; ++i) s ^= a[i] + (u64)m[i];
+    if (s == 123) out[0] = 1.f;
+}
+int main() {
+    float* out; cudaMalloc(&out, 256);
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    int blocks = p.multiProcessorCount, iters = 4096;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const char* names[] = {"6 MUFU back to back + 34 FFMA2", "MUFU every ~6 FFMA2", "MUFU pairs every 11 FFMA2"};
+    for (int mode = 0; mode < 3; ++mode) {
+        float best = 1e9;
+        for (int r = 0; r < 4; ++r) {
+            cudaEventRecord(e0);
+            if (mode == 0) k<0><<<blocks, 384>>>(out, iters); else if (mode == 1) k<1><<<blocks, 384>>>(out, iters); else k<2><<<blocks, 384>>>(out, iters);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            if (r && ms < best) best = ms;
+        }
+        double groups = (double)iters * 4 * 12 / 4;   // per SMSP: 12 warps / 4 schedulers = 3 warps, each iters*4 groups
+        printf("%-34s %.3f ms  cycles per (34 FFMA2 + 6 MUFU) group per SMSP: %.1f  (FMA-only floor 68, MUFU-only floor 48)\n",
+               names[mode], best, best * 1e-3 * 1.965e9 / groups);
+    }
+    return 0;
+}
