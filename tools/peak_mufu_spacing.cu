@@ -10,10 +10,14 @@ __global__ void __launch_bounds__(384, 1) k(float* out, int iters) {
     u64 a[6], x = 0x3f8000013f800001ull, y = 0x3089705f3089705full;
     float m[6];
     for (int i = 0; i < 6; ++i) { a[i] = 0x3dcccccd3dcccccdull + i + threadIdx.x; m[i] = -0.001f * (i + 1); }
+    if (MODE == 3) {   // clustered, but the three warps of a scheduler start a third of a loop body apart
+        int g = (threadIdx.x >> 5) >> 2;          // warps g*4 .. g*4+3 share nothing; warp w runs on scheduler w % 4
+        for (int d = 0; d < g * 12; ++d) FMA2(a[d % 6], x, y);
+    }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int rep = 0; rep < 4; ++rep) {
-            if (MODE == 0) {            // clustered: 6 MUFU, then 34 FFMA2
+            if (MODE == 0 || MODE == 3) {            // clustered: 6 MUFU, then 34 FFMA2
 #pragma unroll
                 for (int i = 0; i < 6; ++i) EX2(m[i]);
 #pragma unroll
@@ -41,12 +45,12 @@ int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     int blocks = p.multiProcessorCount, iters = 4096;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const char* names[] = {"6 MUFU back to back + 34 FFMA2", "MUFU every ~6 FFMA2", "MUFU pairs every 11 FFMA2"};
-    for (int mode = 0; mode < 3; ++mode) {
+    const char* names[] = {"6 MUFU back to back + 34 FFMA2", "MUFU every ~6 FFMA2", "MUFU pairs every 11 FFMA2", "back to back, warps staggered at start"};
+    for (int mode = 0; mode < 4; ++mode) {
         float best = 1e9;
         for (int r = 0; r < 4; ++r) {
             cudaEventRecord(e0);
-            if (mode == 0) k<0><<<blocks, 384>>>(out, iters); else if (mode == 1) k<1><<<blocks, 384>>>(out, iters); else k<2><<<blocks, 384>>>(out, iters);
+            if (mode == 0) k<0><<<blocks, 384>>>(out, iters); else if (mode == 1) k<1><<<blocks, 384>>>(out, iters); else if (mode == 2) k<2><<<blocks, 384>>>(out, iters); else k<3><<<blocks, 384>>>(out, iters);
             cudaEventRecord(e1); cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1);
             if (r && ms < best) best = ms;
