@@ -11,7 +11,8 @@ import numpy as np
 from . import _lib
 from ._lib import FzbConfig, FzbFitOut, FzbStats, dptr, f64, iptr
 
-_LPROB_KEYS = ("free_scale", "ignore_model_err", "dim_prior", "ltol", "return_scale", "lnprior", "precision")
+_LPROB_KEYS = ("free_scale", "ignore_model_err", "dim_prior", "ltol", "return_scale", "lnprior", "lnprior_bin",
+               "precision")
 
 
 def default_device():
@@ -84,7 +85,21 @@ class Engine(object):
     __del__ = close
 
     # ---- configuration -------------------------------------------------------------------------
-    def set_lnprior(self, lnprior):
+    def set_lnprior(self, lnprior, bins=None):
+        """Per-model ln-prior [Nmodel], or an object-conditioned table [Nbins, Nmodel] with `bins` [Ndata] giving the
+        row of every object of the next fit call (the built-in replacement for a prior-carrying Python lprob_func)."""
+        _lib.check(self.lib.fzb_set_lnprior_table(self.h, None, 0, 0))
+        if lnprior is not None and np.ndim(lnprior) == 2:
+            if bins is None:
+                raise ValueError("a 2-D `lnprior` table needs `lnprior_bin` (one row index per object)")
+            tab = f64(lnprior)
+            if tab.shape[1] != self.Nm:
+                raise ValueError("lnprior table must have shape (Nbins, Nmodel)")
+            b = np.ascontiguousarray(bins, dtype=np.int32)
+            _lib.check(self.lib.fzb_set_lnprior(self.h, None, 0))
+            _lib.check(self.lib.fzb_set_lnprior_table(self.h, dptr(tab), tab.shape[0], self.Nm))
+            _lib.check(self.lib.fzb_set_object_prior_bins(self.h, b.ctypes.data_as(_lib.c_int32_p), len(b)))
+            return
         if lnprior is None:
             _lib.check(self.lib.fzb_set_lnprior(self.h, None, 0))
         else:

@@ -52,6 +52,8 @@ SIGNATURES = {
     "fzb_measure_peaks": (C.c_int, [_H, C.c_int, c_double_p, c_double_p]),
     "fzb_set_models": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int32]),
     "fzb_set_lnprior": (C.c_int, [_H, c_double_p, C.c_int64]),
+    "fzb_set_lnprior_table": (C.c_int, [_H, c_double_p, C.c_int32, C.c_int64]),
+    "fzb_set_object_prior_bins": (C.c_int, [_H, c_int32_p, C.c_int64]),
     "fzb_set_kde_dict": (C.c_int, [_H, C.c_int32, C.c_int32, c_int32_p, c_int64_p, c_double_p, c_double_p]),
     "fzb_set_labels_dict": (C.c_int, [_H, c_int64_p, c_int64_p, C.c_int64]),
     "fzb_set_kde_grid": (C.c_int, [_H, c_double_p, C.c_int32]),

@@ -64,7 +64,7 @@ class BruteForce(object):
             raise IndexError("tuple index out of range: `track_scale` needs lprob_kwargs free_scale=True and "
                              "return_scale=True")
         eng = self._eng()
-        eng.set_lnprior(lk.get("lnprior", None))
+        eng.set_lnprior(lk.get("lnprior", None), lk.get("lnprior_bin", None))
         return eng, make_config(lk, kde_kwargs, track_scale=track_scale)
 
     def _store(self, res, Ndata):

@@ -57,6 +57,18 @@ int download(fzb_context* h, T* dst, const void* src, size_t n) {
 
 void reset_stats(fzb_context* h) { h->stats = FzbStats{}; }
 
+int check_prior_bins(fzb_context* h, int64_t No) {
+    if (h->prior_nbins > 0 && h->prior_bins_n > 0)
+        FZB_CHECK(h->prior_bins_n == No, "prior bins were set for %lld objects, this call has %lld",
+                  (long long)h->prior_bins_n, (long long)No);
+    h->prior_o0 = 0;
+    return 0;
+}
+void consume_prior_bins(fzb_context* h) {
+    h->prior_bins_n = 0;
+    h->prior_o0 = 0;
+}
+
 int check_models(fzb_context* h) {
     FZB_CHECK(h->Nm > 0 && h->Nf > 0, "no models loaded: call fzb_set_models first");
     return 0;
@@ -325,7 +337,7 @@ int fzb_destroy(fzb_handle h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    DevBuf* bufs[] = {&h->models, &h->models_err, &h->models_mask, &h->lnprior, &h->widths, &h->koff, &h->kernels,
+    DevBuf* bufs[] = {&h->models, &h->models_err, &h->models_mask, &h->lnprior, &h->prior_table, &h->prior_bins, &h->widths, &h->koff, &h->kernels,
                       &h->kcdf, &h->yidx, &h->ysidx, &h->grid, &h->y, &h->ystd, &h->lowers, &h->uppers, &h->rows,
                       &h->knn_feats, &h->knn_cand, &h->knn_redo, &h->fast.recs, &h->fast.recs64, &h->fast.aux64, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
                       &h->fast.d_slot_sidx};
@@ -402,6 +414,38 @@ int fzb_set_lnprior(fzb_handle h, const double* lnprior, int64_t Nm) {
     FZB_CUDA(cudaStreamSynchronize(h->stream));
     h->has_lnprior = true;
     h->fast_dirty = true;
+    return 0;
+}
+
+int fzb_set_lnprior_table(fzb_handle h, const double* table, int32_t nbins, int64_t Nm) {
+    if (use_device(h) || check_models(h)) return 2;
+    if (table == nullptr) {
+        h->prior_nbins = 0;
+        h->prior_bins_n = 0;
+        return 0;
+    }
+    FZB_CHECK(nbins > 0, "nbins must be positive");
+    FZB_CHECK(Nm == h->Nm, "prior table has %lld columns, model set has %lld", (long long)Nm, (long long)h->Nm);
+    if (upload(h, h->prior_table, table, (size_t)nbins * Nm)) return 1;
+    FZB_CUDA(cudaStreamSynchronize(h->stream));
+    h->prior_nbins = nbins;
+    h->prior_bins_n = 0;
+    return 0;
+}
+
+int fzb_set_object_prior_bins(fzb_handle h, const int32_t* bins, int64_t No) {
+    if (use_device(h)) return 2;
+    if (bins == nullptr) {
+        h->prior_bins_n = 0;
+        return 0;
+    }
+    FZB_CHECK(h->prior_nbins > 0, "call fzb_set_lnprior_table first");
+    for (int64_t i = 0; i < No; ++i)
+        FZB_CHECK(bins[i] >= 0 && bins[i] < h->prior_nbins, "object %lld: prior bin %d outside [0, %d)", (long long)i,
+                  bins[i], h->prior_nbins);
+    if (upload(h, h->prior_bins, bins, (size_t)No)) return 1;
+    FZB_CUDA(cudaStreamSynchronize(h->stream));
+    h->prior_bins_n = No;
     return 0;
 }
 
@@ -493,6 +537,7 @@ int fzb_fit(fzb_handle h, const double* data, const double* data_err, const doub
     FZB_CHECK(No >= 0, "negative object count");
     reset_stats(h);
     if (No == 0) return 0;
+    if (check_prior_bins(h, No)) return 2;
     const int64_t Nm = h->Nm;
     const int Nf = h->Nf;
     // chunk the objects so that the staged (chunk x Nm) outputs stay within ~6 GB of HBM
@@ -526,6 +571,7 @@ int fzb_fit(fzb_handle h, const double* data, const double* data_err, const doub
             upload(h, h->obj_in[2], data_mask + o0 * Nf, nin))
             return 1;
         if (dl.fence_compute(last_push)) return 1;     // the previous chunk's outputs have left the device buffers
+        h->prior_o0 = o0;
         if (fzb_generic_fit_dev(h, h->obj_in[0].as<double>(), h->obj_in[1].as<double>(), h->obj_in[2].as<double>(), nc,
                                 *cfg, d_o[0], d_o[1], d_o[2], d_nd, d_o[3], d_o[4], d_o[5]))
             return 1;
@@ -535,6 +581,7 @@ int fzb_fit(fzb_handle h, const double* data, const double* data_err, const doub
         if (out->Ndim && dl.push(out->Ndim + (size_t)o0 * Nm, d_nd, no * sizeof(int64_t), &last_push)) return 1;
     }
     int rc = t.stop();
+    consume_prior_bins(h);
     FZB_CHECK(dl.finish() == 0, "device-to-host copy of the fit arrays failed");
     return rc;
 }
@@ -557,9 +604,11 @@ int fzb_fit_predict_dev(fzb_handle h, const double* d_data, const double* d_err,
     FZB_CHECK(cfg != nullptr, "null config");
     reset_stats(h);
     if (No == 0) return 0;
+    if (check_prior_bins(h, No)) return 2;
     Timer t(h);
     int rc = fit_predict_dev_impl(h, d_data, d_err, d_mask, No, cfg, d_pdfs, d_lmap, d_levid, d_best_idx, d_best_chi2,
                                   d_best_scale);
+    consume_prior_bins(h);
     if (rc) return rc;
     return t.stop();
 }
@@ -574,6 +623,7 @@ int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, co
     FZB_CHECK(No >= 0, "negative object count");
     reset_stats(h);
     if (No == 0) return 0;
+    if (check_prior_bins(h, No)) return 2;
     const int Nf = h->Nf;
     const int Ng = h->Ng;
     size_t nin = (size_t)No * Nf;
@@ -610,6 +660,7 @@ int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, co
     for (int64_t o0 = 0; o0 < No; o0 += chunk, ++c) {
         int64_t nc = std::min(chunk, No - o0);
         int b = (int)(c & 1);
+        h->prior_o0 = o0;
         // device buffer b was last read by the download of chunk c-2 (issued before that of chunk c-1)
         if (pdfs && c >= 2 && dl.fence_compute(push_id[b])) return 1;
         int rc = fit_predict_dev_impl(h, d_x + o0 * Nf, d_xe + o0 * Nf, d_xm + o0 * Nf, nc, cfg,
@@ -620,6 +671,7 @@ int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, co
             return 1;
     }
     FZB_CUDA(cudaEventRecord(h->ev[1], h->stream));
+    consume_prior_bins(h);
     if (download(h, lmap, d_lmap, (size_t)No) || download(h, levid, d_levid, (size_t)No) ||
         download(h, best_idx, d_bi, (size_t)No) || download(h, best_chi2, d_bc, (size_t)No) ||
         download(h, best_scale, d_bs, (size_t)No))
@@ -759,6 +811,7 @@ int fzb_knn_fit(fzb_handle h, const double* qfeats, const double* data, const do
     FZB_CHECK(k > 0 && k <= h->knn_Nm, "k=%d must be in [1, Nmodel=%lld]", k, (long long)h->knn_Nm);
     reset_stats(h);
     if (No == 0) return 0;
+    if (check_prior_bins(h, No)) return 2;
     const int Nf = h->Nf;
     const int64_t W = (int64_t)h->knn_K * k;
     // chunk the objects: 2 int64 + 7 output arrays of width W
@@ -786,6 +839,7 @@ int fzb_knn_fit(fzb_handle h, const double* qfeats, const double* data, const do
         if (upload(h, h->obj_in[0], data + o0 * Nf, nin) || upload(h, h->obj_in[1], data_err + o0 * Nf, nin) ||
             upload(h, h->obj_in[2], data_mask + o0 * Nf, nin) || upload(h, h->misc[5], qfeats + o0 * Nf, nin))
             return 1;
+        h->prior_o0 = o0;
         int64_t* d_idx = h->out_i64[0].as<int64_t>();
         int64_t* d_nb = h->misc[3].as<int64_t>();
         int64_t* d_nn = h->misc[4].as<int64_t>();
@@ -803,6 +857,7 @@ int fzb_knn_fit(fzb_handle h, const double* qfeats, const double* data, const do
             return 1;
         FZB_CUDA(cudaStreamSynchronize(h->stream));
     }
+    consume_prior_bins(h);
     return t.stop();
 }
 

@@ -98,6 +98,11 @@ struct fzb_context {
     int Nf = 0;
     DevBuf models, models_err, models_mask, lnprior;
     bool has_lnprior = false;
+    // object-conditioned tabulated prior: table [nbins][Nm]; bins of the objects of the next call
+    DevBuf prior_table, prior_bins;
+    int prior_nbins = 0;
+    int64_t prior_bins_n = 0;      // 0: no bins pending
+    int64_t prior_o0 = 0;          // first object of the chunk being processed (host API chunking)
     bool mask_all_one = false;     // every model mask entry == 1
     bool err_all_zero = false;     // every model error == 0
     bool models_finite = false;

@@ -1331,6 +1331,7 @@ bool fzb_fast_supported(const fzb_context* h, const FzbConfig& cfg) {
     int mode = mode_of(cfg);
     if (mode < 0) return false;                                  // iterated free scale: generic path
     if (mode == FM_FX1 && !cfg.dim_prior) return false;          // per-pair sum of ln(var): generic path
+    if (h->prior_nbins > 0 && h->prior_bins_n > 0) return false;   // object-conditioned prior table: generic path
     if (h->Nf < 4 || h->Nf > 6) return false;
     if (!h->mask_all_one || !h->models_finite) return false;     // model masks: generic path
     if (h->Nm >= (int64_t)1 << 31) return false;

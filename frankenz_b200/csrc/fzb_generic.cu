@@ -44,6 +44,8 @@ struct GenParams {
     const double *x, *xe, *xm;        // objects (No x Nf)
     const double *m, *me, *mm;        // models (Nm x Nf)
     const double* lnprior;            // per model, nullable
+    const double* prior_table;        // [nbins][Nm], nullable: row prior_bins[o - prior_o0] replaces lnprior
+    const int32_t* prior_bins;
     int64_t No, Nm;
     int Nf;
     int free_scale, ime, iterate, dim_prior, track_scale;
@@ -375,14 +377,15 @@ __global__ void __launch_bounds__(GT) k_generic(GenParams P) {
             }
         }
         // finalise: dimensionality prior, prior, outputs, arg-max
+        const double* lnp = P.prior_table ? P.prior_table + (size_t)P.prior_bins[o] * P.Nm : P.lnprior;
         double bv = -CUDART_INF;
         long long bi = 0x7fffffffffffffffll;
         for (int64_t c = tid; c < n; c += GT) {
             int64_t mj = map ? map[c] : c;
             double ndim = r_ndim[c], chi2 = r_chi2[c], lnl = r_lnl[c];
             if (P.dim_prior) lnl = chi2_logpdf(chi2, P.free_scale ? 0.5 * (ndim - 1.0) : 0.5 * ndim);
-            double lp = P.lnprior ? P.lnprior[mj] : 0.0;
-            double lpost = P.lnprior ? lnl + lp : lnl;
+            double lp = lnp ? lnp[mj] : 0.0;
+            double lpost = lnp ? lnl + lp : lnl;
             r_lnl[c] = lpost;
             if (lpost > bv) { bv = lpost; bi = c; }
             if (P.stage == ST_FIT) {
@@ -508,6 +511,10 @@ void fill_common(fzb_context* h, GenParams& P, const double* x, const double* xe
     P.me = h->models_err.as<double>();
     P.mm = h->models_mask.as<double>();
     P.lnprior = h->has_lnprior ? h->lnprior.as<double>() : nullptr;
+    if (h->prior_nbins > 0 && h->prior_bins_n > 0) {
+        P.prior_table = h->prior_table.as<double>();
+        P.prior_bins = h->prior_bins.as<int32_t>() + h->prior_o0;
+    }
     P.No = No; P.Nm = h->Nm; P.Nf = h->Nf;
     P.free_scale = cfg.free_scale; P.ime = cfg.ignore_model_err != 0; P.dim_prior = cfg.dim_prior;
     P.iterate = cfg.free_scale && cfg.ignore_model_err != 1;   // pdf.py:197: `ignore_model_err is not True`

@@ -108,7 +108,7 @@ class NearestNeighbors(object):
                              "return_scale=True")
         if rstate is None:
             rstate = np.random
-        self._engine.set_lnprior(lk.get("lnprior", None))
+        self._engine.set_lnprior(lk.get("lnprior", None), lk.get("lnprior_bin", None))
         cfg = make_config(lk, None, track_scale=track_scale)
         # the reference cleans each object only inside logprob, i.e. AFTER its Monte-Carlo draw
         q = self._query_features(data, data_err, rstate)

@@ -102,6 +102,13 @@ int fzb_set_models(fzb_handle h, const double* models, const double* models_err,
  * lprob_func).  NULL => zeros (pdf.py:406). host, [Nm]. */
 int fzb_set_lnprior(fzb_handle h, const double* lnprior, int64_t Nm);
 
+/* Object-conditioned tabulated prior: lnprior of model j for an object in bin b is
+ * table[b*Nm + j] (e.g. ln P(z_j, t_j | magnitude bin), the built-in replacement for demo 2's Python lprob_bpz,
+ * demos/2 cell 69).  fzb_set_object_prior_bins gives the bin of every object of the NEXT fit / fit_predict /
+ * knn_fit call (host int32 [No], values in [0, nbins)); it is consumed by that call.  NULL table / bins clear it. */
+int fzb_set_lnprior_table(fzb_handle h, const double* table, int32_t nbins, int64_t Nm);
+int fzb_set_object_prior_bins(fzb_handle h, const int32_t* bins, int64_t No);
+
 /* Dictionary KDE tables: what PDFDict.__init__ tabulates (pdf.py:800-819).
  * widths[Ndict]; koff[Ndict+1] offsets into kernels/kcdf (each kernel has 2*w+1 entries). */
 int fzb_set_kde_dict(fzb_handle h, int32_t Ngrid, int32_t Ndict, const int32_t* widths,

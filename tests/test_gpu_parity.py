@@ -276,3 +276,37 @@ def test_model_sharded_two_shards_one_gpu(fz, precision):
         tot += part
     p = (tot / tot.sum(dim=1, keepdim=True)).cpu().numpy()
     assert l1(p, g["pdf_dict"]) <= tol
+
+
+def test_object_conditioned_prior_table(fz):
+    """lnprior[i, j] = table[bin_i, j] (the built-in form of demo 2's Python lprob_bpz)."""
+    g = golden("bruteforce_c1small.npz")
+    _, rdict = _dict(fz)
+    m, me, mm = g["models"], g["models_err"], g["models_mask"]
+    x, xe, xm = g["data"], g["data_err"], g["data_mask"]
+    rs = np.random.RandomState(8)
+    table = rs.normal(size=(4, len(m))) * 2.0
+    table[2, ::7] = -np.inf                       # some models excluded for bin 2
+    bins = rs.randint(0, 4, size=len(x))
+    bf = fz.BruteForce(m, me, mm)
+    kw = dict(lnprior=table, lnprior_bin=bins)
+    bf.fit(x.copy(), xe.copy(), xm.copy(), lprob_kwargs=kw, verbose=False)
+    kd = fo.KernelDict(np.arange(0, 7 + 1e-5, 0.01), np.linspace(0.005, 2, 500))
+    for i in (0, 5, 17, 31):
+        r = fo.logprob(x[i].copy(), xe[i].copy(), xm[i].copy(), m, me, mm, lnprior=table[bins[i]])
+        assert np.array_equal(bf.fit_lnprior[i], table[bins[i]])
+        assert same_special(bf.fit_lnprob[i], r[2]) and max_rel(bf.fit_lnprob[i], r[2]) <= REL64
+        assert max_rel(bf.fit_lnlike[i], r[1]) <= REL64
+    p, (lm, le) = bf.fit_predict(x.copy(), xe.copy(), xm.copy(), g["labels"], g["label_errs"], label_dict=rdict,
+                                 lprob_kwargs=kw, return_gof=True, verbose=False, save_fits=False)
+    for i in (0, 5, 17, 31):
+        r = fo.logprob(x[i].copy(), xe[i].copy(), xm[i].copy(), m, me, mm, lnprior=table[bins[i]])
+        yi, si = kd.fit(g["labels"], g["label_errs"])
+        po, lmo, leo = fo.weights_to_pdf(r[2], g["labels"], g["label_errs"], yi, si, label_dict=kd)
+        assert np.sum(np.abs(p[i] - po)) <= 1e-9 and abs(lm[i] - lmo) <= 1e-9 * max(1, abs(lmo))
+        assert abs(le[i] - leo) <= 1e-9 * max(1, abs(leo))
+    # the bins are consumed by the call: a second call without them uses no prior
+    bf.fit(x.copy(), xe.copy(), xm.copy(), verbose=False)
+    assert np.all(bf.fit_lnprior == 0)
+    with pytest.raises(ValueError):
+        bf.fit(x.copy(), xe.copy(), xm.copy(), lprob_kwargs=dict(lnprior=table), verbose=False)
