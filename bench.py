@@ -290,7 +290,7 @@ def main():
     dom_ms = max(ms_scan, ms_acc)
     dom_pairs = float(no) * nm if ms_scan >= ms_acc else float(no - n64) * nm
     achieved = FLOPS_PER_PAIR * dom_pairs / (dom_ms * 1e-3) / 1e12
-    roofline = {"bound": "fp32_fma", "kernel": "k_sweep<pass %d>" % (1 if ms_scan >= ms_acc else 2),
+    roofline = {"bound": "fp32_fma", "kernel": "k_sweep2<pass %d>" % (1 if ms_scan >= ms_acc else 2),
                 "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                 "peak_source": "fzb_measure_peaks (dependency-free FFMA loop, this run; MEASURED_PEAKS.json has no "
                                "fp32 entry)",
