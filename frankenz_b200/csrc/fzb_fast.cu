@@ -1338,6 +1338,7 @@ bool fzb_fast_supported(const fzb_context* h, const FzbConfig& cfg) {
     if (h->kde_mode == FZB_KDE_GRID) return false;               // exact-Gaussian KDE: generic path
     if (h->kde_mode == FZB_KDE_DICT) {
         if (!h->labels_dict_set) return false;
+        if (h->Ng > 8192) return false;                              // k_finish keeps histogram + PDF in shared memory
         if (!cfg.use_wt_thresh && cfg.use_cdf_thresh) return false;   // CDF rule needs a sort: generic path
     }
     if (cfg.use_wt_thresh && !(cfg.wt_thresh > 0.0 && cfg.wt_thresh < 1.0)) return false;
