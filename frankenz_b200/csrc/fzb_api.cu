@@ -379,14 +379,16 @@ int fzb_set_models(fzb_handle h, const double* models, const double* models_err,
     FZB_CHECK(Nm > 0 && Nf > 0, "empty model set (Nm=%lld, Nf=%d)", (long long)Nm, Nf);
     FZB_CHECK(Nf <= FZB_MAXF, "Nf=%d exceeds the supported maximum %d", Nf, FZB_MAXF);
     size_t n = (size_t)Nm * Nf;
-    bool all_one = true, all_zero = true, finite = true, f32_exact = true;
+    bool all_one = true, all_zero = true, finite = true, f32_exact = true, binary = true;
     for (size_t i = 0; i < n; ++i) {
         all_one &= (models_mask[i] == 1.0);
+        binary &= (models_mask[i] == 1.0 || models_mask[i] == 0.0);
         all_zero &= (models_err[i] == 0.0);
         finite &= std::isfinite(models[i]) && std::isfinite(models_err[i]);
         f32_exact &= ((double)(float)models[i] == models[i]);
     }
     h->mask_all_one = all_one;
+    h->mask_binary = binary;
     h->err_all_zero = all_zero;
     h->models_finite = finite;
     h->models_f32_exact = f32_exact;

@@ -104,6 +104,7 @@ struct fzb_context {
     int64_t prior_bins_n = 0;      // 0: no bins pending
     int64_t prior_o0 = 0;          // first object of the chunk being processed (host API chunking)
     bool mask_all_one = false;     // every model mask entry == 1
+    bool mask_binary = false;      // every model mask entry is 0 or 1
     bool err_all_zero = false;     // every model error == 0
     bool models_finite = false;
     bool models_f32_exact = false; // every model flux is exactly representable in float32

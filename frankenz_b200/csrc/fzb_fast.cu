@@ -94,6 +94,9 @@ struct SweepParams {
     const float* ox;      // FS0: d*w
     const float* odl;     // 2 * d_lo
     const float* oA;      // [No_pad] (dof/2 - 1) or 0
+    const int32_t* obits; // [No_pad] band-mask bits of the object (model-mask variant)
+    float Atab[16];       // model-mask variant: (dof/2 - 1) by pair dimensionality
+    float Ktab[16];       //                     ndim-dependent constant of the ln-likelihood, log2 units
     int64_t No_pad;
     int64_t No;           // objects in this launch (pass 1) / entries of objlist (pass 2)
     // models
@@ -158,9 +161,10 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b) {
     return d;
 }
 
-__host__ __device__ constexpr int rec2_floats(int nf, int mode, bool mlo) {
-    // pairs (v, v): m[nf], aux[nf] (FS0: m^2, FX1: err^2), ml[nf] (MLO); tail: prior2 x2, invnorm x2, bin
-    int n = 2 * nf * (1 + ((mode == FM_FX0) ? 0 : 1) + (mlo ? 1 : 0)) + 5;
+__host__ __device__ constexpr int rec2_floats(int nf, int mode, bool mlo, bool mm = false) {
+    // pairs (v, v): m[nf], aux[nf] (FS0: m^2, FX1: err^2), ml[nf] (MLO), k[nf] (MM: band mask 0/1);
+    // tail: prior2 x2, invnorm x2, bin, (MM: mask bits)
+    int n = 2 * nf * (1 + ((mode == FM_FX0) ? 0 : 1) + (mlo ? 1 : 0) + (mm ? 1 : 0)) + 5 + (mm ? 1 : 0);
     return (n + 3) / 4 * 4;
 }
 
@@ -173,9 +177,10 @@ struct ObjPack {     // two objects (lo half, hi half)
     f2 A;
 };
 
-template <int NF, int MODE, bool MLO>
+template <int NF, int MODE, bool MLO, bool MM = false>
 __device__ __forceinline__ f2 pack_chi2(const ObjPack<NF, MODE>& o, const f2* __restrict__ m,
-                                        const f2* __restrict__ aux, const f2* __restrict__ ml) {
+                                        const f2* __restrict__ aux, const f2* __restrict__ ml,
+                                        const f2* __restrict__ km = nullptr) {
     f2 ns = 0;   // minus the optimal scale (FS0)
     if (MODE == FM_FS0) {
         f2 inter = mul2(o.x[0], m[0]);
@@ -201,6 +206,7 @@ __device__ __forceinline__ f2 pack_chi2(const ObjPack<NF, MODE>& o, const f2* __
         } else {
             w = o.w[b];
         }
+        if (MM) w = mul2(w, km[b]);             // model band mask (the record stores m = m^2 = 0 for masked bands)
         f2 t = mul2(r, w);
         f2 u = add2(r, o.dl[b]);                // chi2 + first-order lo correction: sum t * (r + 2 d_lo)
         if (b == 0) {
@@ -215,19 +221,26 @@ __device__ __forceinline__ f2 pack_chi2(const ObjPack<NF, MODE>& o, const f2* __
     return chi2;
 }
 
-template <int NF, int MODE, bool DP, bool MLO, bool PRIOR, int R, int PASS>
+template <int NF, int MODE, bool DP, bool MLO, bool PRIOR, int R, int PASS, bool MM = false>
 __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P) {
     static_assert(R % 2 == 0, "objects come in packed pairs");
     constexpr int FT2 = ft2_of(R);
     constexpr int NP = R / 2;
-    constexpr int REC = rec2_floats(NF, MODE, MLO);
+    constexpr int REC = rec2_floats(NF, MODE, MLO, MM);
     constexpr int AUXOFF = 2 * NF;
     constexpr int MLOFF = 2 * NF * (1 + ((MODE == FM_FX0) ? 0 : 1));
-    constexpr int TAILOFF = MLOFF + (MLO ? 2 * NF : 0);   // prior2 x2, invnorm x2, bin
+    constexpr int KMOFF = MLOFF + (MLO ? 2 * NF : 0);      // band-mask pairs (MM)
+    constexpr int TAILOFF = KMOFF + (MM ? 2 * NF : 0);     // prior2 x2, invnorm x2, bin, (mask bits)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage = reinterpret_cast<float*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * TM * REC * sizeof(float));
+    // MM: the dimensionality of a pair is popc(object bits & model bits); (dof/2 - 1) and the ndim-dependent constant
+    // of the ln-likelihood come from two small shared-memory tables
+    float* sA = reinterpret_cast<float*>(bars + NSTAGE);
+    float* sK = sA + 16;
     const int tid = threadIdx.x;
+    if (MM && tid < 16) { sA[tid] = P.Atab[tid]; sK[tid] = P.Ktab[tid]; }
+    int obits[R];
 
     ObjPack<NF, MODE> ob[NP];
     int oidx[R];
@@ -257,6 +270,7 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
             Sd[r] = 0.0;
             Mfl[r] = -FLT_MAX;
             thr[r] = (PASS == 2) ? P.thr2[oo[h]] : 0.f;
+            obits[r] = MM ? P.obits[oo[h]] : 0;
         }
 #pragma unroll
         for (int b = 0; b < NF; ++b) {
@@ -324,23 +338,35 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
                     cur_bin = bin;
                 }
             }
-            f2 m[NF], aux[NF], ml[NF];
+            f2 m[NF], aux[NF], ml[NF], km[NF];
 #pragma unroll
             for (int b = 0; b < NF; ++b) {
                 m[b] = rec2[b];
                 aux[b] = (MODE == FM_FX0) ? 0 : rec2[AUXOFF / 2 + b];
                 ml[b] = MLO ? rec2[MLOFF / 2 + b] : 0;
+                km[b] = MM ? rec2[KMOFF / 2 + b] : 0;
             }
+            const int mbits = MM ? __float_as_int(rec[TAILOFF + 5]) : 0;
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
-                f2 chi2 = pack_chi2<NF, MODE, MLO>(ob[p], m, aux, ml);
+                f2 chi2 = pack_chi2<NF, MODE, MLO, MM>(ob[p], m, aux, ml, km);
                 // ln-likelihood in log2 units up to a per-object constant.  For FS0 / FX0 the factor -log2(e)/2 is
                 // folded into the object weights (k_prep_objects), so `chi2` already holds c = -chi2*log2(e)/2 and
                 // l = (dof/2-1) log2|c| + c (+ prior): one packed FMA.  FX1 weights are per pair, so c is formed here.
                 f2 c = (MODE == FM_FX1) ? mul2(chi2, kNegHalfLog2e) : chi2;
                 if (PRIOR) c = add2(c, prior2);
                 f2 l = c;
-                if (DP) {
+                if (MM) {
+                    const int n0 = __popc(obits[2 * p] & mbits), n1 = __popc(obits[2 * p + 1] & mbits);
+                    f2 cc = (MODE == FM_FX1) ? mul2(chi2, kNegHalfLog2e) : chi2;
+                    // a free-scale fit through a single common band is exact: chi2 = 0 in the reference (float64),
+                    // which then produces inf / NaN under dim_prior; fp32 leaves a rounding residue, so force it
+                    if (MODE == FM_FS0) cc = pack2(n0 <= 1 ? 0.f : lo2(cc), n1 <= 1 ? 0.f : hi2(cc));
+                    c = add2(add2(cc, prior2), pack2(sK[n0], sK[n1]));
+                    l = c;
+                    if (DP)
+                        l = fma2(pack2(sA[n0], sA[n1]), pack2(fast_lg2(fabsf(lo2(cc))), fast_lg2(fabsf(hi2(cc)))), c);
+                } else if (DP) {
                     f2 cc = (MODE == FM_FX1 || PRIOR) ? ((MODE == FM_FX1) ? mul2(chi2, kNegHalfLog2e) : chi2) : c;
                     l = fma2(ob[p].A, pack2(fast_lg2(fabsf(lo2(cc))), fast_lg2(fabsf(hi2(cc)))), c);
                 }
@@ -927,12 +953,15 @@ struct PrepParams {
     int64_t No, No_pad;
     int Nf, mode, free_scale, dim_prior;
     float *od, *ow, *ox, *odl, *oA, *osnr;
+    int32_t* obits;
 };
 
 __global__ void k_prep_objects(PrepParams P) {
     int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= P.No_pad) return;
     double ndim = 0.0, snr2 = 0.0;
+    int bits = 0;
+    bool binary = true;
     for (int b = 0; b < P.Nf; ++b) {
         double d = 0.0, e = 1.0, k = 0.0;
         if (o < P.No) {
@@ -958,12 +987,26 @@ __global__ void k_prep_objects(PrepParams P) {
             P.ox[q] = (float)(d * wk);
         }
         ndim += k;
+        if (k != 0.0) bits |= 1 << b;
+        if (k != 0.0 && k != 1.0) binary = false;
         double sn = (k != 0.0) ? fabs(d) / e : 0.0;
         snr2 += sn * sn;
     }
     double a = P.free_scale ? 0.5 * (ndim - 1.0) : 0.5 * ndim;
     P.oA[o] = P.dim_prior ? (float)(a - 1.0) : 0.f;
-    P.osnr[o] = (float)sqrt(snr2);
+    // a non-binary object mask makes the pair dimensionality non-integer: leave such objects to the float64 kernels
+    P.osnr[o] = binary ? (float)sqrt(snr2) : CUDART_INF_F;
+    if (P.obits) P.obits[o] = bits;
+}
+
+// ndim-dependent part of the ln-likelihood in sweep units (log2, chi2 scaled by log2(e)/2), used when the pair
+// dimensionality varies from model to model (model masks):
+//   dim_prior: -(lgamma(a) + a ln2) log2(e) - (a - 1) log2(log2(e)/2),  a = dof/2       (pdf.py:93 / :229)
+//   else     : -ndim ln(2 pi)/2 log2(e)                                                  (pdf.py:96-98)
+__host__ __device__ inline double fzb_ktab(double ndim, int free_scale, int dim_prior) {
+    if (!dim_prior) return -0.5 * ndim * 1.83787706640934548356 * 1.4426950408889634;
+    const double a = free_scale ? 0.5 * (ndim - 1.0) : 0.5 * ndim;
+    return -(lgamma(a) + a * 0.69314718055994530942) * 1.4426950408889634 - (a - 1.0) * log2(0.72134752044448170368);
 }
 
 // ---- merge of the model splits + exact re-evaluation of the best pair + routing -------------------
@@ -981,6 +1024,7 @@ struct MergeParams {
     double log2_wt_thresh;              // log2(wt_thresh) or -inf
     double chi2_max, snr_max, consist_tol;
     int force_fp32;
+    int mmv;                            // model-mask variant: the sweep value includes the ndim-dependent constant
     int stage;                          // 0: after the fp32 sweep (all objects); 1: after the float64 sweep (in_list)
     const int32_t* in_list;
     int64_t n_in;
@@ -1042,6 +1086,7 @@ __global__ void k_merge(MergeParams P) {
     const double cc = 0.72134752044448170368 * st.chi2;
     double vary = -cc + lp * 1.4426950408889634;
     if (P.dim_prior && (a - 1.0) != 0.0) vary += (a - 1.0) * log2(cc);
+    if (P.mmv) vary += fzb_ktab(st.ndim, P.free_scale, P.dim_prior);
     const bool finite = !bad && isfinite(M) && M > -1e300 && isfinite(S) && S >= 0.5 && isfinite(lmap);
     const bool consistent = fabs(vary - M) <= P.consist_tol * fmax(1.0, fabs(vary));
     bool precise = consistent;
@@ -1156,7 +1201,8 @@ struct RecParams {
     const int32_t* bins;
     const float* invnorm;
     int64_t nm;
-    int Nf, mode, rec, mlo, packed;
+    int Nf, mode, rec, mlo, packed, mm;
+    const double* mask;     // model masks (MM)
     float* recs;
 };
 
@@ -1170,8 +1216,16 @@ __global__ void k_build_records(RecParams P) {
         const int nf = P.Nf;
         const int auxoff = 2 * nf, mloff = 2 * nf * (1 + ((P.mode == FM_FX0) ? 0 : 1));
         const float sgn = (P.mode == FM_FS0) ? 1.f : -1.f;
+        const int kmoff = mloff + (P.mlo ? 2 * nf : 0);
+        int mbits = 0;
         for (int b = 0; b < nf; ++b) {
             double v = P.m[j * nf + b];
+            if (P.mm) {
+                const bool on = P.mask[j * nf + b] != 0.0;
+                r[kmoff + 2 * b] = r[kmoff + 2 * b + 1] = on ? 1.f : 0.f;
+                if (on) mbits |= 1 << b;
+                else v = 0.0;          // masked band: m = m^2 = 0 drops it from the scale; the mask pair drops it from chi2
+            }
             float hi = (float)v;
             r[2 * b] = r[2 * b + 1] = sgn * hi;
             if (P.mlo) r[mloff + 2 * b] = r[mloff + 2 * b + 1] = sgn * 2.f * (float)(v - (double)hi);
@@ -1181,11 +1235,13 @@ __global__ void k_build_records(RecParams P) {
                 r[auxoff + 2 * b] = r[auxoff + 2 * b + 1] = (float)(e * e);
             }
         }
-        int tail = mloff + (P.mlo ? 2 * nf : 0);
+        int tail = kmoff + (P.mm ? 2 * nf : 0);
         r[tail] = r[tail + 1] = P.lnprior ? (float)(P.lnprior[j] * 1.4426950408889634) : 0.f;
         r[tail + 2] = r[tail + 3] = P.invnorm ? P.invnorm[p] : 0.f;
         r[tail + 4] = __int_as_float(P.bins ? P.bins[p] : -1);
-        for (int i = tail + 5; i < P.rec; ++i) r[i] = 0.f;
+        int used = tail + 5;
+        if (P.mm) r[used++] = __int_as_float(mbits);
+        for (int i = used; i < P.rec; ++i) r[i] = 0.f;
         return;
     }
 }
@@ -1201,10 +1257,22 @@ double env_double(const char* name, double dflt) {
     return v ? atof(v) : dflt;
 }
 
+template <int NF, int MODE, bool DP, int R, int PASS>
+int launch_sweep2_mm(fzb_context* h, const SweepParams& P, dim3 grid) {
+    constexpr int REC = rec2_floats(NF, MODE, true, true);
+    size_t smem = (size_t)NSTAGE * TM * REC * sizeof(float) + NSTAGE * sizeof(uint64_t) + 128;
+    auto kern = k_sweep2<NF, MODE, DP, true, true, R, PASS, true>;
+    FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, ft2_of(R), smem, h->stream>>>(P);
+    fzb_count_launch(h);
+    FZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
 template <int NF, int MODE, bool DP, bool MLO, int R, int PASS>
 int launch_sweep2_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prior) {
     constexpr int REC = rec2_floats(NF, MODE, MLO);
-    size_t smem = (size_t)NSTAGE * TM * REC * sizeof(float) + NSTAGE * sizeof(uint64_t);
+    size_t smem = (size_t)NSTAGE * TM * REC * sizeof(float) + NSTAGE * sizeof(uint64_t) + 128;
     if (prior) {
         auto kern = k_sweep2<NF, MODE, DP, MLO, true, R, PASS>;
         FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1239,6 +1307,14 @@ int launch_sweep3_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prior)
 
 template <int NF, int MODE, bool DP, bool MLO>
 int launch_sweep_r(fzb_context* h, const SweepParams& P, dim3 grid, int R, int pass) {
+    if constexpr (MLO) {
+        if (P.obits != nullptr) {   // model-mask variant
+            if (pass == 1) return (R == -4) ? launch_sweep2_mm<NF, MODE, DP, 4, 1>(h, P, grid)
+                                            : launch_sweep2_mm<NF, MODE, DP, 2, 1>(h, P, grid);
+            return (R == -4) ? launch_sweep2_mm<NF, MODE, DP, 4, 2>(h, P, grid)
+                             : launch_sweep2_mm<NF, MODE, DP, 2, 2>(h, P, grid);
+        }
+    }
     if constexpr (!MLO && MODE != FM_FX1) {
         // hand-scheduled software pipeline (MUFUs spaced through the FMA stream): opt-in experiment.  ptxas re-clusters
         // the MUFUs (it hoists them as early as their operands allow), so as compiled it is ~8 % slower than k_sweep2.
@@ -1333,7 +1409,7 @@ bool fzb_fast_supported(const fzb_context* h, const FzbConfig& cfg) {
     if (mode == FM_FX1 && !cfg.dim_prior) return false;          // per-pair sum of ln(var): generic path
     if (h->prior_nbins > 0 && h->prior_bins_n > 0) return false;   // object-conditioned prior table: generic path
     if (h->Nf < 4 || h->Nf > 6) return false;
-    if (!h->mask_all_one || !h->models_finite) return false;     // model masks: generic path
+    if (!(h->mask_all_one || h->mask_binary) || !h->models_finite) return false;   // non-binary model masks: generic path
     if (h->Nm >= (int64_t)1 << 31) return false;
     if (h->kde_mode == FZB_KDE_GRID) return false;               // exact-Gaussian KDE: generic path
     if (h->kde_mode == FZB_KDE_DICT) {
@@ -1394,9 +1470,10 @@ static int fast_prepare_mode(fzb_context* h, int mode) {
     }
     F.nf = nf;
     F.nm = nm;
-    const bool mlo = !h->models_f32_exact;
+    const bool mm = !h->mask_all_one;                  // model masks present (binary, checked by fzb_fast_supported)
+    const bool mlo = mm || !h->models_f32_exact;      // the mask variant is only instantiated with lo parts + prior slot
     const bool packed = true;
-    F.rec = rec2_floats(nf, mode, mlo);
+    F.rec = rec2_floats(nf, mode, mlo, mm);
     h->fast_packed = packed;
     if (F.recs.reserve((size_t)nm * F.rec * sizeof(float) + 64) || F.perm.reserve((size_t)nm * 4 + 16)) return 1;
     FZB_CUDA(cudaMemcpyAsync(F.perm.p, perm.data(), (size_t)nm * 4, cudaMemcpyHostToDevice, h->stream));
@@ -1417,6 +1494,7 @@ static int fast_prepare_mode(fzb_context* h, int mode) {
     R.bins = kde ? F.bins.as<int32_t>() : nullptr;
     R.invnorm = kde ? F.invnorm.as<float>() : nullptr;
     R.nm = nm; R.Nf = nf; R.mode = mode; R.rec = F.rec; R.mlo = mlo ? 1 : 0; R.packed = packed ? 1 : 0;
+    R.mm = mm ? 1 : 0; R.mask = h->models_mask.as<double>();
     R.recs = F.recs.as<float>();
     k_build_records<<<(unsigned)((nm + 255) / 256), 256, 0, h->stream>>>(R);
     fzb_count_launch(h);
@@ -1492,7 +1570,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     // scratch: object SoA (4 x nf + 2 planes), partials, routing
     DevBuf& so = h->misc[0];
     size_t plane = (size_t)chunk_pad * sizeof(float);
-    if (so.reserve(plane * (4 * nf + 2 + 2) + 256)) return 1;
+    if (so.reserve(plane * (4 * nf + 2 + 2 + 1) + 256)) return 1;
     float* base = so.as<float>();
     float* od = base;
     float* ow = od + (size_t)nf * chunk_pad;
@@ -1502,6 +1580,8 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     float* osnr = oA + chunk_pad;
     float* M2 = osnr + chunk_pad;
     float* thr2 = M2 + chunk_pad;
+    int32_t* obits = reinterpret_cast<int32_t*>(thr2 + chunk_pad);
+    const bool mm = !h->mask_all_one;
     if (h->misc[1].reserve((size_t)nsplit * chunk_pad * 20 + 256)) return 1;
     double* pS = h->misc[1].as<double>();
     double* pM = pS + (size_t)nsplit * chunk_pad;
@@ -1524,7 +1604,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
 
     const double chi2_max = env_double("FZB_FAST_CHI2_MAX", 24.0);
     const double snr_max = env_double("FZB_FAST_SNR_MAX", 20000.0);
-    const bool use_sweep64 = getenv("FZB_NO_SWEEP64") == nullptr;
+    const bool use_sweep64 = getenv("FZB_NO_SWEEP64") == nullptr && !mm;   // k_sweep64 has no model-mask variant yet
 
     float ms;
     for (int64_t o0 = 0; o0 < No; o0 += chunk) {
@@ -1534,7 +1614,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         PP.x = d_x + o0 * nf; PP.xe = d_xe + o0 * nf; PP.xm = d_xm + o0 * nf;
         PP.No = nc; PP.No_pad = nc_pad; PP.Nf = nf; PP.mode = mode;
         PP.free_scale = cfg.free_scale; PP.dim_prior = cfg.dim_prior;
-        PP.od = od; PP.ow = ow; PP.ox = ox; PP.odl = odl; PP.oA = oA; PP.osnr = osnr;
+        PP.od = od; PP.ow = ow; PP.ox = ox; PP.odl = odl; PP.oA = oA; PP.osnr = osnr; PP.obits = obits;
         k_prep_objects<<<(unsigned)((nc_pad + 255) / 256), 256, 0, h->stream>>>(PP);
         fzb_count_launch(h);
         FZB_CUDA(cudaGetLastError());
@@ -1548,6 +1628,14 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         S6.pM = pM; S6.pS = pS; S6.pbest = pbest;
         SweepParams SP = {};
         SP.od = od; SP.ow = ow; SP.ox = ox; SP.odl = odl; SP.oA = oA;
+        SP.obits = mm ? obits : nullptr;
+        if (mm) {
+            for (int n = 0; n < 16; ++n) {
+                double a = cfg.free_scale ? 0.5 * (n - 1.0) : 0.5 * n;
+                SP.Atab[n] = cfg.dim_prior ? (float)(a - 1.0) : 0.f;
+                SP.Ktab[n] = (float)fzb_ktab((double)n, cfg.free_scale, cfg.dim_prior);
+            }
+        }
         SP.No_pad = nc_pad; SP.No = nc;
         SP.recs = F.recs.as<float>(); SP.nm = nm; SP.has_prior = h->has_lnprior ? 1 : 0;
         SP.tiles_per_split = tiles_per_split;
@@ -1573,6 +1661,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         MP.log2_wt_thresh = cfg.use_wt_thresh ? std::log2(cfg.wt_thresh) : -INFINITY;
         MP.chi2_max = chi2_max; MP.snr_max = snr_max; MP.consist_tol = 1e-4;
         MP.force_fp32 = (cfg.precision == FZB_PREC_FP32);
+        MP.mmv = mm ? 1 : 0;
         MP.stage = 0;
         MP.lmap = d_lmap; MP.levid = d_levid; MP.best_chi2 = d_best_chi2; MP.best_scale = d_best_scale;
         MP.best_idx = d_best_idx;

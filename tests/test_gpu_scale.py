@@ -205,3 +205,46 @@ def test_model_sharded_fast_path_matches_unsharded(c3):
         tot += part
     p = (tot / tot.sum(dim=1, keepdim=True)).cpu().numpy()
     assert np.max(np.sum(np.abs(p - c3["p"][:n]), axis=1)) <= 3e-6
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(free_scale=True, ignore_model_err=True),
+                                dict(free_scale=False, ignore_model_err=True, dim_prior=False),
+                                dict(free_scale=True, ignore_model_err=True, dim_prior=False)])
+def test_model_masks_on_the_sweep_path(kw):
+    """Config C2 flavour: training rows with 5 % band dropouts (model masks) and objects with dropouts and NaNs.
+    The packed sweep handles binary model masks (pair dimensionality = popc(object bits & model bits)); results
+    must agree with the float64 reference-order kernel and with the oracle."""
+    import frankenz_b200 as fz
+    m, me, mm, z, x, xe, xm, _ = bench_data.c1_dataset(20000, 3000)
+    rs = np.random.RandomState(12)
+    mm = (rs.uniform(size=m.shape) > 0.05).astype(float)
+    mm[:, 2] = 1.0                                   # keep one band everywhere so that no pair is empty
+    xm = (rs.uniform(size=x.shape) > 0.10).astype(float)
+    xm[:, 2] = 1.0
+    x = x.copy()
+    x[rs.uniform(size=x.shape) < 0.005] = np.nan
+    zgrid, sig = bench_data.c3_kde()
+    rdict = fz.pdf.PDFDict(zgrid, sig)
+    labe = 0.01 * (1 + z)                            # several kernel widths
+    bf = fz.BruteForce(m, me, mm)
+    p, (lm, le) = bf.fit_predict(x.copy(), xe.copy(), xm.copy(), z, labe, label_dict=rdict, return_gof=True,
+                                 verbose=False, save_fits=False, lprob_kwargs=kw)
+    st = bf._eng().stats()
+    assert st["pairs_fp32"] >= len(x) * len(m), st                        # the sweep kernels ran
+    sub = np.arange(0, len(x), 5)
+    p64, (lm64, le64) = bf.fit_predict(x[sub].copy(), xe[sub].copy(), xm[sub].copy(), z, labe, label_dict=rdict,
+                                       return_gof=True, verbose=False, save_fits=False,
+                                       lprob_kwargs=dict(kw, precision="fp64"))
+    ok = np.isfinite(p64).all(axis=1)
+    assert ok.mean() > 0.5       # free scale + dim_prior: a one-band pair has chi2 = 0, a = 0 -> NaN row in the reference too
+    assert np.array_equal(np.isfinite(p[sub]).all(axis=1), ok)
+    assert np.max(np.sum(np.abs(p[sub][ok] - p64[ok]), axis=1)) <= 1e-5
+    assert np.all(np.abs(lm[sub][ok] - lm64[ok]) <= 1e-5 * np.maximum(1, np.abs(lm64[ok])))
+    assert np.all(np.abs(le[sub][ok] - le64[ok]) <= 1e-5 * np.maximum(1, np.abs(le64[ok])))
+    kd = fo.KernelDict(zgrid, sig)
+    o = np.arange(6)
+    po, lmo, leo = fo.bruteforce_fit_predict(m, me, mm, x[o].copy(), xe[o].copy(), xm[o].copy(), z, labe,
+                                             label_dict=kd, **kw)
+    fin = np.isfinite(po).all(axis=1)
+    assert np.max(np.sum(np.abs(p[o][fin] - po[fin]), axis=1)) <= 1e-5
+    assert np.all(np.abs(lm[o][fin] - lmo[fin]) <= 1e-5 * np.maximum(1, np.abs(lmo[fin])))
