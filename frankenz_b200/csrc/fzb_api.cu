@@ -339,7 +339,7 @@ int fzb_destroy(fzb_handle h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->models, &h->models_err, &h->models_mask, &h->lnprior, &h->prior_table, &h->prior_bins, &h->widths, &h->koff, &h->kernels,
                       &h->kcdf, &h->yidx, &h->ysidx, &h->grid, &h->y, &h->ystd, &h->lowers, &h->uppers, &h->rows,
-                      &h->knn_feats, &h->knn_cand, &h->knn_redo, &h->fast.recs, &h->fast.recs64, &h->fast.aux64, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
+                      &h->knn_feats, &h->knn_cand, &h->knn_redo, &h->fast.recs, &h->fast.tiles_tc, &h->fast.recs64, &h->fast.aux64, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
                       &h->fast.d_slot_sidx};
     for (auto* b : bufs) b->release();
     for (auto& b : h->obj_in) b.release();

@@ -70,6 +70,8 @@ struct FastModels {
     int rec = 0;           // floats per model record
     DevBuf recs;           // [nm_pad][rec] float: see fzb_fast.cu for the record layout
     DevBuf recs64;         // [nm][rec64] double records of the float64 sweep
+    DevBuf tiles_tc;       // tensor-core sweep: 256-model tiles (MMA operand + packed pairs + tails), fzb_sweep_tc.cuh
+    bool tc_valid = false;
     DevBuf aux64;          // per-object float64 pass-2 inputs
     DevBuf perm;           // int32 [nm_pad]: sorted position -> original model index (-1 = padding)
     DevBuf bins;           // int32 [nm_pad]: KDE histogram bin (slot*Ng + pos) of each sorted model, -1 = none

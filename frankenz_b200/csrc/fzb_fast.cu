@@ -31,6 +31,7 @@
 #include <float.h>
 #include <cstdlib>
 #include <numeric>
+#include <type_traits>
 
 #include "fzb_common.cuh"
 #include "fzb_pair64.cuh"
@@ -424,6 +425,8 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
 }
 
 
+
+#include "fzb_sweep_tc.cuh"
 
 // =====================================================================================================
 // Software-pipelined packed sweep (k_sweep3).
@@ -1305,6 +1308,38 @@ int launch_sweep3_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prior)
     return 0;
 }
 
+// tensor-core sweep (FS0, fp32-exact models, no model masks): 512 objects per CTA
+template <int NF, bool DP, int PASS>
+int launch_sweep_tc_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prior) {
+    const unsigned char* tiles = h->fast.tiles_tc.as<unsigned char>();
+    if (prior) {
+        auto kern = k_sweep_tc<NF, DP, true, PASS>;
+        FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        kern<<<grid, TC_THREADS, TC_SMEM, h->stream>>>(P, tiles, 128u, 256u);
+    } else {
+        auto kern = k_sweep_tc<NF, DP, false, PASS>;
+        FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        kern<<<grid, TC_THREADS, TC_SMEM, h->stream>>>(P, tiles, 128u, 256u);
+    }
+    fzb_count_launch(h);
+    FZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_sweep_tc(fzb_context* h, const SweepParams& P, dim3 grid, int nf, bool dp, int pass) {
+    const bool prior = P.has_prior != 0;
+    if (nf == 5) {
+        if (dp) return pass == 1 ? launch_sweep_tc_t<5, true, 1>(h, P, grid, prior) : launch_sweep_tc_t<5, true, 2>(h, P, grid, prior);
+        return pass == 1 ? launch_sweep_tc_t<5, false, 1>(h, P, grid, prior) : launch_sweep_tc_t<5, false, 2>(h, P, grid, prior);
+    }
+    if (nf == 4) {
+        if (dp) return pass == 1 ? launch_sweep_tc_t<4, true, 1>(h, P, grid, prior) : launch_sweep_tc_t<4, true, 2>(h, P, grid, prior);
+        return pass == 1 ? launch_sweep_tc_t<4, false, 1>(h, P, grid, prior) : launch_sweep_tc_t<4, false, 2>(h, P, grid, prior);
+    }
+    fzb_set_error("tensor-core sweep: unsupported filter count %d", nf);
+    return 2;
+}
+
 template <int NF, int MODE, bool DP, bool MLO>
 int launch_sweep_r(fzb_context* h, const SweepParams& P, dim3 grid, int R, int pass) {
     if constexpr (MLO) {
@@ -1509,6 +1544,19 @@ static int fast_prepare_mode(fzb_context* h, int mode) {
         fzb_count_launch(h);
         FZB_CUDA(cudaGetLastError());
     }
+    F.tc_valid = false;
+    if (mode == FM_FS0 && !mm && !mlo && nf >= 4 && nf <= 5) {
+        const int64_t ntile = (nm + TC_TM - 1) / TC_TM;
+        if (F.tiles_tc.reserve((size_t)ntile * TC_TILE_BYTES + 64)) return 1;
+        FZB_CUDA(cudaMemsetAsync(F.tiles_tc.p, 0, (size_t)ntile * TC_TILE_BYTES, h->stream));
+        TcRecParams T = {};
+        T.m = R.m; T.lnprior = R.lnprior; T.perm = R.perm; T.bins = R.bins; T.invnorm = R.invnorm;
+        T.nm = nm; T.Nf = nf; T.tiles = F.tiles_tc.as<unsigned char>();
+        k_build_tiles_tc<<<(unsigned)((nm + 255) / 256), 256, 0, h->stream>>>(T);
+        fzb_count_launch(h);
+        FZB_CUDA(cudaGetLastError());
+        F.tc_valid = true;
+    }
     FZB_CUDA(cudaStreamSynchronize(h->stream));
     F.valid = true;
     h->fast_dirty = false;
@@ -1555,11 +1603,13 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     int Robj = (chunk >= 48 * 1024) ? 4 : 2;
     if (packed && getenv("FZB_FAST_R")) Robj = atoi(getenv("FZB_FAST_R")) >= 4 ? 4 : 2;
     const int R = packed ? -Robj : Robj;
-    const int64_t tile_objs = (int64_t)ft2_of(Robj) * Robj;
     const bool mlo = !h->models_f32_exact;
+    // tensor-core sweep (fzb_sweep_tc.cuh): free scale without model errors, fp32-exact models, no model masks
+    const bool use_tc = F.tc_valid && mode == FM_FS0 && h->mask_all_one && !mlo && getenv("FZB_NO_TC") == nullptr;
+    const int64_t tile_objs = use_tc ? (int64_t)TC_OBJS : (int64_t)ft2_of(Robj) * Robj;
     const int64_t obj_tiles = (chunk_pad + tile_objs - 1) / tile_objs;
     const int64_t ntiles = (nm + TM - 1) / TM;
-    int64_t want_ctas = (int64_t)h->sm_count * ((packed && Robj >= 4) ? 24 : 48);   // many short waves: small tail
+    int64_t want_ctas = (int64_t)h->sm_count * ((use_tc || (packed && Robj >= 4)) ? 24 : 48);   // many short waves: small tail
     int64_t nsplit = (want_ctas + obj_tiles - 1) / obj_tiles;
     if (nsplit > ntiles) nsplit = ntiles;
     if (nsplit > 256) nsplit = 256;
@@ -1582,10 +1632,12 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     float* thr2 = M2 + chunk_pad;
     int32_t* obits = reinterpret_cast<int32_t*>(thr2 + chunk_pad);
     const bool mm = !h->mask_all_one;
-    if (h->misc[1].reserve((size_t)nsplit * chunk_pad * 20 + 256)) return 1;
+    // partial (max, sum, arg-max) per model split; the tensor-core sweep reports TC_SPLIT partials per split
+    const int64_t npart = use_tc ? nsplit * TC_SPLIT : nsplit;
+    if (h->misc[1].reserve((size_t)npart * chunk_pad * 20 + 256)) return 1;
     double* pS = h->misc[1].as<double>();
-    double* pM = pS + (size_t)nsplit * chunk_pad;
-    int32_t* pbest = reinterpret_cast<int32_t*>(pM + (size_t)nsplit * chunk_pad);
+    double* pM = pS + (size_t)npart * chunk_pad;
+    int32_t* pbest = reinterpret_cast<int32_t*>(pM + (size_t)npart * chunk_pad);
     if (h->misc[2].reserve((size_t)chunk_pad * 16 + 64)) return 1;
     int32_t* safe_list = h->misc[2].as<int32_t>();
     int32_t* unsafe_list = safe_list + chunk_pad;
@@ -1603,7 +1655,8 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     double* shard_scale = M2d_local + chunk_pad;
 
     const double chi2_max = env_double("FZB_FAST_CHI2_MAX", 24.0);
-    const double snr_max = env_double("FZB_FAST_SNR_MAX", 20000.0);
+    // the tf32-split scale of the tensor-core sweep costs ~1e-12 S/N^2 in chi2: send the very bright objects to float64
+    const double snr_max = use_tc ? env_double("FZB_TC_SNR_MAX", 8000.0) : env_double("FZB_FAST_SNR_MAX", 20000.0);
     const bool use_sweep64 = getenv("FZB_NO_SWEEP64") == nullptr && !mm;   // k_sweep64 has no model-mask variant yet
 
     float ms;
@@ -1644,7 +1697,9 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         int64_t nsafe = 0, nsafe64 = 0, nunsafe = 0;
         if (shard_mode != 2) {
         FZB_CUDA(cudaEventRecord(h->ev[2], h->stream));
-        if (launch_sweep(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 1)) return 1;
+        if (use_tc ? launch_sweep_tc(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, cfg.dim_prior != 0, 1)
+                   : launch_sweep(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 1))
+            return 1;
         FZB_CUDA(cudaEventRecord(h->ev[3], h->stream));
         h->stats.pairs_fp32 += nc * nm;
 
@@ -1655,7 +1710,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         MP.lnprior = h->has_lnprior ? h->lnprior.as<double>() : nullptr;
         MP.perm = F.perm.as<int32_t>();
         MP.No = nc; MP.No_pad = nc_pad; MP.o_base = o0;
-        MP.Nf = nf; MP.nsplit = (int)nsplit; MP.free_scale = cfg.free_scale; MP.ime = cfg.ignore_model_err != 0;
+        MP.Nf = nf; MP.nsplit = (int)npart; MP.free_scale = cfg.free_scale; MP.ime = cfg.ignore_model_err != 0;
         MP.dim_prior = cfg.dim_prior;
         MP.pM = pM; MP.pS = pS; MP.pbest = pbest; MP.osnr = osnr;
         MP.log2_wt_thresh = cfg.use_wt_thresh ? std::log2(cfg.wt_thresh) : -INFINITY;
@@ -1686,7 +1741,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             const int64_t t64 = (nprec + FT64 * R64 - 1) / (FT64 * R64);
             if (launch_sweep64(h, S6, dim3((unsigned)t64, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, 1)) return 1;
             h->stats.pairs_fp64 += nprec * nm;
-            MP.stage = 1; MP.in_list = prec_list; MP.n_in = nprec; MP.consist_tol = 1e-6;
+            MP.stage = 1; MP.in_list = prec_list; MP.n_in = nprec; MP.consist_tol = 1e-6; MP.nsplit = (int)nsplit;
             k_merge<<<(unsigned)((nprec + 255) / 256), 256, 0, h->stream>>>(MP);
             fzb_count_launch(h);
             FZB_CUDA(cudaGetLastError());
@@ -1737,7 +1792,8 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                 SP.No = nsafe; SP.objlist = safe_list; SP.M2 = M2; SP.thr2 = thr2; SP.hist = hist;
                 SP.hist_stride = hist_stride;
                 const int64_t tiles2 = (nsafe + tile_objs - 1) / tile_objs;
-                if (launch_sweep(h, SP, dim3((unsigned)tiles2, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 2))
+                if (use_tc ? launch_sweep_tc(h, SP, dim3((unsigned)tiles2, (unsigned)nsplit), nf, cfg.dim_prior != 0, 2)
+                           : launch_sweep(h, SP, dim3((unsigned)tiles2, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 2))
                     return 1;
                 h->stats.pairs_fp32 += nsafe * nm;
             }

@@ -1,0 +1,483 @@
+// Tensor-core sweep (tcgen05 + TMEM) for the free-scale / no-model-error likelihood (FS0), included by fzb_fast.cu.
+//
+// Per pair the packed FP32 sweep (k_sweep2) spends 15 of its ~35 FMA-pipe operations on three dot products with the
+// model fluxes: inter = sum (w d)_b m_b, shape = sum w_b m_b^2 (-> optimal scale, pdf.py:181-185) and the first-order
+// correction for the low half of the float64 data, G = sum (2 w d_lo)_b m_b.  They are GEMMs with K = Nf, so here the
+// 5th-generation tensor cores compute them:  D[object][model] = A[object][K] . B[model][K]^T,  kind::tf32, M = 128,
+// N = 32, operands K-major in shared memory without swizzle, accumulators in TMEM, one elected thread issuing.
+// tf32 keeps 11 significant bits, so inter and shape use the split x = hi + lo on both sides and three products per
+// band (hi*hi + hi*lo + lo*hi: 3 Nf <= 16 K-slots, two K = 8 instructions), which leaves a relative error of ~5e-7 in
+// the scale; the scale is the minimiser of chi2, so that error enters chi2 only as S/N^2 (ds/s)^2 (envelope theorem),
+// ~1e-12 S/N^2.  G is a correction of relative size 1e-7 and is taken at plain tf32.  The residual part,
+// chi2 = K_o - s G + sum_b w_b (d_b - s m_b)^2, the ln-likelihood and the online reductions stay in packed FP32 on the
+// CUDA cores exactly as in k_sweep2, now 20 FMA-pipe operations per pair.
+//
+// Sizing.  tools/tc_rate.cu: one tcgen05.mma of this kind (M = 128, K = 8, operands in shared memory) takes ~118
+// cycles whatever N is (16 .. 64), so the five MMAs of an (M-tile, chunk) must cover enough pairs: N = 32 gives
+// 128 x 32 pairs per 590 cycles = 6.9 pairs / clk / SM (2e12 pairs/s per GPU), above the MUFU / FMA ceilings of the
+// CUDA-core part.  TMEM: 2 M-tiles x 3 products x 32 columns, double buffered = 384 of 512 columns.
+//
+// CTA = 18 warps, 256 objects: warps 0-15 are four consumer warpgroups (warp w reads TMEM lanes 32 (w % 4) ..); warpgroup
+// g works on M-tile g >> 1 and, of every 32-model chunk, on the two 8-model sub-batches of parity g & 1, so an object
+// is shared by two threads that each see half of the models (their partial reductions are merged by k_merge like two
+// model splits; pass 2 accumulates with atomics anyway).  Every consumer thread evaluates two models at a time in the
+// two halves of packed registers.  Warp 16 stages 256-model tiles with TMA bulk copies, warp 17 issues the MMAs.
+//
+// Shared-memory / global layout of a model tile (TC_TILE_BYTES, one bulk copy):
+//   [k-step s (5)][row group (32)][k chunk (2)][row (8)][4 floats]   MMA B operand, SBO = 256 B, LBO = 128 B
+//        k-steps 0-1: m_hi | m_lo | m_hi | 0        (paired with  -x_hi | -x_hi | -x_lo | 0,  x = w d)
+//        k-steps 2-3: q_hi | q_lo | q_hi | 0        (q = m^2;     w_hi |  w_hi |  w_lo | 0)
+//        k-step  4  : m_hi | 0 0 0                  (             g           , g = 2 w d_lo)
+//   [model pair (128)][6] float2   (m_even, m_odd) per band, then the prior pair   (48 B, three LDS.128)
+//   [model pair (128)]    {invnorm_even, invnorm_odd, bin_even, bin_odd}
+//   [8 models (32)]       {bin of the first, 1 if all eight share it}
+#pragma once
+
+constexpr int TC_TM = 256;                       // models per shared-memory tile
+constexpr int TC_NC = 32;                        // models per MMA / TMEM chunk
+constexpr int TC_NSUB = TC_NC / 8;               // 8-model sub-batches per chunk
+constexpr int TC_NWG = 4;                        // consumer warpgroups
+constexpr int TC_MT = 2;                         // 128-object M-tiles per CTA
+constexpr int TC_SPLIT = TC_NWG / TC_MT;         // warpgroups (threads) sharing an object = partial results per object
+constexpr int TC_OBJS = TC_MT * 128;             // objects per CTA
+constexpr int TC_THREADS = TC_NWG * 128 + 64;    // + TMA warp + MMA warp
+constexpr int TC_CW = TC_NWG * 4;                // consumer warps; warp TC_CW = TMA, TC_CW + 1 = MMA
+constexpr int TC_KSTEPS = 5;
+constexpr int TC_OPSEC = TC_KSTEPS * TC_TM * 32;
+constexpr int TC_PAIRSEC = (TC_TM / 2) * 48;
+constexpr int TC_TAILSEC = (TC_TM / 2) * 16;
+constexpr int TC_SUBSEC = (TC_TM / 8) * 8;         // per 8 models: {KDE bin of the first, 1 if all eight share it}
+constexpr int TC_TILE_BYTES = TC_OPSEC + TC_PAIRSEC + TC_TAILSEC + TC_SUBSEC;
+constexpr int TC_OBJA_TILE = TC_KSTEPS * 128 * 32;
+constexpr int TC_OBJA_BYTES = TC_MT * TC_OBJA_TILE;
+constexpr int TC_NSTAGE = 2;
+constexpr int TC_CHUNK_COLS = TC_MT * 3 * TC_NC;  // TMEM columns of one chunk buffer
+constexpr int TC_TMEM_COLS = 512;
+constexpr size_t TC_SMEM = (size_t)TC_OBJA_BYTES + (size_t)TC_NSTAGE * TC_TILE_BYTES + 512;
+static_assert(TC_TILE_BYTES == 49408 && TC_TILE_BYTES % 128 == 0, "tile layout");
+static_assert(2 * TC_CHUNK_COLS <= TC_TMEM_COLS, "TMEM budget");
+static_assert(TC_SPLIT == 2 && TC_NSUB == 4, "sub-batch assignment below assumes two warpgroups per M-tile, four sub-batches");
+
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// mbarrier wait that lets the hardware suspend the warp until the phase completes (suspend-time hint) instead of
+// polling: a polling producer warp takes issue slots from the consumer warps that share its scheduler
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITS_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONES_%=;\n"
+        "bra WAITS_%=;\n"
+        "DONES_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(0x989680)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor: no swizzle, K-major; core matrices (8 rows x 16 B) LBO apart along K, SBO apart
+// along the rows (verified on the hardware by tools/tc_probe.cu)
+__device__ __forceinline__ uint64_t tc_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+// D[tmem] (+)= A[smem] . B[smem]^T; the descriptors are passed as (low word, high word): the high word (SBO, version) is
+// the same for every operand, the low word is base + (byte offset >> 4)
+template <bool ACC>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "n"(ACC ? 1 : 0)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+#define TC_TIE8(v) "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])
+
+// chi2 part of one object against a pair of models: sum_b w_b (d_b - s m_b)^2 + K - s G in the units of the weights
+template <int NF>
+__device__ __forceinline__ f2 tc_pair_c(f2 B2, f2 C2, f2 G2, const f2* __restrict__ m2, const f2* d2, const f2* w2, f2 K2) {
+    const f2 rc = pack2(fast_rcp(lo2(C2)), fast_rcp(hi2(C2)));
+    const f2 ns = mul2(B2, rc);          // minus the optimal scale (the A operand of the inter product is negated)
+    f2 c = fma2(ns, G2, K2);             // first-order correction for the low half of the data
+#pragma unroll
+    for (int b = 0; b < NF; ++b) {
+        f2 r = fma2(ns, m2[b], d2[b]);
+        f2 t = mul2(r, w2[b]);
+        c = fma2(t, r, c);
+    }
+    return c;
+}
+// ln-likelihood (log2 units, up to the per-object constant); the weights carry -log2(e)/2: c = -chi2 log2(e)/2
+template <int NF, bool DP, bool PRIOR, bool TAIL>
+__device__ __forceinline__ f2 tc_pair_l(f2 B2, f2 C2, f2 G2, const f2* __restrict__ m2, f2 prior2, const f2* d2, const f2* w2,
+                                        f2 K2, f2 A2) {
+    f2 c = tc_pair_c<NF>(B2, C2, G2, m2, d2, w2, K2);
+    const f2 cc = c;
+    if (PRIOR) c = add2(c, prior2);
+    f2 l = c;
+    if (DP) l = fma2(A2, pack2(fast_lg2(fabsf(lo2(cc))), fast_lg2(fabsf(hi2(cc)))), c);
+    if (TAIL) l = pack2(lo2(l), -FLT_MAX);   // odd model count: the second model of the last pair is padding
+    return l;
+}
+// exact 2^k for an integer-valued float k (0 below the normal range)
+__device__ __forceinline__ float pow2i(float k) {
+    return (k >= -126.f) ? __int_as_float(((int)fminf(k, 127.f) + 127) << 23) : 0.f;
+}
+
+template <int NF, bool DP, bool PRIOR, int PASS>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const unsigned char* __restrict__ tiles, uint32_t lbo,
+                                                            uint32_t sbo) {
+    static_assert(NF <= 5, "3 NF K-slots must fit two K = 8 instructions");
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* objA = smem_raw;
+    unsigned char* stage = smem_raw + TC_OBJA_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage + (size_t)TC_NSTAGE * TC_TILE_BYTES);
+    uint64_t* tile_full = bars;                       // [NSTAGE]  TMA -> MMA + consumers
+    uint64_t* tile_empty = bars + 2;                  // [NSTAGE]  MMA commit + consumer warps -> TMA
+    uint64_t* acc_full = bars + 4;                    // [mt][buf] MMA commit -> consumers
+    uint64_t* acc_empty = bars + 4 + 2 * TC_MT;       // [mt][buf] consumer warps of the M-tile -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 4 * TC_MT);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    const int64_t ntiles_all = (P.nm + TC_TM - 1) / TC_TM;
+    const int64_t t0 = (int64_t)blockIdx.y * P.tiles_per_split;
+    int64_t t1 = t0 + P.tiles_per_split;
+    if (t1 > ntiles_all) t1 = ntiles_all;
+    const int nt = (int)(t1 - t0);
+    const int64_t tile_base = (int64_t)blockIdx.x * TC_OBJS;
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_NSTAGE; ++s) { mbar_init(&tile_full[s], 1); mbar_init(&tile_empty[s], 1 + TC_CW); }
+        for (int i = 0; i < 2 * TC_MT; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * TC_SPLIT); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == TC_CW + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+
+    // ---- consumer state --------------------------------------------------------------------------------------
+    const int wg = warp >> 2;                   // consumer warpgroup
+    const int mt = wg >> 1;                     // its M-tile
+    const int half = wg & 1;                    // its sub-batch parity
+    const int row = (warp & 3) * 32 + lane;     // row of the M-tile = TMEM lane
+    f2 d2[NF], w2[NF], K2 = 0, A2 = 0;
+    f2 M2 = 0, S2 = 0, acc2 = 0;
+    float thr = 0.f, Mfl = -FLT_MAX;
+    double Sd = 0.0;
+    int best0 = 0, best1 = 0, oidx = -1;
+    if (warp < TC_CW) {
+        const int64_t slot = tile_base + (int64_t)mt * 128 + row;
+        int64_t o;
+        if (PASS == 1) o = slot < P.No_pad ? slot : P.No_pad - 1;
+        else o = slot < P.No ? P.objlist[slot] : -1;
+        oidx = (int)o;
+        const int64_t oo = o < 0 ? 0 : o;
+        float arow[40];
+#pragma unroll
+        for (int i = 0; i < 40; ++i) arow[i] = 0.f;
+        float kk = 0.f;
+#pragma unroll
+        for (int b = 0; b < NF; ++b) {
+            const float d = P.od[b * P.No_pad + oo], w = P.ow[b * P.No_pad + oo];
+            const float x = P.ox[b * P.No_pad + oo], dl = P.odl[b * P.No_pad + oo];
+            d2[b] = pack2(d, d);
+            w2[b] = pack2(w, w);
+            const float g = w * dl;
+            kk = fmaf(g, d, kk);
+            const float xh = tf32_rn(x), xl = tf32_rn(x - xh);
+            const float wh = tf32_rn(w), wl = tf32_rn(w - wh);
+            arow[b] = -xh; arow[5 + b] = -xh; arow[10 + b] = -xl;
+            arow[16 + b] = wh; arow[21 + b] = wh; arow[26 + b] = wl;
+            arow[32 + b] = tf32_rn(g);
+        }
+        K2 = pack2(kk, kk);
+        const float a = P.oA[oo];
+        A2 = pack2(a, a);
+        if (half == 0) {        // one of the two threads of the object writes its row of the A operand
+            unsigned char* dst = objA + (size_t)mt * TC_OBJA_TILE + (row >> 3) * 256 + (row & 7) * 16;
+#pragma unroll
+            for (int s = 0; s < TC_KSTEPS; ++s)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    *reinterpret_cast<float4*>(dst + s * 4096 + c * 128) =
+                        make_float4(arow[s * 8 + c * 4], arow[s * 8 + c * 4 + 1], arow[s * 8 + c * 4 + 2], arow[s * 8 + c * 4 + 3]);
+        }
+        thr = (PASS == 2) ? P.thr2[oo] : 0.f;
+        if (PASS == 1) { M2 = pack2(-FLT_MAX, -FLT_MAX); S2 = pack2(0.f, 0.f); }
+        else { const float m = P.M2[oo]; M2 = pack2(m, m); acc2 = pack2(0.f, 0.f); }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == TC_CW) {
+        // ===== TMA producer ======================================================================================
+        if (lane == 0) {
+            for (int it = 0; it < nt; ++it) {
+                const int st = it % TC_NSTAGE, n = it / TC_NSTAGE;
+                if (n > 0) mbar_wait_hint(&tile_empty[st], (uint32_t)((n - 1) & 1));
+                mbar_expect_tx(&tile_full[st], TC_TILE_BYTES);
+                bulk_g2s(stage + (size_t)st * TC_TILE_BYTES, tiles + (size_t)(t0 + it) * TC_TILE_BYTES, TC_TILE_BYTES, &tile_full[st]);
+            }
+        }
+    } else if (warp == TC_CW + 1) {
+        // ===== MMA issuer: the whole warp walks the loop (uniform control flow keeps the descriptors in uniform
+        // registers), one elected lane issues ==================================================================
+        // instruction descriptor: D fp32, A / B tf32, both K-major, N = TC_NC, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_NC >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t d0 = tc_desc(smem_u32(objA), lbo, sbo);
+        const uint32_t a_lo = (uint32_t)d0, desc_hi = (uint32_t)(d0 >> 32);
+        uint32_t gch = 0;
+        for (int it = 0; it < nt; ++it) {
+            const int st = it % TC_NSTAGE, n = it / TC_NSTAGE;
+            mbar_wait_hint(&tile_full[st], (uint32_t)(n & 1));
+            tc_fence_after();
+            const int64_t first = (t0 + it) * TC_TM;
+            const int cnt = (int)((P.nm - first) < TC_TM ? (P.nm - first) : TC_TM);
+            const int nch = (cnt + TC_NC - 1) / TC_NC;
+            const uint32_t b_lo = (uint32_t)tc_desc(smem_u32(stage + (size_t)st * TC_TILE_BYTES), lbo, sbo);
+            for (int ch = 0; ch < nch; ++ch, ++gch) {
+                const uint32_t buf = gch & 1, use = gch >> 1;
+                const uint32_t b0 = b_lo + ch * ((TC_NC / 8) * 256 >> 4);
+#pragma unroll
+                for (int m = 0; m < TC_MT; ++m) {
+                    mbar_wait_hint(&acc_empty[m * 2 + buf], (use & 1) ^ 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t dcol = tmem + buf * TC_CHUNK_COLS + m * (3 * TC_NC);
+                        const uint32_t a0 = a_lo + ((m * TC_OBJA_TILE) >> 4);
+                        tc_mma<false>(dcol, a0, b0, desc_hi, idesc);
+                        tc_mma<true>(dcol, a0 + (4096 >> 4), b0 + (8192 >> 4), desc_hi, idesc);
+                        tc_mma<false>(dcol + TC_NC, a0 + (2 * 4096 >> 4), b0 + (2 * 8192 >> 4), desc_hi, idesc);
+                        tc_mma<true>(dcol + TC_NC, a0 + (3 * 4096 >> 4), b0 + (3 * 8192 >> 4), desc_hi, idesc);
+                        tc_mma<false>(dcol + 2 * TC_NC, a0 + (4 * 4096 >> 4), b0 + (4 * 8192 >> 4), desc_hi, idesc);
+                        tc_commit(&acc_full[m * 2 + buf]);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (elect_one()) tc_commit(&tile_empty[st]);     // the tensor core is done reading this stage
+            __syncwarp();
+        }
+    } else {
+        // ===== consumers =========================================================================================
+        const f2 kMinusOne = pack2(-1.f, -1.f);
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + mt * (3 * TC_NC);
+        int cur_bin = -1;
+        uint32_t gch = 0;
+        auto flush = [&](float v, int bin) {
+            if (v != 0.f && oidx >= 0) atomicAdd(P.hist + (int64_t)oidx * P.hist_stride + bin, v);
+        };
+        const ulonglong2* pairs = nullptr;
+        const float4* tails = nullptr;
+        const int2* subs = nullptr;
+        int first_i = 0, npair_full = 0;
+        bool odd = false;
+        // four model pairs (eight TMEM columns) against the object of the thread
+        auto process = [&](auto slow_tag, const int p0, float (&Bv)[8], float (&Cv)[8], float (&Gv)[8]) {
+            constexpr bool SLOW = decltype(slow_tag)::value;
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                const int p = p0 + jp;
+                bool tail = false;
+                if (SLOW) {
+                    tail = (p == npair_full) && odd;
+                    if (p >= npair_full && !tail) continue;      // warp-uniform
+                }
+                const ulonglong2 q0 = pairs[p * 3], q1 = pairs[p * 3 + 1], q2 = pairs[p * 3 + 2];
+                f2 m2[5] = {q0.x, q0.y, q1.x, q1.y, q2.x};
+                const f2 prior2 = q2.y;
+                const int idx0 = first_i + 2 * p;
+                const f2 B2 = pack2(Bv[2 * jp], Bv[2 * jp + 1]);
+                const f2 C2 = pack2(Cv[2 * jp], Cv[2 * jp + 1]);
+                const f2 G2 = pack2(Gv[2 * jp], Gv[2 * jp + 1]);
+                f2 l;
+                if (SLOW && tail) l = tc_pair_l<NF, DP, PRIOR, true>(B2, C2, G2, m2, prior2, d2, w2, K2, A2);
+                else l = tc_pair_l<NF, DP, PRIOR, false>(B2, C2, G2, m2, prior2, d2, w2, K2, A2);
+                const f2 delta = fma2(M2, kMinusOne, l);
+                if (PASS == 1) {
+                    const float e0 = fast_ex2(-fabsf(lo2(delta))), e1 = fast_ex2(-fabsf(hi2(delta)));
+                    const bool g0 = lo2(delta) > 0.f, g1 = hi2(delta) > 0.f;
+                    S2 = fma2(S2, pack2(g0 ? e0 : 1.f, g1 ? e1 : 1.f), pack2(g0 ? 1.f : e0, g1 ? 1.f : e1));
+                    M2 = pack2(g0 ? lo2(l) : lo2(M2), g1 ? hi2(l) : hi2(M2));
+                    best0 = g0 ? idx0 : best0;
+                    best1 = g1 ? idx0 + 1 : best1;
+                } else {
+                    const float4 tl = tails[p];
+                    float u0 = fast_ex2(lo2(delta)), u1 = fast_ex2(hi2(delta));
+                    u0 = (lo2(l) > thr) ? u0 : 0.f;
+                    u1 = (hi2(l) > thr) ? u1 : 0.f;
+                    if (!SLOW) {
+                        acc2 = fma2(pack2(u0, u1), pack2(tl.x, tl.y), acc2);
+                    } else {
+                        const int bin0 = __float_as_int(tl.z), bin1 = tail ? bin0 : __float_as_int(tl.w);
+                        if (bin0 != cur_bin) {             // warp-uniform
+                            if (cur_bin >= 0) { flush(lo2(acc2) + hi2(acc2), cur_bin); acc2 = pack2(0.f, 0.f); }
+                            cur_bin = bin0;
+                        }
+                        if (bin1 == bin0) {
+                            acc2 = fma2(pack2(u0, u1), pack2(tl.x, tl.y), acc2);
+                        } else {                           // the pair straddles a bin boundary
+                            flush(fmaf(u0, tl.x, lo2(acc2) + hi2(acc2)), bin0);
+                            acc2 = pack2(0.f, u1 * tl.y);
+                            cur_bin = bin1;
+                        }
+                    }
+                }
+            }
+        };
+        for (int it = 0; it < nt; ++it) {
+            const int st = it % TC_NSTAGE, n = it / TC_NSTAGE;
+            mbar_wait_hint(&tile_full[st], (uint32_t)(n & 1));
+            const unsigned char* tile = stage + (size_t)st * TC_TILE_BYTES;
+            pairs = reinterpret_cast<const ulonglong2*>(tile + TC_OPSEC);
+            tails = reinterpret_cast<const float4*>(tile + TC_OPSEC + TC_PAIRSEC);
+            subs = reinterpret_cast<const int2*>(tile + TC_OPSEC + TC_PAIRSEC + TC_TAILSEC);
+            const int64_t first = (t0 + it) * TC_TM;
+            const int cnt = (int)((P.nm - first) < TC_TM ? (P.nm - first) : TC_TM);
+            const int nch = (cnt + TC_NC - 1) / TC_NC;
+            first_i = (int)first;
+            npair_full = cnt >> 1;
+            odd = (cnt & 1) != 0;
+            for (int ch = 0; ch < nch; ++ch, ++gch) {
+                const uint32_t buf = gch & 1, use = gch >> 1;
+                mbar_wait_hint(&acc_full[mt * 2 + buf], use & 1);
+                tc_fence_after();
+                const uint32_t cbase = lane_addr + buf * TC_CHUNK_COLS;
+#pragma unroll
+                for (int k = 0; k < TC_NSUB / TC_SPLIT; ++k) {
+                    const int sub = half + TC_SPLIT * k;          // this warpgroup's sub-batches of the chunk
+                    float Bv[8], Cv[8], Gv[8];
+                    tmem_ld8(cbase + sub * 8, Bv);
+                    tmem_ld8(cbase + TC_NC + sub * 8, Cv);
+                    tmem_ld8(cbase + 2 * TC_NC + sub * 8, Gv);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" : TC_TIE8(Bv), TC_TIE8(Cv), TC_TIE8(Gv)::"memory");
+                    if (k == TC_NSUB / TC_SPLIT - 1) {   // everything this warp needs of the chunk is in registers
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[mt * 2 + buf]);
+                    }
+                    const int p0 = ch * (TC_NC / 2) + sub * 4;
+                    // fast path: four complete model pairs and (pass 2) one KDE bin for all eight models -> one
+                    // branch-free block in which the chains of the four pair evaluations interleave
+                    bool fast = p0 + 4 <= npair_full;
+                    if (PASS == 2) {
+                        const int2 si = subs[ch * TC_NSUB + sub];
+                        fast = fast && (si.y != 0);
+                        if (fast && si.x != cur_bin) {         // warp-uniform
+                            if (cur_bin >= 0) { flush(lo2(acc2) + hi2(acc2), cur_bin); acc2 = pack2(0.f, 0.f); }
+                            cur_bin = si.x;
+                        }
+                    }
+                    if (fast) process(std::false_type{}, p0, Bv, Cv, Gv);
+                    else process(std::true_type{}, p0, Bv, Cv, Gv);
+                }
+            }
+            if (PASS == 1) {
+                // fp32 sums only within a tile; tiles (and the two model lanes) are combined in float64
+                const float m0 = lo2(M2), m1 = hi2(M2);
+                const float mn = fmaxf(m0, m1);
+                Sd = Sd * (double)fast_ex2(Mfl - mn) + (double)(lo2(S2) * fast_ex2(m0 - mn)) + (double)(hi2(S2) * fast_ex2(m1 - mn));
+                Mfl = mn;
+                S2 = pack2(0.f, 0.f);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tile_empty[st]);     // done with the pair / tail sections of this stage
+        }
+        if (PASS == 1) {
+            const int64_t slot = tile_base + (int64_t)mt * 128 + row;
+            if (slot < P.No_pad) {
+                const float m0 = lo2(M2), m1 = hi2(M2);
+                const int b = (m0 > m1) ? best0 : ((m1 > m0) ? best1 : min(best0, best1));
+                // the two threads of an object report like two model splits
+                const size_t q = ((size_t)blockIdx.y * TC_SPLIT + half) * P.No_pad + slot;
+                P.pM[q] = (double)Mfl;
+                P.pS[q] = Sd;
+                P.pbest[q] = b;
+            }
+        } else if (cur_bin >= 0) {
+            flush(lo2(acc2) + hi2(acc2), cur_bin);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_CW + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_TMEM_COLS));
+}
+
+// ---- tile builder ------------------------------------------------------------------------------------------
+struct TcRecParams {
+    const double* m;
+    const double* lnprior;
+    const int32_t* perm;
+    const int32_t* bins;
+    const float* invnorm;
+    int64_t nm;
+    int Nf;
+    unsigned char* tiles;
+};
+
+__global__ void k_build_tiles_tc(TcRecParams P) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P.nm) return;
+    const int64_t j = P.perm[p];
+    const int r = (int)(p % TC_TM);
+    unsigned char* T = P.tiles + (size_t)(p / TC_TM) * TC_TILE_BYTES;
+    float rowv[40];
+    for (int i = 0; i < 40; ++i) rowv[i] = 0.f;
+    float* pr = reinterpret_cast<float*>(T + TC_OPSEC) + (r >> 1) * 12;
+    for (int b = 0; b < P.Nf; ++b) {
+        const double v = P.m[j * P.Nf + b];
+        const float mf = (float)v, q = (float)(v * v);
+        const float mh = tf32_rn(mf), ml = tf32_rn(mf - mh);
+        const float qh = tf32_rn(q), ql = tf32_rn(q - qh);
+        rowv[b] = mh; rowv[5 + b] = ml; rowv[10 + b] = mh;
+        rowv[16 + b] = qh; rowv[21 + b] = ql; rowv[26 + b] = qh;
+        rowv[32 + b] = mh;
+        pr[2 * b + (r & 1)] = mf;
+    }
+    pr[10 + (r & 1)] = P.lnprior ? (float)(P.lnprior[j] * 1.4426950408889634) : 0.f;
+    float* tl = reinterpret_cast<float*>(T + TC_OPSEC + TC_PAIRSEC) + (r >> 1) * 4;
+    tl[r & 1] = P.invnorm ? P.invnorm[p] : 0.f;
+    tl[2 + (r & 1)] = __int_as_float(P.bins ? P.bins[p] : -1);
+    if ((r & 7) == 0) {
+        int uniform = (P.bins != nullptr && p + 8 <= P.nm) ? 1 : 0;
+        const int b0 = P.bins ? P.bins[p] : -1;
+        for (int i = 1; i < 8 && uniform; ++i) uniform = (P.bins[p + i] == b0) ? 1 : 0;
+        reinterpret_cast<int2*>(T + TC_OPSEC + TC_PAIRSEC + TC_TAILSEC)[r >> 3] = make_int2(b0, uniform);
+    }
+    unsigned char* dst = T + (r >> 3) * 256 + (r & 7) * 16;
+    for (int s = 0; s < TC_KSTEPS; ++s)
+        for (int c = 0; c < 2; ++c)
+            *reinterpret_cast<float4*>(dst + s * (TC_TM * 32) + c * 128) =
+                make_float4(rowv[s * 8 + c * 4], rowv[s * 8 + c * 4 + 1], rowv[s * 8 + c * 4 + 2], rowv[s * 8 + c * 4 + 3]);
+}
