@@ -142,6 +142,7 @@ struct fzb_context {
     int64_t shard_No = 0;
     int shard_counts[4] = {0, 0, 0, 0};
     int shard_cfg_key = 0;
+    bool shard_lin = false;        // pass 1 ran the linear-domain tensor-core sweep
 
     // kNN
     DevBuf knn_feats;       // float32 K x Nm x Nf (+ 64 B pad)

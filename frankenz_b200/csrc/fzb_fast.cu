@@ -957,6 +957,7 @@ struct PrepParams {
     int Nf, mode, free_scale, dim_prior;
     float *od, *ow, *ox, *odl, *oA, *osnr;
     int32_t* obits;
+    int32_t* n_not_one;   // nullable: counts the objects of the chunk whose (dof/2 - 1) != 1
 };
 
 __global__ void k_prep_objects(PrepParams P) {
@@ -997,6 +998,7 @@ __global__ void k_prep_objects(PrepParams P) {
     }
     double a = P.free_scale ? 0.5 * (ndim - 1.0) : 0.5 * ndim;
     P.oA[o] = P.dim_prior ? (float)(a - 1.0) : 0.f;
+    if (P.n_not_one && o < P.No && P.dim_prior && (a - 1.0) != 1.0) atomicAdd(P.n_not_one, 1);
     // a non-binary object mask makes the pair dimensionality non-integer: leave such objects to the float64 kernels
     P.osnr[o] = binary ? (float)sqrt(snr2) : CUDART_INF_F;
     if (P.obits) P.obits[o] = bits;
@@ -1028,6 +1030,7 @@ struct MergeParams {
     double chi2_max, snr_max, consist_tol;
     int force_fp32;
     int mmv;                            // model-mask variant: the sweep value includes the ndim-dependent constant
+    const float* lin_oA;                // linear-domain tensor-core sweep: objects with (dof/2 - 1) != 1 go to float64
     int stage;                          // 0: after the fp32 sweep (all objects); 1: after the float64 sweep (in_list)
     const int32_t* in_list;
     int64_t n_in;
@@ -1058,7 +1061,8 @@ __global__ void k_merge(MergeParams P) {
     int bs = 0;
     for (int s = 0; s < P.nsplit; ++s) {
         double v = P.pM[(size_t)s * P.No_pad + o];
-        if (v > M) { M = v; bs = s; }
+        // exact ties go to the smallest model position, whatever the partition of the models was
+        if (v > M || (v == M && P.pbest[(size_t)s * P.No_pad + o] < P.pbest[(size_t)bs * P.No_pad + o])) { M = v; bs = s; }
     }
     double S = 0.0;
     bool bad = false;
@@ -1094,8 +1098,13 @@ __global__ void k_merge(MergeParams P) {
     const bool consistent = fabs(vary - M) <= P.consist_tol * fmax(1.0, fabs(vary));
     bool precise = consistent;
     if (P.stage == 0 && !P.force_fp32) precise = precise && (st.chi2 <= P.chi2_max) && ((double)P.osnr[o] <= P.snr_max);
+    if (P.stage == 0 && P.lin_oA && P.lin_oA[o] != 1.f) precise = false;
     int64_t og = P.o_base + o;
     if (P.lmap) P.lmap[og] = lmap;
+    // sum_j exp(lnprob_j) = exp(C) 2^M S with the sweep's own (fp32 or float64) maximum M, and lmap = C + vary ln 2 exactly:
+    // refer the sum to the exact maximum so that the rounding error of M does not shift the evidence; the best model's own
+    // term is exactly 1 then
+    if (finite && consistent) S = 1.0 + fmax(S - 1.0, 0.0) * exp2(M - vary);
     if (P.levid) P.levid[og] = lmap + log(S);
     if (P.Sout) P.Sout[og] = S;
     if (P.lmap_local) P.lmap_local[o] = lmap;
@@ -1308,16 +1317,16 @@ int launch_sweep3_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prior)
     return 0;
 }
 
-// tensor-core sweep (FS0, fp32-exact models, no model masks): 512 objects per CTA
-template <int NF, bool DP, int PASS>
+// tensor-core sweep (FS0, fp32-exact models, no model masks): 256 objects per CTA
+template <int NF, bool DP, int PASS, bool LIN>
 int launch_sweep_tc_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prior) {
     const unsigned char* tiles = h->fast.tiles_tc.as<unsigned char>();
     if (prior) {
-        auto kern = k_sweep_tc<NF, DP, true, PASS>;
+        auto kern = k_sweep_tc<NF, DP, true, PASS, LIN>;
         FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
         kern<<<grid, TC_THREADS, TC_SMEM, h->stream>>>(P, tiles, 128u, 256u);
     } else {
-        auto kern = k_sweep_tc<NF, DP, false, PASS>;
+        auto kern = k_sweep_tc<NF, DP, false, PASS, LIN>;
         FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
         kern<<<grid, TC_THREADS, TC_SMEM, h->stream>>>(P, tiles, 128u, 256u);
     }
@@ -1326,15 +1335,17 @@ int launch_sweep_tc_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prio
     return 0;
 }
 
-int launch_sweep_tc(fzb_context* h, const SweepParams& P, dim3 grid, int nf, bool dp, int pass) {
+// lin: linear-domain form, valid when every object handled by the fp32 pass has (dof/2 - 1) = 1 (Nf = 5, dim_prior)
+int launch_sweep_tc(fzb_context* h, const SweepParams& P, dim3 grid, int nf, bool dp, int pass, bool lin) {
     const bool prior = P.has_prior != 0;
     if (nf == 5) {
-        if (dp) return pass == 1 ? launch_sweep_tc_t<5, true, 1>(h, P, grid, prior) : launch_sweep_tc_t<5, true, 2>(h, P, grid, prior);
-        return pass == 1 ? launch_sweep_tc_t<5, false, 1>(h, P, grid, prior) : launch_sweep_tc_t<5, false, 2>(h, P, grid, prior);
+        if (lin && dp) return pass == 1 ? launch_sweep_tc_t<5, true, 1, true>(h, P, grid, prior) : launch_sweep_tc_t<5, true, 2, true>(h, P, grid, prior);
+        if (dp) return pass == 1 ? launch_sweep_tc_t<5, true, 1, false>(h, P, grid, prior) : launch_sweep_tc_t<5, true, 2, false>(h, P, grid, prior);
+        return pass == 1 ? launch_sweep_tc_t<5, false, 1, false>(h, P, grid, prior) : launch_sweep_tc_t<5, false, 2, false>(h, P, grid, prior);
     }
     if (nf == 4) {
-        if (dp) return pass == 1 ? launch_sweep_tc_t<4, true, 1>(h, P, grid, prior) : launch_sweep_tc_t<4, true, 2>(h, P, grid, prior);
-        return pass == 1 ? launch_sweep_tc_t<4, false, 1>(h, P, grid, prior) : launch_sweep_tc_t<4, false, 2>(h, P, grid, prior);
+        if (dp) return pass == 1 ? launch_sweep_tc_t<4, true, 1, false>(h, P, grid, prior) : launch_sweep_tc_t<4, true, 2, false>(h, P, grid, prior);
+        return pass == 1 ? launch_sweep_tc_t<4, false, 1, false>(h, P, grid, prior) : launch_sweep_tc_t<4, false, 2, false>(h, P, grid, prior);
     }
     fzb_set_error("tensor-core sweep: unsupported filter count %d", nf);
     return 2;
@@ -1668,9 +1679,24 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         PP.No = nc; PP.No_pad = nc_pad; PP.Nf = nf; PP.mode = mode;
         PP.free_scale = cfg.free_scale; PP.dim_prior = cfg.dim_prior;
         PP.od = od; PP.ow = ow; PP.ox = ox; PP.odl = odl; PP.oA = oA; PP.osnr = osnr; PP.obits = obits;
+        bool use_lin = use_tc && nf == 5 && cfg.dim_prior && shard_mode != 2 && getenv("FZB_NO_LIN") == nullptr;
+        if (use_lin) {
+            FZB_CUDA(cudaMemsetAsync(counts + 4, 0, 4, h->stream));
+            PP.n_not_one = counts + 4;
+        }
         k_prep_objects<<<(unsigned)((nc_pad + 255) / 256), 256, 0, h->stream>>>(PP);
         fzb_count_launch(h);
         FZB_CUDA(cudaGetLastError());
+        if (use_lin) {
+            // the linear-domain kernel serves (dof/2 - 1) = 1 only; the other objects take the float64 sweep, so it is
+            // worth it only when they are few
+            int32_t n1 = 0;
+            FZB_CUDA(cudaMemcpyAsync(&n1, counts + 4, 4, cudaMemcpyDeviceToHost, h->stream));
+            FZB_CUDA(cudaStreamSynchronize(h->stream));
+            if ((int64_t)n1 * 50 > nc) use_lin = false;
+        }
+        if (shard_mode == 2) use_lin = h->shard_lin;
+        else h->shard_lin = use_lin;
 
         // ---- pass 1 (fp32, every object) ------------------------------------------------------------
         int32_t hc[4] = {0, 0, 0, 0};
@@ -1697,7 +1723,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         int64_t nsafe = 0, nsafe64 = 0, nunsafe = 0;
         if (shard_mode != 2) {
         FZB_CUDA(cudaEventRecord(h->ev[2], h->stream));
-        if (use_tc ? launch_sweep_tc(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, cfg.dim_prior != 0, 1)
+        if (use_tc ? launch_sweep_tc(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, cfg.dim_prior != 0, 1, use_lin)
                    : launch_sweep(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 1))
             return 1;
         FZB_CUDA(cudaEventRecord(h->ev[3], h->stream));
@@ -1717,6 +1743,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         MP.chi2_max = chi2_max; MP.snr_max = snr_max; MP.consist_tol = 1e-4;
         MP.force_fp32 = (cfg.precision == FZB_PREC_FP32);
         MP.mmv = mm ? 1 : 0;
+        MP.lin_oA = use_lin ? oA : nullptr;
         MP.stage = 0;
         MP.lmap = d_lmap; MP.levid = d_levid; MP.best_chi2 = d_best_chi2; MP.best_scale = d_best_scale;
         MP.best_idx = d_best_idx;
@@ -1792,7 +1819,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                 SP.No = nsafe; SP.objlist = safe_list; SP.M2 = M2; SP.thr2 = thr2; SP.hist = hist;
                 SP.hist_stride = hist_stride;
                 const int64_t tiles2 = (nsafe + tile_objs - 1) / tile_objs;
-                if (use_tc ? launch_sweep_tc(h, SP, dim3((unsigned)tiles2, (unsigned)nsplit), nf, cfg.dim_prior != 0, 2)
+                if (use_tc ? launch_sweep_tc(h, SP, dim3((unsigned)tiles2, (unsigned)nsplit), nf, cfg.dim_prior != 0, 2, use_lin)
                            : launch_sweep(h, SP, dim3((unsigned)tiles2, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 2))
                     return 1;
                 h->stats.pairs_fp32 += nsafe * nm;

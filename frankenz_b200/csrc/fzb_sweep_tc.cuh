@@ -8,13 +8,14 @@
 // tf32 keeps 11 significant bits, so inter and shape use the split x = hi + lo on both sides and three products per
 // band (hi*hi + hi*lo + lo*hi: 3 Nf <= 16 K-slots, two K = 8 instructions), which leaves a relative error of ~5e-7 in
 // the scale; the scale is the minimiser of chi2, so that error enters chi2 only as S/N^2 (ds/s)^2 (envelope theorem),
-// ~1e-12 S/N^2.  G is a correction of relative size 1e-7 and is taken at plain tf32.  The residual part,
+// ~1e-12 S/N^2.  G takes the same split: the correction K_o - s G = sum g_b (d_b - s m_b) is small, but K_o and s G are
+// each ~1e-7 S/N^2 and cancel, so G needs fp32-level accuracy as well.  The residual part,
 // chi2 = K_o - s G + sum_b w_b (d_b - s m_b)^2, the ln-likelihood and the online reductions stay in packed FP32 on the
 // CUDA cores exactly as in k_sweep2, now 20 FMA-pipe operations per pair.
 //
 // Sizing.  tools/tc_rate.cu: one tcgen05.mma of this kind (M = 128, K = 8, operands in shared memory) takes ~118
-// cycles whatever N is (16 .. 64), so the five MMAs of an (M-tile, chunk) must cover enough pairs: N = 32 gives
-// 128 x 32 pairs per 590 cycles = 6.9 pairs / clk / SM (2e12 pairs/s per GPU), above the MUFU / FMA ceilings of the
+// cycles whatever N is (16 .. 64), so the six MMAs of an (M-tile, chunk) must cover enough pairs: N = 32 gives
+// 128 x 32 pairs per 708 cycles = 5.8 pairs / clk / SM (1.7e12 pairs/s per GPU), above the MUFU / FMA ceilings of the
 // CUDA-core part.  TMEM: 2 M-tiles x 3 products x 32 columns, double buffered = 384 of 512 columns.
 //
 // CTA = 18 warps, 256 objects: warps 0-15 are four consumer warpgroups (warp w reads TMEM lanes 32 (w % 4) ..); warpgroup
@@ -24,10 +25,10 @@
 // two halves of packed registers.  Warp 16 stages 256-model tiles with TMA bulk copies, warp 17 issues the MMAs.
 //
 // Shared-memory / global layout of a model tile (TC_TILE_BYTES, one bulk copy):
-//   [k-step s (5)][row group (32)][k chunk (2)][row (8)][4 floats]   MMA B operand, SBO = 256 B, LBO = 128 B
-//        k-steps 0-1: m_hi | m_lo | m_hi | 0        (paired with  -x_hi | -x_hi | -x_lo | 0,  x = w d)
+//   [k-step s (4)][row group (32)][k chunk (2)][row (8)][4 floats]   MMA B operand, SBO = 256 B, LBO = 128 B
+//        k-steps 0-1: m_hi | m_lo | m_hi | 0        (paired with  -x_hi | -x_hi | -x_lo | 0,  x = w d, for inter
+//                                                    and with      g_hi |  g_hi |  g_lo | 0,  g = 2 w d_lo, for G)
 //        k-steps 2-3: q_hi | q_lo | q_hi | 0        (q = m^2;     w_hi |  w_hi |  w_lo | 0)
-//        k-step  4  : m_hi | 0 0 0                  (             g           , g = 2 w d_lo)
 //   [model pair (128)][6] float2   (m_even, m_odd) per band, then the prior pair   (48 B, three LDS.128)
 //   [model pair (128)]    {invnorm_even, invnorm_odd, bin_even, bin_odd}
 //   [8 models (32)]       {bin of the first, 1 if all eight share it}
@@ -42,19 +43,20 @@ constexpr int TC_SPLIT = TC_NWG / TC_MT;         // warpgroups (threads) sharing
 constexpr int TC_OBJS = TC_MT * 128;             // objects per CTA
 constexpr int TC_THREADS = TC_NWG * 128 + 64;    // + TMA warp + MMA warp
 constexpr int TC_CW = TC_NWG * 4;                // consumer warps; warp TC_CW = TMA, TC_CW + 1 = MMA
-constexpr int TC_KSTEPS = 5;
+constexpr int TC_KSTEPS = 4;                     // K = 8 steps of the model operand: m rows (2), m^2 rows (2)
+constexpr int TC_AKSTEPS = 6;                    // ... of the object operand: -x (2), w (2), g (2)
 constexpr int TC_OPSEC = TC_KSTEPS * TC_TM * 32;
 constexpr int TC_PAIRSEC = (TC_TM / 2) * 48;
 constexpr int TC_TAILSEC = (TC_TM / 2) * 16;
 constexpr int TC_SUBSEC = (TC_TM / 8) * 8;         // per 8 models: {KDE bin of the first, 1 if all eight share it}
 constexpr int TC_TILE_BYTES = TC_OPSEC + TC_PAIRSEC + TC_TAILSEC + TC_SUBSEC;
-constexpr int TC_OBJA_TILE = TC_KSTEPS * 128 * 32;
+constexpr int TC_OBJA_TILE = TC_AKSTEPS * 128 * 32;
 constexpr int TC_OBJA_BYTES = TC_MT * TC_OBJA_TILE;
 constexpr int TC_NSTAGE = 2;
 constexpr int TC_CHUNK_COLS = TC_MT * 3 * TC_NC;  // TMEM columns of one chunk buffer
 constexpr int TC_TMEM_COLS = 512;
 constexpr size_t TC_SMEM = (size_t)TC_OBJA_BYTES + (size_t)TC_NSTAGE * TC_TILE_BYTES + 512;
-static_assert(TC_TILE_BYTES == 49408 && TC_TILE_BYTES % 128 == 0, "tile layout");
+static_assert(TC_TILE_BYTES == 41216 && TC_TILE_BYTES % 128 == 0, "tile layout");
 static_assert(2 * TC_CHUNK_COLS <= TC_TMEM_COLS, "TMEM budget");
 static_assert(TC_SPLIT == 2 && TC_NSUB == 4, "sub-batch assignment below assumes two warpgroups per M-tile, four sub-batches");
 
@@ -150,11 +152,12 @@ __device__ __forceinline__ float pow2i(float k) {
     return (k >= -126.f) ? __int_as_float(((int)fminf(k, 127.f) + 127) << 23) : 0.f;
 }
 
-template <int NF, bool DP, bool PRIOR, int PASS>
+template <int NF, bool DP, bool PRIOR, int PASS, bool LIN = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const unsigned char* __restrict__ tiles, uint32_t lbo,
                                                             uint32_t sbo) {
     static_assert(NF <= 5, "3 NF K-slots must fit two K = 8 instructions");
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    static_assert(!LIN || DP, "the linear-domain form is the dim_prior likelihood with (dof/2 - 1) = 1");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* objA = smem_raw;
     unsigned char* stage = smem_raw + TC_OBJA_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage + (size_t)TC_NSTAGE * TC_TILE_BYTES);
@@ -191,6 +194,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
     f2 d2[NF], w2[NF], K2 = 0, A2 = 0;
     f2 M2 = 0, S2 = 0, acc2 = 0;
     float thr = 0.f, Mfl = -FLT_MAX;
+    float Rf = 0.f;                             // LIN: reference exponent of the linear-domain weights
     double Sd = 0.0;
     int best0 = 0, best1 = 0, oidx = -1;
     if (warp < TC_CW) {
@@ -200,23 +204,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
         else o = slot < P.No ? P.objlist[slot] : -1;
         oidx = (int)o;
         const int64_t oo = o < 0 ? 0 : o;
-        float arow[40];
+        float arow[8 * TC_AKSTEPS];
 #pragma unroll
-        for (int i = 0; i < 40; ++i) arow[i] = 0.f;
+        for (int i = 0; i < 8 * TC_AKSTEPS; ++i) arow[i] = 0.f;
         float kk = 0.f;
 #pragma unroll
         for (int b = 0; b < NF; ++b) {
             const float d = P.od[b * P.No_pad + oo], w = P.ow[b * P.No_pad + oo];
             const float x = P.ox[b * P.No_pad + oo], dl = P.odl[b * P.No_pad + oo];
             d2[b] = pack2(d, d);
-            w2[b] = pack2(w, w);
-            const float g = w * dl;
+            w2[b] = LIN ? pack2(-w, -w) : pack2(w, w);      // LIN: positive weights, x = chi2 log2(e)/2 >= 0
+            const float g = LIN ? -(w * dl) : w * dl;
             kk = fmaf(g, d, kk);
             const float xh = tf32_rn(x), xl = tf32_rn(x - xh);
             const float wh = tf32_rn(w), wl = tf32_rn(w - wh);
             arow[b] = -xh; arow[5 + b] = -xh; arow[10 + b] = -xl;
             arow[16 + b] = wh; arow[21 + b] = wh; arow[26 + b] = wl;
-            arow[32 + b] = tf32_rn(g);
+            const float gh = tf32_rn(g), gl = tf32_rn(g - gh);
+            arow[32 + b] = gh; arow[37 + b] = gh; arow[42 + b] = gl;
         }
         K2 = pack2(kk, kk);
         const float a = P.oA[oo];
@@ -224,15 +229,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
         if (half == 0) {        // one of the two threads of the object writes its row of the A operand
             unsigned char* dst = objA + (size_t)mt * TC_OBJA_TILE + (row >> 3) * 256 + (row & 7) * 16;
 #pragma unroll
-            for (int s = 0; s < TC_KSTEPS; ++s)
+            for (int s = 0; s < TC_AKSTEPS; ++s)
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
                     *reinterpret_cast<float4*>(dst + s * 4096 + c * 128) =
                         make_float4(arow[s * 8 + c * 4], arow[s * 8 + c * 4 + 1], arow[s * 8 + c * 4 + 2], arow[s * 8 + c * 4 + 3]);
         }
         thr = (PASS == 2) ? P.thr2[oo] : 0.f;
-        if (PASS == 1) { M2 = pack2(-FLT_MAX, -FLT_MAX); S2 = pack2(0.f, 0.f); }
-        else { const float m = P.M2[oo]; M2 = pack2(m, m); acc2 = pack2(0.f, 0.f); }
+        if (PASS == 1) { M2 = LIN ? pack2(0.f, 0.f) : pack2(-FLT_MAX, -FLT_MAX); S2 = pack2(0.f, 0.f); Rf = FLT_MAX; }
+        else {
+            const float m = P.M2[oo];
+            M2 = pack2(m, m);
+            acc2 = pack2(0.f, 0.f);
+            if (LIN) { Rf = -m; thr = exp2f(thr - m); }      // weight cut in the linear domain: 2^(l - M) > 2^(thr - M)
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core (async proxy) reads
     }
     tc_fence_before();
@@ -276,11 +286,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                     if (elect_one()) {
                         const uint32_t dcol = tmem + buf * TC_CHUNK_COLS + m * (3 * TC_NC);
                         const uint32_t a0 = a_lo + ((m * TC_OBJA_TILE) >> 4);
-                        tc_mma<false>(dcol, a0, b0, desc_hi, idesc);
+                        tc_mma<false>(dcol, a0, b0, desc_hi, idesc);                                                // inter
                         tc_mma<true>(dcol, a0 + (4096 >> 4), b0 + (8192 >> 4), desc_hi, idesc);
-                        tc_mma<false>(dcol + TC_NC, a0 + (2 * 4096 >> 4), b0 + (2 * 8192 >> 4), desc_hi, idesc);
+                        tc_mma<false>(dcol + TC_NC, a0 + (2 * 4096 >> 4), b0 + (2 * 8192 >> 4), desc_hi, idesc);    // shape
                         tc_mma<true>(dcol + TC_NC, a0 + (3 * 4096 >> 4), b0 + (3 * 8192 >> 4), desc_hi, idesc);
-                        tc_mma<false>(dcol + 2 * TC_NC, a0 + (4 * 4096 >> 4), b0 + (4 * 8192 >> 4), desc_hi, idesc);
+                        tc_mma<false>(dcol + 2 * TC_NC, a0 + (4 * 4096 >> 4), b0, desc_hi, idesc);                   // G
+                        tc_mma<true>(dcol + 2 * TC_NC, a0 + (5 * 4096 >> 4), b0 + (8192 >> 4), desc_hi, idesc);
                         tc_commit(&acc_full[m * 2 + buf]);
                     }
                     __syncwarp();
@@ -356,6 +367,133 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                 }
             }
         };
+        // ---- linear-domain form (LIN): with (dof/2 - 1) = 1 the likelihood is 2^l = x 2^(-x), x = chi2 log2(e)/2, so the
+        // weight relative to a reference exponent R is y = x 2^(R - x + prior): one ex2 and no lg2 per pair, a plain sum
+        // and a plain max.  Pass 1 keeps R per object (integer valued, so that a change of R rescales the sums by an
+        // exact power of two) and lowers it whenever the largest weight passes 2^8; a jump beyond 2^24 (or an
+        // overflow) has the sub-batch redone from the saved state in a frame at the new minimum.  Pass 2 uses R = -M.
+        auto process_lin = [&](auto slow_tag, const int p0, float (&Bv)[8], float (&Cv)[8], float (&Gv)[8]) {
+            constexpr bool SLOW = decltype(slow_tag)::value;
+            f2 xs[4], pr[4];
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                const int p = p0 + jp;
+                const ulonglong2 q0 = pairs[p * 3], q1 = pairs[p * 3 + 1], q2 = pairs[p * 3 + 2];
+                f2 m2[5] = {q0.x, q0.y, q1.x, q1.y, q2.x};
+                pr[jp] = q2.y;
+                const f2 B2 = pack2(Bv[2 * jp], Bv[2 * jp + 1]);
+                const f2 C2 = pack2(Cv[2 * jp], Cv[2 * jp + 1]);
+                const f2 G2 = pack2(Gv[2 * jp], Gv[2 * jp + 1]);
+                f2 x = tc_pair_c<NF>(B2, C2, G2, m2, d2, w2, K2);
+                if (SLOW) {      // padding models (beyond the last one) get x = FLT_MAX: weight 0, never the minimum
+                    const int cnt_i = 2 * npair_full + (odd ? 1 : 0);
+                    x = pack2(2 * p < cnt_i ? lo2(x) : FLT_MAX, 2 * p + 1 < cnt_i ? hi2(x) : FLT_MAX);
+                }
+                xs[jp] = x;
+            }
+            if (PASS == 1) {
+                // running sums in the frame of R; the maximum itself is kept in the log domain (Mfl, best0), evaluated only
+                // for the rare candidates y > Yt = (1 - 2^-18) max y, so that the arg-max does not depend on the frame
+                const f2 S2s = S2;
+                const float Yms = lo2(M2), Yts = hi2(M2), Mls = Mfl, Rfs = Rf;
+                const double Sds = Sd;
+                const int bs = best0;
+                const int ig0 = first_i + 2 * p0;
+                auto accumulate = [&]() {
+                    const f2 R2 = pack2(Rf, Rf);
+                    f2 ys[4];
+                    bool cand = false;
+                    const float Yt = hi2(M2);
+#pragma unroll
+                    for (int jp = 0; jp < 4; ++jp) {
+                        const f2 arg = fma2(xs[jp], kMinusOne, PRIOR ? add2(pr[jp], R2) : R2);
+                        ys[jp] = mul2(xs[jp], pack2(fast_ex2(lo2(arg)), fast_ex2(hi2(arg))));
+                        S2 = add2(S2, ys[jp]);
+                        cand = cand || (lo2(ys[jp]) > Yt) || (hi2(ys[jp]) > Yt);
+                    }
+                    if (__any_sync(0xffffffffu, cand)) {
+                        float Ym = lo2(M2);
+#pragma unroll
+                        for (int jp = 0; jp < 4; ++jp) {
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const float y = e ? hi2(ys[jp]) : lo2(ys[jp]);
+                                if (y > Yt) {
+                                    const float x = e ? hi2(xs[jp]) : lo2(xs[jp]);
+                                    float l = fast_lg2(x) - x;
+                                    if (PRIOR) l += e ? hi2(pr[jp]) : lo2(pr[jp]);
+                                    if (l > Mfl) { Mfl = l; best0 = ig0 + 2 * jp + e; }
+                                    Ym = fmaxf(Ym, y);
+                                }
+                            }
+                        }
+                        // keep the largest weight below 2^8 (the fp32 rounding of R - x grows with |R - x|): an exact
+                        // power-of-two change of frame, no recomputation
+                        if (Ym >= 256.f && Ym < 16777216.f) {
+                            const int k = ((__float_as_int(Ym) >> 23) & 0xff) - 127;
+                            const float f = __int_as_float((127 - k) << 23);
+                            S2 = mul2(S2, pack2(f, f));
+                            Sd *= (double)f;
+                            Ym *= f;
+                            Rf -= (float)k;
+                        }
+                        M2 = pack2(Ym, Ym * 0.99999618530273438f);
+                    }
+                };
+                accumulate();
+                const float tsum = lo2(S2) + hi2(S2);
+                // a jump of more than 2^24 (or an overflow: inf / NaN in the sum) is redone in a frame at the new minimum
+                const bool ovf = !(lo2(M2) < 16777216.f) || !(tsum < 1.2676506e30f);
+                if (__any_sync(0xffffffffu, ovf)) {
+                    Rf = Rfs;          // undo a frame shift the first attempt may have made: everything restarts from the saved state
+                    Sd = Sds;
+                    float mn = FLT_MAX;
+#pragma unroll
+                    for (int jp = 0; jp < 4; ++jp) {
+                        const f2 v = PRIOR ? fma2(pr[jp], kMinusOne, xs[jp]) : xs[jp];
+                        mn = fminf(mn, fminf(lo2(v), hi2(v)));
+                    }
+                    const float Rn = ovf ? fminf(floorf(mn), Rf - 1.f) : Rf;
+                    const float f = ovf ? ((Rf < 1e38f) ? pow2i(Rn - Rf) : 0.f) : 1.f;
+                    S2 = mul2(S2s, pack2(f, f));
+                    M2 = pack2(Yms * f, Yts * f);
+                    Sd *= (double)f;
+                    Mfl = Mls;
+                    best0 = bs;
+                    Rf = Rn;
+                    accumulate();
+                }
+            } else {
+                const f2 R2 = pack2(Rf, Rf);
+#pragma unroll
+                for (int jp = 0; jp < 4; ++jp) {
+                    const int p = p0 + jp;
+                    const float4 tl = tails[p];
+                    const f2 arg = fma2(xs[jp], kMinusOne, PRIOR ? add2(pr[jp], R2) : R2);
+                    const f2 u = mul2(xs[jp], pack2(fast_ex2(lo2(arg)), fast_ex2(hi2(arg))));
+                    const float u0 = (lo2(u) > thr) ? lo2(u) : 0.f;
+                    const float u1 = (hi2(u) > thr) ? hi2(u) : 0.f;
+                    if (!SLOW) {
+                        acc2 = fma2(pack2(u0, u1), pack2(tl.x, tl.y), acc2);
+                    } else {
+                        if (p > npair_full || (p == npair_full && !odd)) continue;      // warp-uniform: nothing but padding
+                        const bool tail = (p == npair_full);
+                        const int bin0 = __float_as_int(tl.z), bin1 = tail ? bin0 : __float_as_int(tl.w);
+                        if (bin0 != cur_bin) {             // warp-uniform
+                            if (cur_bin >= 0) { flush(lo2(acc2) + hi2(acc2), cur_bin); acc2 = pack2(0.f, 0.f); }
+                            cur_bin = bin0;
+                        }
+                        if (bin1 == bin0) {
+                            acc2 = fma2(pack2(u0, u1), pack2(tl.x, tl.y), acc2);
+                        } else {                           // the pair straddles a bin boundary
+                            flush(fmaf(u0, tl.x, lo2(acc2) + hi2(acc2)), bin0);
+                            acc2 = pack2(0.f, u1 * tl.y);
+                            cur_bin = bin1;
+                        }
+                    }
+                }
+            }
+        };
         for (int it = 0; it < nt; ++it) {
             const int st = it % TC_NSTAGE, n = it / TC_NSTAGE;
             mbar_wait_hint(&tile_full[st], (uint32_t)(n & 1));
@@ -399,11 +537,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                             cur_bin = si.x;
                         }
                     }
-                    if (fast) process(std::false_type{}, p0, Bv, Cv, Gv);
-                    else process(std::true_type{}, p0, Bv, Cv, Gv);
+                    if (LIN) {
+                        if (fast) process_lin(std::false_type{}, p0, Bv, Cv, Gv);
+                        else process_lin(std::true_type{}, p0, Bv, Cv, Gv);
+                    } else {
+                        if (fast) process(std::false_type{}, p0, Bv, Cv, Gv);
+                        else process(std::true_type{}, p0, Bv, Cv, Gv);
+                    }
                 }
             }
-            if (PASS == 1) {
+            if (PASS == 1 && LIN) {
+                Sd += (double)(lo2(S2) + hi2(S2));
+                S2 = pack2(0.f, 0.f);
+            } else if (PASS == 1) {
                 // fp32 sums only within a tile; tiles (and the two model lanes) are combined in float64
                 const float m0 = lo2(M2), m1 = hi2(M2);
                 const float mn = fmaxf(m0, m1);
@@ -418,12 +564,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
             const int64_t slot = tile_base + (int64_t)mt * 128 + row;
             if (slot < P.No_pad) {
                 const float m0 = lo2(M2), m1 = hi2(M2);
-                const int b = (m0 > m1) ? best0 : ((m1 > m0) ? best1 : min(best0, best1));
                 // the two threads of an object report like two model splits
                 const size_t q = ((size_t)blockIdx.y * TC_SPLIT + half) * P.No_pad + slot;
-                P.pM[q] = (double)Mfl;
-                P.pS[q] = Sd;
-                P.pbest[q] = b;
+                if (LIN) {
+                    // y = 2^(l + R): sum 2^(l - max l) = sum y / 2^(max l + R)
+                    const bool any = Mfl > -FLT_MAX;
+                    P.pM[q] = (double)Mfl;
+                    P.pS[q] = any ? Sd * exp2(-((double)Mfl + (double)Rf)) : 0.0;
+                    P.pbest[q] = best0;
+                } else {
+                    P.pM[q] = (double)Mfl;
+                    P.pS[q] = Sd;
+                    P.pbest[q] = (m0 > m1) ? best0 : ((m1 > m0) ? best1 : min(best0, best1));
+                }
             }
         } else if (cur_bin >= 0) {
             flush(lo2(acc2) + hi2(acc2), cur_bin);
@@ -452,8 +605,8 @@ __global__ void k_build_tiles_tc(TcRecParams P) {
     const int64_t j = P.perm[p];
     const int r = (int)(p % TC_TM);
     unsigned char* T = P.tiles + (size_t)(p / TC_TM) * TC_TILE_BYTES;
-    float rowv[40];
-    for (int i = 0; i < 40; ++i) rowv[i] = 0.f;
+    float rowv[8 * TC_KSTEPS];
+    for (int i = 0; i < 8 * TC_KSTEPS; ++i) rowv[i] = 0.f;
     float* pr = reinterpret_cast<float*>(T + TC_OPSEC) + (r >> 1) * 12;
     for (int b = 0; b < P.Nf; ++b) {
         const double v = P.m[j * P.Nf + b];
@@ -462,7 +615,6 @@ __global__ void k_build_tiles_tc(TcRecParams P) {
         const float qh = tf32_rn(q), ql = tf32_rn(q - qh);
         rowv[b] = mh; rowv[5 + b] = ml; rowv[10 + b] = mh;
         rowv[16 + b] = qh; rowv[21 + b] = ql; rowv[26 + b] = qh;
-        rowv[32 + b] = mh;
         pr[2 * b + (r & 1)] = mf;
     }
     pr[10 + (r & 1)] = P.lnprior ? (float)(P.lnprior[j] * 1.4426950408889634) : 0.f;
