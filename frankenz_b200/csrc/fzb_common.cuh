@@ -137,6 +137,7 @@ struct fzb_context {
     bool fast_packed = true;
     int fast_wmax = 0;
     int fast_Ngpad = 0;
+    int fast_ns64 = 0;             // model splits of the last float64 sweep
     // state a model-sharded pass 1 leaves for pass 2
     bool shard_valid = false;
     int64_t shard_No = 0;

@@ -755,7 +755,8 @@ struct Sweep64Params {
     const double* recs;             // [nm][REC64]
     int64_t nm;
     int tiles_per_split;
-    double* pM;                     // [nsplit][No_pad]  pass 1 out
+    double* pM;                     // pass 1 out: [nsplit][No_pad] by object, or [nsplit][part_stride] by list position
+    int64_t part_stride;            // > 0: partials indexed by position in objlist (compact, allows many splits)
     double* pS;
     int32_t* pbest;
     const double* M2;               // [No_pad]  pass 2 in
@@ -905,7 +906,8 @@ __global__ void __launch_bounds__(FT64, 2) k_sweep64(Sweep64Params P) {
 #pragma unroll
         for (int r = 0; r < R64; ++r)
             if (oidx[r] >= 0) {
-                size_t q = (size_t)blockIdx.y * P.No_pad + oidx[r];
+                const int64_t slot = (int64_t)blockIdx.x * (FT64 * R64) + (int64_t)r * FT64 + tid;
+                size_t q = P.part_stride > 0 ? (size_t)blockIdx.y * P.part_stride + slot : (size_t)blockIdx.y * P.No_pad + oidx[r];
                 P.pM[q] = Mfl[r];
                 P.pS[q] = Sd[r];
                 P.pbest[q] = best[r];
@@ -1034,6 +1036,7 @@ struct MergeParams {
     int stage;                          // 0: after the fp32 sweep (all objects); 1: after the float64 sweep (in_list)
     const int32_t* in_list;
     int64_t n_in;
+    int64_t part_stride;                // stage 1, > 0: partials indexed by position in in_list
     // outputs
     double *lmap, *levid, *best_chi2, *best_scale;   // absolute object index
     double* Sout;                       // nullable: sum exp(l - lmap) (model-sharded pass 1)
@@ -1059,20 +1062,23 @@ __global__ void k_merge(MergeParams P) {
     }
     double M = -DBL_MAX;
     int bs = 0;
+    const bool by_pos = (P.stage == 1 && P.part_stride > 0);
+    const size_t pstride = by_pos ? (size_t)P.part_stride : (size_t)P.No_pad;
+    const size_t pcol = by_pos ? (size_t)i : (size_t)o;
     for (int s = 0; s < P.nsplit; ++s) {
-        double v = P.pM[(size_t)s * P.No_pad + o];
+        double v = P.pM[(size_t)s * pstride + pcol];
         // exact ties go to the smallest model position, whatever the partition of the models was
-        if (v > M || (v == M && P.pbest[(size_t)s * P.No_pad + o] < P.pbest[(size_t)bs * P.No_pad + o])) { M = v; bs = s; }
+        if (v > M || (v == M && P.pbest[(size_t)s * pstride + pcol] < P.pbest[(size_t)bs * pstride + pcol])) { M = v; bs = s; }
     }
     double S = 0.0;
     bool bad = false;
     for (int s = 0; s < P.nsplit; ++s) {
-        double v = P.pM[(size_t)s * P.No_pad + o];
-        double ss = P.pS[(size_t)s * P.No_pad + o];
+        double v = P.pM[(size_t)s * pstride + pcol];
+        double ss = P.pS[(size_t)s * pstride + pcol];
         if (!(ss == ss) || isinf(ss)) bad = true;
         if (v > -1e300) S += ss * exp2(v - M);
     }
-    int64_t sorted_best = P.pbest[(size_t)bs * P.No_pad + o];
+    int64_t sorted_best = P.pbest[(size_t)bs * pstride + pcol];
     int64_t j = P.perm[sorted_best];
     // exact float64 evaluation of (object, best model): pdf.py:27-235 via fzb_pair64.cuh
     double sx[FZB_FAST_MAXF], sxe[FZB_FAST_MAXF], sxm[FZB_FAST_MAXF];
@@ -1764,11 +1770,26 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
 
         // ---- objects whose fp32 result is not trusted: float64 sweep, pass 1 ---------------------------
         if (nprec > 0) {
+            // few objects, all models: split the models finely enough to fill the GPU (partials compact, by list position)
             S6.objlist = prec_list; S6.nlist = nprec;
             const int64_t t64 = (nprec + FT64 * R64 - 1) / (FT64 * R64);
-            if (launch_sweep64(h, S6, dim3((unsigned)t64, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, 1)) return 1;
+            int64_t ns64 = ((int64_t)h->sm_count * 4 + t64 - 1) / t64;
+            ns64 = std::min(ns64, std::max<int64_t>(1, ((int64_t)32 << 20) / (t64 * FT64 * R64)));
+            ns64 = std::max<int64_t>(1, std::min(ns64, ntiles));
+            const int tps64 = (int)((ntiles + ns64 - 1) / ns64);
+            ns64 = (ntiles + tps64 - 1) / tps64;
+            const int64_t stride64 = t64 * FT64 * R64;
+            if (h->misc[6].reserve((size_t)ns64 * stride64 * 20 + 256)) return 1;
+            S6.pS = h->misc[6].as<double>();
+            S6.pM = S6.pS + (size_t)ns64 * stride64;
+            S6.pbest = reinterpret_cast<int32_t*>(S6.pM + (size_t)ns64 * stride64);
+            S6.part_stride = stride64;
+            S6.tiles_per_split = tps64;
+            h->fast_ns64 = (int)ns64;
+            if (launch_sweep64(h, S6, dim3((unsigned)t64, (unsigned)ns64), nf, mode, cfg.dim_prior != 0, 1)) return 1;
             h->stats.pairs_fp64 += nprec * nm;
-            MP.stage = 1; MP.in_list = prec_list; MP.n_in = nprec; MP.consist_tol = 1e-6; MP.nsplit = (int)nsplit;
+            MP.stage = 1; MP.in_list = prec_list; MP.n_in = nprec; MP.consist_tol = 1e-6; MP.nsplit = (int)ns64;
+            MP.pM = S6.pM; MP.pS = S6.pS; MP.pbest = S6.pbest; MP.part_stride = stride64;
             k_merge<<<(unsigned)((nprec + 255) / 256), 256, 0, h->stream>>>(MP);
             fzb_count_launch(h);
             FZB_CUDA(cudaGetLastError());
@@ -1828,7 +1849,11 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                 S6.objlist = safe64_list; S6.nlist = nsafe64; S6.M2 = M2d; S6.thr2 = thr2d; S6.hist = hist;
                 S6.hist_stride = hist_stride;
                 const int64_t t64 = (nsafe64 + FT64 * R64 - 1) / (FT64 * R64);
-                if (launch_sweep64(h, S6, dim3((unsigned)t64, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, 2)) return 1;
+                int64_t ns64 = std::max<int64_t>(1, std::min<int64_t>(((int64_t)h->sm_count * 4 + t64 - 1) / t64, ntiles));
+                const int tps64 = (int)((ntiles + ns64 - 1) / ns64);
+                ns64 = (ntiles + tps64 - 1) / tps64;
+                S6.tiles_per_split = tps64;
+                if (launch_sweep64(h, S6, dim3((unsigned)t64, (unsigned)ns64), nf, mode, cfg.dim_prior != 0, 2)) return 1;
                 h->stats.pairs_fp64 += nsafe64 * nm;
             }
             FZB_CUDA(cudaEventRecord(h->ev[5], h->stream));
