@@ -36,6 +36,8 @@ MUFU_PER_PAIR = 3.0
 # DRAM traffic of one k_sweep2 launch from the `ncu --set full` capture in profiles/r1_sweep_ncu.md
 # (dram__bytes_read.sum + dram__bytes_write.sum = 85.9 MB for 196,608 objects): bytes per object of the launch
 NCU_DRAM_BYTES_PER_OBJECT = 85.9e6 / 196608
+# the same for one k_sweep_tc pass-1 launch (profiles/r1_sweep_tc_ncu.md): 50.7 + 15.0 MB for 196,608 objects
+NCU_TC_DRAM_BYTES_PER_OBJECT = 65.7e6 / 196608
 LPROB = dict(free_scale=True, ignore_model_err=True, dim_prior=True)
 
 
@@ -290,15 +292,26 @@ def main():
     dom_ms = max(ms_scan, ms_acc)
     dom_pairs = float(no) * nm if ms_scan >= ms_acc else float(no - n64) * nm
     achieved = FLOPS_PER_PAIR * dom_pairs / (dom_ms * 1e-3) / 1e12
-    roofline = {"bound": "fp32_fma", "kernel": "k_sweep2<pass %d>" % (1 if ms_scan >= ms_acc else 2),
+    kind = int(st_acc[-1].get("sweep_kind", 1))
+    kname = {1: "k_sweep2", 2: "k_sweep_tc", 3: "k_sweep_tc<LIN>"}.get(kind, "k_sweep2")
+    tc = kind >= 2
+    mufu_per_pair = 2.0 if kind == 3 else MUFU_PER_PAIR
+    roofline = {"bound": "fp32_fma", "kernel": "%s<pass %d>" % (kname, 1 if ms_scan >= ms_acc else 2),
                 "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                 "peak_source": "fzb_measure_peaks (dependency-free FFMA loop, this run; MEASURED_PEAKS.json has no "
                                "fp32 entry)",
-                "mufu": {"achieved_gops": MUFU_PER_PAIR * dom_pairs / (dom_ms * 1e-3) / 1e9, "peak_gops": mufu_peak},
-                "traffic": NCU_DRAM_BYTES_PER_OBJECT * float(no),
-                "traffic_note": "bytes per launch scaled from the ncu --set full capture in profiles/r1_sweep_ncu.md "
-                                "(437 B/object: photometry planes in, per-split partials out); the kernel is "
-                                "compute-bound, HBM carries ~0.002 B per pair",
+                "note": ("algorithmic 54 flop/pair (SURVEY 8d) against the FP32 FMA peak; the tensor-core sweep executes "
+                         "30 of them (the three K=Nf dot products, as tf32x3 tcgen05 MMAs: 12.3 kflop of tensor work "
+                         "per pair incl. the split and padding) on the tensor pipe and ~40 on the FMA pipe, so the "
+                         "fraction is a figure of merit of the whole SM, not an FMA-pipe utilisation")
+                if tc else "algorithmic 54 flop/pair (SURVEY 8d) against the FP32 FMA peak",
+                "mufu": {"per_pair": mufu_per_pair,
+                         "achieved_gops": mufu_per_pair * dom_pairs / (dom_ms * 1e-3) / 1e9, "peak_gops": mufu_peak},
+                "traffic": (NCU_TC_DRAM_BYTES_PER_OBJECT if tc else NCU_DRAM_BYTES_PER_OBJECT) * float(no),
+                "traffic_note": "bytes per launch scaled from the ncu --set full capture in profiles/ (%s: photometry "
+                                "planes in, per-split partials out, pass 2 adds the histogram atomics); the kernel is "
+                                "compute-bound, HBM carries ~0.002 B per pair"
+                                % ("r1_sweep_tc_ncu.md" if tc else "r1_sweep_ncu.md"),
                 "algorithmic_flops_per_pair": FLOPS_PER_PAIR,
                 "pairs_per_s_kernel": dom_pairs / (dom_ms * 1e-3),
                 "fit_only_pairs_per_s": float(no) * nm / (ms_scan * 1e-3),
@@ -321,7 +334,7 @@ def main():
 
     out = {"metric": "object-model likelihood pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": max(1, world),
            "steps": args.steps, "warmup": warm, "ms_per_step": t_all / args.steps, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32 sweep + f64 best-fit/PDF (f64 fallback per object)",
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32 sweep (tf32x3 tensor-core dot products) + f64 best-fit/PDF (f64 fallback per object)",
            "data": "synthetic", "config": cfg_json, "objects_per_s": value / nm, "clocks": clocks, "e2e": e2e,
            "gpu_launches": int(sum(s["kernel_launches"] for s in st_acc)), "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(out))

@@ -34,7 +34,7 @@ class FzbFitOut(C.Structure):
 class FzbStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("pairs_fp32", C.c_int64), ("pairs_fp64", C.c_int64),
                 ("objects_fp64", C.c_int64), ("ms_scan", C.c_double), ("ms_accum", C.c_double),
-                ("ms_finish", C.c_double), ("ms_total", C.c_double)]
+                ("ms_finish", C.c_double), ("ms_total", C.c_double), ("sweep_kind", C.c_int64)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/frankenz_b200.h

@@ -1703,6 +1703,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         }
         if (shard_mode == 2) use_lin = h->shard_lin;
         else h->shard_lin = use_lin;
+        h->stats.sweep_kind = use_tc ? (use_lin ? 3 : 2) : 1;
 
         // ---- pass 1 (fp32, every object) ------------------------------------------------------------
         int32_t hc[4] = {0, 0, 0, 0};

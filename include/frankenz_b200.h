@@ -76,6 +76,8 @@ typedef struct FzbStats {
     double  ms_accum;          /* CUDA-event time of pass 2 (weights -> histogram)       */
     double  ms_finish;         /* CUDA-event time of histogram (*) kernel + normalise    */
     double  ms_total;          /* CUDA-event time of all device work of the call        */
+    int64_t sweep_kind;        /* fused path of the last call: 0 none, 1 packed FP32 sweep (k_sweep2), 2 tensor-core
+                                  sweep (k_sweep_tc), 3 tensor-core sweep in its linear-domain form           */
 } FzbStats;
 
 const char* fzb_last_error(void);

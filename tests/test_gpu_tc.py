@@ -1,0 +1,123 @@
+"""Tensor-core sweep (csrc/fzb_sweep_tc.cuh) against the CPU oracle (oracle/fz_oracle.py, the restatement of
+frankenz/bruteforce.py:505-631 + pdf.py:103-235) on the branches the full-size C3 tests do not reach: partial / odd
+model tiles, a per-model prior, the log-domain form (dim_prior=False; four bands), objects with masked or non-finite
+bands and very bright objects (both leave the fp32 path), and batch / split invariance.  Bounds are the north_star's:
+PDFs 1e-5 L1, lmap / levid 1e-5 max(1, |x|)."""
+import numpy as np
+import pytest
+
+import bench_data
+from oracle import fz_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fz():
+    import frankenz_b200
+    return frankenz_b200
+
+
+def _case(nm, no, nf=5, seed=5):
+    models, labels, depth = bench_data.c3_models()
+    rs = np.random.RandomState(seed)
+    pick = np.sort(rs.choice(len(models), nm, replace=False))
+    m = np.ascontiguousarray(models[pick][:, :nf])
+    x, xe, xm, _, _ = bench_data.c3_objects(no, models[pick], depth, seed=seed + 1)
+    return m, labels[pick], np.ascontiguousarray(x[:, :nf]), np.ascontiguousarray(xe[:, :nf]), np.ones((no, nf))
+
+
+def _run(fz, m, lab, x, xe, xm, lprob, lnprior=None):
+    zgrid, sig = bench_data.c3_kde()
+    rdict = fz.pdf.PDFDict(zgrid, sig)
+    labe = np.full(len(m), 0.05)
+    bf = fz.BruteForce(m, np.zeros_like(m), np.ones_like(m))
+    kw = dict(lprob)
+    if lnprior is not None:
+        kw["lnprior"] = lnprior
+    p, (lm, le) = bf.fit_predict(x.copy(), xe.copy(), xm.copy(), lab, labe, label_dict=rdict, return_gof=True,
+                                 verbose=False, save_fits=False, lprob_kwargs=kw)
+    st = bf._eng().stats()
+    kd = fo.KernelDict(zgrid, sig)
+    with np.errstate(all="ignore"):
+        po, lmo, leo = fo.bruteforce_fit_predict(m, np.zeros_like(m), np.ones_like(m), x.copy(), xe.copy(), xm.copy(),
+                                                 lab, labe, label_dict=kd, lnprior=lnprior, **lprob)
+    return p, lm, le, po, lmo, leo, st
+
+
+def _check(p, lm, le, po, lmo, leo):
+    ok = np.isfinite(lmo)
+    assert np.array_equal(np.isfinite(lm), ok)
+    assert np.max(np.sum(np.abs(p[ok] - po[ok]), axis=1)) <= 1e-5
+    assert np.all(np.abs(lm[ok] - lmo[ok]) <= 1e-5 * np.maximum(1, np.abs(lmo[ok])))
+    assert np.all(np.abs(le[ok] - leo[ok]) <= 1e-5 * np.maximum(1, np.abs(leo[ok])))
+
+
+FS = dict(free_scale=True, ignore_model_err=True, dim_prior=True)
+
+
+@pytest.mark.parametrize("nm", [5003, 4098, 777])
+def test_partial_and_odd_model_tiles(fz, nm):
+    """Model counts that end in an odd pair / a partial 8-model sub-batch / a partial 32-model chunk."""
+    m, lab, x, xe, xm = _case(nm, 300)
+    p, lm, le, po, lmo, leo, st = _run(fz, m, lab, x, xe, xm, FS)
+    assert st["sweep_kind"] == 3 and st["pairs_fp32"] > 0           # linear-domain tensor-core sweep
+    _check(p, lm, le, po, lmo, leo)
+
+
+def test_per_model_prior(fz):
+    m, lab, x, xe, xm = _case(6001, 256)
+    lnprior = np.random.RandomState(2).uniform(-6, 0, len(m))
+    p, lm, le, po, lmo, leo, st = _run(fz, m, lab, x, xe, xm, FS, lnprior=lnprior)
+    assert st["sweep_kind"] == 3
+    _check(p, lm, le, po, lmo, leo)
+
+
+def test_log_domain_forms(fz):
+    """dim_prior=False (plain exp(-chi2/2) weights) and four bands ((dof/2 - 1) = 1/2) keep the lg2 form."""
+    m, lab, x, xe, xm = _case(5003, 256)
+    p, lm, le, po, lmo, leo, st = _run(fz, m, lab, x, xe, xm, dict(FS, dim_prior=False))
+    assert st["sweep_kind"] == 2
+    _check(p, lm, le, po, lmo, leo)
+    m, lab, x, xe, xm = _case(5003, 256, nf=4)
+    p, lm, le, po, lmo, leo, st = _run(fz, m, lab, x, xe, xm, FS)
+    assert st["sweep_kind"] == 2
+    _check(p, lm, le, po, lmo, leo)
+
+
+def test_masked_nonfinite_and_bright_objects_leave_the_fp32_path(fz):
+    m, lab, x, xe, xm = _case(5003, 512)
+    xm[3, 1] = 0.0                      # masked band: (dof/2 - 1) = 1/2, not served by the linear-domain kernel
+    x[7, 4] = np.nan                    # cleaned to a masked band (pdf.py:310-311)
+    xe[9, 0] = -1.0
+    x[11] = 3e4 * xe[11] * m[100] / m[100, 2]       # S/N ~ 1e5: beyond the tf32-split bound
+    p, lm, le, po, lmo, leo, st = _run(fz, m, lab, x, xe, xm, FS)
+    assert st["sweep_kind"] == 3 and st["objects_fp64"] >= 4
+    _check(p, lm, le, po, lmo, leo)
+
+
+def test_many_masked_objects_switch_to_the_log_domain_kernel(fz):
+    m, lab, x, xe, xm = _case(4098, 256)
+    xm[::3, 0] = 0.0
+    p, lm, le, po, lmo, leo, st = _run(fz, m, lab, x, xe, xm, FS)
+    assert st["sweep_kind"] == 2
+    _check(p, lm, le, po, lmo, leo)
+
+
+def test_batch_and_split_invariance(fz):
+    """The arg-max (hence lmap) is decided on frame-independent log-domain values: the same object gives the same
+    lmap bit for bit whatever the batch (which sets the model split count) it is processed in."""
+    m, lab, x, xe, xm = _case(20011, 3000)
+    zgrid, sig = bench_data.c3_kde()
+    rdict = fz.pdf.PDFDict(zgrid, sig)
+    labe = np.full(len(m), 0.05)
+    bf = fz.BruteForce(m, np.zeros_like(m), np.ones_like(m))
+    out = []
+    for sel in (slice(0, 3000), slice(0, 100), slice(50, 1500)):
+        p, (lm, le) = bf.fit_predict(x[sel].copy(), xe[sel].copy(), xm[sel].copy(), lab, labe, label_dict=rdict,
+                                     return_gof=True, verbose=False, save_fits=False, lprob_kwargs=FS)
+        out.append((sel, p, lm, le, bf.best_idx.copy()))
+    _, p0, lm0, le0, b0 = out[0]
+    for sel, p, lm, le, b in out[1:]:
+        assert np.array_equal(b, b0[sel]) and np.array_equal(lm, lm0[sel])
+        assert np.max(np.abs(le - le0[sel])) <= 2e-6 and np.max(np.sum(np.abs(p - p0[sel]), axis=1)) <= 2e-6
