@@ -407,11 +407,15 @@ int fzb_set_models(fzb_handle h, const double* models, const double* models_err,
 int fzb_set_lnprior(fzb_handle h, const double* lnprior, int64_t Nm) {
     if (use_device(h) || check_models(h)) return 2;
     if (lnprior == nullptr) {
+        if (h->has_lnprior) h->fast_dirty = true;      // (every fit call passes through here: only a change costs a rebuild)
         h->has_lnprior = false;
-        h->fast_dirty = true;
+        h->h_lnprior.clear();
         return 0;
     }
     FZB_CHECK(Nm == h->Nm, "lnprior has %lld entries, model set has %lld", (long long)Nm, (long long)h->Nm);
+    if (h->has_lnprior && h->h_lnprior.size() == (size_t)Nm && memcmp(h->h_lnprior.data(), lnprior, (size_t)Nm * sizeof(double)) == 0)
+        return 0;
+    h->h_lnprior.assign(lnprior, lnprior + Nm);
     if (upload(h, h->lnprior, lnprior, (size_t)Nm)) return 1;
     FZB_CUDA(cudaStreamSynchronize(h->stream));
     h->has_lnprior = true;
@@ -459,9 +463,19 @@ int fzb_set_kde_dict(fzb_handle h, int32_t Ngrid, int32_t Ndict, const int32_t* 
     for (int i = 0; i < Ndict; ++i)
         FZB_CHECK(koff[i + 1] - koff[i] == 2 * (int64_t)widths[i] + 1 || koff[i + 1] - koff[i] >= 0,
                   "malformed kernel table");
+    size_t tot = (size_t)koff[Ndict];
+    // the same dictionary as last time (fit_predict passes it with every call): keep the tables and whatever was derived
+    // from them (sorted model records, tiles)
+    if (h->kde_mode == FZB_KDE_DICT && h->Ng == Ngrid && h->Ndict == Ndict && h->h_kernels.size() == tot &&
+        h->h_kcdf.size() == tot && h->h_widths.size() == (size_t)Ndict &&
+        memcmp(h->h_widths.data(), widths, (size_t)Ndict * sizeof(int32_t)) == 0 &&
+        memcmp(h->h_koff.data(), koff, ((size_t)Ndict + 1) * sizeof(int64_t)) == 0 &&
+        memcmp(h->h_kernels.data(), kernels, tot * sizeof(double)) == 0 && memcmp(h->h_kcdf.data(), kcdf, tot * sizeof(double)) == 0)
+        return 0;
     h->h_widths.assign(widths, widths + Ndict);
     h->h_koff.assign(koff, koff + Ndict + 1);
-    size_t tot = (size_t)koff[Ndict];
+    h->h_kernels.assign(kernels, kernels + tot);
+    h->h_kcdf.assign(kcdf, kcdf + tot);
     if (upload(h, h->widths, widths, (size_t)Ndict) || upload(h, h->koff, koff, (size_t)Ndict + 1) ||
         upload(h, h->kernels, kernels, tot) || upload(h, h->kcdf, kcdf, tot))
         return 1;
@@ -493,6 +507,10 @@ int fzb_set_labels_dict(fzb_handle h, const int64_t* y_idx, const int64_t* y_std
                   "label %lld lies further outside the grid than its kernel width (the reference raises here)",
                   (long long)j);
     }
+    if (h->labels_dict_set && h->h_yidx.size() == (size_t)Nm && h->h_ysidx.size() == (size_t)Nm &&
+        memcmp(h->h_yidx.data(), y_idx, (size_t)Nm * sizeof(int64_t)) == 0 &&
+        memcmp(h->h_ysidx.data(), y_std_idx, (size_t)Nm * sizeof(int64_t)) == 0)
+        return 0;          // unchanged labels: the sorted records stay valid
     h->h_yidx.assign(y_idx, y_idx + Nm);
     h->h_ysidx.assign(y_std_idx, y_std_idx + Nm);
     if (upload(h, h->yidx, y_idx, (size_t)Nm) || upload(h, h->ysidx, y_std_idx, (size_t)Nm)) return 1;
@@ -645,8 +663,9 @@ int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, co
     double* d_bs = h->out_f64[4].as<double>();
     int64_t* d_bi = h->out_i64[0].as<int64_t>();
 
-    // chunk size: large enough for full waves of the sweep kernels, small enough to pipeline
-    int64_t chunk = 98304;
+    // chunk size: large enough for long CTAs of the sweep kernels (few model splits), small enough to pipeline; the chunks
+    // taper towards the end (below), so the size of the main ones does not set the un-hidden tail
+    int64_t chunk = 196608;
     if (const char* e = getenv("FZB_E2E_CHUNK")) chunk = std::max<int64_t>(1024, atoll(e));
     if (!pdfs || No <= chunk + chunk / 2) chunk = No;
     const size_t chunk_bytes = (size_t)chunk * Ng * sizeof(double);
@@ -659,8 +678,13 @@ int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, co
     FZB_CUDA(cudaEventRecord(h->ev[0], h->stream));
     int64_t c = 0;
     int64_t push_id[2] = {-1, -1};
-    for (int64_t o0 = 0; o0 < No; o0 += chunk, ++c) {
-        int64_t nc = std::min(chunk, No - o0);
+    int64_t nc = 0;
+    for (int64_t o0 = 0; o0 < No; o0 += nc, ++c) {
+        // the download of the last chunk is the only one nothing hides: taper the chunk size towards the end
+        const int64_t rem = No - o0;
+        nc = chunk;
+        if (pdfs && rem < 2 * chunk) nc = std::max<int64_t>(std::min<int64_t>(rem, 8192), (rem / 2 + 4095) / 4096 * 4096);
+        nc = std::min(nc, rem);
         int b = (int)(c & 1);
         h->prior_o0 = o0;
         // device buffer b was last read by the download of chunk c-2 (issued before that of chunk c-1)

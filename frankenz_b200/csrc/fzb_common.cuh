@@ -100,6 +100,7 @@ struct fzb_context {
     int Nf = 0;
     DevBuf models, models_err, models_mask, lnprior;
     bool has_lnprior = false;
+    std::vector<double> h_lnprior;   // host copy: detect an unchanged prior
     // object-conditioned tabulated prior: table [nbins][Nm]; bins of the objects of the next call
     DevBuf prior_table, prior_bins;
     int prior_nbins = 0;
@@ -117,6 +118,7 @@ struct fzb_context {
     int Ndict = 0;
     std::vector<int32_t> h_widths;
     std::vector<int64_t> h_koff;
+    std::vector<double> h_kernels, h_kcdf;  // host copies: detect an unchanged dictionary
     DevBuf widths, koff, kernels, kcdf;     // dictionary
     DevBuf yidx, ysidx;                     // int64 per model
     std::vector<int64_t> h_yidx, h_ysidx;
