@@ -254,3 +254,43 @@ class Engine(object):
         s = FzbStats()
         _lib.check(self.lib.fzb_get_stats(self.h, C.byref(s)))
         return {name: getattr(s, name) for name, _ in FzbStats._fields_}
+
+
+class SummaryEngine(object):
+    """Handle for the model-free entry points (PDF summaries)."""
+    _cache = {}
+
+    def __init__(self, device=None):
+        self.lib = _lib.load()
+        self.h = C.c_void_p()
+        self.device = default_device() if device is None else int(device)
+        _lib.check(self.lib.fzb_create(self.device, C.byref(self.h)))
+
+    @classmethod
+    def get(cls, device=None):
+        dev = default_device() if device is None else int(device)
+        if dev not in cls._cache:
+            cls._cache[dev] = cls(dev)
+        return cls._cache[dev]
+
+    def summarize(self, pdfs, pgrid, loss, urand, renormalize):
+        """Stage 1 of pdfs_summarize (pdf.py:978-1036, :1064-1068): returns est, std, risk, quant ([4, No]), mc, rowsum."""
+        no, ng = pdfs.shape
+        est, sd, risk, quant = (np.empty((4, no)) for _ in range(4))
+        mc, rowsum = np.empty(no), np.empty(no)
+        _lib.check(self.lib.fzb_pdfs_summarize(self.h, dptr(pdfs), dptr(pgrid), dptr(loss), dptr(urand), no, ng,
+                                               1 if renormalize else 0, dptr(rowsum), dptr(est), dptr(sd), dptr(risk),
+                                               dptr(quant), dptr(mc)))
+        return est, sd, risk, quant, mc, rowsum
+
+    def conf(self, points, widths):
+        """Stage 2 (pdf.py:1038-1062): probability within +-width of each estimator."""
+        points, widths = f64(points), f64(widths)
+        out = np.empty_like(points)
+        _lib.check(self.lib.fzb_pdfs_conf(self.h, dptr(points), dptr(widths), points.shape[1], dptr(out)))
+        return out
+
+    def stats(self):
+        s = FzbStats()
+        _lib.check(self.lib.fzb_get_stats(self.h, C.byref(s)))
+        return {name: getattr(s, name) for name, _ in FzbStats._fields_}

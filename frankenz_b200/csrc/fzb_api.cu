@@ -339,7 +339,7 @@ int fzb_destroy(fzb_handle h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->models, &h->models_err, &h->models_mask, &h->lnprior, &h->prior_table, &h->prior_bins, &h->widths, &h->koff, &h->kernels,
                       &h->kcdf, &h->yidx, &h->ysidx, &h->grid, &h->y, &h->ystd, &h->lowers, &h->uppers, &h->rows,
-                      &h->knn_feats, &h->knn_cand, &h->knn_redo, &h->fast.recs, &h->fast.tiles_tc, &h->fast.recs64, &h->fast.aux64, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
+                      &h->knn_feats, &h->knn_cand, &h->knn_redo, &h->summ[0], &h->summ[1], &h->summ[2], &h->summ[3], &h->summ[4], &h->summ[5], &h->fast.recs, &h->fast.tiles_tc, &h->fast.recs64, &h->fast.aux64, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
                       &h->fast.d_slot_sidx};
     for (auto* b : bufs) b->release();
     for (auto& b : h->obj_in) b.release();
@@ -888,3 +888,18 @@ int fzb_knn_fit(fzb_handle h, const double* qfeats, const double* data, const do
 }
 
 }  // extern "C"
+
+// ---- PDF summaries (pdf.py:899-1074) --------------------------------------------------------------------------------
+int fzb_pdfs_summarize(fzb_handle h, const double* pdfs, const double* pgrid, const double* loss, const double* urand,
+                       int64_t No, int32_t Ng, int32_t renormalize, double* rowsum, double* est, double* sd, double* risk,
+                       double* quant, double* mc) {
+    if (use_device(h)) return 2;
+    FZB_CHECK(pdfs && pgrid && loss && urand && est && sd && risk && quant && mc && No > 0, "null argument");
+    return fzb_summarize_impl(h, pdfs, pgrid, loss, urand, No, Ng, renormalize, rowsum, est, sd, risk, quant, mc);
+}
+
+int fzb_pdfs_conf(fzb_handle h, const double* points, const double* widths, int64_t No, double* conf) {
+    if (use_device(h)) return 2;
+    FZB_CHECK(points && widths && conf && No > 0, "null argument");
+    return fzb_conf_impl(h, points, widths, No, conf);
+}

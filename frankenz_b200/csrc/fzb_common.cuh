@@ -133,6 +133,11 @@ struct fzb_context {
     DevBuf out_i64[2];
     DevBuf misc[8];
 
+    // pdfs_summarize (fzb_summarize.cu): grid, loss matrix, CDFs of the last call, outputs, staging
+    DevBuf summ[6];
+    int64_t summ_No = 0;
+    int summ_Ng = 0;
+
     FastModels fast;
     bool fast_dirty = true;
     int fast_mode = -1;
@@ -192,6 +197,12 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                              const FzbConfig& cfg, double* d_pdfs, double* d_lmap, double* d_levid,
                              int64_t* d_best_idx, double* d_best_chi2, double* d_best_scale, int shard_mode = 0,
                              double* d_psum = nullptr, const double* d_glmap = nullptr);
+
+// ---- PDF summaries (fzb_summarize.cu) ---------------------------------------------------------
+int fzb_summarize_impl(fzb_context* h, const double* pdfs, const double* pgrid, const double* loss, const double* urand,
+                       int64_t No, int32_t Ng, int32_t renormalize, double* rowsum, double* est, double* sd, double* risk,
+                       double* quant, double* mc);
+int fzb_conf_impl(fzb_context* h, const double* points, const double* widths, int64_t No, double* conf);
 
 // ---- kNN (fzb_knn.cu) -------------------------------------------------------------------------
 int fzb_knn_query_dev(fzb_context* h, const double* d_q, int64_t No, int k, double p, int64_t* d_idx, double* d_dist);

@@ -6,9 +6,10 @@ consume; the magnitude transforms are the feature maps of the kNN estimator.
 """
 import numpy as np
 
-from ._engine import Engine, clean_inplace, make_config
+from ._engine import Engine, SummaryEngine, clean_inplace, make_config
 
-__all__ = ["loglike", "logprob", "gaussian", "magnitude", "inv_magnitude", "luptitude", "inv_luptitude", "PDFDict"]
+__all__ = ["loglike", "logprob", "gaussian", "magnitude", "inv_magnitude", "luptitude", "inv_luptitude", "PDFDict",
+           "pdfs_resample", "pdfs_summarize"]
 
 
 def _one_object(data, data_err, data_mask, models, models_err, models_mask, free_scale, ignore_model_err,
@@ -119,3 +120,67 @@ class PDFDict(object):
         Xe_idx = np.array(np.round((Xe - self.sigma_grid[0]) / self.dsigma), dtype='int')
         np.clip(Xe_idx, 0, self.Ndict - 1, out=Xe_idx)
         return X_idx, Xe_idx
+
+
+def pdfs_resample(pdfs, old_grid, new_grid, renormalize=True, left=0., right=0.):
+    """Drop-in for frankenz.pdf.pdfs_resample (pdf.py:855-896): numpy.interp of every PDF onto `new_grid` (host; a
+    convenience around the hot path, not part of it)."""
+    new_pdfs = np.array([np.interp(new_grid, old_grid, row, left=left, right=right) for row in pdfs])
+    if renormalize:
+        new_pdfs /= new_pdfs.sum(axis=1)[:, None]
+    return new_pdfs
+
+
+def _loss_kernel(pgrid, pkern, pkern_grid):
+    """The (truth x guess) kernel of the `best` estimator (pdf.py:1003-1023), evaluated on the host with numpy like
+    the reference so that a user-supplied callable keeps working."""
+    ng = len(pgrid)
+    if pkern_grid is None:
+        truth, guess = pgrid.reshape(ng, 1), pgrid.reshape(1, ng)
+        pkern_grid = (truth - guess) / ((1. + truth) * 0.15)
+    if pkern == 'tophat':
+        return (np.square(pkern_grid) < 1.)
+    if pkern == 'gaussian':
+        return np.exp(-0.5 * np.square(pkern_grid))
+    if pkern == 'lorentz':
+        return 1. / (1. + np.square(pkern_grid))
+    try:
+        return pkern(pkern_grid)
+    except Exception:
+        raise RuntimeError("The input kernel does not appear to be valid.")
+
+
+def pdfs_summarize(pdfs, pgrid, renormalize=True, rstate=None, pkern='lorentz', pkern_grid=None, wconf_func=None):
+    """Drop-in for frankenz.pdf.pdfs_summarize (pdf.py:899-1074): same arguments, same 6-tuple
+    ((mean, std, conf, risk), (median, ...), (mode, ...), (best, ...), (low95, low68, high68, high95), mc).
+
+    The per-object work (row sums, CDFs, quantile interpolation, the (Nobj x Ngrid) x (Ngrid x Ngrid) risk product,
+    moments) runs in `fzb_pdfs_summarize` / `fzb_pdfs_conf`; the loss kernel, `wconf_func` and the random draws are
+    evaluated on the host exactly as the reference does (one `rstate.rand()` per object, in order), so callables keep
+    working.  Like the reference, `renormalize=True` divides `pdfs` in place by its row sums."""
+    if rstate is None:
+        rstate = np.random
+    if not (isinstance(pdfs, np.ndarray) and pdfs.dtype == np.float64 and pdfs.flags.c_contiguous):
+        if renormalize:
+            raise TypeError("pdfs must be a C-contiguous float64 array (it is renormalised in place, pdf.py:980)")
+        pdfs = np.ascontiguousarray(pdfs, dtype=np.float64)
+    pgrid = np.ascontiguousarray(pgrid, dtype=np.float64)
+    nobj = len(pdfs)
+    urand = np.array([rstate.rand() for _ in range(nobj)]) if nobj < 64 else np.ascontiguousarray(rstate.rand(nobj))
+    loss = np.ascontiguousarray(1.0 - _loss_kernel(pgrid, pkern, pkern_grid), dtype=np.float64)
+    eng = SummaryEngine.get()
+    est, sd, risk, quant, mc, rowsum = eng.summarize(pdfs, pgrid, loss, urand, renormalize)
+    if renormalize:
+        pdfs /= rowsum[:, None]          # the same sums, the same IEEE division as pdf.py:980
+    if wconf_func is None:
+        widths = (1. + est) * 0.03
+    else:
+        try:
+            widths = np.asarray(wconf_func(est), dtype=np.float64)
+            if widths.shape != est.shape:
+                raise ValueError
+        except Exception:
+            widths = np.array([[wconf_func(v) for v in row] for row in est], dtype=np.float64)
+    conf = eng.conf(est, widths)
+    out = tuple((est[k], sd[k], conf[k], risk[k]) for k in range(4))
+    return out + ((quant[0], quant[1], quant[2], quant[3]), mc)

@@ -178,6 +178,20 @@ int fzb_knn_fit(fzb_handle h, const double* qfeats, const double* data, const do
                 const double* data_mask, int64_t No, int32_t k, double p, const FzbConfig* cfg,
                 int64_t* neighbors, int64_t* nneighbors, const FzbFitOut* out);
 
+/* PDF summary statistics: replaces pdf.pdfs_summarize (pdf.py:899-1074).
+ * pdfs: host (No x Ng) float64, not modified; pgrid: host [Ng] (2 <= Ng <= 1024); loss: host (Ng x Ng) float64 =
+ * 1 - kernel[truth, guess] as pdf.py:1003-1024 builds it; urand: host [No], the rstate.rand() of each object in order
+ * (pdf.py:995).  renormalize != 0: every row is divided by its sum (numpy's pairwise order) first and rowsum (nullable,
+ * host [No]) receives the sums, so that the caller can mirror the reference's in-place `pdfs /= sum` (pdf.py:980).
+ * Outputs, host: est / std / risk [4][No] for (mean, median, mode, best); quant [4][No] = 2.5, 16, 84, 97.5 %
+ * quantiles; mc [No] Monte-Carlo draws.  The CDFs stay on the device for fzb_pdfs_conf. */
+int fzb_pdfs_summarize(fzb_handle h, const double* pdfs, const double* pgrid, const double* loss, const double* urand,
+                       int64_t No, int32_t Ng, int32_t renormalize, double* rowsum, double* est, double* std,
+                       double* risk, double* quant, double* mc);
+/* Second stage (pdf.py:1038-1062): conf[e][i] = CDF_i(point + width) - CDF_i(point - width) for points / widths [4][No]
+ * (the four estimators and the caller's wconf_func evaluated at them), on the PDFs of the last fzb_pdfs_summarize. */
+int fzb_pdfs_conf(fzb_handle h, const double* points, const double* widths, int64_t No, double* conf);
+
 #ifdef __cplusplus
 }
 #endif

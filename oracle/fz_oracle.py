@@ -493,3 +493,71 @@ def knn_predict(fit, labels, label_errs, label_dict=None, label_grid=None, logwt
             None if y_idx is None else y_idx[u], None if y_std_idx is None else y_std_idx[u],
             label_dict, label_grid, **kde_kwargs)
     return pdfs, lmap, levid
+
+
+# ---- PDF summaries ------------------------------------------------------
+
+def pdfs_resample(pdfs, old_grid, new_grid, renormalize=True, left=0., right=0.):
+    """frankenz/pdf.py:855-896: linear interpolation of every PDF onto a new grid, then rows summed to one."""
+    out = np.array([np.interp(new_grid, old_grid, row, left=left, right=right) for row in pdfs])
+    if renormalize:
+        out /= out.sum(axis=1)[:, None]
+    return out
+
+
+def loss_kernel(pgrid, pkern="lorentz", pkern_grid=None):
+    """frankenz/pdf.py:1003-1023: the (truth x guess) loss kernel of the `best` estimator.  The default
+    argument is (truth - guess) / ((1 + truth) * 0.15), a photo-z convention."""
+    if pkern_grid is None:
+        truth = pgrid.reshape(-1, 1)
+        guess = pgrid.reshape(1, -1)
+        pkern_grid = (truth - guess) / ((1. + truth) * 0.15)
+    if pkern == "tophat":
+        return (np.square(pkern_grid) < 1.)
+    if pkern == "gaussian":
+        return np.exp(-0.5 * np.square(pkern_grid))
+    if pkern == "lorentz":
+        return 1. / (1. + np.square(pkern_grid))
+    try:
+        return pkern(pkern_grid)
+    except Exception:
+        raise RuntimeError("The input kernel does not appear to be valid.")
+
+
+def pdfs_summarize(pdfs, pgrid, renormalize=True, rstate=None, pkern="lorentz", pkern_grid=None, wconf_func=None):
+    """frankenz/pdf.py:899-1074.  Point estimators (mean / median / mode / minimum-risk `best`), for each of them
+    the standard deviation about it, the probability within +-wconf_func(point) and the risk at it; the 2.5 / 16 /
+    84 / 97.5 % quantiles; one Monte-Carlo draw per object (inverse CDF at rstate.rand(), drawn in object order,
+    pdf.py:995).  `renormalize` divides `pdfs` IN PLACE by its row sums (pdf.py:980)."""
+    if rstate is None:
+        rstate = np.random
+    nobj, ng = len(pdfs), len(pgrid)
+    if renormalize:
+        pdfs /= pdfs.sum(axis=1)[:, None]
+    mean = np.dot(pdfs, pgrid)                                  # pdf.py:983
+    mode = pgrid[np.argmax(pdfs, axis=1)]                       # pdf.py:986
+    cdfs = pdfs.cumsum(axis=1)                                  # pdf.py:989
+    quant = np.zeros((nobj, 6))
+    for i in range(nobj):                                       # pdf.py:994-997
+        quant[i] = np.interp([0.025, 0.16, 0.5, 0.84, 0.975, rstate.rand()], cdfs[i], pgrid)
+    med = quant[:, 2].copy()
+    risk = np.dot(pdfs, 1.0 - loss_kernel(pgrid, pkern, pkern_grid))   # pdf.py:1024
+    best = pgrid[np.argmin(risk, axis=1)]                              # pdf.py:1025
+    grid = pgrid.reshape(1, ng)
+    points = (mean, med, mode, best)
+    stds = [np.sqrt(np.sum(np.square(grid - p.reshape(nobj, 1)) * pdfs, axis=1)) for p in points]   # pdf.py:1028-1036
+    if wconf_func is None:
+        def wconf_func(point):
+            return (1. + point) * 0.03
+    conf = np.zeros((4, nobj))
+    rsk = np.zeros((4, nobj))
+    for i in range(nobj):
+        lo_hi = []
+        for p in points:                                        # pdf.py:1044-1062
+            w = wconf_func(p[i])
+            lo_hi += [p[i] - w, p[i] + w]
+        c = np.interp(np.array(lo_hi), pgrid, cdfs[i])
+        conf[:, i] = c[1::2] - c[0::2]
+        rsk[:, i] = np.interp([p[i] for p in points], pgrid, risk[i])   # pdf.py:1066-1068
+    est = tuple((points[k], stds[k], conf[k], rsk[k]) for k in range(4))
+    return est + ((quant[:, 0].copy(), quant[:, 1].copy(), quant[:, 3].copy(), quant[:, 4].copy()), quant[:, 5].copy())

@@ -226,6 +226,67 @@ def case_fs1_iters():
     print("fs1_ltol ok")
 
 
+
+def mock_pdfs(n, zgrid, seed):
+    """Seeded PDFs on `zgrid`: Gaussian mixtures (narrow, broad, multi-modal), exact zeros between the peaks
+    (CDF plateaus), a single-bin spike, a flat row, un-normalised."""
+    rs = np.random.RandomState(seed)
+    p = np.zeros((n, len(zgrid)))
+    for i in range(n):
+        for _ in range(rs.randint(1, 4)):
+            mu, sg, a = rs.uniform(0.05, 6.5), 10 ** rs.uniform(-2, -0.2), rs.uniform(0.2, 1.0)
+            g = a * np.exp(-0.5 * ((zgrid - mu) / sg) ** 2)
+            g[g < 1e-6 * g.max()] = 0.0
+            p[i] += g
+    p[0] = 0.0
+    p[0, min(137, len(zgrid) - 3)] = 3.0
+    p[1] = 1.0
+    p[2, :min(50, len(zgrid) // 3)] = 0.0
+    return p * rs.uniform(0.5, 20.0, size=(n, 1))
+
+
+def case_summarize():
+    """pdf.pdfs_summarize with the three built-in loss kernels, a custom kernel, a custom
+    confidence width, with / without renormalisation; pdf.pdfs_resample."""
+    zgrid = np.arange(0, 7 + 1e-5, 0.01)
+    out = dict(zgrid=zgrid)
+    names = ["mean", "med", "mode", "best"]
+
+    def store(tag, res, pdfs_after):
+        for k, nme in enumerate(names):
+            for j, q in enumerate(("", "_std", "_conf", "_risk")):
+                out["%s_%s%s" % (tag, nme, q)] = res[k][j]
+        for j, q in enumerate(("low95", "low68", "high68", "high95")):
+            out["%s_%s" % (tag, q)] = res[4][j]
+        out[tag + "_mc"] = res[5]
+        out[tag + "_pdfs_after"] = pdfs_after
+
+    p0 = mock_pdfs(96, zgrid, 11)
+    out["pdfs"] = p0
+    for kern in ("lorentz", "gaussian", "tophat"):
+        p = p0.copy()
+        store(kern, rpdf.pdfs_summarize(p, zgrid, rstate=np.random.RandomState(5), pkern=kern), p)
+    p = p0 / p0.sum(axis=1)[:, None]
+    out["pdfs_normed"] = p.copy()
+    store("noren", rpdf.pdfs_summarize(p, zgrid, renormalize=False, rstate=np.random.RandomState(6)), p)
+    p = p0.copy()
+    store("custom", rpdf.pdfs_summarize(p, zgrid, rstate=np.random.RandomState(7),
+                                        pkern=lambda x: np.exp(-np.abs(x)), wconf_func=lambda z: 0.02 + 0.05 * z * z), p)
+    # a coarse grid (Ngrid not a multiple of anything) and a user kernel argument grid
+    g2 = np.linspace(0.0, 3.0, 61)
+    q0 = mock_pdfs(40, g2 * 7 / 3, 12)
+    out["grid2"], out["pdfs2"] = g2, q0
+    kg = (g2.reshape(-1, 1) - g2.reshape(1, -1)) / 0.1
+    out["kgrid2"] = kg
+    q = q0.copy()
+    store("grid2", rpdf.pdfs_summarize(q, g2, rstate=np.random.RandomState(8), pkern="gaussian", pkern_grid=kg), q)
+    new_grid = np.linspace(-0.5, 7.5, 333)
+    out["resample_grid"] = new_grid
+    out["resampled"] = rpdf.pdfs_resample(p0.copy(), zgrid, new_grid)
+    out["resampled_noren"] = rpdf.pdfs_resample(p0.copy(), zgrid, new_grid, renormalize=False, left=0.5, right=0.25)
+    np.savez_compressed(os.path.join(HERE, "pdfs_summarize.npz"), **out)
+    print("pdfs_summarize.npz", len(out), "arrays")
+
 if __name__ == "__main__":
     case_loglike()
     case_degenerate()
@@ -233,3 +294,4 @@ if __name__ == "__main__":
     case_kde_edges()
     case_knn()
     case_fs1_iters()
+    case_summarize()

@@ -140,3 +140,36 @@ def test_knn_exact(name, K, k, fmap):
     assert exact(p, g[name + "_pdf"]) and exact(lm, g[name + "_lmap"]) and exact(le, g[name + "_levid"])
     p, _, _ = fo.knn_predict(fit, g["labels"], g["label_errs"], label_grid=zgrid)
     assert np.allclose(p, g[name + "_pdf_grid"], rtol=1e-13, atol=1e-300)
+
+
+# ---- PDF summaries ----------------------------------------------------------------
+SUMM_KEYS = ["%s%s" % (n, q) for n in ("mean", "med", "mode", "best") for q in ("", "_std", "_conf", "_risk")] + \
+            ["low95", "low68", "high68", "high95", "mc"]
+
+
+def _summ_flat(res):
+    return [res[k][j] for k in range(4) for j in range(4)] + list(res[4]) + [res[5]]
+
+
+@pytest.mark.parametrize("tag,kw,seed", [("lorentz", dict(pkern="lorentz"), 5), ("gaussian", dict(pkern="gaussian"), 5),
+                                         ("tophat", dict(pkern="tophat"), 5), ("noren", dict(renormalize=False), 6),
+                                         ("custom", dict(pkern=lambda x: np.exp(-np.abs(x)),
+                                                         wconf_func=lambda z: 0.02 + 0.05 * z * z), 7)])
+def test_pdfs_summarize_bit_exact(tag, kw, seed):
+    g = golden("pdfs_summarize.npz")
+    p = (g["pdfs_normed"] if tag == "noren" else g["pdfs"]).copy()
+    res = fo.pdfs_summarize(p, g["zgrid"], rstate=np.random.RandomState(seed), **kw)
+    for name, got in zip(SUMM_KEYS, _summ_flat(res)):
+        assert exact(got, g["%s_%s" % (tag, name)]), (tag, name)
+    assert exact(p, g[tag + "_pdfs_after"])          # in-place renormalisation (pdf.py:980)
+
+
+def test_pdfs_summarize_user_kernel_grid_and_resample():
+    g = golden("pdfs_summarize.npz")
+    q = g["pdfs2"].copy()
+    res = fo.pdfs_summarize(q, g["grid2"], rstate=np.random.RandomState(8), pkern="gaussian", pkern_grid=g["kgrid2"])
+    for name, got in zip(SUMM_KEYS, _summ_flat(res)):
+        assert exact(got, g["grid2_" + name]), name
+    assert exact(fo.pdfs_resample(g["pdfs"].copy(), g["zgrid"], g["resample_grid"]), g["resampled"])
+    assert exact(fo.pdfs_resample(g["pdfs"].copy(), g["zgrid"], g["resample_grid"], renormalize=False, left=0.5,
+                                  right=0.25), g["resampled_noren"])
