@@ -1178,8 +1178,8 @@ struct FinishParams {
 
 __global__ void __launch_bounds__(256) k_finish(FinishParams P) {
     extern __shared__ double sm_f[];
-    double* h = sm_f;                 // Ngpad
-    double* pdf = h + P.Ngpad;        // Ng
+    double* h = sm_f;                 // Ngpad + 4 (zero tail for the 4-wide windows)
+    double* pdf = h + P.Ngpad + 4;    // Ng
     __shared__ double red[8];
     const int tid = threadIdx.x;
     const int64_t o = P.objlist[blockIdx.x];
@@ -1187,16 +1187,27 @@ __global__ void __launch_bounds__(256) k_finish(FinishParams P) {
     for (int s = 0; s < P.nslot; ++s) {
         __syncthreads();
         const float* row = P.hist + o * P.hist_stride + (size_t)s * P.Ngpad;
-        for (int g = tid; g < P.Ngpad; g += 256) h[g] = (double)row[g];
+        for (int g = tid; g < P.Ngpad + 4; g += 256) h[g] = (g < P.Ngpad) ? (double)row[g] : 0.0;
         __syncthreads();
         const int si = P.slot_sidx[s];
         const int w = P.widths[si];
         const double* kern = P.kernels + P.koff[si];
-        for (int x = tid; x < P.Ng; x += 256) {
-            double a = 0.0;
-            // model at grid position pos contributes kern[x - pos + w]; histogram index = pos + wmax
-            for (int t = -w; t <= w; ++t) a += h[x + t + P.wmax] * kern[w - t];
-            pdf[x] += a;
+        // model at grid position pos contributes kern[x - pos + w]; histogram index = pos + wmax.  Four adjacent grid
+        // points per thread: one kernel tap and one new histogram value per step feed four accumulators
+        for (int x0 = 4 * tid; x0 < P.Ng; x0 += 4 * 256) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            const double* hh = h + x0 + P.wmax;          // hh[t] = h[x0 + t + wmax]; reads up to x0 + 3 + w + wmax < Ngpad + 3
+            double h0 = hh[-w], h1 = hh[-w + 1], h2 = hh[-w + 2];
+            for (int t = -w; t <= w; ++t) {
+                const double k = kern[w - t];
+                const double h3 = hh[t + 3];
+                a0 += h0 * k; a1 += h1 * k; a2 += h2 * k; a3 += h3 * k;
+                h0 = h1; h1 = h2; h2 = h3;
+            }
+            pdf[x0] += a0;
+            if (x0 + 1 < P.Ng) pdf[x0 + 1] += a1;
+            if (x0 + 2 < P.Ng) pdf[x0 + 2] += a2;
+            if (x0 + 3 < P.Ng) pdf[x0 + 3] += a3;
         }
     }
     __syncthreads();
@@ -1864,7 +1875,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             FP.slot_sidx = F.d_slot_sidx.as<int32_t>(); FP.widths = h->widths.as<int32_t>();
             FP.koff = h->koff.as<int64_t>(); FP.kernels = h->kernels.as<double>(); FP.pdfs = d_pdfs;
             FP.normalise = (shard_mode == 2) ? 0 : 1;
-            size_t smem = sizeof(double) * ((size_t)h->fast_Ngpad + h->Ng);
+            size_t smem = sizeof(double) * ((size_t)h->fast_Ngpad + 4 + h->Ng);
             FZB_CUDA(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             if (nsafe > 0) {
                 FP.objlist = safe_list;
