@@ -31,7 +31,8 @@
 //        k-steps 2-3: q_hi | q_lo | q_hi | 0        (q = m^2;     w_hi |  w_hi |  w_lo | 0)
 //   [model pair (128)][6] float2   (m_even, m_odd) per band, then the prior pair   (48 B, three LDS.128)
 //   [model pair (128)]    {invnorm_even, invnorm_odd, bin_even, bin_odd}
-//   [8 models (32)]       {bin of the first, 1 if all eight share it}
+//   [8 models (32)]       {bin of the first, 1 if all eight share it, 1/norm of that bin (same bin = same kernel
+//                          width and grid position = same edge normalisation), -}
 #pragma once
 
 constexpr int TC_TM = 256;                       // models per shared-memory tile
@@ -48,7 +49,7 @@ constexpr int TC_AKSTEPS = 6;                    // ... of the object operand: -
 constexpr int TC_OPSEC = TC_KSTEPS * TC_TM * 32;
 constexpr int TC_PAIRSEC = (TC_TM / 2) * 48;
 constexpr int TC_TAILSEC = (TC_TM / 2) * 16;
-constexpr int TC_SUBSEC = (TC_TM / 8) * 8;         // per 8 models: {KDE bin of the first, 1 if all eight share it}
+constexpr int TC_SUBSEC = (TC_TM / 8) * 16;        // per 8 models: {KDE bin of the first, 1 if all eight share it, 1/norm of that bin}
 constexpr int TC_TILE_BYTES = TC_OPSEC + TC_PAIRSEC + TC_TAILSEC + TC_SUBSEC;
 constexpr int TC_OBJA_TILE = TC_AKSTEPS * 128 * 32;
 constexpr int TC_OBJA_BYTES = TC_MT * TC_OBJA_TILE;
@@ -56,7 +57,7 @@ constexpr int TC_NSTAGE = 2;
 constexpr int TC_CHUNK_COLS = TC_MT * 3 * TC_NC;  // TMEM columns of one chunk buffer
 constexpr int TC_TMEM_COLS = 512;
 constexpr size_t TC_SMEM = (size_t)TC_OBJA_BYTES + (size_t)TC_NSTAGE * TC_TILE_BYTES + 512;
-static_assert(TC_TILE_BYTES == 41216 && TC_TILE_BYTES % 128 == 0, "tile layout");
+static_assert(TC_TILE_BYTES == 41472 && TC_TILE_BYTES % 128 == 0, "tile layout");
 static_assert(2 * TC_CHUNK_COLS <= TC_TMEM_COLS, "TMEM budget");
 static_assert(TC_SPLIT == 2 && TC_NSUB == 4, "sub-batch assignment below assumes two warpgroups per M-tile, four sub-batches");
 
@@ -311,7 +312,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
         };
         const ulonglong2* pairs = nullptr;
         const float4* tails = nullptr;
-        const int2* subs = nullptr;
+        const int4* subs = nullptr;
+        float sub_inv = 0.f;                   // pass 2, fast path: the common 1/norm of the current sub-batch
         int first_i = 0, npair_full = 0;
         bool odd = false;
         // four model pairs (eight TMEM columns) against the object of the thread
@@ -344,13 +346,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                     best0 = g0 ? idx0 : best0;
                     best1 = g1 ? idx0 + 1 : best1;
                 } else {
-                    const float4 tl = tails[p];
                     float u0 = fast_ex2(lo2(delta)), u1 = fast_ex2(hi2(delta));
                     u0 = (lo2(l) > thr) ? u0 : 0.f;
                     u1 = (hi2(l) > thr) ? u1 : 0.f;
                     if (!SLOW) {
-                        acc2 = fma2(pack2(u0, u1), pack2(tl.x, tl.y), acc2);
+                        acc2 = fma2(pack2(u0, u1), pack2(sub_inv, sub_inv), acc2);
                     } else {
+                        const float4 tl = tails[p];
                         const int bin0 = __float_as_int(tl.z), bin1 = tail ? bin0 : __float_as_int(tl.w);
                         if (bin0 != cur_bin) {             // warp-uniform
                             if (cur_bin >= 0) { flush(lo2(acc2) + hi2(acc2), cur_bin); acc2 = pack2(0.f, 0.f); }
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
         // weight relative to a reference exponent R is y = x 2^(R - x + prior): one ex2 and no lg2 per pair, a plain sum
         // and a plain max.  Pass 1 keeps R per object (integer valued, so that a change of R rescales the sums by an
         // exact power of two) and lowers it whenever the largest weight passes 2^8; a jump beyond 2^24 (or an
-        // overflow) has the sub-batch redone from the saved state in a frame at the new minimum.  Pass 2 uses R = -M.
+        // overflow) has the weights of the sub-batch formed again in a frame at its minimum.  Pass 2 uses R = -M.
         auto process_lin = [&](auto slow_tag, const int p0, float (&Bv)[8], float (&Cv)[8], float (&Gv)[8]) {
             constexpr bool SLOW = decltype(slow_tag)::value;
             f2 xs[4], pr[4];
@@ -392,90 +394,91 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                 xs[jp] = x;
             }
             if (PASS == 1) {
-                // running sums in the frame of R; the maximum itself is kept in the log domain (Mfl, best0), evaluated only
-                // for the rare candidates y > Yt = (1 - 2^-18) max y, so that the arg-max does not depend on the frame
-                const f2 S2s = S2;
-                const float Yms = lo2(M2), Yts = hi2(M2), Mls = Mfl, Rfs = Rf;
-                const double Sds = Sd;
-                const int bs = best0;
+                // running sum S2 in the frame of R; M2 = (max weight Ym, candidate threshold Yt = (1 - 2^-18) Ym).  The
+                // maximum itself is kept in the log domain (Mfl, best0), evaluated only for the candidates y > Yt, so that
+                // the arg-max does not depend on the frame.  The weights of the sub-batch are formed first and applied to
+                // the running state only once they are known to be representable.
                 const int ig0 = first_i + 2 * p0;
-                auto accumulate = [&]() {
+                f2 ys[4], Ssub = 0;
+                float ysub = 0.f;
+                auto weights = [&]() {
                     const f2 R2 = pack2(Rf, Rf);
-                    f2 ys[4];
-                    bool cand = false;
-                    const float Yt = hi2(M2);
+                    ysub = 0.f;
 #pragma unroll
                     for (int jp = 0; jp < 4; ++jp) {
                         const f2 arg = fma2(xs[jp], kMinusOne, PRIOR ? add2(pr[jp], R2) : R2);
                         ys[jp] = mul2(xs[jp], pack2(fast_ex2(lo2(arg)), fast_ex2(hi2(arg))));
-                        S2 = add2(S2, ys[jp]);
-                        cand = cand || (lo2(ys[jp]) > Yt) || (hi2(ys[jp]) > Yt);
-                    }
-                    if (__any_sync(0xffffffffu, cand)) {
-                        float Ym = lo2(M2);
-#pragma unroll
-                        for (int jp = 0; jp < 4; ++jp) {
-#pragma unroll
-                            for (int e = 0; e < 2; ++e) {
-                                const float y = e ? hi2(ys[jp]) : lo2(ys[jp]);
-                                if (y > Yt) {
-                                    const float x = e ? hi2(xs[jp]) : lo2(xs[jp]);
-                                    float l = fast_lg2(x) - x;
-                                    if (PRIOR) l += e ? hi2(pr[jp]) : lo2(pr[jp]);
-                                    if (l > Mfl) { Mfl = l; best0 = ig0 + 2 * jp + e; }
-                                    Ym = fmaxf(Ym, y);
-                                }
-                            }
-                        }
-                        // keep the largest weight below 2^8 (the fp32 rounding of R - x grows with |R - x|): an exact
-                        // power-of-two change of frame, no recomputation
-                        if (Ym >= 256.f && Ym < 16777216.f) {
-                            const int k = ((__float_as_int(Ym) >> 23) & 0xff) - 127;
-                            const float f = __int_as_float((127 - k) << 23);
-                            S2 = mul2(S2, pack2(f, f));
-                            Sd *= (double)f;
-                            Ym *= f;
-                            Rf -= (float)k;
-                        }
-                        M2 = pack2(Ym, Ym * 0.99999618530273438f);
+                        Ssub = jp ? add2(Ssub, ys[jp]) : ys[jp];
+                        ysub = fmaxf(ysub, fmaxf(lo2(ys[jp]), hi2(ys[jp])));
                     }
                 };
-                accumulate();
-                const float tsum = lo2(S2) + hi2(S2);
-                // a jump of more than 2^24 (or an overflow: inf / NaN in the sum) is redone in a frame at the new minimum
-                const bool ovf = !(lo2(M2) < 16777216.f) || !(tsum < 1.2676506e30f);
+                weights();
+                // a weight beyond 2^24 (R far above this sub-batch's chi2) or an overflow (inf / NaN in the sum): move the
+                // frame of this object to the sub-batch's minimum (an exact power-of-two rescale of the running state) and
+                // form the weights again
+                const bool ovf = !(ysub < 16777216.f) || !(lo2(Ssub) + hi2(Ssub) < 1.2676506e30f);
                 if (__any_sync(0xffffffffu, ovf)) {
-                    Rf = Rfs;          // undo a frame shift the first attempt may have made: everything restarts from the saved state
-                    Sd = Sds;
-                    float mn = FLT_MAX;
+                    if (ovf) {
+                        float mn = FLT_MAX;
+#pragma unroll
+                        for (int jp = 0; jp < 4; ++jp) {
+                            const f2 v = PRIOR ? fma2(pr[jp], kMinusOne, xs[jp]) : xs[jp];
+                            mn = fminf(mn, fminf(lo2(v), hi2(v)));
+                        }
+                        // y = x 2^(R - x): R = floor(x_min) - log2(x_min) puts the largest weight near 1
+                        const float ex = (mn >= 2.f && mn < 1e38f) ? (float)(((__float_as_int(mn) >> 23) & 0xff) - 127) : 0.f;
+                        const float Rn = fminf(floorf(mn) - ex, Rf - 1.f);
+                        const float f = (Rf < 1e38f) ? pow2i(Rn - Rf) : 0.f;
+                        S2 = mul2(S2, pack2(f, f));
+                        M2 = mul2(M2, pack2(f, f));
+                        Sd *= (double)f;
+                        Rf = Rn;
+                    }
+                    weights();
+                }
+                S2 = add2(S2, Ssub);
+                const float Yt = hi2(M2);
+                if (__any_sync(0xffffffffu, ysub > Yt)) {
+                    float Ym = lo2(M2);
 #pragma unroll
                     for (int jp = 0; jp < 4; ++jp) {
-                        const f2 v = PRIOR ? fma2(pr[jp], kMinusOne, xs[jp]) : xs[jp];
-                        mn = fminf(mn, fminf(lo2(v), hi2(v)));
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const float y = e ? hi2(ys[jp]) : lo2(ys[jp]);
+                            if (y > Yt) {
+                                const float x = e ? hi2(xs[jp]) : lo2(xs[jp]);
+                                float l = fast_lg2(x) - x;
+                                if (PRIOR) l += e ? hi2(pr[jp]) : lo2(pr[jp]);
+                                if (l > Mfl) { Mfl = l; best0 = ig0 + 2 * jp + e; }
+                                Ym = fmaxf(Ym, y);
+                            }
+                        }
                     }
-                    const float Rn = ovf ? fminf(floorf(mn), Rf - 1.f) : Rf;
-                    const float f = ovf ? ((Rf < 1e38f) ? pow2i(Rn - Rf) : 0.f) : 1.f;
-                    S2 = mul2(S2s, pack2(f, f));
-                    M2 = pack2(Yms * f, Yts * f);
-                    Sd *= (double)f;
-                    Mfl = Mls;
-                    best0 = bs;
-                    Rf = Rn;
-                    accumulate();
+                    // keep the largest weight below 2^8 (the fp32 rounding of R - x grows with |R - x|): an exact
+                    // power-of-two change of frame, no recomputation
+                    if (Ym >= 256.f && Ym < 1e30f) {
+                        const int k = ((__float_as_int(Ym) >> 23) & 0xff) - 127;
+                        const float f = __int_as_float((127 - k) << 23);
+                        S2 = mul2(S2, pack2(f, f));
+                        Sd *= (double)f;
+                        Ym *= f;
+                        Rf -= (float)k;
+                    }
+                    M2 = pack2(Ym, Ym * 0.99999618530273438f);
                 }
             } else {
                 const f2 R2 = pack2(Rf, Rf);
 #pragma unroll
                 for (int jp = 0; jp < 4; ++jp) {
                     const int p = p0 + jp;
-                    const float4 tl = tails[p];
                     const f2 arg = fma2(xs[jp], kMinusOne, PRIOR ? add2(pr[jp], R2) : R2);
                     const f2 u = mul2(xs[jp], pack2(fast_ex2(lo2(arg)), fast_ex2(hi2(arg))));
                     const float u0 = (lo2(u) > thr) ? lo2(u) : 0.f;
                     const float u1 = (hi2(u) > thr) ? hi2(u) : 0.f;
                     if (!SLOW) {
-                        acc2 = fma2(pack2(u0, u1), pack2(tl.x, tl.y), acc2);
+                        acc2 = fma2(pack2(u0, u1), pack2(sub_inv, sub_inv), acc2);
                     } else {
+                        const float4 tl = tails[p];
                         if (p > npair_full || (p == npair_full && !odd)) continue;      // warp-uniform: nothing but padding
                         const bool tail = (p == npair_full);
                         const int bin0 = __float_as_int(tl.z), bin1 = tail ? bin0 : __float_as_int(tl.w);
@@ -500,7 +503,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
             const unsigned char* tile = stage + (size_t)st * TC_TILE_BYTES;
             pairs = reinterpret_cast<const ulonglong2*>(tile + TC_OPSEC);
             tails = reinterpret_cast<const float4*>(tile + TC_OPSEC + TC_PAIRSEC);
-            subs = reinterpret_cast<const int2*>(tile + TC_OPSEC + TC_PAIRSEC + TC_TAILSEC);
+            subs = reinterpret_cast<const int4*>(tile + TC_OPSEC + TC_PAIRSEC + TC_TAILSEC);
             const int64_t first = (t0 + it) * TC_TM;
             const int cnt = (int)((P.nm - first) < TC_TM ? (P.nm - first) : TC_TM);
             const int nch = (cnt + TC_NC - 1) / TC_NC;
@@ -530,8 +533,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                     // branch-free block in which the chains of the four pair evaluations interleave
                     bool fast = p0 + 4 <= npair_full;
                     if (PASS == 2) {
-                        const int2 si = subs[ch * TC_NSUB + sub];
+                        const int4 si = subs[ch * TC_NSUB + sub];
                         fast = fast && (si.y != 0);
+                        sub_inv = __int_as_float(si.z);
                         if (fast && si.x != cur_bin) {         // warp-uniform
                             if (cur_bin >= 0) { flush(lo2(acc2) + hi2(acc2), cur_bin); acc2 = pack2(0.f, 0.f); }
                             cur_bin = si.x;
@@ -625,7 +629,8 @@ __global__ void k_build_tiles_tc(TcRecParams P) {
         int uniform = (P.bins != nullptr && p + 8 <= P.nm) ? 1 : 0;
         const int b0 = P.bins ? P.bins[p] : -1;
         for (int i = 1; i < 8 && uniform; ++i) uniform = (P.bins[p + i] == b0) ? 1 : 0;
-        reinterpret_cast<int2*>(T + TC_OPSEC + TC_PAIRSEC + TC_TAILSEC)[r >> 3] = make_int2(b0, uniform);
+        reinterpret_cast<int4*>(T + TC_OPSEC + TC_PAIRSEC + TC_TAILSEC)[r >> 3] =
+            make_int4(b0, uniform, __float_as_int(P.invnorm ? P.invnorm[p] : 0.f), 0);
     }
     unsigned char* dst = T + (r >> 3) * 256 + (r & 7) * 16;
     for (int s = 0; s < TC_KSTEPS; ++s)

@@ -87,44 +87,83 @@ def _dev_f64(a, device):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device)
 
 
+class ModelShardedBruteForce(object):
+    """Model-sharded `BruteForce.fit_predict(save_fits=False)` with the shard resident on this rank's GPU.
+
+    Rank g of `group` keeps models [lo_g, hi_g) (records, tiles and KDE tables are built once and reused from call to
+    call); every call takes ALL objects of the batch on every rank and exchanges, per object, the partial
+    (max, sum, arg-max) of pass 1 (all-reduce MAX / SUM / MIN: 24 B) and the un-normalised PDF partial of pass 2
+    (all-reduce SUM: Ngrid x 8 B) over NCCL.  SURVEY.md section 8e."""
+
+    def __init__(self, models, models_err, models_mask, group=None, device=None):
+        self.group = group
+        self.rank, self.world = _world(group)
+        self.lo, self.hi = shard_bounds(len(models), self.world, self.rank)
+        self.eng = Engine(models[self.lo:self.hi], models_err[self.lo:self.hi], models_mask[self.lo:self.hi], device=device)
+        self.dev = torch.device("cuda", self.eng.device)
+        self._buf = {}
+
+    def _tensor(self, name, shape, dtype):
+        t = self._buf.get(name)
+        if t is None or t.shape != torch.Size(shape) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.dev)
+            self._buf[name] = t
+        return t
+
+    def fit_predict(self, data, data_err, data_mask, model_labels, model_label_errs, label_dict=None, label_grid=None,
+                    lprob_kwargs=None, kde_kwargs=None, return_best=False, as_torch=False):
+        """Returns (pdfs, (lmap, levid)[, best]) identical on every rank: numpy arrays, or device tensors with
+        as_torch=True (no device-to-host copy)."""
+        eng, lo, hi = self.eng, self.lo, self.hi
+        lk = dict(lprob_kwargs or {})
+        eng.set_lnprior(None if lk.get("lnprior", None) is None else np.asarray(lk["lnprior"])[lo:hi])
+        lk.pop("lnprior", None)
+        eng.set_kde(np.asarray(model_labels)[lo:hi], np.asarray(model_label_errs)[lo:hi], label_dict=label_dict,
+                    label_grid=label_grid, kde_kwargs=kde_kwargs)
+        cfg = make_config(lk, kde_kwargs)
+        if torch.is_tensor(data):
+            d_x, d_xe, d_xm = (t.to(self.dev, torch.float64).contiguous() for t in (data, data_err, data_mask))
+        else:
+            clean_inplace(data, data_err, data_mask)
+            d_x, d_xe, d_xm = _dev_f64(data, self.dev), _dev_f64(data_err, self.dev), _dev_f64(data_mask, self.dev)
+        no = len(d_x)
+        pmax = self._tensor("pmax", (no,), torch.float64)
+        psum = self._tensor("psum", (no,), torch.float64)
+        pbest = self._tensor("pbest", (no,), torch.int64)
+        lib = eng.lib
+        _lib.check(lib.fzb_shard_pass1_dev(eng.h, d_x.data_ptr(), d_xe.data_ptr(), d_xm.data_ptr(), no, C.byref(cfg),
+                                           pmax.data_ptr(), psum.data_ptr(), pbest.data_ptr()))
+        lmap, levid, best = merge_pass1(pmax, psum, pbest, lo, self.group)
+        part = self._tensor("part", (no, eng.Ng), torch.float64)
+        _lib.check(lib.fzb_shard_pass2_dev(eng.h, d_x.data_ptr(), d_xe.data_ptr(), d_xm.data_ptr(), no, C.byref(cfg),
+                                           lmap.data_ptr(), levid.data_ptr(), part.data_ptr()))
+        pdfs = merge_pdfs(part, self.group)
+        if as_torch:
+            out = (pdfs, (lmap, levid))
+            return out + (best,) if return_best else out
+        out = (pdfs.cpu().numpy(), (lmap.cpu().numpy(), levid.cpu().numpy()))
+        return out + (best.cpu().numpy(),) if return_best else out
+
+    def close(self):
+        self.eng.close()
+
+
 def fit_predict_model_sharded(models, models_err, models_mask, data, data_err, data_mask, model_labels,
                               model_label_errs, label_dict=None, label_grid=None, lprob_kwargs=None,
                               kde_kwargs=None, group=None, device=None, return_best=False):
-    """Model-sharded BruteForce.fit_predict(save_fits=False).
+    """One-shot form of `ModelShardedBruteForce` (builds the shard, runs one batch, frees it).
 
     Every rank passes the FULL model arrays (or arrays of which it only needs its own slice) and all
     objects; rank g keeps models [lo_g, hi_g).  Returns (pdfs, (lmap, levid)) as numpy arrays, identical
     on every rank.
     """
-    rank, world = _world(group)
-    lo, hi = shard_bounds(len(models), world, rank)
-    eng = Engine(models[lo:hi], models_err[lo:hi], models_mask[lo:hi], device=device)
-    lk = dict(lprob_kwargs or {})
-    if lk.get("lnprior", None) is not None:
-        eng.set_lnprior(np.asarray(lk["lnprior"])[lo:hi])
-    eng.set_kde(np.asarray(model_labels)[lo:hi], np.asarray(model_label_errs)[lo:hi], label_dict=label_dict,
-                label_grid=label_grid, kde_kwargs=kde_kwargs)
-    cfg = make_config(lk, kde_kwargs)
-    clean_inplace(data, data_err, data_mask)
-    dev = torch.device("cuda", eng.device)
-    d_x, d_xe, d_xm = _dev_f64(data, dev), _dev_f64(data_err, dev), _dev_f64(data_mask, dev)
-    no = len(data)
-    pmax = torch.empty(no, dtype=torch.float64, device=dev)
-    psum = torch.empty(no, dtype=torch.float64, device=dev)
-    pbest = torch.empty(no, dtype=torch.int64, device=dev)
-    lib = eng.lib
-    _lib.check(lib.fzb_shard_pass1_dev(eng.h, d_x.data_ptr(), d_xe.data_ptr(), d_xm.data_ptr(), no, C.byref(cfg),
-                                       pmax.data_ptr(), psum.data_ptr(), pbest.data_ptr()))
-    lmap, levid, best = merge_pass1(pmax, psum, pbest, lo, group)
-    part = torch.empty((no, eng.Ng), dtype=torch.float64, device=dev)
-    _lib.check(lib.fzb_shard_pass2_dev(eng.h, d_x.data_ptr(), d_xe.data_ptr(), d_xm.data_ptr(), no, C.byref(cfg),
-                                       lmap.data_ptr(), levid.data_ptr(), part.data_ptr()))
-    pdfs = merge_pdfs(part, group)
-    out = (pdfs.cpu().numpy(), (lmap.cpu().numpy(), levid.cpu().numpy()))
-    eng.close()
-    if return_best:
-        return out + (best.cpu().numpy(),)
-    return out
+    sb = ModelShardedBruteForce(models, models_err, models_mask, group=group, device=device)
+    try:
+        return sb.fit_predict(data, data_err, data_mask, model_labels, model_label_errs, label_dict=label_dict,
+                              label_grid=label_grid, lprob_kwargs=lprob_kwargs, kde_kwargs=kde_kwargs,
+                              return_best=return_best)
+    finally:
+        sb.close()
 
 
 def fit_predict_object_sharded(bf, data, data_err, data_mask, model_labels, model_label_errs, gather=True,
