@@ -131,10 +131,14 @@ class ModelShardedBruteForce(object):
         psum = self._tensor("psum", (no,), torch.float64)
         pbest = self._tensor("pbest", (no,), torch.int64)
         lib = eng.lib
+        # the library works on its own stream (and synchronises it before returning): what torch has enqueued on its
+        # stream - uploads, collectives - must be complete before the library reads it
+        torch.cuda.current_stream(self.dev).synchronize()
         _lib.check(lib.fzb_shard_pass1_dev(eng.h, d_x.data_ptr(), d_xe.data_ptr(), d_xm.data_ptr(), no, C.byref(cfg),
                                            pmax.data_ptr(), psum.data_ptr(), pbest.data_ptr()))
         lmap, levid, best = merge_pass1(pmax, psum, pbest, lo, self.group)
         part = self._tensor("part", (no, eng.Ng), torch.float64)
+        torch.cuda.current_stream(self.dev).synchronize()      # lmap / levid come out of the all-reduces on torch's stream
         _lib.check(lib.fzb_shard_pass2_dev(eng.h, d_x.data_ptr(), d_xe.data_ptr(), d_xm.data_ptr(), no, C.byref(cfg),
                                            lmap.data_ptr(), levid.data_ptr(), part.data_ptr()))
         pdfs = merge_pdfs(part, self.group)

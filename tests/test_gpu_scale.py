@@ -197,6 +197,7 @@ def test_model_sharded_fast_path_matches_unsharded(c3):
     assert np.allclose(gmax.cpu().numpy(), c3["lm"][:n], rtol=0, atol=1e-6)
     assert np.allclose(levid.cpu().numpy(), c3["le"][:n], rtol=0, atol=3e-6)
     tot = torch.zeros((n, 701), dtype=torch.float64).cuda()
+    torch.cuda.synchronize()          # the library runs on its own stream: torch's results must be complete before it reads them
     for e in engs:
         part = torch.empty((n, 701), dtype=torch.float64).cuda()
         _lib.check(e.lib.fzb_shard_pass2_dev(e.h, x[0].data_ptr(), x[1].data_ptr(), x[2].data_ptr(), n, C.byref(cfg),
