@@ -249,3 +249,21 @@ def test_model_masks_on_the_sweep_path(kw):
     fin = np.isfinite(po).all(axis=1)
     assert np.max(np.sum(np.abs(p[o][fin] - po[fin]), axis=1)) <= 1e-5
     assert np.all(np.abs(lm[o][fin] - lmo[fin]) <= 1e-5 * np.maximum(1, np.abs(lmo[fin])))
+
+
+def test_model_sharded_driver_single_rank(c3):
+    """frankenz_b200.distributed.ModelShardedBruteForce with one rank (no process group): device tensors in, device
+    tensors out, the shard kept between calls; equals the unsharded run."""
+    import torch
+    from frankenz_b200.distributed import ModelShardedBruteForce
+    n = 3000
+    sb = ModelShardedBruteForce(c3["models"], np.zeros_like(c3["models"]), np.ones_like(c3["models"]))
+    tx = [torch.from_numpy(np.ascontiguousarray(a[:n])).cuda() for a in (c3["x"], c3["xe"], c3["xm"])]
+    for rep in range(2):
+        p, (lm, le), best = sb.fit_predict(tx[0], tx[1], tx[2], c3["labels"], c3["labe"], label_dict=c3["rdict"],
+                                           lprob_kwargs=LPROB, return_best=True, as_torch=True)
+        assert np.max(np.sum(np.abs(p.cpu().numpy() - c3["p"][:n]), axis=1)) <= 3e-6
+        assert np.allclose(lm.cpu().numpy(), c3["lm"][:n], rtol=0, atol=1e-6)
+        assert np.allclose(le.cpu().numpy(), c3["le"][:n], rtol=0, atol=3e-6)
+        assert np.array_equal(best.cpu().numpy(), c3["best"][:n])
+    sb.close()
