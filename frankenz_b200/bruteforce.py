@@ -29,6 +29,11 @@ def _check_args(args, name):
         raise NotImplementedError("positional `%s` are not supported; use the keyword form" % name)
 
 
+# object-conditioned prior tables: from this many object-model pairs on, fit_predict(save_fits=False) goes through the
+# fused kernels one table row at a time instead of the float64 kernel that reads the table per pair
+TABLE_PRIOR_GROUP_MIN_PAIRS = 1e8
+
+
 class BruteForce(object):
     """Fits data and generates predictions with a brute-force scan of all models."""
 
@@ -161,6 +166,11 @@ class BruteForce(object):
         _check_args(kde_args, "kde_args")
         if label_dict is None and label_grid is None:
             raise ValueError("`label_dict` or `label_grid` must be specified.")
+        lk0 = dict(lprob_kwargs or {})
+        if (not save_fits and lk0.get("lnprior", None) is not None and np.ndim(lk0["lnprior"]) == 2
+                and float(len(data)) * self.NMODEL >= TABLE_PRIOR_GROUP_MIN_PAIRS):
+            return self._fit_predict_by_prior_bin(data, data_err, data_mask, model_labels, model_label_errs, lprob_func,
+                                                  label_dict, label_grid, kde_kwargs, lprob_args, lk0, track_scale)
         eng, cfg = self._setup(lprob_func, lprob_args, lprob_kwargs, track_scale, kde_kwargs)
         eng.set_kde(model_labels, model_label_errs, label_dict=label_dict, label_grid=label_grid,
                     kde_kwargs=kde_kwargs)
@@ -172,6 +182,34 @@ class BruteForce(object):
             return eng.predict_logwt(res["lnprob"], cfg)
         pdfs, lmap, levid, best, bchi2, bscale = eng.fit_predict(data, data_err, data_mask, cfg)
         self.best_idx, self.best_chi2, self.best_scale = best, bchi2, bscale   # extras of the fused path
+        return pdfs, lmap, levid
+
+    def _fit_predict_by_prior_bin(self, data, data_err, data_mask, model_labels, model_label_errs, lprob_func, label_dict,
+                                  label_grid, kde_kwargs, lprob_args, lk, track_scale):
+        """Object-conditioned tabulated prior on the fused path: the objects of one table row share a
+        per-model prior, which the sweep kernels carry in their model records, so the batch is processed row by row of the
+        table (the float64 kernel that reads the table per pair remains the path of small problems and of `fit`)."""
+        table, bins = np.asarray(lk["lnprior"], dtype=np.float64), lk.get("lnprior_bin", None)
+        if bins is None:
+            raise ValueError("a 2-D `lnprior` table needs `lnprior_bin` (one row index per object)")
+        bins = np.asarray(bins)
+        if bins.shape != (len(data),) or bins.min() < 0 or bins.max() >= len(table):
+            raise ValueError("`lnprior_bin` must hold one row index of the table per object")
+        clean_inplace(data, data_err, data_mask)
+        out = None
+        for b in np.unique(bins):
+            idx = np.nonzero(bins == b)[0]
+            lkb = dict(lk, lnprior=table[b])
+            lkb.pop("lnprior_bin", None)
+            eng, cfg = self._setup(lprob_func, lprob_args, lkb, track_scale, kde_kwargs)
+            eng.set_kde(model_labels, model_label_errs, label_dict=label_dict, label_grid=label_grid, kde_kwargs=kde_kwargs)
+            res = eng.fit_predict(data[idx], data_err[idx], data_mask[idx], cfg)
+            if out is None:
+                out = [np.empty((len(data),) + r.shape[1:], dtype=r.dtype) for r in res]
+            for o, r in zip(out, res):
+                o[idx] = r
+        pdfs, lmap, levid, best, bchi2, bscale = out
+        self.best_idx, self.best_chi2, self.best_scale = best, bchi2, bscale
         return pdfs, lmap, levid
 
     def _fit_predict(self, data, data_err, data_mask, model_labels, model_label_errs, lprob_func=None,

@@ -121,3 +121,35 @@ def test_batch_and_split_invariance(fz):
     for sel, p, lm, le, b in out[1:]:
         assert np.array_equal(b, b0[sel]) and np.array_equal(lm, lm0[sel])
         assert np.max(np.abs(le - le0[sel])) <= 2e-6 and np.max(np.sum(np.abs(p - p0[sel]), axis=1)) <= 2e-6
+
+
+def test_object_conditioned_prior_table_on_the_fused_path(fz, monkeypatch):
+    """SURVEY 8f rank 1 at scale: fit_predict(save_fits=False) with lnprior[i, j] = table[bin_i, j] runs the fused sweep
+    once per table row; it must agree with the float64 kernel that reads the table per pair and with the oracle."""
+    import frankenz_b200.bruteforce as bfm
+    m, lab, x, xe, xm = _case(6001, 400)
+    rs = np.random.RandomState(4)
+    table = rs.uniform(-5, 0, size=(6, len(m)))
+    bins = rs.randint(0, 6, size=len(x))
+    zgrid, sig = bench_data.c3_kde()
+    rdict = fz.pdf.PDFDict(zgrid, sig)
+    labe = np.full(len(m), 0.05)
+    kw = dict(FS, lnprior=table, lnprior_bin=bins)
+    bf = fz.BruteForce(m, np.zeros_like(m), np.ones_like(m))
+    res = {}
+    for name, thresh in (("table_kernel", 1e30), ("by_row", 0.0)):
+        monkeypatch.setattr(bfm, "TABLE_PRIOR_GROUP_MIN_PAIRS", thresh)
+        p, (lm, le) = bf.fit_predict(x.copy(), xe.copy(), xm.copy(), lab, labe, label_dict=rdict, return_gof=True,
+                                     verbose=False, save_fits=False, lprob_kwargs=kw)
+        res[name] = (p, lm, le, bf._eng().stats()["sweep_kind"])
+    assert res["by_row"][3] == 3 and res["table_kernel"][3] == 0
+    assert np.max(np.sum(np.abs(res["by_row"][0] - res["table_kernel"][0]), axis=1)) <= 1e-5
+    assert np.allclose(res["by_row"][1], res["table_kernel"][1], rtol=0, atol=1e-5)
+    assert np.allclose(res["by_row"][2], res["table_kernel"][2], rtol=0, atol=1e-5)
+    kd = fo.KernelDict(zgrid, sig)
+    for b in range(6):
+        idx = np.nonzero(bins == b)[0][:12]
+        with np.errstate(all="ignore"):
+            po, lmo, leo = fo.bruteforce_fit_predict(m, np.zeros_like(m), np.ones_like(m), x[idx].copy(), xe[idx].copy(),
+                                                     xm[idx].copy(), lab, labe, label_dict=kd, lnprior=table[b], **FS)
+        _check(res["by_row"][0][idx], res["by_row"][1][idx], res["by_row"][2][idx], po, lmo, leo)
