@@ -76,6 +76,8 @@ SIGNATURES = {
     "fzb_pdfs_summarize": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int32, C.c_int32,
                                      c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "fzb_pdfs_conf": (C.c_int, [_H, c_double_p, c_double_p, C.c_int64, c_double_p]),
+    "fzb_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "fzb_free_pinned": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

@@ -99,8 +99,10 @@ class StagedDownloader {
   public:
     explicit StagedDownloader(fzb_context* h) : h_(h) {}
     ~StagedDownloader() { finish(); }
-    int init(size_t piece_bytes = (size_t)64 << 20) {
+    // direct: every destination of this downloader is page-locked host memory
+    int init(size_t piece_bytes = (size_t)64 << 20, bool direct = false) {
         piece_ = piece_bytes;
+        direct_ = direct;
         if (!h_->stream2) FZB_CUDA(cudaStreamCreateWithFlags(&h_->stream2, cudaStreamNonBlocking));
         for (int b = 0; b < 2; ++b) {
             if (h_->pinned_cap[b] < piece_) {
@@ -125,6 +127,7 @@ class StagedDownloader {
         r.dst = static_cast<char*>(dst);
         r.src = static_cast<const char*>(src);
         r.bytes = bytes;
+        r.direct = direct_;
         FZB_CUDA(cudaEventCreateWithFlags(&r.ready, cudaEventDisableTiming));
         FZB_CUDA(cudaEventCreateWithFlags(&r.left_device, cudaEventDisableTiming));
         FZB_CUDA(cudaEventRecord(r.ready, h_->stream));
@@ -170,6 +173,7 @@ class StagedDownloader {
         char* dst;
         const char* src;
         size_t bytes;
+        bool direct;
         cudaEvent_t ready, left_device;
     };
     // one worker: enqueue the device->pinned copy of piece p, then spread piece p-1 into the caller's array while
@@ -194,6 +198,17 @@ class StagedDownloader {
                 r = reqs_[(size_t)q];
             }
             if (cudaStreamWaitEvent(h_->stream2, r.ready, 0) != cudaSuccess) err_ = 1;
+            if (r.direct) {
+                // page-locked destination (fzb_alloc_pinned): the copy engine writes the caller's array itself
+                if (cudaMemcpyAsync(r.dst, r.src, r.bytes, cudaMemcpyDeviceToHost, h_->stream2) != cudaSuccess) err_ = 1;
+                if (cudaEventRecord(r.left_device, h_->stream2) != cudaSuccess) err_ = 1;
+                {
+                    std::lock_guard<std::mutex> lk(mu_);
+                    issued_ = q + 1;
+                }
+                cv_.notify_all();
+                continue;
+            }
             for (size_t off = 0; off < r.bytes; off += piece_) {
                 size_t n = std::min(piece_, r.bytes - off);
                 int b = (int)(piece & 1);
@@ -218,8 +233,10 @@ class StagedDownloader {
             cv_.notify_all();
         }
         drain_prev();
+        if (direct_ && cudaStreamSynchronize(h_->stream2) != cudaSuccess) err_ = 1;
     }
     fzb_context* h_;
+    bool direct_ = false;
     size_t piece_ = 0;
     int nthreads_ = 1;
     bool started_ = false, closing_ = false;
@@ -671,7 +688,11 @@ int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, co
     const size_t chunk_bytes = (size_t)chunk * Ng * sizeof(double);
     StagedDownloader dl(h);
     if (pdfs) {
-        if (dl.init()) return 1;
+        // a destination from fzb_alloc_pinned takes the DMA directly (no staging buffer, no host-side copy)
+        cudaPointerAttributes pa = {};
+        const bool pinned_dst = cudaPointerGetAttributes(&pa, pdfs) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (dl.init((size_t)64 << 20, pinned_dst)) return 1;
         for (int b = 0; b < 2; ++b)
             if (h->pdf_dev[b].reserve(chunk_bytes)) return 1;
     }
@@ -902,4 +923,17 @@ int fzb_pdfs_conf(fzb_handle h, const double* points, const double* widths, int6
     if (use_device(h)) return 2;
     FZB_CHECK(points && widths && conf && No > 0, "null argument");
     return fzb_conf_impl(h, points, widths, No, conf);
+}
+
+// ---- page-locked host buffers for large outputs ---------------------------------------------------------------------
+int fzb_alloc_pinned(size_t bytes, void** out) {
+    FZB_CHECK(out != nullptr && bytes > 0, "bad arguments");
+    *out = nullptr;
+    FZB_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return 0;
+}
+
+int fzb_free_pinned(void* p) {
+    if (p) FZB_CUDA(cudaFreeHost(p));
+    return 0;
 }

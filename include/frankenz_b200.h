@@ -192,6 +192,12 @@ int fzb_pdfs_summarize(fzb_handle h, const double* pdfs, const double* pgrid, co
  * (the four estimators and the caller's wconf_func evaluated at them), on the PDFs of the last fzb_pdfs_summarize. */
 int fzb_pdfs_conf(fzb_handle h, const double* points, const double* widths, int64_t No, double* conf);
 
+/* Page-locked host memory for large outputs (the (Ndata x Ngrid) PDFs): when the `pdfs` argument of fzb_fit_predict
+ * points into such a buffer, the device-to-host copies go straight into it, without the staging buffer and the host-side
+ * copy a pageable destination needs. */
+int fzb_alloc_pinned(size_t bytes, void** out);
+int fzb_free_pinned(void* p);
+
 #ifdef __cplusplus
 }
 #endif

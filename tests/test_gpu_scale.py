@@ -267,3 +267,23 @@ def test_model_sharded_driver_single_rank(c3):
         assert np.allclose(le.cpu().numpy(), c3["le"][:n], rtol=0, atol=3e-6)
         assert np.array_equal(best.cpu().numpy(), c3["best"][:n])
     sb.close()
+
+
+def test_pinned_output_pool(c3, monkeypatch):
+    """Page-locked output arrays (the multi-rank default): same results, buffers recycled once the arrays are gone."""
+    from frankenz_b200 import _engine
+    pool = _engine.PinnedPool(max_bytes=1 << 30)
+    pool.MIN_BYTES = 1 << 20
+    monkeypatch.setattr(_engine, "_pinned_pool", pool)
+    fz = c3["fz"]
+    n = 3000
+    bf = fz.BruteForce(c3["models"], np.zeros_like(c3["models"]), np.ones_like(c3["models"]))
+    for rep in range(2):
+        p = bf.fit_predict(c3["x"][:n].copy(), c3["xe"][:n].copy(), c3["xm"][:n].copy(), c3["labels"], c3["labe"],
+                           label_dict=c3["rdict"], verbose=False, save_fits=False, lprob_kwargs=LPROB)
+        assert pool.total == n * 701 * 8 and not pool.free            # one pinned buffer, in use
+        assert np.max(np.sum(np.abs(p - c3["p"][:n]), axis=1)) <= 2e-6
+        q = p[5:10].copy()
+        del p
+        assert len(pool.free) == 1                                     # back in the pool, reused by the next call
+    assert np.all(np.isfinite(q))
