@@ -53,6 +53,14 @@ def clean_inplace(data, data_err, data_mask):
     The reference mutates the caller's arrays one row at a time; the drop-in does the same
     for all rows at once so callers observe identical arrays afterwards.
     """
+    arrs = (data, data_err, data_mask)
+    if (data.size >= (1 << 18) and all(isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous
+                                      and a.flags.writeable and a.shape == data.shape for a in arrs)):
+        try:      # large float64 batches: the same rule on several host threads
+            _lib.check(_lib.load().fzb_clean_inplace_f64(dptr(data), dptr(data_err), dptr(data_mask), data.size))
+            return data, data_err, data_mask
+        except Exception:
+            pass
     with np.errstate(invalid="ignore"):
         bad = ~(np.isfinite(data) & np.isfinite(data_err) & (data_err > 0.))
     if bad.any():

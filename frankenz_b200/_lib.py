@@ -78,6 +78,7 @@ SIGNATURES = {
     "fzb_pdfs_conf": (C.c_int, [_H, c_double_p, c_double_p, C.c_int64, c_double_p]),
     "fzb_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "fzb_free_pinned": (C.c_int, [C.c_void_p]),
+    "fzb_clean_inplace_f64": (C.c_int, [c_double_p, c_double_p, c_double_p, C.c_int64]),
 }
 
 _lib = None

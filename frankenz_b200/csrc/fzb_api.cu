@@ -937,3 +937,21 @@ int fzb_free_pinned(void* p) {
     if (p) FZB_CUDA(cudaFreeHost(p));
     return 0;
 }
+
+// ---- host helper: the reference's in-place cleaning (pdf.py:310-311) for float64 arrays, on several threads ------------
+int fzb_clean_inplace_f64(double* data, double* err, double* mask, int64_t n) {
+    FZB_CHECK(data && err && mask && n >= 0, "bad arguments");
+    const int nt = (int)std::min<int64_t>(std::max<int64_t>(1, n >> 18), std::max(1u, std::thread::hardware_concurrency() / 2));
+    auto work = [=](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            const double d = data[i], e = err[i];
+            if (!(std::isfinite(d) && std::isfinite(e) && e > 0.0)) { data[i] = 0.0; err[i] = 1.0; mask[i] = 0.0; }
+        }
+    };
+    if (nt <= 1) { work(0, n); return 0; }
+    std::vector<std::thread> pool;
+    const int64_t per = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) pool.emplace_back(work, std::min<int64_t>(n, t * per), std::min<int64_t>(n, (t + 1) * per));
+    for (auto& th : pool) th.join();
+    return 0;
+}

@@ -198,6 +198,10 @@ int fzb_pdfs_conf(fzb_handle h, const double* points, const double* widths, int6
 int fzb_alloc_pinned(size_t bytes, void** out);
 int fzb_free_pinned(void* p);
 
+/* Host helper: pdf.loglike's in-place cleaning (pdf.py:310-311) of n = Ndata x Nfilt float64 entries: where data or
+ * err is non-finite or err <= 0, data = 0, err = 1, mask = 0.  Multi-threaded; no device involved. */
+int fzb_clean_inplace_f64(double* data, double* err, double* mask, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

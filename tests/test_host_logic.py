@@ -98,3 +98,24 @@ def test_ordered_union_and_exact_knn_oracle():
     feats = np.array([[[0., 0.], [1., 0.], [0., 2.], [1., 0.]]], dtype=np.float32)
     i, d = fo.knn_query_exact(feats, np.array([0.9, 0.0]), 3, 2)
     assert i.tolist() == [[1, 3, 0]] and np.allclose(d[0], [0.1, 0.1, 0.9])     # tie -> lowest index first
+
+
+def test_clean_inplace_threaded_helper_matches_numpy_rule():
+    """pdf.py:310-311 on large float64 batches runs in libfzb200 (host threads, no device): same arrays afterwards as the
+    numpy form used for small / non-float64 inputs."""
+    from frankenz_b200._engine import clean_inplace
+    rs = np.random.RandomState(0)
+    x = rs.normal(size=(80000, 5))
+    xe = np.abs(rs.normal(size=x.shape)) + 0.1
+    xm = np.ones_like(x)
+    x[rs.uniform(size=x.shape) < 0.01] = np.nan
+    xe[rs.uniform(size=x.shape) < 0.01] = -1.0
+    x[3, 2], xe[4, 1], xe[5, 0] = np.inf, np.nan, 0.0
+    a, b, c = x.copy(), xe.copy(), xm.copy()
+    clean_inplace(a, b, c)                                   # 400k entries: threaded helper
+    bad = ~(np.isfinite(x) & np.isfinite(xe) & (xe > 0))
+    assert np.all(a[bad] == 0) and np.all(b[bad] == 1) and np.all(c[bad] == 0)
+    assert np.array_equal(a[~bad], x[~bad]) and np.array_equal(b[~bad], xe[~bad]) and np.all(c[~bad] == 1)
+    a2, b2, c2 = x[:100].copy(), xe[:100].copy(), xm[:100].astype(bool)       # small + bool mask: numpy form
+    clean_inplace(a2, b2, c2)
+    assert np.array_equal(a2, a[:100]) and np.array_equal(b2, b[:100]) and np.array_equal(c2, c[:100].astype(bool))
