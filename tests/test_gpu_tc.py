@@ -56,10 +56,10 @@ def _check(p, lm, le, po, lmo, leo):
 FS = dict(free_scale=True, ignore_model_err=True, dim_prior=True)
 
 
-@pytest.mark.parametrize("nm", [5003, 4098, 777])
+@pytest.mark.parametrize("nm", [5003, 4098, 777, 37, 9])
 def test_partial_and_odd_model_tiles(fz, nm):
     """Model counts that end in an odd pair / a partial 8-model sub-batch / a partial 32-model chunk."""
-    m, lab, x, xe, xm = _case(nm, 300)
+    m, lab, x, xe, xm = _case(nm, 300 if nm > 100 else 7)
     p, lm, le, po, lmo, leo, st = _run(fz, m, lab, x, xe, xm, FS)
     assert st["sweep_kind"] == 3 and st["pairs_fp32"] > 0           # linear-domain tensor-core sweep
     _check(p, lm, le, po, lmo, leo)
