@@ -7,7 +7,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import bench_data  # noqa: E402
 import frankenz_b200 as fz  # noqa: E402
 from oracle import fz_oracle as fo  # noqa: E402

@@ -1,8 +1,8 @@
 """Timing of pdf.pdfs_summarize on PDFs shaped like the C3 output (Nobj x 701, float64).
-Usage: python tools/bench_summarize.py [Nobj] [cpu_sample]"""
+Usage: python tests/scripts/bench_summarize.py [Nobj] [cpu_sample]"""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import frankenz_b200 as fz
 from frankenz_b200._engine import SummaryEngine
 from oracle import fz_oracle as fo

@@ -61,3 +61,9 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("the oracle", ""), "%s references oracle/" % f
+    # tools/ are measurement and debugging aids of the product: they may not execute the oracle either (scripts that time
+    # the oracle beside the GPU live under tests/scripts/)
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith((".py", ".sh")):
+            txt = open(os.path.join(ROOT, "tools", f)).read()
+            assert "import fz_oracle" not in txt and "from oracle" not in txt, "tools/%s imports the oracle" % f

@@ -9,5 +9,5 @@ d=json.loads([l for l in open('gpurun_out/bench_r1_tc.json') if l.startswith('{'
 print('value %.4g e2e %.4g frac %.3f' % (d['value'], d['e2e']['value'], d['roofline']['frac']), d['roofline']['ms'], d['roofline']['kernel'], d['cpu_baseline']['value'], d['clocks'])
 "
 cat gpurun_out/bench_r1_ref.json | cut -c1-300
-timeout 400 python tools/bench_c1.py > gpurun_out/r1_c1_c2.log 2>&1; tail -8 gpurun_out/r1_c1_c2.log | cut -c1-330
+timeout 400 python tests/scripts/bench_c1.py > gpurun_out/r1_c1_c2.log 2>&1; tail -8 gpurun_out/r1_c1_c2.log | cut -c1-330
 timeout 500 python tools/bench_knn.py 1000000 65536 20 25 > gpurun_out/r1_knn.log 2>&1; tail -7 gpurun_out/r1_knn.log | cut -c1-250

@@ -1,4 +1,4 @@
-"""Small tensor-core-sweep run (for compute-sanitizer): 96 objects x 4081 models, checked against the oracle."""
+"""Small tensor-core-sweep run (for compute-sanitizer): 96 objects x 4081 models."""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
