@@ -429,308 +429,6 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
 #include "fzb_sweep_tc.cuh"
 
 // =====================================================================================================
-// Software-pipelined packed sweep (k_sweep3).
-// tools/peak_mufu_spacing.cu: 34 FFMA2 + 6 MUFU take 116 cycles per SMSP when the six MUFUs are issued back to
-// back (68 + 48: the in-order warps of a scheduler fall into step, all waiting on the XU pipe, then all on the FMA
-// pipe) but 70 cycles when one MUFU pair is issued every ~11 FFMA2.  k_sweep2 leaves the order to the compiler,
-// which clusters the rcp / lg2 / ex2 of the two object pairs of a thread.  Here the two pairs (A, B) of a thread run
-// a hand-scheduled pipeline in which B lags A by most of a model and the tail of model j-1 (log-likelihood, exp,
-// reduction update) is interleaved with the head of model j, so that one MUFU pair follows every 10-13 packed
-// FMAs.  All arithmetic is issued through `asm volatile` so that the source order is the program order.
-//   cycle j:  A.S1(j) rcpA | B.S2a(j-1) A.S3(j-1) ex2A | B.S2b(j-1) lg2B | A.S2a(j) A.S4(j-1) B.S3(j-1) ex2B |
-//             A.S2b(j) lg2A | B.S1(j) rcpB | B.S4(j-1)
-//   S1 = the two dot products, S2a/b = residuals + chi2 (bands 0-2 / 3-), S3 = ln-likelihood and distance to the
-//   running max, S4 = reduction update.
-// Same arithmetic, same results as k_sweep2 (bit-identical per pair), FS0 / FX0 with fp32-exact models only.
-// =====================================================================================================
-__device__ __forceinline__ f2 vfma2(f2 a, f2 b, f2 c) {
-    f2 d;
-    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ f2 vmul2(f2 a, f2 b) {
-    f2 d;
-    asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ f2 vadd2(f2 a, f2 b) {
-    f2 d;
-    asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ float vrcp(float x) {
-    float y;
-    asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float vlg2(float x) {
-    float y;
-    asm volatile("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float vex2(float x) {
-    float y;
-    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// Make `x` data-dependent on `dep` without changing it (unless dep is NaN, which already poisons the object):
-// ptxas otherwise hoists the independent tail of the previous model to the top of the cycle, next to the rcp pair.
-__device__ __forceinline__ void order_after(f2& x, f2 dep) {
-    asm volatile("{\n.reg .pred p;\n.reg .f32 lo, hi;\nmov.b64 {lo, hi}, %1;\nsetp.num.f32 p, lo, lo;\n@!p mov.b64 %0, 0;\n}\n"
-                 : "+l"(x)
-                 : "l"(dep));
-}
-
-template <int NF, int MODE>
-struct PipeRegs {          // in-flight values of one object pair
-    f2 m[NF];              // model fluxes (duplicated halves) of the model in S1/S2
-    f2 inter, shape;       // S1 -> rcp
-    float inv0, inv1;      // rcp results
-    f2 ns;                 // minus the scale
-    f2 chi2;               // S2 -> lg2 / S3   (already scaled by -log2(e)/2)
-    float lg0, lg1;        // lg2 results
-    f2 l;                  // S3
-    float d0, d1;          // distance to the running max
-    float e0, e1;          // ex2 results
-};
-
-template <int NF, int MODE, bool DP, bool PRIOR, int PASS>
-__global__ void __launch_bounds__(384, 1) k_sweep3(SweepParams P) {
-    static_assert(MODE != FM_FX1, "model-error mode keeps the compiler-scheduled kernel");
-    constexpr int FT2 = 384;
-    constexpr int R = 4;
-    constexpr int NP = 2;
-    constexpr int REC = rec2_floats(NF, MODE, false);
-    constexpr int AUXOFF = 2 * NF;
-    constexpr int TAILOFF = 2 * NF * (1 + ((MODE == FM_FX0) ? 0 : 1));
-    constexpr int NB1 = (NF + 1) / 2;      // bands handled by S2a
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* stage = reinterpret_cast<float*>(smem_raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NSTAGE * TM * REC * sizeof(float));
-    const int tid = threadIdx.x;
-
-    ObjPack<NF, MODE> ob[NP];
-    PipeRegs<NF, MODE> pr[NP];
-    int oidx[R];
-    f2 M[NP], S[NP], acc[NP];
-    float thr[R];
-    int best[R];
-    double Sd[R];
-    float Mfl[R];
-    const int64_t tile_base = (int64_t)blockIdx.x * (FT2 * R);
-#pragma unroll
-    for (int p = 0; p < NP; ++p) {
-        int64_t oo[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            int r = 2 * p + h;
-            int64_t slot = tile_base + (int64_t)r * FT2 + tid;
-            int64_t o;
-            if (PASS == 1) o = slot < P.No_pad ? slot : P.No_pad - 1;
-            else o = slot < P.No ? P.objlist[slot] : -1;
-            oidx[r] = (int)o;
-            oo[h] = o < 0 ? 0 : o;
-            best[r] = 0;
-            Sd[r] = 0.0;
-            Mfl[r] = -FLT_MAX;
-            thr[r] = (PASS == 2) ? P.thr2[oo[h]] : 0.f;
-        }
-#pragma unroll
-        for (int b = 0; b < NF; ++b) {
-            ob[p].d[b] = pack2(P.od[b * P.No_pad + oo[0]], P.od[b * P.No_pad + oo[1]]);
-            ob[p].w[b] = pack2(P.ow[b * P.No_pad + oo[0]], P.ow[b * P.No_pad + oo[1]]);
-            ob[p].dl[b] = pack2(P.odl[b * P.No_pad + oo[0]], P.odl[b * P.No_pad + oo[1]]);
-            if (MODE == FM_FS0) ob[p].x[b] = pack2(P.ox[b * P.No_pad + oo[0]], P.ox[b * P.No_pad + oo[1]]);
-            pr[p].m[b] = 0;
-        }
-        ob[p].A = pack2(P.oA[oo[0]], P.oA[oo[1]]);
-        if (PASS == 1) { M[p] = pack2(-FLT_MAX, -FLT_MAX); S[p] = pack2(0.f, 0.f); }
-        else { M[p] = pack2(P.M2[oo[0]], P.M2[oo[1]]); acc[p] = pack2(0.f, 0.f); }
-        pr[p].inter = pr[p].shape = pr[p].ns = pr[p].chi2 = pr[p].l = 0;
-        pr[p].inv0 = pr[p].inv1 = pr[p].lg0 = pr[p].lg1 = pr[p].d0 = pr[p].d1 = pr[p].e0 = pr[p].e1 = 0.f;
-    }
-
-    const int64_t ntiles_all = (P.nm + TM - 1) / TM;
-    const int64_t t0 = (int64_t)blockIdx.y * P.tiles_per_split;
-    int64_t t1 = t0 + P.tiles_per_split;
-    if (t1 > ntiles_all) t1 = ntiles_all;
-    const int nt = (int)(t1 - t0);
-    if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    auto issue = [&](int it) {
-        int64_t first = (t0 + it) * TM;
-        int cnt = (int)((P.nm - first) < TM ? (P.nm - first) : TM);
-        uint32_t bytes = (uint32_t)cnt * REC * sizeof(float);
-        uint64_t* bar = &bars[it % NSTAGE];
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(stage + (size_t)(it % NSTAGE) * TM * REC, P.recs + first * REC, bytes, bar);
-    };
-    if (tid == 0) {
-        for (int it = 0; it < NSTAGE && it < nt; ++it) issue(it);
-    }
-    const f2 kMinusOne = pack2(-1.f, -1.f);
-    int cur_bin = -1;
-    // values of the model whose tail (S3 / S4) is in flight: model j-1 while cycle j runs
-    f2 prior_prev[NP] = {0, 0};
-    f2 invnorm_prev = 0;
-    int bin_prev = -1;
-    int idx_prev = 0;
-
-    // ---- pipeline stages (p = 0: pair A, p = 1: pair B) ------------------------------------------------
-    auto S1 = [&](int p, const f2* rec2) {            // dot products of model j; issues the rcp pair
-#pragma unroll
-        for (int b = 0; b < NF; ++b) pr[p].m[b] = rec2[b];
-        if (MODE == FM_FS0) {
-            pr[p].inter = vmul2(ob[p].x[0], pr[p].m[0]);
-            pr[p].shape = vmul2(ob[p].w[0], rec2[AUXOFF / 2]);
-#pragma unroll
-            for (int b = 1; b < NF; ++b) {
-                pr[p].inter = vfma2(ob[p].x[b], pr[p].m[b], pr[p].inter);
-                pr[p].shape = vfma2(ob[p].w[b], rec2[AUXOFF / 2 + b], pr[p].shape);
-            }
-            pr[p].inv0 = vrcp(lo2(pr[p].shape));
-            pr[p].inv1 = vrcp(hi2(pr[p].shape));
-        }
-    };
-    auto S2 = [&](int p, int b0, int b1) {            // residuals and chi2 over bands [b0, b1)
-        if (b0 == 0 && MODE == FM_FS0)
-            pr[p].ns = pack2(__fmul_rn(-lo2(pr[p].inter), pr[p].inv0), __fmul_rn(-hi2(pr[p].inter), pr[p].inv1));
-#pragma unroll
-        for (int b = b0; b < b1; ++b) {
-            f2 r = (MODE == FM_FS0) ? vfma2(pr[p].ns, pr[p].m[b], ob[p].d[b]) : vadd2(ob[p].d[b], pr[p].m[b]);
-            f2 t = vmul2(r, ob[p].w[b]);
-            f2 u = vadd2(r, ob[p].dl[b]);
-            pr[p].chi2 = (b == 0) ? vmul2(t, u) : vfma2(t, u, pr[p].chi2);
-        }
-    };
-    auto LG = [&](int p) {                            // issues the lg2 pair
-        if (DP) {
-            pr[p].lg0 = vlg2(fabsf(lo2(pr[p].chi2)));
-            pr[p].lg1 = vlg2(fabsf(hi2(pr[p].chi2)));
-        }
-    };
-    auto S3 = [&](int p) {                            // ln-likelihood, distance to the max; issues the ex2 pair
-        f2 c = pr[p].chi2;
-        if (PRIOR) c = vadd2(c, prior_prev[p]);
-        pr[p].l = DP ? vfma2(ob[p].A, pack2(pr[p].lg0, pr[p].lg1), c) : c;
-        f2 delta = vfma2(M[p], kMinusOne, pr[p].l);
-        pr[p].d0 = lo2(delta);
-        pr[p].d1 = hi2(delta);
-        if (PASS == 1) {
-            pr[p].e0 = vex2(-fabsf(pr[p].d0));
-            pr[p].e1 = vex2(-fabsf(pr[p].d1));
-        } else {
-            pr[p].e0 = vex2(pr[p].d0);
-            pr[p].e1 = vex2(pr[p].d1);
-        }
-    };
-    auto S4 = [&](int p) {                            // reduction update for the model in the tail
-        if (PASS == 1) {
-            bool g0 = pr[p].d0 > 0.f, g1 = pr[p].d1 > 0.f;
-            S[p] = vfma2(S[p], pack2(g0 ? pr[p].e0 : 1.f, g1 ? pr[p].e1 : 1.f),
-                         pack2(g0 ? 1.f : pr[p].e0, g1 ? 1.f : pr[p].e1));
-            M[p] = pack2(g0 ? lo2(pr[p].l) : lo2(M[p]), g1 ? hi2(pr[p].l) : hi2(M[p]));
-            best[2 * p] = g0 ? idx_prev : best[2 * p];
-            best[2 * p + 1] = g1 ? idx_prev : best[2 * p + 1];
-        } else {
-            float u0 = (lo2(pr[p].l) > thr[2 * p]) ? pr[p].e0 : 0.f;
-            float u1 = (hi2(pr[p].l) > thr[2 * p + 1]) ? pr[p].e1 : 0.f;
-            acc[p] = vfma2(pack2(u0, u1), invnorm_prev, acc[p]);
-        }
-    };
-    auto flush = [&]() {
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            float a0 = lo2(acc[p]), a1 = hi2(acc[p]);
-            if (a0 != 0.f && oidx[2 * p] >= 0) atomicAdd(P.hist + (int64_t)oidx[2 * p] * P.hist_stride + cur_bin, a0);
-            if (a1 != 0.f && oidx[2 * p + 1] >= 0)
-                atomicAdd(P.hist + (int64_t)oidx[2 * p + 1] * P.hist_stride + cur_bin, a1);
-            acc[p] = pack2(0.f, 0.f);
-        }
-    };
-    // one cycle; NEW: start model `rec`, LAG: finish the previous model
-    auto cycle = [&](const float* rec, int gidx, bool do_new, bool do_lag) {
-        const f2* rec2 = reinterpret_cast<const f2*>(rec);
-        if (PASS == 2 && do_lag && bin_prev != cur_bin) {     // warp-uniform
-            if (cur_bin >= 0) flush();
-            cur_bin = bin_prev;
-        }
-        if (do_new) S1(0, rec2);                              // A.S1(j)            -> rcp A
-        if (do_lag) S2(1, 0, NB1);                            // B.S2a(j-1)
-        if (do_lag) { order_after(pr[0].chi2, pr[1].chi2); S3(0); }   // A.S3(j-1)  -> ex2 A
-        if (do_lag) { S2(1, NB1, NF); LG(1); }                // B.S2b(j-1)         -> lg2 B
-        if (do_new) S2(0, 0, NB1);                            // A.S2a(j)
-        if (do_lag) S4(0);                                    // A.S4(j-1)
-        if (do_lag) S3(1);                                    // B.S3(j-1)          -> ex2 B
-        if (do_new) { S2(0, NB1, NF); LG(0); }                // A.S2b(j)           -> lg2 A
-        if (do_new) { order_after(ob[1].x[0], pr[0].chi2); S1(1, rec2); }   // B.S1(j)   -> rcp B
-        if (do_lag) S4(1);                                    // B.S4(j-1)
-        if (do_new) {
-            if (PRIOR) { prior_prev[0] = prior_prev[1] = rec2[TAILOFF / 2]; }
-            if (PASS == 2) {
-                invnorm_prev = rec2[TAILOFF / 2 + 1];
-                bin_prev = __float_as_int(rec[TAILOFF + 4]);
-            }
-            idx_prev = gidx;
-        }
-    };
-
-    bool primed = false;
-    const float* last_rec = stage;
-    for (int it = 0; it < nt; ++it) {
-        const int st = it % NSTAGE;
-        mbar_wait(&bars[st], (uint32_t)((it / NSTAGE) & 1));
-        const float* tile = stage + (size_t)st * TM * REC;
-        const int64_t first = (t0 + it) * TM;
-        const int cnt = (int)((P.nm - first) < TM ? (P.nm - first) : TM);
-        int jj = 0;
-        if (!primed && cnt > 0) {                 // pipeline fill: first model of the split
-            cycle(tile, (int)first, true, false);
-            primed = true;
-            jj = 1;
-        }
-#pragma unroll 1
-        for (; jj < cnt; ++jj) cycle(tile + jj * REC, (int)(first + jj), true, true);
-        if (cnt > 0) last_rec = tile + (cnt - 1) * REC;
-        if (it == nt - 1 && primed) cycle(last_rec, 0, false, true);    // drain (the stage buffer is still valid)
-        if (PASS == 1) {
-#pragma unroll
-            for (int p = 0; p < NP; ++p) {
-                // B's last model of this tile is still in flight except after the drain; folding S into the float64
-                // sum at any point is exact bookkeeping (S is relative to the current M)
-                float m0 = lo2(M[p]), m1 = hi2(M[p]);
-                Sd[2 * p] = Sd[2 * p] * (double)fast_ex2(Mfl[2 * p] - m0) + (double)lo2(S[p]);
-                Sd[2 * p + 1] = Sd[2 * p + 1] * (double)fast_ex2(Mfl[2 * p + 1] - m1) + (double)hi2(S[p]);
-                Mfl[2 * p] = m0;
-                Mfl[2 * p + 1] = m1;
-                S[p] = pack2(0.f, 0.f);
-            }
-        }
-        __syncthreads();
-        if (tid == 0 && it + NSTAGE < nt) issue(it + NSTAGE);
-    }
-    if (PASS == 1) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            int64_t slot = tile_base + (int64_t)r * FT2 + tid;
-            if (slot < P.No_pad) {
-                size_t q = (size_t)blockIdx.y * P.No_pad + slot;
-                P.pM[q] = (double)Mfl[r];
-                P.pS[q] = Sd[r];
-                P.pbest[q] = best[r];
-            }
-        }
-    } else {
-        if (bin_prev != cur_bin) { /* nothing accumulated for bin_prev beyond the drain */ }
-        if (cur_bin >= 0) flush();
-    }
-}
-
-// =====================================================================================================
 // Float64 register-tiled sweep: same structure as k_sweep2 (objects in registers, model tiles staged by
 // TMA bulk copies, online reductions) with chi2 evaluated in double precision, for the objects whose
 // best-fit chi2 is too large for fp32 (template mismatch, very bright objects).  Only log2 / exp2 go
@@ -1316,24 +1014,6 @@ int launch_sweep2_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prior)
     return 0;
 }
 
-template <int NF, int MODE, bool DP, int PASS>
-int launch_sweep3_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prior) {
-    constexpr int REC = rec2_floats(NF, MODE, false);
-    size_t smem = (size_t)NSTAGE * TM * REC * sizeof(float) + NSTAGE * sizeof(uint64_t);
-    if (prior) {
-        auto kern = k_sweep3<NF, MODE, DP, true, PASS>;
-        FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 384, smem, h->stream>>>(P);
-    } else {
-        auto kern = k_sweep3<NF, MODE, DP, false, PASS>;
-        FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, 384, smem, h->stream>>>(P);
-    }
-    fzb_count_launch(h);
-    FZB_CUDA(cudaGetLastError());
-    return 0;
-}
-
 // tensor-core sweep (FS0, fp32-exact models, no model masks): 256 objects per CTA
 template <int NF, bool DP, int PASS, bool LIN>
 int launch_sweep_tc_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prior) {
@@ -1376,14 +1056,6 @@ int launch_sweep_r(fzb_context* h, const SweepParams& P, dim3 grid, int R, int p
                                             : launch_sweep2_mm<NF, MODE, DP, 2, 1>(h, P, grid);
             return (R == -4) ? launch_sweep2_mm<NF, MODE, DP, 4, 2>(h, P, grid)
                              : launch_sweep2_mm<NF, MODE, DP, 2, 2>(h, P, grid);
-        }
-    }
-    if constexpr (!MLO && MODE != FM_FX1) {
-        // hand-scheduled software pipeline (MUFUs spaced through the FMA stream): opt-in experiment.  ptxas re-clusters
-        // the MUFUs (it hoists them as early as their operands allow), so as compiled it is ~8 % slower than k_sweep2.
-        if (R == -4 && getenv("FZB_SWEEP3") != nullptr) {
-            if (pass == 1) return launch_sweep3_t<NF, MODE, DP, 1>(h, P, grid, P.has_prior != 0);
-            return launch_sweep3_t<NF, MODE, DP, 2>(h, P, grid, P.has_prior != 0);
         }
     }
     if (R < 0) {   // packed kernels: R = -objects per thread
