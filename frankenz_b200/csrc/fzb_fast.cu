@@ -1310,6 +1310,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     const int64_t obj_tiles = (chunk_pad + tile_objs - 1) / tile_objs;
     const int64_t ntiles = (nm + TM - 1) / TM;
     int64_t want_ctas = (int64_t)h->sm_count * ((use_tc || (packed && Robj >= 4)) ? 24 : 48);   // many short waves: small tail
+    if (getenv("FZB_WAVES")) want_ctas = (int64_t)h->sm_count * std::max(1, atoi(getenv("FZB_WAVES")));
     int64_t nsplit = (want_ctas + obj_tiles - 1) / obj_tiles;
     if (nsplit > ntiles) nsplit = ntiles;
     if (nsplit > 256) nsplit = 256;
