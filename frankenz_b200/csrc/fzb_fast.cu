@@ -1020,12 +1020,12 @@ int launch_sweep_tc_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prio
     const unsigned char* tiles = h->fast.tiles_tc.as<unsigned char>();
     if (prior) {
         auto kern = k_sweep_tc<NF, DP, true, PASS, LIN>;
-        FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-        kern<<<grid, TC_THREADS, TC_SMEM, h->stream>>>(P, tiles, 128u, 256u);
+        FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(NF)));
+        kern<<<grid, TC_THREADS, tc_smem(NF), h->stream>>>(P, tiles, 128u, 256u);
     } else {
         auto kern = k_sweep_tc<NF, DP, false, PASS, LIN>;
-        FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-        kern<<<grid, TC_THREADS, TC_SMEM, h->stream>>>(P, tiles, 128u, 256u);
+        FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(NF)));
+        kern<<<grid, TC_THREADS, tc_smem(NF), h->stream>>>(P, tiles, 128u, 256u);
     }
     fzb_count_launch(h);
     FZB_CUDA(cudaGetLastError());
@@ -1043,6 +1043,10 @@ int launch_sweep_tc(fzb_context* h, const SweepParams& P, dim3 grid, int nf, boo
     if (nf == 4) {
         if (dp) return pass == 1 ? launch_sweep_tc_t<4, true, 1, false>(h, P, grid, prior) : launch_sweep_tc_t<4, true, 2, false>(h, P, grid, prior);
         return pass == 1 ? launch_sweep_tc_t<4, false, 1, false>(h, P, grid, prior) : launch_sweep_tc_t<4, false, 2, false>(h, P, grid, prior);
+    }
+    if (nf == 6) {
+        if (dp) return pass == 1 ? launch_sweep_tc_t<6, true, 1, false>(h, P, grid, prior) : launch_sweep_tc_t<6, true, 2, false>(h, P, grid, prior);
+        return pass == 1 ? launch_sweep_tc_t<6, false, 1, false>(h, P, grid, prior) : launch_sweep_tc_t<6, false, 2, false>(h, P, grid, prior);
     }
     fzb_set_error("tensor-core sweep: unsupported filter count %d", nf);
     return 2;
@@ -1245,10 +1249,10 @@ static int fast_prepare_mode(fzb_context* h, int mode) {
         FZB_CUDA(cudaGetLastError());
     }
     F.tc_valid = false;
-    if (mode == FM_FS0 && !mm && !mlo && nf >= 4 && nf <= 5) {
+    if (mode == FM_FS0 && !mm && !mlo && nf >= 4 && nf <= 6) {
         const int64_t ntile = (nm + TC_TM - 1) / TC_TM;
-        if (F.tiles_tc.reserve((size_t)ntile * TC_TILE_BYTES + 64)) return 1;
-        FZB_CUDA(cudaMemsetAsync(F.tiles_tc.p, 0, (size_t)ntile * TC_TILE_BYTES, h->stream));
+        if (F.tiles_tc.reserve((size_t)ntile * tc_tile_bytes(nf) + 64)) return 1;
+        FZB_CUDA(cudaMemsetAsync(F.tiles_tc.p, 0, (size_t)ntile * tc_tile_bytes(nf), h->stream));
         TcRecParams T = {};
         T.m = R.m; T.lnprior = R.lnprior; T.perm = R.perm; T.bins = R.bins; T.invnorm = R.invnorm;
         T.nm = nm; T.Nf = nf; T.tiles = F.tiles_tc.as<unsigned char>();

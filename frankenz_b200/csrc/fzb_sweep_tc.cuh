@@ -6,7 +6,7 @@
 // 5th-generation tensor cores compute them:  D[object][model] = A[object][K] . B[model][K]^T,  kind::tf32, M = 128,
 // N = 32, operands K-major in shared memory without swizzle, accumulators in TMEM, one elected thread issuing.
 // tf32 keeps 11 significant bits, so inter and shape use the split x = hi + lo on both sides and three products per
-// band (hi*hi + hi*lo + lo*hi: 3 Nf <= 16 K-slots, two K = 8 instructions), which leaves a relative error of ~5e-7 in
+// band (hi*hi + hi*lo + lo*hi: 3 Nf K-slots, two K = 8 instructions up to five bands, three for six), which leaves a relative error of ~5e-7 in
 // the scale; the scale is the minimiser of chi2, so that error enters chi2 only as S/N^2 (ds/s)^2 (envelope theorem),
 // ~1e-12 S/N^2.  G takes the same split: the correction K_o - s G = sum g_b (d_b - s m_b) is small, but K_o and s G are
 // each ~1e-7 S/N^2 and cancel, so G needs fp32-level accuracy as well.  The residual part,
@@ -44,20 +44,26 @@ constexpr int TC_SPLIT = TC_NWG / TC_MT;         // warpgroups (threads) sharing
 constexpr int TC_OBJS = TC_MT * 128;             // objects per CTA
 constexpr int TC_THREADS = TC_NWG * 128 + 64;    // + TMA warp + MMA warp
 constexpr int TC_CW = TC_NWG * 4;                // consumer warps; warp TC_CW = TMA, TC_CW + 1 = MMA
-constexpr int TC_KSTEPS = 4;                     // K = 8 steps of the model operand: m rows (2), m^2 rows (2)
-constexpr int TC_AKSTEPS = 6;                    // ... of the object operand: -x (2), w (2), g (2)
-constexpr int TC_OPSEC = TC_KSTEPS * TC_TM * 32;
-constexpr int TC_PAIRSEC = (TC_TM / 2) * 48;
+// K layout: the three products of a band (hi*hi, hi*lo, lo*hi) take the K-slots b, S + b, 2 S + b (S = 5 up to five
+// bands, 6 for six), i.e. KS = 2 (3 for six bands) K = 8 instructions per product
+__host__ __device__ constexpr int tc_slot(int nf) { return nf <= 5 ? 5 : nf; }
+__host__ __device__ constexpr int tc_ks(int nf) { return (3 * tc_slot(nf) + 7) / 8; }
+__host__ __device__ constexpr int tc_ksteps(int nf) { return 2 * tc_ks(nf); }      // model operand: m rows, m^2 rows
+__host__ __device__ constexpr int tc_aksteps(int nf) { return 3 * tc_ks(nf); }     // object operand: -x, w, g
+__host__ __device__ constexpr int tc_pairq(int nf) { return (nf + 2) / 2; }        // 16-byte words per model pair: nf bands + prior
+__host__ __device__ constexpr int tc_opsec(int nf) { return tc_ksteps(nf) * TC_TM * 32; }
+__host__ __device__ constexpr int tc_pairsec(int nf) { return (TC_TM / 2) * 16 * tc_pairq(nf); }
 constexpr int TC_TAILSEC = (TC_TM / 2) * 16;
 constexpr int TC_SUBSEC = (TC_TM / 8) * 16;        // per 8 models: {KDE bin of the first, 1 if all eight share it, 1/norm of that bin}
-constexpr int TC_TILE_BYTES = TC_OPSEC + TC_PAIRSEC + TC_TAILSEC + TC_SUBSEC;
-constexpr int TC_OBJA_TILE = TC_AKSTEPS * 128 * 32;
-constexpr int TC_OBJA_BYTES = TC_MT * TC_OBJA_TILE;
+__host__ __device__ constexpr int tc_tile_bytes(int nf) { return tc_opsec(nf) + tc_pairsec(nf) + TC_TAILSEC + TC_SUBSEC; }
+__host__ __device__ constexpr int tc_obja_tile(int nf) { return tc_aksteps(nf) * 128 * 32; }
+__host__ __device__ constexpr int tc_obja_bytes(int nf) { return TC_MT * tc_obja_tile(nf); }
 constexpr int TC_NSTAGE = 2;
 constexpr int TC_CHUNK_COLS = TC_MT * 3 * TC_NC;  // TMEM columns of one chunk buffer
 constexpr int TC_TMEM_COLS = 512;
-constexpr size_t TC_SMEM = (size_t)TC_OBJA_BYTES + (size_t)TC_NSTAGE * TC_TILE_BYTES + 512;
-static_assert(TC_TILE_BYTES == 41472 && TC_TILE_BYTES % 128 == 0, "tile layout");
+__host__ __device__ constexpr size_t tc_smem(int nf) { return (size_t)tc_obja_bytes(nf) + (size_t)TC_NSTAGE * tc_tile_bytes(nf) + 512; }
+static_assert(tc_tile_bytes(5) == 41472 && tc_tile_bytes(5) % 128 == 0 && tc_tile_bytes(6) % 128 == 0, "tile layout");
+static_assert(tc_smem(6) <= 227 * 1024, "shared memory budget");
 static_assert(2 * TC_CHUNK_COLS <= TC_TMEM_COLS, "TMEM budget");
 static_assert(TC_SPLIT == 2 && TC_NSUB == 4, "sub-batch assignment below assumes two warpgroups per M-tile, four sub-batches");
 
@@ -156,12 +162,15 @@ __device__ __forceinline__ float pow2i(float k) {
 template <int NF, bool DP, bool PRIOR, int PASS, bool LIN = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const unsigned char* __restrict__ tiles, uint32_t lbo,
                                                             uint32_t sbo) {
-    static_assert(NF <= 5, "3 NF K-slots must fit two K = 8 instructions");
+    static_assert(NF >= 1 && NF <= 6, "filters per object");
+    constexpr int SLOT = tc_slot(NF), KS = tc_ks(NF), AKSTEPS = tc_aksteps(NF), PQ = tc_pairq(NF);
+    constexpr int TILE_BYTES = tc_tile_bytes(NF), OPSEC = tc_opsec(NF), PAIRSEC = tc_pairsec(NF);
+    constexpr int OBJA_TILE = tc_obja_tile(NF), OBJA_BYTES = tc_obja_bytes(NF);
     static_assert(!LIN || DP, "the linear-domain form is the dim_prior likelihood with (dof/2 - 1) = 1");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* objA = smem_raw;
-    unsigned char* stage = smem_raw + TC_OBJA_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stage + (size_t)TC_NSTAGE * TC_TILE_BYTES);
+    unsigned char* stage = smem_raw + OBJA_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage + (size_t)TC_NSTAGE * TILE_BYTES);
     uint64_t* tile_full = bars;                       // [NSTAGE]  TMA -> MMA + consumers
     uint64_t* tile_empty = bars + 2;                  // [NSTAGE]  MMA commit + consumer warps -> TMA
     uint64_t* acc_full = bars + 4;                    // [mt][buf] MMA commit -> consumers
@@ -205,9 +214,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
         else o = slot < P.No ? P.objlist[slot] : -1;
         oidx = (int)o;
         const int64_t oo = o < 0 ? 0 : o;
-        float arow[8 * TC_AKSTEPS];
+        float arow[8 * AKSTEPS];
 #pragma unroll
-        for (int i = 0; i < 8 * TC_AKSTEPS; ++i) arow[i] = 0.f;
+        for (int i = 0; i < 8 * AKSTEPS; ++i) arow[i] = 0.f;
         float kk = 0.f;
 #pragma unroll
         for (int b = 0; b < NF; ++b) {
@@ -219,18 +228,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
             kk = fmaf(g, d, kk);
             const float xh = tf32_rn(x), xl = tf32_rn(x - xh);
             const float wh = tf32_rn(w), wl = tf32_rn(w - wh);
-            arow[b] = -xh; arow[5 + b] = -xh; arow[10 + b] = -xl;
-            arow[16 + b] = wh; arow[21 + b] = wh; arow[26 + b] = wl;
+            arow[b] = -xh; arow[SLOT + b] = -xh; arow[2 * SLOT + b] = -xl;
+            arow[8 * KS + b] = wh; arow[8 * KS + SLOT + b] = wh; arow[8 * KS + 2 * SLOT + b] = wl;
             const float gh = tf32_rn(g), gl = tf32_rn(g - gh);
-            arow[32 + b] = gh; arow[37 + b] = gh; arow[42 + b] = gl;
+            arow[16 * KS + b] = gh; arow[16 * KS + SLOT + b] = gh; arow[16 * KS + 2 * SLOT + b] = gl;
         }
         K2 = pack2(kk, kk);
         const float a = P.oA[oo];
         A2 = pack2(a, a);
         if (half == 0) {        // one of the two threads of the object writes its row of the A operand
-            unsigned char* dst = objA + (size_t)mt * TC_OBJA_TILE + (row >> 3) * 256 + (row & 7) * 16;
+            unsigned char* dst = objA + (size_t)mt * OBJA_TILE + (row >> 3) * 256 + (row & 7) * 16;
 #pragma unroll
-            for (int s = 0; s < TC_AKSTEPS; ++s)
+            for (int s = 0; s < AKSTEPS; ++s)
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
                     *reinterpret_cast<float4*>(dst + s * 4096 + c * 128) =
@@ -257,8 +266,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
             for (int it = 0; it < nt; ++it) {
                 const int st = it % TC_NSTAGE, n = it / TC_NSTAGE;
                 if (n > 0) mbar_wait_hint(&tile_empty[st], (uint32_t)((n - 1) & 1));
-                mbar_expect_tx(&tile_full[st], TC_TILE_BYTES);
-                bulk_g2s(stage + (size_t)st * TC_TILE_BYTES, tiles + (size_t)(t0 + it) * TC_TILE_BYTES, TC_TILE_BYTES, &tile_full[st]);
+                mbar_expect_tx(&tile_full[st], TILE_BYTES);
+                bulk_g2s(stage + (size_t)st * TILE_BYTES, tiles + (size_t)(t0 + it) * TILE_BYTES, TILE_BYTES, &tile_full[st]);
             }
         }
     } else if (warp == TC_CW + 1) {
@@ -276,7 +285,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
             const int64_t first = (t0 + it) * TC_TM;
             const int cnt = (int)((P.nm - first) < TC_TM ? (P.nm - first) : TC_TM);
             const int nch = (cnt + TC_NC - 1) / TC_NC;
-            const uint32_t b_lo = (uint32_t)tc_desc(smem_u32(stage + (size_t)st * TC_TILE_BYTES), lbo, sbo);
+            const uint32_t b_lo = (uint32_t)tc_desc(smem_u32(stage + (size_t)st * TILE_BYTES), lbo, sbo);
             for (int ch = 0; ch < nch; ++ch, ++gch) {
                 const uint32_t buf = gch & 1, use = gch >> 1;
                 const uint32_t b0 = b_lo + ch * ((TC_NC / 8) * 256 >> 4);
@@ -286,13 +295,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t dcol = tmem + buf * TC_CHUNK_COLS + m * (3 * TC_NC);
-                        const uint32_t a0 = a_lo + ((m * TC_OBJA_TILE) >> 4);
-                        tc_mma<false>(dcol, a0, b0, desc_hi, idesc);                                                // inter
-                        tc_mma<true>(dcol, a0 + (4096 >> 4), b0 + (8192 >> 4), desc_hi, idesc);
-                        tc_mma<false>(dcol + TC_NC, a0 + (2 * 4096 >> 4), b0 + (2 * 8192 >> 4), desc_hi, idesc);    // shape
-                        tc_mma<true>(dcol + TC_NC, a0 + (3 * 4096 >> 4), b0 + (3 * 8192 >> 4), desc_hi, idesc);
-                        tc_mma<false>(dcol + 2 * TC_NC, a0 + (4 * 4096 >> 4), b0, desc_hi, idesc);                   // G
-                        tc_mma<true>(dcol + 2 * TC_NC, a0 + (5 * 4096 >> 4), b0 + (8192 >> 4), desc_hi, idesc);
+                        const uint32_t a0 = a_lo + ((m * OBJA_TILE) >> 4);
+                        // inter = (-x) . m, shape = w . m^2, G = g . m: KS accumulating K = 8 instructions each; the model
+                        // operand of G is that of inter
+#pragma unroll
+                        for (int k = 0; k < KS; ++k) {
+                            const uint32_t ak = a0 + (k * 4096 >> 4), bk = b0 + (k * 8192 >> 4);
+                            if (k == 0) {
+                                tc_mma<false>(dcol, ak, bk, desc_hi, idesc);
+                                tc_mma<false>(dcol + TC_NC, ak + (KS * 4096 >> 4), bk + (KS * 8192 >> 4), desc_hi, idesc);
+                                tc_mma<false>(dcol + 2 * TC_NC, ak + (2 * KS * 4096 >> 4), bk, desc_hi, idesc);
+                            } else {
+                                tc_mma<true>(dcol, ak, bk, desc_hi, idesc);
+                                tc_mma<true>(dcol + TC_NC, ak + (KS * 4096 >> 4), bk + (KS * 8192 >> 4), desc_hi, idesc);
+                                tc_mma<true>(dcol + 2 * TC_NC, ak + (2 * KS * 4096 >> 4), bk, desc_hi, idesc);
+                            }
+                        }
                         tc_commit(&acc_full[m * 2 + buf]);
                     }
                     __syncwarp();
@@ -327,9 +345,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                     tail = (p == npair_full) && odd;
                     if (p >= npair_full && !tail) continue;      // warp-uniform
                 }
-                const ulonglong2 q0 = pairs[p * 3], q1 = pairs[p * 3 + 1], q2 = pairs[p * 3 + 2];
-                f2 m2[5] = {q0.x, q0.y, q1.x, q1.y, q2.x};
-                const f2 prior2 = q2.y;
+                f2 m2[2 * PQ];        // the bands of the two models, then the prior pair
+#pragma unroll
+                for (int i = 0; i < PQ; ++i) { const ulonglong2 q = pairs[p * PQ + i]; m2[2 * i] = q.x; m2[2 * i + 1] = q.y; }
+                const f2 prior2 = m2[NF];
                 const int idx0 = first_i + 2 * p;
                 const f2 B2 = pack2(Bv[2 * jp], Bv[2 * jp + 1]);
                 const f2 C2 = pack2(Cv[2 * jp], Cv[2 * jp + 1]);
@@ -380,9 +399,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
 #pragma unroll
             for (int jp = 0; jp < 4; ++jp) {
                 const int p = p0 + jp;
-                const ulonglong2 q0 = pairs[p * 3], q1 = pairs[p * 3 + 1], q2 = pairs[p * 3 + 2];
-                f2 m2[5] = {q0.x, q0.y, q1.x, q1.y, q2.x};
-                pr[jp] = q2.y;
+                f2 m2[2 * PQ];
+#pragma unroll
+                for (int i = 0; i < PQ; ++i) { const ulonglong2 q = pairs[p * PQ + i]; m2[2 * i] = q.x; m2[2 * i + 1] = q.y; }
+                pr[jp] = m2[NF];
                 const f2 B2 = pack2(Bv[2 * jp], Bv[2 * jp + 1]);
                 const f2 C2 = pack2(Cv[2 * jp], Cv[2 * jp + 1]);
                 const f2 G2 = pack2(Gv[2 * jp], Gv[2 * jp + 1]);
@@ -500,10 +520,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
         for (int it = 0; it < nt; ++it) {
             const int st = it % TC_NSTAGE, n = it / TC_NSTAGE;
             mbar_wait_hint(&tile_full[st], (uint32_t)(n & 1));
-            const unsigned char* tile = stage + (size_t)st * TC_TILE_BYTES;
-            pairs = reinterpret_cast<const ulonglong2*>(tile + TC_OPSEC);
-            tails = reinterpret_cast<const float4*>(tile + TC_OPSEC + TC_PAIRSEC);
-            subs = reinterpret_cast<const int4*>(tile + TC_OPSEC + TC_PAIRSEC + TC_TAILSEC);
+            const unsigned char* tile = stage + (size_t)st * TILE_BYTES;
+            pairs = reinterpret_cast<const ulonglong2*>(tile + OPSEC);
+            tails = reinterpret_cast<const float4*>(tile + OPSEC + PAIRSEC);
+            subs = reinterpret_cast<const int4*>(tile + OPSEC + PAIRSEC + TC_TAILSEC);
             const int64_t first = (t0 + it) * TC_TM;
             const int cnt = (int)((P.nm - first) < TC_TM ? (P.nm - first) : TC_TM);
             const int nch = (cnt + TC_NC - 1) / TC_NC;
@@ -608,32 +628,34 @@ __global__ void k_build_tiles_tc(TcRecParams P) {
     if (p >= P.nm) return;
     const int64_t j = P.perm[p];
     const int r = (int)(p % TC_TM);
-    unsigned char* T = P.tiles + (size_t)(p / TC_TM) * TC_TILE_BYTES;
-    float rowv[8 * TC_KSTEPS];
-    for (int i = 0; i < 8 * TC_KSTEPS; ++i) rowv[i] = 0.f;
-    float* pr = reinterpret_cast<float*>(T + TC_OPSEC) + (r >> 1) * 12;
-    for (int b = 0; b < P.Nf; ++b) {
-        const double v = P.m[j * P.Nf + b];
+    const int nf = P.Nf, slot = tc_slot(nf), ks = tc_ks(nf), pq = tc_pairq(nf);
+    const int opsec = tc_opsec(nf), pairsec = tc_pairsec(nf);
+    unsigned char* T = P.tiles + (size_t)(p / TC_TM) * tc_tile_bytes(nf);
+    float rowv[8 * 6];
+    for (int i = 0; i < 8 * 6; ++i) rowv[i] = 0.f;
+    float* pr = reinterpret_cast<float*>(T + opsec) + (r >> 1) * (4 * pq);
+    for (int b = 0; b < nf; ++b) {
+        const double v = P.m[j * nf + b];
         const float mf = (float)v, q = (float)(v * v);
         const float mh = tf32_rn(mf), ml = tf32_rn(mf - mh);
         const float qh = tf32_rn(q), ql = tf32_rn(q - qh);
-        rowv[b] = mh; rowv[5 + b] = ml; rowv[10 + b] = mh;
-        rowv[16 + b] = qh; rowv[21 + b] = ql; rowv[26 + b] = qh;
+        rowv[b] = mh; rowv[slot + b] = ml; rowv[2 * slot + b] = mh;
+        rowv[8 * ks + b] = qh; rowv[8 * ks + slot + b] = ql; rowv[8 * ks + 2 * slot + b] = qh;
         pr[2 * b + (r & 1)] = mf;
     }
-    pr[10 + (r & 1)] = P.lnprior ? (float)(P.lnprior[j] * 1.4426950408889634) : 0.f;
-    float* tl = reinterpret_cast<float*>(T + TC_OPSEC + TC_PAIRSEC) + (r >> 1) * 4;
+    pr[2 * nf + (r & 1)] = P.lnprior ? (float)(P.lnprior[j] * 1.4426950408889634) : 0.f;
+    float* tl = reinterpret_cast<float*>(T + opsec + pairsec) + (r >> 1) * 4;
     tl[r & 1] = P.invnorm ? P.invnorm[p] : 0.f;
     tl[2 + (r & 1)] = __int_as_float(P.bins ? P.bins[p] : -1);
     if ((r & 7) == 0) {
         int uniform = (P.bins != nullptr && p + 8 <= P.nm) ? 1 : 0;
         const int b0 = P.bins ? P.bins[p] : -1;
         for (int i = 1; i < 8 && uniform; ++i) uniform = (P.bins[p + i] == b0) ? 1 : 0;
-        reinterpret_cast<int4*>(T + TC_OPSEC + TC_PAIRSEC + TC_TAILSEC)[r >> 3] =
+        reinterpret_cast<int4*>(T + opsec + pairsec + TC_TAILSEC)[r >> 3] =
             make_int4(b0, uniform, __float_as_int(P.invnorm ? P.invnorm[p] : 0.f), 0);
     }
     unsigned char* dst = T + (r >> 3) * 256 + (r & 7) * 16;
-    for (int s = 0; s < TC_KSTEPS; ++s)
+    for (int s = 0; s < 2 * ks; ++s)
         for (int c = 0; c < 2; ++c)
             *reinterpret_cast<float4*>(dst + s * (TC_TM * 32) + c * 128) =
                 make_float4(rowv[s * 8 + c * 4], rowv[s * 8 + c * 4 + 1], rowv[s * 8 + c * 4 + 2], rowv[s * 8 + c * 4 + 3]);

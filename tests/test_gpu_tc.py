@@ -153,3 +153,24 @@ def test_object_conditioned_prior_table_on_the_fused_path(fz, monkeypatch):
             po, lmo, leo = fo.bruteforce_fit_predict(m, np.zeros_like(m), np.ones_like(m), x[idx].copy(), xe[idx].copy(),
                                                      xm[idx].copy(), lab, labe, label_dict=kd, lnprior=table[b], **FS)
         _check(res["by_row"][0][idx], res["by_row"][1][idx], res["by_row"][2][idx], po, lmo, leo)
+
+
+def test_six_bands(fz):
+    """LSST-like six-band free-scale fit: three K = 8 instructions per product, 64-byte pair records; (dof/2 - 1) = 3/2
+    keeps the lg2 form."""
+    models, labels, depth = bench_data.c3_models()
+    rs = np.random.RandomState(8)
+    pick = np.sort(rs.choice(len(models), 5003, replace=False))
+    m5 = models[pick]
+    m = np.concatenate([m5, 0.8 * m5[:, 4:5] + 0.3 * m5[:, 3:4]], axis=1).astype(np.float32).astype(np.float64)
+    d6 = np.append(depth, 0.2)
+    n = 300
+    j = rs.randint(0, len(m), size=n)
+    x = m[j] * (10.0 ** rs.uniform(-1, 2, size=(n, 1))) / m[j, 2:3] + rs.normal(size=(n, 6)) * d6
+    xe = np.broadcast_to(d6, x.shape).copy()
+    xm = np.ones_like(x)
+    xm[5, 0] = 0.0
+    for lprob, lnprior in ((FS, None), (dict(FS, dim_prior=False), rs.uniform(-3, 0, len(m)))):
+        p, lm, le, po, lmo, leo, st = _run(fz, m, labels[pick], x, xe, xm, lprob, lnprior=lnprior)
+        assert st["sweep_kind"] == 2 and st["pairs_fp32"] > 0
+        _check(p, lm, le, po, lmo, leo)
