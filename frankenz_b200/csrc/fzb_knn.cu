@@ -139,6 +139,30 @@ __device__ __forceinline__ void ks_mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// packed FP32 (two queries per 64-bit register pair): the same roundings as the scalar __fsub_rn / __fmul_rn / __fmaf_rn
+typedef unsigned long long kf2;
+__device__ __forceinline__ kf2 ks_pack2(float a, float b) {
+    kf2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void ks_unpack2(kf2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ kf2 ks_add2(kf2 a, kf2 b) {
+    kf2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ kf2 ks_mul2(kf2 a, kf2 b) {
+    kf2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ kf2 ks_fma2(kf2 a, kf2 b, kf2 c) {
+    kf2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 template <int NF>
 __global__ void __launch_bounds__(KS_T, 2) k_knn_scan(const float* __restrict__ feats, int64_t tstride, int64_t Nm,
                                                       const double* __restrict__ q, int64_t No, int KC,
@@ -151,6 +175,7 @@ __global__ void __launch_bounds__(KS_T, 2) k_knn_scan(const float* __restrict__ 
     const int t = blockIdx.y, sp = blockIdx.z, nsp = gridDim.z, K = gridDim.y;
     const float* F = feats + (size_t)t * tstride;
     float qf[KS_R][NF];
+    kf2 nq2[KS_R / 2][NF];        // (-q, -q') of query pairs: f - q = f + (-q) with the same rounding
     float ld[KS_R][KS_KCMAX];
     int li[KS_R][KS_KCMAX];
     float tau[KS_R];
@@ -167,6 +192,10 @@ __global__ void __launch_bounds__(KS_T, 2) k_knn_scan(const float* __restrict__ 
         tau[r] = CUDART_INF_F;
         pmax[r] = 0;
     }
+#pragma unroll
+    for (int r = 0; r < KS_R / 2; ++r)
+#pragma unroll
+        for (int b = 0; b < NF; ++b) nq2[r][b] = ks_pack2(-qf[2 * r][b], -qf[2 * r + 1][b]);
     const int64_t row0 = (int64_t)sp * rows_per_split;
     int64_t row1 = row0 + rows_per_split;
     if (row1 > Nm) row1 = Nm;
@@ -196,20 +225,22 @@ __global__ void __launch_bounds__(KS_T, 2) k_knn_scan(const float* __restrict__ 
         const float* tile = stage + (size_t)(it & 1) * KS_TM * NF;
         const int64_t first = row0 + (int64_t)it * KS_TM;
         const int cnt = (int)((row1 - first) < KS_TM ? (row1 - first) : KS_TM);
-#pragma unroll 2
-        for (int jj = 0; jj < cnt; ++jj) {
-            float f[NF];
+        auto one_row = [&](const float* f, int jj) {
+            float dd[KS_R];
 #pragma unroll
-            for (int b = 0; b < NF; ++b) f[b] = tile[jj * NF + b];
-#pragma unroll
-            for (int r = 0; r < KS_R; ++r) {
-                float d = __fsub_rn(f[0], qf[r][0]);
-                float d2 = __fmul_rn(d, d);
+            for (int rp = 0; rp < KS_R / 2; ++rp) {       // two queries per packed instruction
+                kf2 d = ks_add2(ks_pack2(f[0], f[0]), nq2[rp][0]);
+                kf2 acc = ks_mul2(d, d);
 #pragma unroll
                 for (int b = 1; b < NF; ++b) {
-                    d = __fsub_rn(f[b], qf[r][b]);
-                    d2 = __fmaf_rn(d, d, d2);
+                    d = ks_add2(ks_pack2(f[b], f[b]), nq2[rp][b]);
+                    acc = ks_fma2(d, d, acc);
                 }
+                ks_unpack2(acc, dd[2 * rp], dd[2 * rp + 1]);
+            }
+#pragma unroll
+            for (int r = 0; r < KS_R; ++r) {
+                const float d2 = dd[r];
                 if (d2 < tau[r]) {            // rare after warm-up: replace the current maximum of the list
                     ld[r][pmax[r]] = d2;
                     li[r][pmax[r]] = (int)(first + jj);
@@ -223,6 +254,13 @@ __global__ void __launch_bounds__(KS_T, 2) k_knn_scan(const float* __restrict__ 
                     pmax[r] = pm;
                 }
             }
+        };
+#pragma unroll 2
+        for (int jj = 0; jj < cnt; ++jj) {
+            float f[NF];
+#pragma unroll
+            for (int b = 0; b < NF; ++b) f[b] = tile[jj * NF + b];
+            one_row(f, jj);
         }
         __syncthreads();
         if (tid == 0 && it + 2 < nt) issue(it + 2);
