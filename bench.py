@@ -90,28 +90,52 @@ class ClockSampler(object):
 
 
 # ---- CPU arms ------------------------------------------------------------------------------------
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def reference_available():
+    """The unmodified reference, installed by oracle/build_ref.sh (travels to the GPU box with the snapshot)."""
+    return os.path.isdir(os.path.join(REF_DIR, "frankenz"))
+
+
 def _cpu_chunk(args):
     import warnings
     warnings.filterwarnings("ignore")
-    from oracle import fz_oracle as fo
-    models, labels, x, xe, xm = args
+    models, labels, x, xe, xm, use_ref = args
     zgrid, sig = bench_data.c3_kde()
-    kd = fo.KernelDict(zgrid, sig)
     t = time.time()
+    if use_ref:
+        # the reference's own public API and stock code path: frankenz.fitting.BruteForce.fit_predict
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        from frankenz.fitting import BruteForce
+        from frankenz.pdf import PDFDict
+        with np.errstate(all="ignore"):
+            bf = BruteForce(models, np.zeros_like(models), np.ones_like(models))
+            bf.fit_predict(x, xe, xm, labels, np.full(len(models), 0.05), label_dict=PDFDict(zgrid, sig),
+                           lprob_kwargs=dict(LPROB), return_gof=True, verbose=False, save_fits=False)
+        return time.time() - t
+    from oracle import fz_oracle as fo
+    kd = fo.KernelDict(zgrid, sig)
     with np.errstate(all="ignore"):
         fo.bruteforce_fit_predict(models, np.zeros_like(models), np.ones_like(models), x, xe, xm, labels,
                                   np.full(len(models), 0.05), label_dict=kd, **LPROB)
     return time.time() - t
 
 
-def cpu_baseline(models, labels, x, xe, xm, per_core, cores=None):
-    """Oracle port on `cores` processes, `per_core` objects each (a bounded sample of the workload)."""
+def cpu_baseline(models, labels, x, xe, xm, per_core, cores=None, use_ref=False):
+    """The reference (oracle/_ref, `use_ref`) or the oracle port on `cores` processes, `per_core` objects each (a
+    bounded sample of the workload; the reference is single-threaded, so one process per core)."""
     import multiprocessing as mp
+    if use_ref:      # import once in the parent: the forked workers inherit the loaded package
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        import frankenz.fitting  # noqa: F401
     cores = cores or os.cpu_count() or 1
     n = min(len(x), per_core * cores)
     per = max(1, n // cores)
     chunks = [(models, labels, x[i * per:(i + 1) * per].copy(), xe[i * per:(i + 1) * per].copy(),
-               xm[i * per:(i + 1) * per].copy()) for i in range(cores)]
+               xm[i * per:(i + 1) * per].copy(), use_ref) for i in range(cores)]
     nobj = sum(len(c[2]) for c in chunks)
     ctx = mp.get_context("fork")
     t = time.time()
@@ -162,19 +186,22 @@ def main():
             return
         models, labels, x, xe, xm = workload(max(256, args.cpu_objects_per_core * (os.cpu_count() or 1)), 20260103)
         vals = []
+        use_ref = reference_available()
         for i in range(max(1, args.warmup and 1) + args.steps):
-            v, nobj, dt, cores = cpu_baseline(models, labels, x, xe, xm, args.cpu_objects_per_core)
+            v, nobj, dt, cores = cpu_baseline(models, labels, x, xe, xm, args.cpu_objects_per_core, use_ref=use_ref)
             if i >= 1:
                 vals.append((v, dt))
         v = float(np.mean([a for a, _ in vals]))
         ms = float(np.mean([b for _, b in vals])) * 1e3
-        sample = "%d objects x %d models per step on %d processes (oracle/fz_oracle.py)" % (nobj, len(models), cores)
+        sample = "%d objects x %d models per step on %d processes (%s)" % (
+            nobj, len(models), cores, "unmodified frankenz.fitting.BruteForce.fit_predict from oracle/_ref" if use_ref
+            else "oracle/fz_oracle.py")
         print(json.dumps({"impl": "reference", "metric": "object-model likelihood pairs/sec", "value": v,
                           "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": 1,
                           "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f64", "data": "synthetic", "config": cfg_json,
-                          "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
-                                           "sample": sample},
+                          "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores,
+                                           "kind": "reference" if use_ref else "port", "sample": sample},
                           "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                           "gpu_launches": 0}))
         return
@@ -327,10 +354,12 @@ def main():
 
     cpu = None
     if not args.no_cpu and world == 1:
-        v, nobj, dt, cores = cpu_baseline(models, labels, x, xe, xm, args.cpu_objects_per_core)
-        cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
-               "sample": "%d objects x %d models of the same workload, %.1f s on %d processes "
-                         "(oracle/fz_oracle.py, numpy float64)" % (nobj, nm, dt, cores)}
+        use_ref = reference_available()
+        v, nobj, dt, cores = cpu_baseline(models, labels, x, xe, xm, args.cpu_objects_per_core, use_ref=use_ref)
+        cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference" if use_ref else "port",
+               "sample": "%d objects x %d models of the same workload, %.1f s on %d processes (%s, numpy float64)"
+                         % (nobj, nm, dt, cores, "unmodified frankenz BruteForce.fit_predict, oracle/_ref" if use_ref
+                            else "oracle/fz_oracle.py")}
 
     out = {"metric": "object-model likelihood pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": max(1, world),
            "steps": args.steps, "warmup": warm, "ms_per_step": t_all / args.steps, "higher_is_better": True,

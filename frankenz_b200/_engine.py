@@ -174,6 +174,22 @@ class Engine(object):
                 raise ValueError("lnprior must have shape (Nmodel,)")
             _lib.check(self.lib.fzb_set_lnprior(self.h, dptr(lp), self.Nm))
 
+    def set_kde_dict_idx(self, label_dict, y_idx, y_std_idx):
+        """Dictionary KDE from ready-made indices (the `y_idx` / `y_std_idx` form of pdf.py:529-531)."""
+        widths = np.ascontiguousarray(label_dict.sigma_width, dtype=np.int32)
+        lens = np.array([len(k) for k in label_dict.sigma_dict], dtype=np.int64)
+        koff = np.zeros(len(lens) + 1, dtype=np.int64)
+        koff[1:] = np.cumsum(lens)
+        kern = f64(np.concatenate(label_dict.sigma_dict)) if koff[-1] else np.zeros(1)
+        kcdf = f64(np.concatenate(label_dict.sigma_dict_cdf)) if koff[-1] else np.zeros(1)
+        _lib.check(self.lib.fzb_set_kde_dict(self.h, int(label_dict.Ngrid), int(label_dict.Ndict),
+                                             widths.ctypes.data_as(_lib.c_int32_p), iptr(koff), dptr(kern),
+                                             dptr(kcdf)))
+        yi = np.ascontiguousarray(y_idx, dtype=np.int64)
+        si = np.ascontiguousarray(y_std_idx, dtype=np.int64)
+        _lib.check(self.lib.fzb_set_labels_dict(self.h, iptr(yi), iptr(si), len(yi)))
+        self.Ng = int(label_dict.Ngrid)
+
     def set_kde(self, model_labels, model_label_errs, label_dict=None, label_grid=None, kde_kwargs=None):
         """Upload the KDE tables and per-model label indices (pdf.py:800-852 / :499-502)."""
         if label_dict is None and label_grid is None:
@@ -181,41 +197,28 @@ class Engine(object):
         kk = kde_kwargs or {}
         y, ye = f64(model_labels), f64(model_label_errs)
         if label_dict is not None:
-            widths = np.ascontiguousarray(label_dict.sigma_width, dtype=np.int32)
-            lens = np.array([len(k) for k in label_dict.sigma_dict], dtype=np.int64)
-            koff = np.zeros(len(lens) + 1, dtype=np.int64)
-            koff[1:] = np.cumsum(lens)
-            kern = f64(np.concatenate(label_dict.sigma_dict)) if koff[-1] else np.zeros(1)
-            kcdf = f64(np.concatenate(label_dict.sigma_dict_cdf)) if koff[-1] else np.zeros(1)
-            _lib.check(self.lib.fzb_set_kde_dict(self.h, int(label_dict.Ngrid), int(label_dict.Ndict),
-                                                 widths.ctypes.data_as(_lib.c_int32_p), iptr(koff), dptr(kern),
-                                                 dptr(kcdf)))
             yi, si = label_dict.fit(y, ye)
-            yi = np.ascontiguousarray(yi, dtype=np.int64)
-            si = np.ascontiguousarray(si, dtype=np.int64)
-            _lib.check(self.lib.fzb_set_labels_dict(self.h, iptr(yi), iptr(si), len(yi)))
-            self.Ng = int(label_dict.Ngrid)
-        else:
-            x = f64(label_grid)
-            nx = len(x)
-            dx = kk.get("dx", None)
-            if dx is None:
-                dx = x[1] - x[0]
-            sig = kk.get("sig_thresh", 5.)
-            # pdf.py:499-502: truncation toward zero, upper-exclusive windows clipped to the grid
-            centers = np.array((y - x[0]) / dx, dtype="int")
-            offsets = np.array(sig * ye / dx, dtype="int")
-            uppers, lowers = centers + offsets, centers - offsets
-            uppers[uppers > nx], lowers[lowers < 0] = nx, 0
-            # python slice semantics of x[lower:upper]: a negative upper bound counts from the end
-            lowers = np.minimum(lowers, nx)
-            uppers = np.where(uppers < 0, np.maximum(uppers + nx, 0), uppers)
-            uppers = np.maximum(uppers, lowers)
-            _lib.check(self.lib.fzb_set_kde_grid(self.h, dptr(x), nx))
-            lo = np.ascontiguousarray(lowers, dtype=np.int64)
-            up = np.ascontiguousarray(uppers, dtype=np.int64)
-            _lib.check(self.lib.fzb_set_labels_grid(self.h, dptr(y), dptr(ye), iptr(lo), iptr(up), len(y)))
-            self.Ng = nx
+            return self.set_kde_dict_idx(label_dict, yi, si)
+        x = f64(label_grid)
+        nx = len(x)
+        dx = kk.get("dx", None)
+        if dx is None:
+            dx = x[1] - x[0]
+        sig = kk.get("sig_thresh", 5.)
+        # pdf.py:499-502: truncation toward zero, upper-exclusive windows clipped to the grid
+        centers = np.array((y - x[0]) / dx, dtype="int")
+        offsets = np.array(sig * ye / dx, dtype="int")
+        uppers, lowers = centers + offsets, centers - offsets
+        uppers[uppers > nx], lowers[lowers < 0] = nx, 0
+        # python slice semantics of x[lower:upper]: a negative upper bound counts from the end
+        lowers = np.minimum(lowers, nx)
+        uppers = np.where(uppers < 0, np.maximum(uppers + nx, 0), uppers)
+        uppers = np.maximum(uppers, lowers)
+        _lib.check(self.lib.fzb_set_kde_grid(self.h, dptr(x), nx))
+        lo = np.ascontiguousarray(lowers, dtype=np.int64)
+        up = np.ascontiguousarray(uppers, dtype=np.int64)
+        _lib.check(self.lib.fzb_set_labels_grid(self.h, dptr(y), dptr(ye), iptr(lo), iptr(up), len(y)))
+        self.Ng = nx
 
     # ---- compute ------------------------------------------------------------------------------
     @staticmethod

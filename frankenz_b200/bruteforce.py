@@ -32,6 +32,8 @@ def _check_args(args, name):
 # object-conditioned prior tables: from this many object-model pairs on, fit_predict(save_fits=False) goes through the
 # fused kernels one table row at a time instead of the float64 kernel that reads the table per pair
 TABLE_PRIOR_GROUP_MIN_PAIRS = 1e8
+# generator twins with save_fits=False: host bytes of fit arrays / PDFs alive at a time
+STREAM_BYTES = 1 << 30
 
 
 class BruteForce(object):
@@ -104,11 +106,23 @@ class BruteForce(object):
         clean_inplace(data, data_err, data_mask)
         Ndata = len(data)
         self.NDATA = Ndata
-        res = eng.fit(data, data_err, data_mask, cfg)
         if save_fits:
+            res = eng.fit(data, data_err, data_mask, cfg)
             self._store(res, Ndata)
-        for i in range(Ndata):
-            yield self._rows(res, i, track_scale)
+            for i in range(Ndata):
+                yield self._rows(res, i, track_scale)
+            return
+        # save_fits=False: the reference streams one object at a time (bruteforce.py:192-205); here the objects go
+        # through the device in chunks whose seven (chunk x Nmodel) arrays stay within STREAM_BYTES
+        lk = dict(lprob_kwargs or {})
+        chunk = max(1, int(STREAM_BYTES // (7 * 8 * self.NMODEL)))
+        for o0 in range(0, Ndata, chunk):
+            o1 = min(Ndata, o0 + chunk)
+            if lk.get("lnprior_bin", None) is not None and (o0 > 0 or o1 < Ndata):
+                eng.set_lnprior(lk.get("lnprior", None), np.asarray(lk["lnprior_bin"])[o0:o1])
+            res = eng.fit(data[o0:o1], data_err[o0:o1], data_mask[o0:o1], cfg)
+            for i in range(o1 - o0):
+                yield self._rows(res, i, track_scale)
 
     # ---- predict -------------------------------------------------------------------------------
     def predict(self, model_labels, model_label_errs, label_dict=None, label_grid=None, logwt=None, kde_args=None,
@@ -215,9 +229,22 @@ class BruteForce(object):
     def _fit_predict(self, data, data_err, data_mask, model_labels, model_label_errs, lprob_func=None,
                      label_dict=None, label_grid=None, kde_args=None, kde_kwargs=None, lprob_args=None,
                      lprob_kwargs=None, track_scale=False, save_fits=True):
-        """Generator twin of `fit_predict` (bruteforce.py:505-631): yields (pdf, (lmap, levid))."""
-        pdfs, lmap, levid = self._fit_predict_all(data, data_err, data_mask, model_labels, model_label_errs,
-                                                  lprob_func, label_dict, label_grid, kde_args, kde_kwargs,
-                                                  lprob_args, lprob_kwargs, track_scale, save_fits)
-        for i in range(len(pdfs)):
-            yield pdfs[i], (lmap[i], levid[i])
+        """Generator twin of `fit_predict` (bruteforce.py:505-631): yields (pdf, (lmap, levid)).  With
+        save_fits=False the objects are processed in chunks, so a streaming caller never holds more than STREAM_BYTES
+        of PDFs."""
+        Ndata = len(data)
+        chunk = Ndata
+        if not save_fits and Ndata > 0:
+            ng = label_dict.Ngrid if label_dict is not None else (len(label_grid) if label_grid is not None else 1)
+            chunk = max(16, int(STREAM_BYTES // (8 * max(1, ng))))
+        for o0 in range(0, max(Ndata, 1), max(chunk, 1)):
+            o1 = min(Ndata, o0 + chunk)
+            lk = lprob_kwargs
+            if lk is not None and lk.get("lnprior_bin", None) is not None and (o0 > 0 or o1 < Ndata):
+                lk = dict(lk, lnprior_bin=np.asarray(lk["lnprior_bin"])[o0:o1])
+            pdfs, lmap, levid = self._fit_predict_all(data[o0:o1], data_err[o0:o1], data_mask[o0:o1], model_labels,
+                                                      model_label_errs, lprob_func, label_dict, label_grid, kde_args,
+                                                      kde_kwargs, lprob_args, lk, track_scale, save_fits)
+            for i in range(len(pdfs)):
+                yield pdfs[i], (lmap[i], levid[i])
+        self.NDATA = Ndata

@@ -69,6 +69,23 @@ void consume_prior_bins(fzb_context* h) {
     h->prior_o0 = 0;
 }
 
+// a model whose label lies outside the PDF grid (or uses a malformed dictionary kernel) was selected by the weight
+// threshold: the reference raises there (pdf.py:612-620)
+int check_kde_error(fzb_context* h) {
+    if (h->labels_bad <= 0 || h->kde_mode != FZB_KDE_DICT || !h->kde_err.p) return 0;
+    long long flag[2] = {0, 0};
+    FZB_CUDA(cudaMemcpyAsync(flag, h->kde_err.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    FZB_CUDA(cudaStreamSynchronize(h->stream));
+    if (flag[0] != 0) {
+        FZB_CUDA(cudaMemsetAsync(h->kde_err.p, 0, 16, h->stream));
+        fzb_set_error("model %lld passed the weight threshold but its label lies further outside the PDF grid than its "
+                      "kernel width, or maps to a dictionary kernel wider than the grid (the reference raises here, "
+                      "pdf.py:612-620)", flag[1]);
+        return 2;
+    }
+    return 0;
+}
+
 int check_models(fzb_context* h) {
     FZB_CHECK(h->Nm > 0 && h->Nf > 0, "no models loaded: call fzb_set_models first");
     return 0;
@@ -356,7 +373,7 @@ int fzb_destroy(fzb_handle h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->models, &h->models_err, &h->models_mask, &h->lnprior, &h->prior_table, &h->prior_bins, &h->widths, &h->koff, &h->kernels,
                       &h->kcdf, &h->yidx, &h->ysidx, &h->grid, &h->y, &h->ystd, &h->lowers, &h->uppers, &h->rows,
-                      &h->knn_feats, &h->knn_cand, &h->knn_redo, &h->summ[0], &h->summ[1], &h->summ[2], &h->summ[3], &h->summ[4], &h->summ[5], &h->fast.recs, &h->fast.tiles_tc, &h->fast.recs64, &h->fast.aux64, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
+                      &h->knn_feats, &h->knn_cand, &h->knn_redo, &h->kde_err, &h->summ[0], &h->summ[1], &h->summ[2], &h->summ[3], &h->summ[4], &h->summ[5], &h->fast.recs, &h->fast.tiles_tc, &h->fast.recs64, &h->fast.aux64, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
                       &h->fast.d_slot_sidx};
     for (auto* b : bufs) b->release();
     for (auto& b : h->obj_in) b.release();
@@ -509,20 +526,23 @@ int fzb_set_labels_dict(fzb_handle h, const int64_t* y_idx, const int64_t* y_std
     if (use_device(h) || check_models(h)) return 2;
     FZB_CHECK(h->kde_mode == FZB_KDE_DICT, "call fzb_set_kde_dict first");
     FZB_CHECK(Nm == h->Nm, "labels have %lld entries, model set has %lld", (long long)Nm, (long long)h->Nm);
-    // The reference raises (shape mismatch / IndexError) when a selected model's kernel misses the grid
-    // or uses a wrapped (malformed) dictionary entry (pdf.py:612-620, :814-818); refuse such labels up front.
+    // The reference raises (shape mismatch / IndexError) only when a SELECTED model's kernel misses the grid or uses a
+    // wrapped (malformed) dictionary entry (pdf.py:603-620, :814-818): such labels are accepted here, counted, and the
+    // KDE kernels raise a flag when one of them passes the weight threshold (checked at the end of every call that
+    // builds PDFs); the sweep kernels leave a model set with such labels to the float64 kernel.
+    int64_t nbad = 0;
     for (int64_t j = 0; j < Nm; ++j) {
         int64_t si = y_std_idx[j];
         FZB_CHECK(si >= 0 && si < h->Ndict, "label %lld: dictionary index %lld out of range", (long long)j,
                   (long long)si);
         int64_t w = h->h_widths[si];
-        FZB_CHECK(h->h_koff[si + 1] - h->h_koff[si] == 2 * w + 1,
-                  "label %lld uses dictionary kernel %lld which is wider than the grid (malformed in the reference, "
-                  "pdf.py:814-818)", (long long)j, (long long)si);
         int64_t pos = y_idx[j];
-        FZB_CHECK(pos + w >= 0 && pos - w <= h->Ng - 1 && pos - w < h->Ng && pos + w + 1 > 0,
-                  "label %lld lies further outside the grid than its kernel width (the reference raises here)",
-                  (long long)j);
+        if (h->h_koff[si + 1] - h->h_koff[si] != 2 * w + 1 || !(pos + w >= 0 && pos - w <= h->Ng - 1)) ++nbad;
+    }
+    h->labels_bad = nbad;
+    if (nbad > 0) {
+        if (h->kde_err.reserve(16)) return 1;
+        FZB_CUDA(cudaMemsetAsync(h->kde_err.p, 0, 16, h->stream));
     }
     if (h->labels_dict_set && h->h_yidx.size() == (size_t)Nm && h->h_ysidx.size() == (size_t)Nm &&
         memcmp(h->h_yidx.data(), y_idx, (size_t)Nm * sizeof(int64_t)) == 0 &&
@@ -647,7 +667,8 @@ int fzb_fit_predict_dev(fzb_handle h, const double* d_data, const double* d_err,
                                   d_best_scale);
     consume_prior_bins(h);
     if (rc) return rc;
-    return t.stop();
+    if (t.stop()) return 1;
+    return check_kde_error(h);
 }
 
 // Host-pointer form.  The objects are processed in chunks; the PDFs of chunk c leave through the staged downloader
@@ -683,7 +704,9 @@ int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, co
     // chunk size: large enough for long CTAs of the sweep kernels (few model splits), small enough to pipeline; the chunks
     // taper towards the end (below), so the size of the main ones does not set the un-hidden tail
     int64_t chunk = 196608;
-    if (const char* e = getenv("FZB_E2E_CHUNK")) chunk = std::max<int64_t>(1024, atoll(e));
+    // (an override is rounded up to the 4096-object granularity of the taper below, floor 8192, so that no chunk of the
+    // taper exceeds the reserved staging buffers)
+    if (const char* e = getenv("FZB_E2E_CHUNK")) chunk = std::max<int64_t>(8192, (atoll(e) + 4095) / 4096 * 4096);
     if (!pdfs || No <= chunk + chunk / 2) chunk = No;
     const size_t chunk_bytes = (size_t)chunk * Ng * sizeof(double);
     StagedDownloader dl(h);
@@ -705,7 +728,7 @@ int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, co
         const int64_t rem = No - o0;
         nc = chunk;
         if (pdfs && rem < 2 * chunk) nc = std::max<int64_t>(std::min<int64_t>(rem, 8192), (rem / 2 + 4095) / 4096 * 4096);
-        nc = std::min(nc, rem);
+        nc = std::min(std::min(nc, rem), chunk);
         int b = (int)(c & 1);
         h->prior_o0 = o0;
         // device buffer b was last read by the download of chunk c-2 (issued before that of chunk c-1)
@@ -728,7 +751,7 @@ int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, co
     float ms = 0.f;
     FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
     h->stats.ms_total = ms;
-    return 0;
+    return check_kde_error(h);
 }
 
 int fzb_predict_logwt(fzb_handle h, const double* logwt, int64_t No, int64_t W, const int64_t* neighbors,
@@ -769,7 +792,8 @@ int fzb_predict_logwt(fzb_handle h, const double* logwt, int64_t No, int64_t W, 
             return 1;
         FZB_CUDA(cudaStreamSynchronize(h->stream));
     }
-    return t.stop();
+    if (t.stop()) return 1;
+    return check_kde_error(h);
 }
 
 int fzb_shard_pass1_dev(fzb_handle h, const double* d_data, const double* d_err, const double* d_mask, int64_t No,
@@ -806,7 +830,8 @@ int fzb_shard_pass2_dev(fzb_handle h, const double* d_data, const double* d_err,
         if (fzb_generic_shard_pass2_dev(h, d_data, d_err, d_mask, No, nullptr, 0, *cfg, d_lmap, d_levid, d_pdf_partial))
             return 1;
     }
-    return t.stop();
+    if (t.stop()) return 1;
+    return check_kde_error(h);
 }
 
 int fzb_knn_build(fzb_handle h, const float* feats, int32_t K, int64_t Nm, int32_t Nf) {

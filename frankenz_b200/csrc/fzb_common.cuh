@@ -123,6 +123,8 @@ struct fzb_context {
     DevBuf yidx, ysidx;                     // int64 per model
     std::vector<int64_t> h_yidx, h_ysidx;
     bool labels_dict_set = false;
+    int64_t labels_bad = 0;                 // labels whose kernel misses the grid / is malformed (error only if selected)
+    DevBuf kde_err;                         // {flag, model} raised by kde_add_dict when such a label is selected
     DevBuf grid, y, ystd, lowers, uppers;   // exact-Gaussian KDE
     bool labels_grid_set = false;
 
@@ -189,7 +191,6 @@ int fzb_generic_gather_fit_dev(fzb_context* h, const double* d_x, const double* 
 
 // ---- fp32 fast path (fzb_fast.cu) ------------------------------------------------------------
 bool fzb_fast_supported(const fzb_context* h, const FzbConfig& cfg);
-int fzb_fast_prepare(fzb_context* h);
 // shard_mode 0: whole fit_predict.  1: model-sharded pass 1 (d_lmap = partial max, d_psum = partial sum, d_best_idx =
 // partial arg-max; state for pass 2 stays in the context).  2: model-sharded pass 2 (d_glmap = global lmap in,
 // d_pdfs = un-normalised PDF partial out).

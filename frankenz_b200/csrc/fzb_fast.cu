@@ -1153,6 +1153,7 @@ bool fzb_fast_supported(const fzb_context* h, const FzbConfig& cfg) {
     if (h->kde_mode == FZB_KDE_GRID) return false;               // exact-Gaussian KDE: generic path
     if (h->kde_mode == FZB_KDE_DICT) {
         if (!h->labels_dict_set) return false;
+        if (h->labels_bad > 0) return false;                          // labels off the grid: the float64 kernel raises if selected
         if (h->Ng > 8192) return false;                              // k_finish keeps histogram + PDF in shared memory
         if (!cfg.use_wt_thresh && cfg.use_cdf_thresh) return false;   // CDF rule needs a sort: generic path
     }
@@ -1269,8 +1270,6 @@ static int fast_prepare_mode(fzb_context* h, int mode) {
     h->fast_Ngpad = Ngpad;
     return 0;
 }
-
-int fzb_fast_prepare(fzb_context* h) { return 0; }
 
 int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm, int64_t No,
                              const FzbConfig& cfg, double* d_pdfs, double* d_lmap, double* d_levid,

@@ -37,6 +37,7 @@ struct KdeDev {
     const int64_t* uppers;
     int use_wt, use_cdf;
     double wt_thresh, cdf_thresh;
+    long long* err;            // nullable: {flag, model} set when a selected label cannot be placed on the grid
 };
 
 struct GenParams {
@@ -141,6 +142,10 @@ __device__ __forceinline__ void kde_add_dict(const KdeDev& k, int64_t mj, double
     const double* kern = k.kernels + k.koff[si];
     const double* cdf = k.kcdf + k.koff[si];
     long long len = 2 * w + 1;
+    if (k.err && (k.koff[si + 1] - k.koff[si] != len || pos + w < 0 || pos - w > k.Ng - 1)) {
+        if (lane == 0 && atomicCAS(reinterpret_cast<unsigned long long*>(k.err), 0ull, 1ull) == 0ull) k.err[1] = mj;
+        return;
+    }
     long long low = pos - w > 0 ? pos - w : 0;
     long long high = pos + w + 1 < k.Ng ? pos + w + 1 : k.Ng;
     long long lpad = low - (pos - w), hpad = high - (pos + w + 1);
@@ -473,6 +478,7 @@ KdeDev make_kde(const fzb_context* h, const FzbConfig& cfg) {
     k.use_cdf = cfg.use_wt_thresh ? 0 : cfg.use_cdf_thresh;
     k.wt_thresh = cfg.wt_thresh;
     k.cdf_thresh = cfg.cdf_thresh;
+    k.err = (h->labels_bad > 0 && h->kde_mode == FZB_KDE_DICT) ? h->kde_err.as<long long>() : nullptr;
     return k;
 }
 

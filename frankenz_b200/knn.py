@@ -23,7 +23,12 @@ def _identity(x, xe, *args, **kwargs):
 
 
 class NearestNeighbors(object):
-    """Bayesian nearest-neighbour fits over K Monte-Carlo realisations of the training set."""
+    """Bayesian nearest-neighbour fits over K Monte-Carlo realisations of the training set.
+
+    Differences from the reference (frankenz/knn.py:191, :362-365): the neighbour search is ALWAYS exact.  `eps` is
+    accepted and stored but ignored, so the reference's default call (`eps=1e-3`, approximate cKDTree search) can
+    return slightly different - never worse - neighbours; with `eps=0` the lists are identical to the reference's.
+    A finite `distance_upper_bound` raises NotImplementedError."""
 
     def __init__(self, models, models_err, models_mask, leafsize=50, K=25, feature_map='luptitude',
                  fmap_args=None, fmap_kwargs=None, rstate=None, verbose=True):
@@ -123,9 +128,9 @@ class NearestNeighbors(object):
         return res
 
     def _remember(self, k, eps, lp_norm, distance_upper_bound):
-        self.k, self.eps, self.lp_norm, self.p, self.dbound = k, eps, lp_norm, lp_norm, distance_upper_bound
         if np.isfinite(distance_upper_bound):
             raise NotImplementedError("a finite `distance_upper_bound` is not supported by the brute-force search")
+        self.k, self.eps, self.lp_norm, self.p, self.dbound = k, eps, lp_norm, lp_norm, distance_upper_bound
 
     @staticmethod
     def _rows(res, i, track_scale):

@@ -8,8 +8,8 @@ import numpy as np
 
 from ._engine import Engine, SummaryEngine, clean_inplace, make_config
 
-__all__ = ["loglike", "logprob", "gaussian", "magnitude", "inv_magnitude", "luptitude", "inv_luptitude", "PDFDict",
-           "pdfs_resample", "pdfs_summarize"]
+__all__ = ["_loglike", "_loglike_s", "loglike", "logprob", "gaussian", "gaussian_bin", "gauss_kde", "gauss_kde_dict",
+           "magnitude", "inv_magnitude", "luptitude", "inv_luptitude", "PDFDict", "pdfs_resample", "pdfs_summarize"]
 
 
 def _one_object(data, data_err, data_mask, models, models_err, models_mask, free_scale, ignore_model_err,
@@ -59,10 +59,84 @@ def logprob(data, data_err, data_mask, models, models_err, models_mask, free_sca
     return out
 
 
+def _loglike(data, data_err, data_mask, models, models_err, models_mask, ignore_model_err=False, dim_prior=True,
+             *args, **kwargs):
+    """Fixed-scale ln-likelihood (signature of frankenz/pdf.py:27-29) -> (lnlike, Ndim, chi2).  Unlike the reference's
+    internal function, non-finite entries are cleaned like `loglike` does (the device kernels always clean)."""
+    return loglike(data, data_err, data_mask, models, models_err, models_mask, free_scale=False,
+                   ignore_model_err=ignore_model_err, dim_prior=dim_prior)
+
+
+def _loglike_s(data, data_err, data_mask, models, models_err, models_mask, ignore_model_err=False, dim_prior=True,
+               ltol=1e-4, return_scale=False, *args, **kwargs):
+    """Free-scale ln-likelihood (signature of frankenz/pdf.py:103-105) -> (lnlike, Ndim, chi2[, scale, scale_err])."""
+    return loglike(data, data_err, data_mask, models, models_err, models_mask, free_scale=True,
+                   ignore_model_err=ignore_model_err, dim_prior=dim_prior, ltol=ltol, return_scale=return_scale)
+
+
 def gaussian(mu, std, x):
     """N(x | mu, std) on the grid `x` (frankenz/pdf.py:414-425); used to tabulate `PDFDict`."""
     z = (x - mu) / std
     return np.exp(-0.5 * np.square(z)) / (np.sqrt(2. * np.pi) * std)
+
+
+def gaussian_bin(mu, std, bins):
+    """Gaussian integrated over the bins with edges `bins` (frankenz/pdf.py:428-441; host helper, not on the path)."""
+    from scipy.special import erf
+    cdf = 0.5 * (1. + erf((bins - mu) / (np.sqrt(2) * std)))
+    return cdf[1:] - cdf[:-1]
+
+
+def _kde_selection_sum(y_wt, wt_thresh, cdf_thresh):
+    """Sum of the weights the reference's threshold rule keeps (pdf.py:508-516 / :589-597)."""
+    if wt_thresh is not None:
+        sel = y_wt > (wt_thresh * np.max(y_wt))
+        return float(np.sum(y_wt[sel])), bool(sel.any())
+    idx_sort = np.argsort(y_wt)
+    y_cdf = np.cumsum(y_wt[idx_sort])
+    y_cdf /= y_cdf[-1]
+    sel = idx_sort[y_cdf <= (1. - cdf_thresh)]
+    return float(np.sum(y_wt[sel])), len(sel) > 0
+
+
+def _kde_on_device(ny, y_wt, wt_thresh, cdf_thresh, setup):
+    """Shared body of gauss_kde / gauss_kde_dict: the device KDE kernels work on log-weights of one pseudo-object and
+    return the normalised PDF; the reference returns the un-normalised stack, whose sum is the sum of the kept weights
+    (every kernel is normalised over its window)."""
+    y_wt = np.ones(ny) if y_wt is None else np.asarray(y_wt, dtype=np.float64)
+    total, any_sel = _kde_selection_sum(y_wt, wt_thresh, cdf_thresh)
+    eng = Engine(np.zeros((ny, 1)), np.zeros((ny, 1)), np.ones((ny, 1)))
+    try:
+        setup(eng)
+        if not any_sel or not np.isfinite(total) or total <= 0.:
+            return np.zeros(eng.Ng)
+        cfg = make_config(None, dict(wt_thresh=wt_thresh, cdf_thresh=cdf_thresh))
+        with np.errstate(divide="ignore"):
+            pdfs, _, _ = eng.predict_logwt(np.log(y_wt)[None, :], cfg)
+    finally:
+        eng.close()
+    return pdfs[0] * total
+
+
+def gauss_kde(y, y_std, x, dx=None, y_wt=None, sig_thresh=5., wt_thresh=1e-3, cdf_thresh=2e-4, *args, **kwargs):
+    """Exact-Gaussian KDE of weighted labels on the grid `x` (signature of frankenz/pdf.py:444-445), evaluated by the
+    device kernel the estimators use (`kde_add_grid`).  Returns the un-normalised PDF like the reference."""
+    kk = dict(dx=dx, sig_thresh=sig_thresh)
+    return _kde_on_device(len(y), y_wt, wt_thresh, cdf_thresh,
+                          lambda eng: eng.set_kde(y, y_std, label_grid=x, kde_kwargs=kk))
+
+
+def gauss_kde_dict(pdfdict, y=None, y_std=None, y_idx=None, y_std_idx=None, y_wt=None, wt_thresh=1e-3,
+                   cdf_thresh=2e-4, *args, **kwargs):
+    """Dictionary KDE (signature of frankenz/pdf.py:529-531) through the device kernel `kde_add_dict`; either the
+    labels (`y`, `y_std`) or their dictionary indices (`y_idx`, `y_std_idx`) are given.  Un-normalised like the
+    reference."""
+    if y_idx is None or y_std_idx is None:
+        if y is None or y_std is None:
+            raise ValueError("At least one pair of (y, y_std) or (y_idx, y_std_idx) must be specified.")
+        y_idx, y_std_idx = pdfdict.fit(np.asarray(y, dtype=np.float64), np.asarray(y_std, dtype=np.float64))
+    return _kde_on_device(len(y_idx), y_wt, wt_thresh, cdf_thresh,
+                          lambda eng: eng.set_kde_dict_idx(pdfdict, y_idx, y_std_idx))
 
 
 def magnitude(phot, err, zeropoints=1., *args, **kwargs):

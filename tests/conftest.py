@@ -14,6 +14,28 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _cuda_devices():
+    try:
+        import ctypes as C
+        from frankenz_b200 import _lib
+        n = C.c_int(0)
+        if _lib.load().fzb_device_count(C.byref(n)) != 0:
+            return 0
+        return n.value
+    except Exception:
+        return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """`-m gpu` tests need the CUDA library and a device: skip (not fail) where there is none."""
+    gpu_items = [it for it in items if it.get_closest_marker("gpu") is not None]
+    if not gpu_items or _cuda_devices() > 0:
+        return
+    skip = pytest.mark.skip(reason="no usable CUDA device (the product has no CPU fallback)")
+    for it in gpu_items:
+        it.add_marker(skip)
+
+
 def golden(name):
     return np.load(os.path.join(GOLDEN, name))
 
