@@ -33,11 +33,6 @@ import bench_data  # noqa: E402
 
 FLOPS_PER_PAIR = 54.0   # FS0 at Nf=5, 9*Nf+9 (FMA = 2 flops), + 3 MUFU per pair
 MUFU_PER_PAIR = 3.0
-# DRAM traffic of one k_sweep2 launch from the `ncu --set full` capture in profiles/r1_sweep_ncu.md
-# (dram__bytes_read.sum + dram__bytes_write.sum = 85.9 MB for 196,608 objects): bytes per object of the launch
-NCU_DRAM_BYTES_PER_OBJECT = 85.9e6 / 196608
-# the same for one k_sweep_tc pass-1 launch (profiles/r1_sweep_tc_ncu.md): 50.7 + 15.0 MB for 196,608 objects
-NCU_TC_DRAM_BYTES_PER_OBJECT = 65.7e6 / 196608
 LPROB = dict(free_scale=True, ignore_model_err=True, dim_prior=True)
 
 
@@ -153,6 +148,129 @@ def dist_env():
     return rank, world, local
 
 
+# ---- legs beyond the headline: C5-shaped model-sharded run and C4-shaped kNN ---------------
+def leg_model_sharded(args, rank, world, local, dist, torch, fz):
+    """C5-shaped: 6-band LSST training rows with errors (float64), default likelihood (fixed scale, model errors,
+    dim_prior), models sharded over the ranks, objects replicated; merged with ONE all-gather (24 B/object/rank) and ONE
+    reduce-scatter of fp32 PDF partials per chunk (frankenz_b200/distributed.py).  Rank 0 checks the result against the
+    unsharded fit_predict of the same problem on its own GPU in the same run."""
+    from frankenz_b200.distributed import ModelShardedBruteForce
+    n_train, n_obj = args.c5_models, args.c5_objects
+    tr, tre, trm, ztr, x, xe, xm = bench_data.c5_dataset(n_train, n_obj)
+    zgrid, sig = bench_data.c3_kde()
+    rdict = fz.pdf.PDFDict(zgrid, sig)
+    labe = np.full(n_train, 0.05)
+    dev = torch.device("cuda", local)
+    sb = ModelShardedBruteForce(tr, tre, trm, device=local, chunk=args.c5_chunk)
+    tx, txe, txm = (torch.from_numpy(a).to(dev) for a in (x, xe, xm))
+    times, last = [], None
+    for rep in range(1 + max(1, min(args.steps, 3))):
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        p, (lm, le), best = sb.fit_predict(tx, txe, txm, ztr, labe, label_dict=rdict, as_torch=True, gather=False,
+                                           return_best=True)
+        if rep > 0:
+            times.append(sb.last["ms_total"])
+            last = dict(sb.last)
+    tt = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    # every rank: the same objects against ALL models on one GPU (a sub-batch) = what an independent GPU delivers
+    nsub = min(n_obj, args.c5_check_objects)
+    bf = fz.BruteForce(tr, tre, trm)
+    ref_times = []
+    for rep in range(2):
+        p1, (lm1, le1) = bf.fit_predict(x[:nsub].copy(), xe[:nsub].copy(), xm[:nsub].copy(), ztr, labe, label_dict=rdict,
+                                        return_gof=True, verbose=False, save_fits=False)
+        ref_times.append(bf._eng().stats()["ms_total"])
+    single = float(nsub) * n_train / (min(ref_times) * 1e-3)
+    ts = torch.tensor([single], dtype=torch.float64, device=dev)
+    dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+    # parity: the rows this rank owns among the first nsub objects, against its own unsharded run
+    own = sb.owned_indices(n_obj)
+    sel = own < nsub
+    pd = p[torch.from_numpy(sel).to(dev)].cpu().numpy()
+    l1 = float(np.max(np.sum(np.abs(pd - p1[own[sel]]), axis=1))) if sel.any() else 0.0
+    lmh, leh, bh = lm[:nsub].cpu().numpy(), le[:nsub].cpu().numpy(), best[:nsub].cpu().numpy()
+    dl = float(np.max(np.abs(lmh - lm1) / np.maximum(1.0, np.abs(lm1))))
+    de = float(np.max(np.abs(leh - le1) / np.maximum(1.0, np.abs(le1))))
+    stat = torch.tensor([l1, dl, de, float(np.mean(bh != bf.best_idx))], dtype=torch.float64, device=dev)
+    dist.all_reduce(stat, op=dist.ReduceOp.MAX)
+    sb.close()
+    value = float(n_obj) * n_train / (ms * 1e-3)
+    return {"workload": "C5-shaped: %d objects x %d training rows, 6 bands (LSST ugrizY), default likelihood with model "
+                        "errors, float64 rows, models sharded x%d, dictionary KDE" % (n_obj, n_train, world),
+            "value": value, "unit": "pairs/s", "ms_per_step": ms, "chunk_objects": sb.chunk,
+            "collectives_per_step": last["collectives"], "nccl_bytes_per_rank_per_step": last["nccl_bytes"],
+            "nccl_ms_rank0": last["ms_nccl"], "nccl_share_of_step_rank0": last["ms_nccl"] / last["ms_total"],
+            "pass1_ms_rank0": last["ms_pass1"], "pass2_ms_rank0": last["ms_pass2"],
+            "exposed_ms_rank0": last["ms_total"] - last["ms_pass1"] - last["ms_pass2"],
+            "independent_gpus_pairs_per_s": float(ts.item()), "efficiency_vs_independent_gpus": value / float(ts.item()),
+            "parity_vs_unsharded": {"objects_checked": int(nsub), "pdf_l1_max": float(stat[0].item()),
+                                    "lmap_rel_max": float(stat[1].item()), "levid_rel_max": float(stat[2].item()),
+                                    "best_index_mismatch_fraction": float(stat[3].item()), "bound": 1e-5,
+                                    "ok": bool(stat[0].item() <= 1e-5 and stat[1].item() <= 1e-5 and stat[2].item() <= 1e-5)}}
+
+
+def leg_knn(args, rank, world, local, dist, torch, fz):
+    """C4-shaped: NearestNeighbors over K Monte-Carlo realisations of the training set, queries sharded over the ranks
+    (training features replicated), k neighbours per tree; the search is checked against the all-float64 kernel
+    (FZB_KNN_EXACT_ONLY) on a sub-sample in the same run."""
+    ntr, nq, K, k = args.knn_train, args.knn_queries, args.knn_K, args.knn_k
+    (tr, tre, trm, ztr), (qx, qe, qm), fmap = bench_data.c4_dataset(ntr, nq * max(1, world))
+    qx, qe, qm = (a[rank * nq:(rank + 1) * nq] for a in (qx, qe, qm))
+    t0 = time.perf_counter()
+    nn = fz.NearestNeighbors(tr, tre, trm, K=K, fmap_kwargs=fmap, rstate=np.random.RandomState(1), verbose=False)
+    t_build = time.perf_counter() - t0
+    eng = nn._engine
+    q = nn._query_features(qx, qe, np.random.RandomState(2 + rank))
+    dev = torch.device("cuda", local)
+    ms, redo = [], 0
+    for rep in range(3):
+        idx, _ = eng.knn_query(q, k, p=2, return_dist=False)
+        st = eng.stats()
+        if rep > 0:
+            ms.append(st["ms_total"])
+            redo = int(st["knn_redo"])
+    ncheck = min(nq, args.knn_check)
+    os.environ["FZB_KNN_EXACT_ONLY"] = "1"
+    try:
+        idx_exact, _ = eng.knn_query(q[:ncheck], k, p=2, return_dist=False)
+    finally:
+        del os.environ["FZB_KNN_EXACT_ONLY"]
+    mism = int(np.count_nonzero(idx[:ncheck] != idx_exact))
+    zgrid, sig = bench_data.c3_kde()
+    rdict = fz.pdf.PDFDict(zgrid, sig)
+    labe = np.full(ntr, 0.05)
+    te = []
+    for rep in range(2):
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier()
+        t0 = time.perf_counter()
+        p = nn.fit_predict(qx.copy(), qe.copy(), qm.copy(), ztr, labe, label_dict=rdict, k=k, eps=0,
+                           rstate=np.random.RandomState(2 + rank), verbose=False, save_fits=False)
+        te.append(time.perf_counter() - t0)
+    assert np.max(np.abs(p.sum(axis=1) - 1.0)) < 1e-9
+    vals = torch.tensor([float(np.mean(ms)), te[-1], float(mism), float(redo)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms_scan, t_e2e = float(vals[0].item()), float(vals[1].item())
+    evals = float(nq) * K * ntr * max(1, world)
+    return {"workload": "C4-shaped: %d-row training set x K=%d Monte-Carlo realisations (luptitude features), k=%d, "
+                        "%d queries per GPU, queries sharded x%d" % (ntr, K, k, nq, max(1, world)),
+            "distance_evaluations_per_s": evals / (ms_scan * 1e-3), "search_ms": ms_scan,
+            "queries_per_s_search": float(nq) * max(1, world) / (ms_scan * 1e-3),
+            "e2e_queries_per_s": float(nq) * max(1, world) / t_e2e, "e2e_seconds": t_e2e,
+            "build_seconds_host_mc_featuremap_h2d": t_build, "redo_searches": int(vals[3].item()),
+            "redo_fraction": float(vals[3].item()) / (float(nq) * K),
+            "index_check": {"queries": int(ncheck), "against": "all-float64 kernel (FZB_KNN_EXACT_ONLY)",
+                            "mismatching_indices": int(vals[2].item()), "ok": bool(vals[2].item() == 0)},
+            "roofline": {"bound": "fp32_fma", "flops_per_distance": 15.0,
+                         "achieved_tflops": 15.0 * evals / (ms_scan * 1e-3) / 1e12 / max(1, world)}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,6 +283,18 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--lprob", default="", help="JSON overriding the likelihood flags (experiments only)")
+    ap.add_argument("--grid", default="both", choices=["fp32", "float64", "both"],
+                    help="model grid of the headline: float32-rounded fluxes, the reference's float64 grid, or both")
+    ap.add_argument("--no-legs", action="store_true", help="skip the model-sharded (N > 1) and kNN legs")
+    ap.add_argument("--c5-models", type=int, default=1048576)
+    ap.add_argument("--c5-objects", type=int, default=262144)
+    ap.add_argument("--c5-chunk", type=int, default=65536)
+    ap.add_argument("--c5-check-objects", type=int, default=16384)
+    ap.add_argument("--knn-train", type=int, default=1000000)
+    ap.add_argument("--knn-queries", type=int, default=65536)
+    ap.add_argument("--knn-K", type=int, default=20)
+    ap.add_argument("--knn-k", type=int, default=25)
+    ap.add_argument("--knn-check", type=int, default=2048)
     args = ap.parse_args()
     if args.lprob:
         LPROB.clear()
@@ -209,19 +339,64 @@ def main():
     # ---------------- our arm ------------------------------------------------------------------------
     import torch
     import frankenz_b200 as fz
-    from frankenz_b200._engine import make_config
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     os.environ["FZB_DEVICE"] = str(local)
     use_dist = world > 1
+    dist = None
     if use_dist:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = dict(args=args, rank=rank, world=world, local=local, dist=dist, torch=torch, fz=fz, warm=warm,
+               use_dist=use_dist)
 
-    models, labels, x, xe, xm = workload(args.objects, 20260103 + rank)
+    # headline: the reference's own float64 model grid (simulate.py:954-1021 returns float64); the float32-rounded
+    # grid of round 1 is measured beside it (device-timed only)
+    head_grid = "float64" if args.grid in ("float64", "both") else "fp32"
+    head = run_c3(ctx, head_grid, steps=args.steps, e2e=not args.no_e2e, cpu=not args.no_cpu)
+    other = None
+    if args.grid == "both":
+        other = run_c3(ctx, "fp32", steps=max(1, min(args.steps, 3)), e2e=False, cpu=False)
+
+    legs = {}
+    if not args.no_legs:
+        if use_dist:
+            legs["model_sharded"] = leg_model_sharded(args, rank, world, local, dist, torch, fz)
+        legs["knn"] = leg_knn(args, rank, world, local, dist, torch, fz)
+
+    if rank == 0:
+        cfg_json["model_grid"] = head["grid_note"]
+        out = {"metric": "object-model likelihood pairs/sec", "value": head["value"], "unit": "pairs/s",
+               "n_gpus": max(1, world), "steps": args.steps, "warmup": warm, "ms_per_step": head["ms_per_step"],
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32 sweep (tf32x3 tensor-core dot products) + f64 best-fit/PDF (f64 fallback per object)",
+               "data": "synthetic", "config": cfg_json, "objects_per_s": head["value"] / head["nm"],
+               "clocks": head["clocks"], "e2e": head["e2e"], "e2e_summaries": head.get("e2e_summaries"),
+               "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "cpu_baseline": head["cpu"]}
+        if other is not None:
+            out["fp32_rounded_grid"] = {"value": other["value"], "unit": "pairs/s", "ms_per_step": other["ms_per_step"],
+                                        "grid": other["grid_note"], "roofline_frac": other["roofline"]["frac"],
+                                        "ms": other["roofline"]["ms"], "kernel": other["roofline"]["kernel"]}
+        out.update(legs)
+        print(json.dumps(out))
+    if use_dist:
+        dist.destroy_process_group()
+
+
+def run_c3(ctx, grid, steps, e2e, cpu):
+    """The headline workload on one model grid: K device-timed steps (`value`), then the numpy-in / numpy-out call
+    (`e2e`).  Returns a dict on every rank (rank 0's is printed)."""
+    args, rank, world, local = ctx["args"], ctx["rank"], ctx["world"], ctx["local"]
+    dist, torch, fz, warm, use_dist = ctx["dist"], ctx["torch"], ctx["fz"], ctx["warm"], ctx["use_dist"]
+    from frankenz_b200._engine import make_config
+    models, labels, depth = bench_data.c3_models(float64_grid=(grid == "float64"))
+    x, xe, xm, _, _ = bench_data.c3_objects(args.objects, models, depth, seed=20260103 + rank)
     no, nm = len(x), len(models)
+    f32_exact = bool(np.array_equal(models.astype(np.float32).astype(np.float64), models))
+    grid_note = ("float64 fluxes as frankenz.simulate.make_model_grid returns them (not fp32-representable)"
+                 if not f32_exact else "model fluxes fp32-representable (the float64 grid rounded to float32)")
     zgrid, sig = bench_data.c3_kde()
     rdict = fz.pdf.PDFDict(zgrid, sig)
     labe = np.full(nm, 0.05)
@@ -257,7 +432,7 @@ def main():
     barrier()
     sampler.start()
     ms_steps, st_acc = [], []
-    for _ in range(args.steps):
+    for _ in range(steps):
         flush.fill_(1)
         torch.cuda.synchronize()
         st = step()            # the library times its own stream with CUDA events (ms_total)
@@ -273,19 +448,20 @@ def main():
     else:
         t_all = t_rank
     pairs_step = float(no) * nm * max(1, world)
-    value = pairs_step * args.steps / (t_all * 1e-3)
+    value = pairs_step * steps / (t_all * 1e-3)
 
     # parity spot-check of the timed configuration's outputs (cheap invariants; full parity is in tests/)
     psum = d_pdf[:4096].sum(dim=1)
     assert bool(torch.all(torch.abs(psum[torch.isfinite(psum)] - 1.0) < 1e-9)), "PDFs are not normalised"
+    del d_pdf, flush
 
     # ---- end to end through the public API (numpy in / numpy out) ------------------------------------
-    e2e = None
-    if not args.no_e2e:
+    res_e2e = None
+    if e2e:
         ne = args.e2e_objects or no
         xs, xes, xms = x[:ne], xe[:ne], xm[:ne]
         times = []
-        for i in range(1 + max(1, min(args.steps, 3))):
+        for i in range(1 + max(1, min(steps, 3))):
             barrier()
             t0 = time.perf_counter()
             p, (lm, le) = bf.fit_predict(xs, xes, xms, labels, labe, label_dict=rdict, return_gof=True,
@@ -301,14 +477,10 @@ def main():
             tt = torch.tensor([te], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             te = float(tt.item())
-        e2e = {"value": float(ne) * nm * max(1, world) / te, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "objects_per_gpu": int(ne), "seconds_per_step": te,
-               "objects_per_s": float(ne) * max(1, world) / te}
-
-    if rank != 0:
-        if use_dist:
-            dist.destroy_process_group()
-        return
+        res_e2e = {"value": float(ne) * nm * max(1, world) / te, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": int(d2h), "objects_per_gpu": int(ne), "seconds_per_step": te,
+                   "objects_per_s": float(ne) * max(1, world) / te,
+                   "call": "BruteForce.fit_predict(numpy..., save_fits=False, return_gof=True) -> (No x 701) float64 PDFs"}
 
     # ---- roofline of the dominant kernel (the fp32 sweep), measured live ------------------------------
     fp32_peak, mufu_peak = eng.measure_peaks(5)
@@ -323,25 +495,24 @@ def main():
     kname = {1: "k_sweep2", 2: "k_sweep_tc", 3: "k_sweep_tc<LIN>"}.get(kind, "k_sweep2")
     tc = kind >= 2
     mufu_per_pair = 2.0 if kind == 3 else MUFU_PER_PAIR
+    traffic = ncu_traffic_per_object(tc)
     roofline = {"bound": "fp32_fma", "kernel": "%s<pass %d>" % (kname, 1 if ms_scan >= ms_acc else 2),
                 "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                 "peak_source": "fzb_measure_peaks (dependency-free FFMA loop, this run; MEASURED_PEAKS.json has no "
                                "fp32 entry)",
                 "note": ("algorithmic 54 flop/pair (SURVEY 8d) against the FP32 FMA peak; the tensor-core sweep executes "
-                         "30 of them (the three K=Nf dot products, as tf32x3 tcgen05 MMAs: 12.3 kflop of tensor work "
-                         "per pair incl. the split and padding) on the tensor pipe and ~40 on the FMA pipe, so the "
-                         "fraction is a figure of merit of the whole SM, not an FMA-pipe utilisation")
-                if tc else "algorithmic 54 flop/pair (SURVEY 8d) against the FP32 FMA peak",
+                         "30 of them (the three K=Nf dot products, as tf32x3 tcgen05 MMAs) on the tensor pipe and ~40 "
+                         "on the FMA pipe, so the fraction is a figure of merit of the whole SM, not an FMA-pipe "
+                         "utilisation") if tc else "algorithmic 54 flop/pair (SURVEY 8d) against the FP32 FMA peak",
                 "mufu": {"per_pair": mufu_per_pair,
                          "achieved_gops": mufu_per_pair * dom_pairs / (dom_ms * 1e-3) / 1e9, "peak_gops": mufu_peak},
-                "traffic": (NCU_TC_DRAM_BYTES_PER_OBJECT if tc else NCU_DRAM_BYTES_PER_OBJECT) * float(no),
-                "traffic_note": "bytes per launch scaled from the ncu --set full capture in profiles/ (%s: photometry "
-                                "planes in, per-split partials out, pass 2 adds the histogram atomics); the kernel is "
-                                "compute-bound, HBM carries ~0.002 B per pair"
-                                % ("r1_sweep_tc_ncu.md" if tc else "r1_sweep_ncu.md"),
+                "traffic": None if traffic is None else traffic[0] * float(no),
+                "traffic_note": None if traffic is None else traffic[1],
                 "algorithmic_flops_per_pair": FLOPS_PER_PAIR,
                 "pairs_per_s_kernel": dom_pairs / (dom_ms * 1e-3),
                 "fit_only_pairs_per_s": float(no) * nm / (ms_scan * 1e-3),
+                "whole_step_frac": FLOPS_PER_PAIR * float(no) * nm / (float(np.mean(ms_steps)) * 1e-3) / 1e12 / fp32_peak,
+                "pass2_pairs_evaluated_frac": float(np.mean([s.get("pairs_pass2", 0) for s in st_acc])) / (float(no) * nm),
                 "ms": {"pass1_scan": ms_scan, "pass2_accumulate": ms_acc, "finish": ms_fin,
                        "step_total": float(np.mean(ms_steps))},
                 "objects_routed_to_fp64": n64}
@@ -352,23 +523,45 @@ def main():
         except Exception:
             pass
 
-    cpu = None
-    if not args.no_cpu and world == 1:
+    res_cpu = None
+    if cpu and world == 1 and rank == 0:
         use_ref = reference_available()
         v, nobj, dt, cores = cpu_baseline(models, labels, x, xe, xm, args.cpu_objects_per_core, use_ref=use_ref)
-        cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference" if use_ref else "port",
-               "sample": "%d objects x %d models of the same workload, %.1f s on %d processes (%s, numpy float64)"
-                         % (nobj, nm, dt, cores, "unmodified frankenz BruteForce.fit_predict, oracle/_ref" if use_ref
-                            else "oracle/fz_oracle.py")}
+        res_cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference" if use_ref else "port",
+                   "sample": "%d objects x %d models of the same workload, %.1f s on %d processes (%s, numpy float64)"
+                             % (nobj, nm, dt, cores, "unmodified frankenz BruteForce.fit_predict, oracle/_ref" if use_ref
+                                else "oracle/fz_oracle.py")}
+    launches = int(sum(s["kernel_launches"] for s in st_acc))
+    eng.close()
+    bf._engine = None
+    del d_x, d_xe, d_xm
+    torch.cuda.empty_cache()
+    return {"value": value, "ms_per_step": t_all / steps, "nm": nm, "clocks": clocks, "e2e": res_e2e,
+            "gpu_launches": launches, "roofline": roofline, "cpu": res_cpu, "grid_note": grid_note}
 
-    out = {"metric": "object-model likelihood pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": max(1, world),
-           "steps": args.steps, "warmup": warm, "ms_per_step": t_all / args.steps, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32 sweep (tf32x3 tensor-core dot products) + f64 best-fit/PDF (f64 fallback per object)",
-           "data": "synthetic", "config": cfg_json, "objects_per_s": value / nm, "clocks": clocks, "e2e": e2e,
-           "gpu_launches": int(sum(s["kernel_launches"] for s in st_acc)), "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(out))
-    if use_dist:
-        dist.destroy_process_group()
+
+def ncu_traffic_per_object(tc):
+    """DRAM bytes per object of one pass-1 launch of the dominant kernel, parsed from the committed `ncu --set full`
+    summary (dram__bytes_read.sum + dram__bytes_write.sum over the 196,608 objects of the profiled launch)."""
+    import re
+    names = ["r2_sweep_tc_ncu.md", "r1_sweep_tc_ncu.md"] if tc else ["r1_sweep_ncu.md"]
+    for name in names:
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        txt = open(path).read()
+        sec = txt.split("## ")[1] if "## " in txt else txt      # first kernel section = pass 1
+        rd = re.search(r"dram__bytes_read\.sum`\) \| ([0-9.]+) (\w+)", sec)
+        wr = re.search(r"dram__bytes_write\.sum`\) \| ([0-9.]+) (\w+)", sec)
+        ob = re.search(r"--objects (\d+)", txt)
+        if not (rd and wr and ob):
+            continue
+        unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+        tot = float(rd.group(1)) * unit.get(rd.group(2), 1.0) + float(wr.group(1)) * unit.get(wr.group(2), 1.0)
+        return tot / float(ob.group(1)), ("dram__bytes_read.sum + dram__bytes_write.sum of the pass-1 launch in "
+                                          "profiles/%s, per object x objects of this run (photometry planes in, "
+                                          "per-split partials out; the kernel is compute-bound)" % name)
+    return None
 
 
 if __name__ == "__main__":

@@ -34,7 +34,8 @@ class FzbFitOut(C.Structure):
 class FzbStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("pairs_fp32", C.c_int64), ("pairs_fp64", C.c_int64),
                 ("objects_fp64", C.c_int64), ("ms_scan", C.c_double), ("ms_accum", C.c_double),
-                ("ms_finish", C.c_double), ("ms_total", C.c_double), ("sweep_kind", C.c_int64)]
+                ("ms_finish", C.c_double), ("ms_total", C.c_double), ("sweep_kind", C.c_int64),
+                ("knn_redo", C.c_int64), ("pairs_pass2", C.c_int64)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/frankenz_b200.h
@@ -69,6 +70,13 @@ SIGNATURES = {
                                       C.c_void_p, C.c_void_p]),
     "fzb_shard_pass2_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, _CFG, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "fzb_shard_pass1_packed_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, _CFG, C.c_int64,
+                                             C.c_void_p]),
+    "fzb_shard_merge_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fzb_shard_pass2_f32_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, _CFG, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
+    "fzb_shard_normalise_dev": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "fzb_get_stream": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
     "fzb_knn_build": (C.c_int, [_H, c_float_p, C.c_int32, C.c_int64, C.c_int32]),
     "fzb_knn_query": (C.c_int, [_H, c_double_p, C.c_int64, C.c_int32, C.c_double, c_int64_p, c_double_p]),
     "fzb_knn_fit": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int32, C.c_double,

@@ -815,23 +815,67 @@ int fzb_shard_pass1_dev(fzb_handle h, const double* d_data, const double* d_err,
     return t.stop();
 }
 
-int fzb_shard_pass2_dev(fzb_handle h, const double* d_data, const double* d_err, const double* d_mask, int64_t No,
-                        const FzbConfig* cfg, const double* d_lmap, const double* d_levid, double* d_pdf_partial) {
+static int shard_pass2_impl(fzb_context* h, const double* d_data, const double* d_err, const double* d_mask, int64_t No,
+                            const FzbConfig* cfg, const double* d_lmap, const double* d_levid, double* d_pdf_partial,
+                            float* d_partial32) {
     if (use_device(h) || check_models(h)) return 2;
     FZB_CHECK(cfg != nullptr, "null config");
     reset_stats(h);
     if (No == 0) return 0;
     Timer t(h);
+    h->shard_out32 = d_partial32;
+    int rc = 0;
     if (cfg->precision != FZB_PREC_FP64 && fzb_fast_supported(h, *cfg) && h->shard_valid && h->shard_No == No) {
-        if (fzb_fast_fit_predict_dev(h, d_data, d_err, d_mask, No, *cfg, d_pdf_partial, nullptr, nullptr, nullptr,
-                                     nullptr, nullptr, 2, nullptr, d_lmap))
-            return 1;
+        rc = fzb_fast_fit_predict_dev(h, d_data, d_err, d_mask, No, *cfg, d_pdf_partial, nullptr, nullptr, nullptr,
+                                      nullptr, nullptr, 2, nullptr, d_lmap);
     } else {
-        if (fzb_generic_shard_pass2_dev(h, d_data, d_err, d_mask, No, nullptr, 0, *cfg, d_lmap, d_levid, d_pdf_partial))
-            return 1;
+        rc = fzb_generic_shard_pass2_dev(h, d_data, d_err, d_mask, No, nullptr, 0, *cfg, d_lmap, d_levid, d_pdf_partial);
     }
+    h->shard_out32 = nullptr;
+    if (rc) return 1;
     if (t.stop()) return 1;
     return check_kde_error(h);
+}
+
+int fzb_shard_pass2_dev(fzb_handle h, const double* d_data, const double* d_err, const double* d_mask, int64_t No,
+                        const FzbConfig* cfg, const double* d_lmap, const double* d_levid, double* d_pdf_partial) {
+    FZB_CHECK(d_pdf_partial != nullptr, "null output");
+    return shard_pass2_impl(h, d_data, d_err, d_mask, No, cfg, d_lmap, d_levid, d_pdf_partial, nullptr);
+}
+
+int fzb_shard_pass2_f32_dev(fzb_handle h, const double* d_data, const double* d_err, const double* d_mask, int64_t No,
+                            const FzbConfig* cfg, const double* d_lmap, const double* d_levid, float* d_pdf_partial) {
+    FZB_CHECK(d_pdf_partial != nullptr, "null output");
+    return shard_pass2_impl(h, d_data, d_err, d_mask, No, cfg, d_lmap, d_levid, nullptr, d_pdf_partial);
+}
+
+int fzb_shard_pass1_packed_dev(fzb_handle h, const double* d_data, const double* d_err, const double* d_mask, int64_t No,
+                               const FzbConfig* cfg, int64_t best_offset, double* d_packed) {
+    FZB_CHECK(d_packed != nullptr, "null output");
+    if (No == 0) return 0;
+    int64_t* d_best = reinterpret_cast<int64_t*>(d_packed + 2 * No);
+    int rc = fzb_shard_pass1_dev(h, d_data, d_err, d_mask, No, cfg, d_packed, d_packed + No, d_best);
+    if (rc) return rc;
+    return fzb_shard_add_offset_launch(h, d_best, No, best_offset);     // stream-ordered; no host synchronisation
+}
+
+int fzb_shard_merge_dev(fzb_handle h, const double* d_gathered, int32_t world, int64_t No, double* d_lmap,
+                        double* d_levid, int64_t* d_best) {
+    if (use_device(h)) return 2;
+    FZB_CHECK(d_gathered && d_lmap && d_levid && world > 0 && No >= 0, "bad arguments");
+    return fzb_shard_merge_launch(h, d_gathered, world, No, d_lmap, d_levid, d_best);
+}
+
+int fzb_shard_normalise_dev(fzb_handle h, const float* d_rows, int64_t n, int32_t Ng, double* d_pdfs) {
+    if (use_device(h)) return 2;
+    FZB_CHECK(d_rows && d_pdfs && n >= 0 && Ng > 0, "bad arguments");
+    return fzb_shard_normalise_launch(h, d_rows, n, Ng, d_pdfs);
+}
+
+int fzb_get_stream(fzb_handle h, void** stream) {
+    FZB_CHECK(h && stream, "null pointer");
+    *stream = reinterpret_cast<void*>(h->stream);
+    return 0;
 }
 
 int fzb_knn_build(fzb_handle h, const float* feats, int32_t K, int64_t Nm, int32_t Nf) {

@@ -153,6 +153,7 @@ struct fzb_context {
     int shard_counts[4] = {0, 0, 0, 0};
     int shard_cfg_key = 0;
     bool shard_lin = false;        // pass 1 ran the linear-domain tensor-core sweep
+    float* shard_out32 = nullptr;  // pass 2 writes its PDF partials here in fp32 (set for the duration of the call)
 
     // kNN
     DevBuf knn_feats;       // float32 K x Nm x Nf (+ 64 B pad)
@@ -204,6 +205,12 @@ int fzb_summarize_impl(fzb_context* h, const double* pdfs, const double* pgrid, 
                        int64_t No, int32_t Ng, int32_t renormalize, double* rowsum, double* est, double* sd, double* risk,
                        double* quant, double* mc);
 int fzb_conf_impl(fzb_context* h, const double* points, const double* widths, int64_t No, double* conf);
+
+// ---- model-sharded merge kernels (fzb_shard.cu) --------------------------------------------------
+int fzb_shard_add_offset_launch(fzb_context* h, int64_t* d_best, int64_t No, int64_t offset);
+int fzb_shard_merge_launch(fzb_context* h, const double* d_gathered, int world, int64_t No, double* d_lmap,
+                           double* d_levid, int64_t* d_best);
+int fzb_shard_normalise_launch(fzb_context* h, const float* d_rows, int64_t n, int Ng, double* d_pdfs);
 
 // ---- kNN (fzb_knn.cu) -------------------------------------------------------------------------
 int fzb_knn_query_dev(fzb_context* h, const double* d_q, int64_t No, int k, double p, int64_t* d_idx, double* d_dist);

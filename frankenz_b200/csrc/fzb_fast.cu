@@ -870,6 +870,7 @@ struct FinishParams {
     const int64_t* koff;
     const double* kernels;
     double* pdfs;               // absolute rows
+    float* pdfs32;              // model-sharded partial in fp32 (exchanged over NVLink), instead of `pdfs`
     int normalise;              // 0: write the un-normalised sum (model-sharded partial)
     const double* scale;        // nullable per-object factor (chunk-local), only with normalise == 0
 };
@@ -916,8 +917,13 @@ __global__ void __launch_bounds__(256) k_finish(FinishParams P) {
     __syncthreads();
     double tot = 0.0;
     for (int i = 0; i < 8; ++i) tot += red[i];
-    double* out = P.pdfs + (size_t)(P.o_base + o) * P.Ng;
     if (!P.normalise) tot = P.scale ? 1.0 / P.scale[o] : 1.0;
+    if (P.pdfs32) {
+        float* out32 = P.pdfs32 + (size_t)(P.o_base + o) * P.Ng;
+        for (int g = tid; g < P.Ng; g += 256) out32[g] = (float)(pdf[g] / tot);
+        return;
+    }
+    double* out = P.pdfs + (size_t)(P.o_base + o) * P.Ng;
     for (int g = tid; g < P.Ng; g += 256) out[g] = pdf[g] / tot;
 }
 
@@ -1277,7 +1283,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                              double* d_psum, const double* d_glmap) {
     const int mode = mode_of(cfg);
     const int nf = h->Nf;
-    const bool want_pdf = d_pdfs != nullptr || shard_mode == 1;   // pass 1 of a sharded run prepares the KDE layout too
+    const bool want_pdf = d_pdfs != nullptr || shard_mode == 1 || (shard_mode == 2 && h->shard_out32 != nullptr);   // pass 1 of a sharded run prepares the KDE layout too
     if (want_pdf) FZB_CHECK(h->kde_mode == FZB_KDE_DICT && h->labels_dict_set, "dictionary KDE not configured");
     if (shard_mode != 1) h->shard_valid = (shard_mode == 2) ? h->shard_valid : false;
     if (h->fast_dirty || !h->fast.valid || h->fast_mode != mode) {
@@ -1551,6 +1557,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             FP.Ng = h->Ng; FP.Ngpad = h->fast_Ngpad; FP.wmax = h->fast_wmax; FP.nslot = F.nslot;
             FP.slot_sidx = F.d_slot_sidx.as<int32_t>(); FP.widths = h->widths.as<int32_t>();
             FP.koff = h->koff.as<int64_t>(); FP.kernels = h->kernels.as<double>(); FP.pdfs = d_pdfs;
+            FP.pdfs32 = (shard_mode == 2) ? h->shard_out32 : nullptr;
             FP.normalise = (shard_mode == 2) ? 0 : 1;
             size_t smem = sizeof(double) * ((size_t)h->fast_Ngpad + 4 + h->Ng);
             FZB_CUDA(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -66,6 +66,7 @@ struct GenParams {
     const double* logwt;
     // per-object outputs
     double *pdfs, *lmap, *levid, *best_chi2, *best_scale;
+    float* pdfs32;                    // ST_PASS2: fp32 partial rows instead of `pdfs`
     int64_t* best_idx;
     // sharded passes
     double *pmax, *psum;
@@ -179,7 +180,7 @@ __device__ __forceinline__ void kde_add_grid(const KdeDev& k, int64_t mj, double
 //   given_lmap/levid: non-null for the model-sharded pass 2 (global values, no normalisation)
 __device__ void row_to_pdf(const double* row, int64_t n, const int64_t* map, const KdeDev& k, double* s_pdf,
                            double* red, int* redi, double* out_pdf, double* out_lmap, double* out_levid,
-                           const double* given_lmap, const double* given_levid) {
+                           const double* given_lmap, const double* given_levid, float* out_pdf32 = nullptr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double lmap, levid, amax;
     int has_nan = 0;
@@ -224,7 +225,7 @@ __device__ void row_to_pdf(const double* row, int64_t n, const int64_t* map, con
         levid = lmap;
         amax = lmap;
     }
-    if (out_pdf == nullptr) return;
+    if (out_pdf == nullptr && out_pdf32 == nullptr) return;
 
     for (int g = tid; g < k.Ng; g += GT) s_pdf[g] = 0.0;
     __syncthreads();
@@ -298,7 +299,8 @@ __device__ void row_to_pdf(const double* row, int64_t n, const int64_t* map, con
     }
     __syncthreads();
     if (given_lmap != nullptr) {
-        for (int g = tid; g < k.Ng; g += GT) out_pdf[g] = s_pdf[g];
+        if (out_pdf32) { for (int g = tid; g < k.Ng; g += GT) out_pdf32[g] = (float)s_pdf[g]; }
+        else { for (int g = tid; g < k.Ng; g += GT) out_pdf[g] = s_pdf[g]; }
         return;
     }
     double tot = 0.0;
@@ -444,8 +446,8 @@ __global__ void __launch_bounds__(GT) k_generic(GenParams P) {
             continue;
         }
         if (P.stage == ST_PASS2) {
-            row_to_pdf(r_lnl, n, map, P.kde, s_pdf, red, redi, P.pdfs + (size_t)o * P.kde.Ng, nullptr, nullptr,
-                       P.g_lmap + o, P.g_levid + o);
+            row_to_pdf(r_lnl, n, map, P.kde, s_pdf, red, redi, P.pdfs32 ? nullptr : P.pdfs + (size_t)o * P.kde.Ng, nullptr,
+                       nullptr, P.g_lmap + o, P.g_levid + o, P.pdfs32 ? P.pdfs32 + (size_t)o * P.kde.Ng : nullptr);
             continue;
         }
         // ST_FIT_PREDICT
@@ -616,7 +618,7 @@ int fzb_generic_shard_pass2_dev(fzb_context* h, const double* d_x, const double*
     P.stage = ST_PASS2;
     P.objsel = d_objsel; P.Nsel = Nsel;
     P.kde = make_kde(h, cfg);
-    P.pdfs = d_pdf_partial; P.g_lmap = d_lmap; P.g_levid = d_levid;
+    P.pdfs = d_pdf_partial; P.pdfs32 = h->shard_out32; P.g_lmap = d_lmap; P.g_levid = d_levid;
     int64_t items = d_objsel ? Nsel : No;
     h->stats.pairs_fp64 += items * h->Nm;
     return launch_generic(h, P, items, true);

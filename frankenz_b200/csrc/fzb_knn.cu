@@ -450,6 +450,10 @@ int fzb_knn_query_dev(fzb_context* h, const double* d_q, int64_t No, int k, doub
         if (knn_exact_launch(h, qq, nc, k, p, pmode, d_idx + (size_t)o0 * K * k,
                              d_dist ? d_dist + (size_t)o0 * K * k : nullptr, redo, n_redo, 4096))
             return 1;
+        int nr = 0;
+        FZB_CUDA(cudaMemcpyAsync(&nr, n_redo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        FZB_CUDA(cudaStreamSynchronize(h->stream));
+        h->stats.knn_redo += nr;
     }
     return 0;
 }

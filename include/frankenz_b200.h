@@ -78,6 +78,9 @@ typedef struct FzbStats {
     double  ms_total;          /* CUDA-event time of all device work of the call        */
     int64_t sweep_kind;        /* fused path of the last call: 0 none, 1 packed FP32 sweep (k_sweep2), 2 tensor-core
                                   sweep (k_sweep_tc), 3 tensor-core sweep in its linear-domain form           */
+    int64_t knn_redo;          /* kNN: (query, tree) searches the fp32 scan could not prove exact and the float64
+                                  kernel re-did from scratch                                                    */
+    int64_t pairs_pass2;       /* object-model pairs pass 2 actually evaluated (after sub-batch pruning)       */
 } FzbStats;
 
 const char* fzb_last_error(void);
@@ -160,6 +163,25 @@ int fzb_shard_pass1_dev(fzb_handle h, const double* d_data, const double* d_err,
 int fzb_shard_pass2_dev(fzb_handle h, const double* d_data, const double* d_err, const double* d_mask,
                         int64_t No, const FzbConfig* cfg, const double* d_lmap, const double* d_levid,
                         double* d_pdf_partial);
+
+/* Model-sharded mode as it runs over NCCL (frankenz_b200/distributed.py): objects go through in chunks and, per chunk,
+ *   fzb_shard_pass1_packed_dev   d_packed[3][No] = (max, sum, bit pattern of the int64 GLOBAL arg-max = local + best_offset)
+ *                                -> ONE ncclAllGather of 24 B / object / rank
+ *   fzb_shard_merge_dev          d_gathered[world][3][No] -> global lmap / levid / best (numpy NaN rules, bruteforce.py:359)
+ *   fzb_shard_pass2_f32_dev      un-normalised PDF partial of the local models in fp32, (No x Ngrid)
+ *                                -> ONE ncclReduceScatter(sum): every rank receives the rows of the objects it owns
+ *   fzb_shard_normalise_dev      float64 normalisation of the n reduced rows a rank owns (bruteforce.py:370)
+ * merge / normalise only enqueue work on the handle's stream (no host synchronisation), so that the caller can order
+ * them against its communication stream with events: fzb_get_stream returns the handle's cudaStream_t for that. */
+int fzb_shard_pass1_packed_dev(fzb_handle h, const double* d_data, const double* d_err, const double* d_mask,
+                               int64_t No, const FzbConfig* cfg, int64_t best_offset, double* d_packed);
+int fzb_shard_merge_dev(fzb_handle h, const double* d_gathered, int32_t world, int64_t No, double* d_lmap,
+                        double* d_levid, int64_t* d_best);
+int fzb_shard_pass2_f32_dev(fzb_handle h, const double* d_data, const double* d_err, const double* d_mask,
+                            int64_t No, const FzbConfig* cfg, const double* d_lmap, const double* d_levid,
+                            float* d_pdf_partial);
+int fzb_shard_normalise_dev(fzb_handle h, const float* d_rows, int64_t n, int32_t Ngrid, double* d_pdfs);
+int fzb_get_stream(fzb_handle h, void** stream);
 
 /* kNN: brute-force replacement of K cKDTrees (knn.py:186, :362-365).
  * feats: host float32 (K x Nm x Nf), the MC-realised, feature-mapped training sets

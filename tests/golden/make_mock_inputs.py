@@ -10,6 +10,10 @@ import the reference:
   hsc_brown_grid.npz  HSC grizy / brown template x redshift model grid
                       (SURVEY.md section 8d, C3): models[Nz*Nt, 5] float32, zgrid,
                       depth_flux1sig.
+  hsc_brown_grid_lo.npz  the part of make_model_grid's float64 output that float32 drops:
+                      models_lo = models64 - float32(models64) (exact in float64), so that
+                      float64(models) + models_lo IS the reference's float64 grid, bit for bit.
+  lsst_brown_grid.npz LSST ugrizY / brown grid, 6 bands: models float32.
 
 Reference calls exercised: frankenz/simulate.py:398 (MockSurvey), :444
 (load_survey; Npoints passed as int because the 5e4 default crashes np.linspace),
@@ -56,12 +60,33 @@ def hsc_grid(nz=1550):
     s.make_model_grid(zgrid, verbose=False)
     m = s.models["data"]  # (Nz, Nt, Nf)
     depth = np.array([f["depth_flux1sig"] for f in s.filters])
-    np.savez_compressed(os.path.join(HERE, "hsc_brown_grid.npz"),
-                        models=m.reshape(-1, m.shape[-1]).astype(np.float32),
-                        zgrid=zgrid, ntemplate=np.int64(m.shape[1]),
-                        depth_flux1sig=depth)
+    m64 = np.ascontiguousarray(m.reshape(-1, m.shape[-1]), dtype=np.float64)
+    m32 = m64.astype(np.float32)
+    old = os.path.join(HERE, "hsc_brown_grid.npz")
+    if os.path.exists(old):      # the committed float32 grid stays as it is; only check that it is reproduced
+        assert np.array_equal(np.load(old)["models"], m32), "float32 grid changed"
+    else:
+        np.savez_compressed(old, models=m32, zgrid=zgrid, ntemplate=np.int64(m.shape[1]), depth_flux1sig=depth)
+    lo = m64 - m32.astype(np.float64)
+    assert np.array_equal(m32.astype(np.float64) + lo, m64)
+    np.savez_compressed(os.path.join(HERE, "hsc_brown_grid_lo.npz"), models_lo=lo)
     print("hsc grid:", m.shape, "finite:", bool(np.isfinite(m).all()),
-          "min:", float(m.min()))
+          "min:", float(m.min()), "fp32-exact fraction:", float(np.mean(lo == 0)))
+
+
+def lsst_grid(nz=1550):
+    from frankenz import simulate
+    s = simulate.MockSurvey(templates="brown")
+    s.load_survey("lsst", Npoints=50000)
+    zgrid = np.linspace(0, 6, nz)
+    s.make_model_grid(zgrid, verbose=False)
+    m = s.models["data"]
+    depth = np.array([f["depth_flux1sig"] for f in s.filters])
+    np.savez_compressed(os.path.join(HERE, "lsst_brown_grid.npz"),
+                        models=m.reshape(-1, m.shape[-1]).astype(np.float32), zgrid=zgrid,
+                        ntemplate=np.int64(m.shape[1]), depth_flux1sig=depth,
+                        filters=np.array([f["name"] for f in s.filters]))
+    print("lsst grid:", m.shape, "finite:", bool(np.isfinite(m).all()), "min:", float(m.min()), "depth:", depth)
 
 
 if __name__ == "__main__":
@@ -70,3 +95,5 @@ if __name__ == "__main__":
         sdss_mock()
     if which in ("all", "hsc"):
         hsc_grid()
+    if which in ("all", "lsst"):
+        lsst_grid()

@@ -75,6 +75,88 @@ def test_model_sharded_merge_gloo():
     assert np.max(np.sum(np.abs(pdfs[1:] - g["pdf_dict"][1:]), axis=1)) < 1e-12
 
 
+def _worker_chunked(rank, world, port, q):
+    """The collective sequence of ModelShardedBruteForce on CPU tensors over gloo: ONE all-gather of the packed pass-1
+    partials, merge_gathered, ONE reduce-scatter of fp32 PDF partials per chunk, normalisation by the owner."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from frankenz_b200.distributed import merge_gathered, owned_rows, shard_bounds
+        g = golden("bruteforce_c1small.npz")
+        m, me, mm = g["models"], g["models_err"], g["models_mask"]
+        x, xe, xm = g["data"].copy(), g["data_err"].copy(), g["data_mask"].copy()
+        lab, labe = g["labels"], g["label_errs"]
+        zgrid = np.arange(0, 7 + 1e-5, 0.01)
+        kd = fo.KernelDict(zgrid, np.linspace(0.005, 2, 500))
+        lo, hi = shard_bounds(len(m), world, rank)
+        yi, si = kd.fit(lab[lo:hi], labe[lo:hi])
+        chunk = 10                                   # 32 objects -> chunks of 10, 10, 10, 2 (ragged tail)
+        rows, idx, lm_all, best_all = [], [], [], []
+        for c0 in range(0, len(x), chunk):
+            sl = slice(c0, min(len(x), c0 + chunk))
+            nc = sl.stop - sl.start
+            lp = fo.bruteforce_fit(m[lo:hi], me[lo:hi], mm[lo:hi], x[sl], xe[sl], xm[sl])["lnprob"]
+            pmax = lp.max(axis=1)
+            packed = np.stack([pmax, np.exp(lp - pmax[:, None]).sum(axis=1),
+                               (lp.argmax(axis=1) + lo).astype(np.int64).view(np.float64)])
+            if rank == 1 and c0 == 0:
+                packed[0, 0] = packed[1, 0] = np.nan          # a poisoned object
+            gathered = torch.empty((world * 3, nc), dtype=torch.float64)
+            dist.all_gather_into_tensor(gathered, torch.from_numpy(packed))
+            lmap, levid, best = merge_gathered(gathered.view(world, 3, nc))
+            olo, ohi, qrows = owned_rows(nc, world, rank)
+            part = np.zeros((qrows * world, kd.Ngrid), dtype=np.float32)
+            for i in range(nc):
+                if np.isnan(lmap[i].item()):
+                    continue
+                wt = np.exp(lp[i] - lmap[i].item())            # weights relative to the GLOBAL maximum
+                wt = np.where(wt > 1e-3, wt, 0.0)
+                part[i] = fo.kde_dict(kd, yi, si, y_wt=wt, wt_thresh=None, cdf_thresh=None)
+            own = torch.empty((qrows, kd.Ngrid), dtype=torch.float32)
+            dist.reduce_scatter_tensor(own, torch.from_numpy(part), op=dist.ReduceOp.SUM)
+            own = own[:ohi - olo].double()
+            rows.append((own / own.sum(dim=1, keepdim=True)).numpy())
+            idx.append(np.arange(c0 + olo, c0 + ohi))
+            lm_all.append(lmap.numpy())
+            best_all.append(best.numpy())
+        q.put((rank, np.concatenate(idx), np.concatenate(rows), np.concatenate(lm_all), np.concatenate(best_all)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_chunked_allgather_reduce_scatter_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_chunked, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(), q.get()]
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    g = golden("bruteforce_c1small.npz")
+    seen = np.zeros(32, dtype=int)
+    for rank, idx, rows, lmap, best in got:
+        seen[idx] += 1
+        ok = idx != 0
+        assert np.max(np.sum(np.abs(rows[ok] - g["pdf_dict"][idx[ok]]), axis=1)) < 5e-6       # fp32 partials
+        assert np.isnan(lmap[0]) and np.allclose(lmap[1:], g["lmap"][1:], rtol=1e-13)
+        assert np.array_equal(best[1:], g["fit_lnprob"][1:].argmax(axis=1))
+    assert np.all(seen == 1)                      # every object is owned by exactly one rank
+
+
+def test_owned_rows_partition():
+    from frankenz_b200.distributed import owned_rows
+    for n in (1, 2, 7, 8, 65536, 65537):
+        for w in (1, 2, 3, 8):
+            parts = [owned_rows(n, w, r) for r in range(w)]
+            assert parts[0][0] == 0 and max(p[1] for p in parts) == n
+            assert sum(p[1] - p[0] for p in parts) == n
+            assert all(p[2] * w >= n for p in parts)
+
+
 def test_shard_bounds_cover_everything():
     from frankenz_b200.distributed import shard_bounds
     for n in (0, 1, 7, 8, 1000003):

@@ -1,0 +1,176 @@
+"""Model-sharded mode over real NCCL ranks: two processes, one GPU each, when the box has two
+GPUs (skipped otherwise); plus the same kernels driven shard by shard on one GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import bench_data
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _problem(nm=6000, no=700):
+    m, me, mm, z, x, xe, xm, _ = bench_data.c1_dataset(nm, no)
+    x = x.copy()
+    x[5, 1] = np.nan                      # cleaned band (pdf.py:310-311)
+    xm = xm.copy()
+    xm[9] = 0.0                           # all-masked object: NaN row, poisons lmap / levid on every rank
+    zgrid, sig = bench_data.c3_kde()
+    return m, me, mm, z, np.full(nm, 0.05), x, xe, xm, zgrid, sig
+
+
+def _nccl_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), FZB_DEVICE=str(rank))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import frankenz_b200 as fz
+        from frankenz_b200.distributed import ModelShardedBruteForce
+        m, me, mm, z, labe, x, xe, xm, zgrid, sig = _problem()
+        rdict = fz.pdf.PDFDict(zgrid, sig)
+        out = {}
+        for name, kw in (("default", dict()), ("free", dict(free_scale=True, ignore_model_err=True))):
+            sb = ModelShardedBruteForce(m, me, mm, device=rank, chunk=256)      # 700 objects: chunks 256, 256, 188
+            p, (lm, le), best = sb.fit_predict(x.copy(), xe.copy(), xm.copy(), z, labe, label_dict=rdict,
+                                               lprob_kwargs=kw, return_best=True, gather=True)
+            p_own, _ = sb.fit_predict(x.copy(), xe.copy(), xm.copy(), z, labe, label_dict=rdict, lprob_kwargs=kw,
+                                      gather=False)
+            own = sb.owned_indices(len(x))
+            assert sb.last["collectives"] == 2 * 3 and sb.last["nccl_bytes"] > 0
+            assert np.array_equal(p_own, p[own], equal_nan=True)
+            out[name] = (p, lm, le, best, own)
+            sb.close()
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_model_sharded_over_two_nccl_ranks():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    import frankenz_b200 as fz
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict([q.get(), q.get()])
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    m, me, mm, z, labe, x, xe, xm, zgrid, sig = _problem()
+    rdict = fz.pdf.PDFDict(zgrid, sig)
+    seen = np.zeros(len(x), dtype=int)
+    for r in (0, 1):
+        seen[got[r]["default"][4]] += 1
+    assert np.all(seen == 1)
+    for name, kw in (("default", dict()), ("free", dict(free_scale=True, ignore_model_err=True))):
+        bf = fz.BruteForce(m, me, mm)
+        p1, (lm1, le1) = bf.fit_predict(x.copy(), xe.copy(), xm.copy(), z, labe, label_dict=rdict, return_gof=True,
+                                        verbose=False, save_fits=False, lprob_kwargs=dict(kw, precision="fp64"))
+        good = np.isfinite(lm1)
+        assert not good[9]
+        for r in (0, 1):
+            p, lm, le, best, _ = got[r][name]
+            assert np.array_equal(np.isfinite(lm), good) and np.array_equal(np.isfinite(le), good)
+            assert np.max(np.sum(np.abs(p[good] - p1[good]), axis=1)) <= 1e-5
+            assert np.all(np.abs(lm[good] - lm1[good]) <= 1e-5 * np.maximum(1, np.abs(lm1[good])))
+            assert np.all(np.abs(le[good] - le1[good]) <= 1e-5 * np.maximum(1, np.abs(le1[good])))
+            assert np.array_equal(best[good], bf.best_idx[good])
+        assert np.array_equal(got[0][name][0], got[1][name][0], equal_nan=True)       # identical on every rank
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(free_scale=True, ignore_model_err=True)])
+def test_shard_kernels_three_shards_one_gpu(kw):
+    """pass1_packed -> k_shard_merge -> pass2_f32 -> sum -> k_shard_normalise with three shards on one GPU (the
+    collectives replaced by their definitions): against the unsharded float64 run and against the torch restatement
+    of the merge."""
+    import ctypes as C
+    import torch
+    import frankenz_b200 as fz
+    from frankenz_b200 import _lib
+    from frankenz_b200._engine import Engine, make_config
+    from frankenz_b200.distributed import merge_gathered, shard_bounds
+    m, me, mm, z, labe, x, xe, xm, zgrid, sig = _problem()
+    rdict = fz.pdf.PDFDict(zgrid, sig)
+    n, nm, W = len(x), len(m), 3
+    tx = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (x, xe, xm)]
+    cfg = make_config(kw, None)
+    engs = []
+    gathered = torch.empty((W, 3, n), dtype=torch.float64).cuda()
+    for r in range(W):
+        lo, hi = shard_bounds(nm, W, r)
+        e = Engine(m[lo:hi], me[lo:hi], mm[lo:hi])
+        e.set_kde(z[lo:hi], labe[lo:hi], label_dict=rdict)
+        _lib.check(e.lib.fzb_shard_pass1_packed_dev(e.h, tx[0].data_ptr(), tx[1].data_ptr(), tx[2].data_ptr(), n,
+                                                    C.byref(cfg), lo, gathered[r].data_ptr()))
+        engs.append(e)
+    torch.cuda.synchronize()
+    lmap = torch.empty(n, dtype=torch.float64).cuda()
+    levid = torch.empty(n, dtype=torch.float64).cuda()
+    best = torch.empty(n, dtype=torch.int64).cuda()
+    e0 = engs[0]
+    _lib.check(e0.lib.fzb_shard_merge_dev(e0.h, gathered.data_ptr(), W, n, lmap.data_ptr(), levid.data_ptr(),
+                                          best.data_ptr()))
+    _lib.check(e0.lib.fzb_synchronize(e0.h))
+    tl, te, tb = merge_gathered(gathered.cpu())
+    assert np.array_equal(lmap.cpu().numpy(), tl.numpy(), equal_nan=True)
+    assert np.allclose(levid.cpu().numpy(), te.numpy(), rtol=1e-15, atol=0, equal_nan=True)
+    ok = np.isfinite(tl.numpy())
+    assert np.array_equal(best.cpu().numpy()[ok], tb.numpy()[ok])
+    tot = torch.zeros((n, 701), dtype=torch.float32).cuda()
+    for e in engs:
+        part = torch.full((n, 701), float("nan"), dtype=torch.float32).cuda()
+        torch.cuda.synchronize()
+        _lib.check(e.lib.fzb_shard_pass2_f32_dev(e.h, tx[0].data_ptr(), tx[1].data_ptr(), tx[2].data_ptr(), n,
+                                                 C.byref(cfg), lmap.data_ptr(), levid.data_ptr(), part.data_ptr()))
+        tot += part
+    torch.cuda.synchronize()
+    pdfs = torch.empty((n, 701), dtype=torch.float64).cuda()
+    _lib.check(e0.lib.fzb_shard_normalise_dev(e0.h, tot.data_ptr(), n, 701, pdfs.data_ptr()))
+    _lib.check(e0.lib.fzb_synchronize(e0.h))
+    bf = fz.BruteForce(m, me, mm)
+    p1, (lm1, le1) = bf.fit_predict(x.copy(), xe.copy(), xm.copy(), z, labe, label_dict=rdict, return_gof=True,
+                                    verbose=False, save_fits=False, lprob_kwargs=dict(kw, precision="fp64"))
+    good = np.isfinite(lm1)
+    p = pdfs.cpu().numpy()
+    assert np.array_equal(np.isfinite(lmap.cpu().numpy()), good)
+    assert np.max(np.sum(np.abs(p[good] - p1[good]), axis=1)) <= 1e-5
+    assert np.all(np.abs(lmap.cpu().numpy()[good] - lm1[good]) <= 1e-5 * np.maximum(1, np.abs(lm1[good])))
+    assert np.all(np.abs(levid.cpu().numpy()[good] - le1[good]) <= 1e-5 * np.maximum(1, np.abs(le1[good])))
+    assert np.array_equal(best.cpu().numpy()[good], bf.best_idx[good])
+
+
+def test_single_rank_driver_chunks_and_ragged_tail():
+    """ModelShardedBruteForce without a process group, several chunks with a ragged tail: the chunk loop, the event
+    ordering between the library stream and the communication stream, the fp32 partials."""
+    import frankenz_b200 as fz
+    from frankenz_b200.distributed import ModelShardedBruteForce
+    m, me, mm, z, labe, x, xe, xm, zgrid, sig = _problem()
+    rdict = fz.pdf.PDFDict(zgrid, sig)
+    sb = ModelShardedBruteForce(m, me, mm, chunk=300)
+    p, (lm, le), best = sb.fit_predict(x.copy(), xe.copy(), xm.copy(), z, labe, label_dict=rdict, return_best=True)
+    assert sb.last["chunks"] == 3 and np.array_equal(sb.owned_indices(len(x)), np.arange(len(x)))
+    bf = fz.BruteForce(m, me, mm)
+    p1, (lm1, le1) = bf.fit_predict(x.copy(), xe.copy(), xm.copy(), z, labe, label_dict=rdict, return_gof=True,
+                                    verbose=False, save_fits=False)
+    good = np.isfinite(lm1)
+    assert np.array_equal(np.isfinite(lm), good)
+    assert np.max(np.sum(np.abs(p[good] - p1[good]), axis=1)) <= 1e-5
+    assert np.allclose(lm[good], lm1[good], rtol=0, atol=1e-6) and np.array_equal(best[good], bf.best_idx[good])
+    sb.close()
