@@ -36,87 +36,11 @@
 #include "fzb_common.cuh"
 #include "fzb_pair64.cuh"
 
+#include "fzb_sweep_common.cuh"
+
 namespace {
 
-constexpr int TM = 256;          // models per shared-memory tile
-constexpr int NSTAGE = 2;
-constexpr float kHalfLog2e = 0.7213475204444817f;
-
-enum FastMode { FM_FS0 = 0, FM_FX0 = 1, FM_FX1 = 2 };
-
-// ---- PTX helpers: mbarrier + TMA bulk copy ----------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ float fast_rcp(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float fast_lg2(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float fast_ex2(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// ---- kernel parameters -------------------------------------------------------------------------
-struct SweepParams {
-    // objects, SoA [field][band][No_pad]
-    const float* od;      // d_hi
-    const float* ow;      // FS0/FX0: mask/err^2        FX1: err^2 (+inf where masked)
-    const float* ox;      // FS0: d*w
-    const float* odl;     // 2 * d_lo
-    const float* oA;      // [No_pad] (dof/2 - 1) or 0
-    const int32_t* obits; // [No_pad] band-mask bits of the object (model-mask variant)
-    float Atab[16];       // model-mask variant: (dof/2 - 1) by pair dimensionality
-    float Ktab[16];       //                     ndim-dependent constant of the ln-likelihood, log2 units
-    int64_t No_pad;
-    int64_t No;           // objects in this launch (pass 1) / entries of objlist (pass 2)
-    // models
-    const float* recs;    // [nm][REC]
-    int64_t nm;
-    int tiles_per_split;
-    int has_prior;
-    // pass 1 outputs: [nsplit][No_pad]
-    double* pM;
-    double* pS;
-    int32_t* pbest;
-    // pass 2
-    const int32_t* objlist;
-    const float* M2;      // [No_pad] final max (log2 units, without the per-object constant)
-    const float* thr2;    // [No_pad] selection cut in the same units
-    float* hist;          // [No_pad][hist_stride]
-    int64_t hist_stride;
-};
-
+using namespace fzbsweep;
 
 // =====================================================================================================
 // Packed-FP32 sweep (FFMA2 / FMUL2 / FADD2): two objects per 64-bit register pair.
@@ -129,38 +53,6 @@ struct SweepParams {
 // threads per CTA / CTAs per SM of the packed kernel: R=4 -> 384 threads x 1 (<= 168 registers), R=2 -> 256 threads x 3 (<= 85)
 __host__ __device__ constexpr int ft2_of(int R) { return R >= 4 ? 384 : 256; }
 __host__ __device__ constexpr int minb2_of(int R) { return R >= 4 ? 1 : 3; }
-
-typedef unsigned long long f2;
-__device__ __forceinline__ f2 pack2(float a, float b) {
-    f2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ float lo2(f2 v) {
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-    return a;
-}
-__device__ __forceinline__ float hi2(f2 v) {
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-    return b;
-}
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
-    f2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
-    f2 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ f2 add2(f2 a, f2 b) {
-    f2 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
 
 __host__ __device__ constexpr int rec2_floats(int nf, int mode, bool mlo, bool mm = false) {
     // pairs (v, v): m[nf], aux[nf] (FS0: m^2, FX1: err^2), ml[nf] (MLO), k[nf] (MM: band mask 0/1);
@@ -426,7 +318,6 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
 
 
 
-#include "fzb_sweep_tc.cuh"
 
 // =====================================================================================================
 // Float64 register-tiled sweep: same structure as k_sweep2 (objects in registers, model tiles staged by
@@ -1020,44 +911,6 @@ int launch_sweep2_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prior)
     return 0;
 }
 
-// tensor-core sweep (FS0, fp32-exact models, no model masks): 256 objects per CTA
-template <int NF, bool DP, int PASS, bool LIN>
-int launch_sweep_tc_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prior) {
-    const unsigned char* tiles = h->fast.tiles_tc.as<unsigned char>();
-    if (prior) {
-        auto kern = k_sweep_tc<NF, DP, true, PASS, LIN>;
-        FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(NF)));
-        kern<<<grid, TC_THREADS, tc_smem(NF), h->stream>>>(P, tiles, 128u, 256u);
-    } else {
-        auto kern = k_sweep_tc<NF, DP, false, PASS, LIN>;
-        FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(NF)));
-        kern<<<grid, TC_THREADS, tc_smem(NF), h->stream>>>(P, tiles, 128u, 256u);
-    }
-    fzb_count_launch(h);
-    FZB_CUDA(cudaGetLastError());
-    return 0;
-}
-
-// lin: linear-domain form, valid when every object handled by the fp32 pass has (dof/2 - 1) = 1 (Nf = 5, dim_prior)
-int launch_sweep_tc(fzb_context* h, const SweepParams& P, dim3 grid, int nf, bool dp, int pass, bool lin) {
-    const bool prior = P.has_prior != 0;
-    if (nf == 5) {
-        if (lin && dp) return pass == 1 ? launch_sweep_tc_t<5, true, 1, true>(h, P, grid, prior) : launch_sweep_tc_t<5, true, 2, true>(h, P, grid, prior);
-        if (dp) return pass == 1 ? launch_sweep_tc_t<5, true, 1, false>(h, P, grid, prior) : launch_sweep_tc_t<5, true, 2, false>(h, P, grid, prior);
-        return pass == 1 ? launch_sweep_tc_t<5, false, 1, false>(h, P, grid, prior) : launch_sweep_tc_t<5, false, 2, false>(h, P, grid, prior);
-    }
-    if (nf == 4) {
-        if (dp) return pass == 1 ? launch_sweep_tc_t<4, true, 1, false>(h, P, grid, prior) : launch_sweep_tc_t<4, true, 2, false>(h, P, grid, prior);
-        return pass == 1 ? launch_sweep_tc_t<4, false, 1, false>(h, P, grid, prior) : launch_sweep_tc_t<4, false, 2, false>(h, P, grid, prior);
-    }
-    if (nf == 6) {
-        if (dp) return pass == 1 ? launch_sweep_tc_t<6, true, 1, false>(h, P, grid, prior) : launch_sweep_tc_t<6, true, 2, false>(h, P, grid, prior);
-        return pass == 1 ? launch_sweep_tc_t<6, false, 1, false>(h, P, grid, prior) : launch_sweep_tc_t<6, false, 2, false>(h, P, grid, prior);
-    }
-    fzb_set_error("tensor-core sweep: unsupported filter count %d", nf);
-    return 2;
-}
-
 template <int NF, int MODE, bool DP, bool MLO>
 int launch_sweep_r(fzb_context* h, const SweepParams& P, dim3 grid, int R, int pass) {
     if constexpr (MLO) {
@@ -1256,17 +1109,9 @@ static int fast_prepare_mode(fzb_context* h, int mode) {
         FZB_CUDA(cudaGetLastError());
     }
     F.tc_valid = false;
-    if (mode == FM_FS0 && !mm && !mlo && nf >= 4 && nf <= 6) {
-        const int64_t ntile = (nm + TC_TM - 1) / TC_TM;
-        if (F.tiles_tc.reserve((size_t)ntile * tc_tile_bytes(nf) + 64)) return 1;
-        FZB_CUDA(cudaMemsetAsync(F.tiles_tc.p, 0, (size_t)ntile * tc_tile_bytes(nf), h->stream));
-        TcRecParams T = {};
-        T.m = R.m; T.lnprior = R.lnprior; T.perm = R.perm; T.bins = R.bins; T.invnorm = R.invnorm;
-        T.nm = nm; T.Nf = nf; T.tiles = F.tiles_tc.as<unsigned char>();
-        k_build_tiles_tc<<<(unsigned)((nm + 255) / 256), 256, 0, h->stream>>>(T);
-        fzb_count_launch(h);
-        FZB_CUDA(cudaGetLastError());
-        F.tc_valid = true;
+    if (mode == FM_FS0 && !mm && nf >= 4 && nf <= 6) {
+        // tensor-core sweep tiles; models that are not fp32-representable carry their float64 remainder (MLO)
+        if (fzb_build_tiles_tc(h, R.lnprior, R.bins, R.invnorm, !h->models_f32_exact)) return 1;
     }
     FZB_CUDA(cudaStreamSynchronize(h->stream));
     F.valid = true;
@@ -1313,9 +1158,9 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     if (packed && getenv("FZB_FAST_R")) Robj = atoi(getenv("FZB_FAST_R")) >= 4 ? 4 : 2;
     const int R = packed ? -Robj : Robj;
     const bool mlo = !h->models_f32_exact;
-    // tensor-core sweep (fzb_sweep_tc.cuh): free scale without model errors, fp32-exact models, no model masks
-    const bool use_tc = F.tc_valid && mode == FM_FS0 && h->mask_all_one && !mlo && getenv("FZB_NO_TC") == nullptr;
-    const int64_t tile_objs = use_tc ? (int64_t)TC_OBJS : (int64_t)ft2_of(Robj) * Robj;
+    // tensor-core sweep (fzb_sweep_tc.cuh): free scale without model errors, no model masks
+    const bool use_tc = F.tc_valid && mode == FM_FS0 && h->mask_all_one && getenv("FZB_NO_TC") == nullptr;
+    const int64_t tile_objs = use_tc ? (int64_t)fzb_tc_tile_objects() : (int64_t)ft2_of(Robj) * Robj;
     const int64_t obj_tiles = (chunk_pad + tile_objs - 1) / tile_objs;
     const int64_t ntiles = (nm + TM - 1) / TM;
     // many short waves: small tail (the 256-object CTAs of the tensor-core sweep: 32 waves measured 1.3 % faster than 24)
@@ -1344,7 +1189,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     int32_t* obits = reinterpret_cast<int32_t*>(thr2 + chunk_pad);
     const bool mm = !h->mask_all_one;
     // partial (max, sum, arg-max) per model split; the tensor-core sweep reports TC_SPLIT partials per split
-    const int64_t npart = use_tc ? nsplit * TC_SPLIT : nsplit;
+    const int64_t npart = use_tc ? nsplit * fzb_tc_split() : nsplit;
     if (h->misc[1].reserve((size_t)npart * chunk_pad * 20 + 256)) return 1;
     double* pS = h->misc[1].as<double>();
     double* pM = pS + (size_t)npart * chunk_pad;
@@ -1424,7 +1269,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         int64_t nsafe = 0, nsafe64 = 0, nunsafe = 0;
         if (shard_mode != 2) {
         FZB_CUDA(cudaEventRecord(h->ev[2], h->stream));
-        if (use_tc ? launch_sweep_tc(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, cfg.dim_prior != 0, 1, use_lin)
+        if (use_tc ? fzb_launch_sweep_tc(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, cfg.dim_prior != 0, 1, use_lin, mlo)
                    : launch_sweep(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 1))
             return 1;
         FZB_CUDA(cudaEventRecord(h->ev[3], h->stream));
@@ -1535,7 +1380,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                 SP.No = nsafe; SP.objlist = safe_list; SP.M2 = M2; SP.thr2 = thr2; SP.hist = hist;
                 SP.hist_stride = hist_stride;
                 const int64_t tiles2 = (nsafe + tile_objs - 1) / tile_objs;
-                if (use_tc ? launch_sweep_tc(h, SP, dim3((unsigned)tiles2, (unsigned)nsplit), nf, cfg.dim_prior != 0, 2, use_lin)
+                if (use_tc ? fzb_launch_sweep_tc(h, SP, dim3((unsigned)tiles2, (unsigned)nsplit), nf, cfg.dim_prior != 0, 2, use_lin, mlo)
                            : launch_sweep(h, SP, dim3((unsigned)tiles2, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 2))
                     return 1;
                 h->stats.pairs_fp32 += nsafe * nm;

@@ -38,6 +38,7 @@ struct KdeDev {
     int use_wt, use_cdf;
     double wt_thresh, cdf_thresh;
     long long* err;            // nullable: {flag, model} set when a selected label cannot be placed on the grid
+    int raw;                   // 1: leave the stack of kernels un-normalised (module-level gauss_kde / gauss_kde_dict)
 };
 
 struct GenParams {
@@ -303,6 +304,10 @@ __device__ void row_to_pdf(const double* row, int64_t n, const int64_t* map, con
         else { for (int g = tid; g < k.Ng; g += GT) out_pdf[g] = s_pdf[g]; }
         return;
     }
+    if (k.raw) {
+        for (int g = tid; g < k.Ng; g += GT) out_pdf[g] = s_pdf[g];
+        return;
+    }
     double tot = 0.0;
     for (int g = tid; g < k.Ng; g += GT) tot += s_pdf[g];
     tot = block_sum(tot, red);
@@ -480,6 +485,7 @@ KdeDev make_kde(const fzb_context* h, const FzbConfig& cfg) {
     k.use_cdf = cfg.use_wt_thresh ? 0 : cfg.use_cdf_thresh;
     k.wt_thresh = cfg.wt_thresh;
     k.cdf_thresh = cfg.cdf_thresh;
+    k.raw = cfg.reserved & 1;
     k.err = (h->labels_bad > 0 && h->kde_mode == FZB_KDE_DICT) ? h->kde_err.as<long long>() : nullptr;
     return k;
 }

@@ -1,0 +1,132 @@
+// Pieces shared by the sweep kernels (fzb_fast.cu: packed FP32 and float64 sweeps; fzb_sweep_tc.cu: tensor-core sweep):
+// mbarrier / TMA bulk-copy PTX helpers, packed f32x2 arithmetic, kernel parameter block.
+#pragma once
+#include <cfloat>
+
+#include "fzb_common.cuh"
+
+namespace fzbsweep {
+
+constexpr int TM = 256;          // models per shared-memory tile
+constexpr int NSTAGE = 2;
+constexpr float kHalfLog2e = 0.7213475204444817f;
+
+enum FastMode { FM_FS0 = 0, FM_FX0 = 1, FM_FX1 = 2 };
+
+// ---- PTX helpers: mbarrier + TMA bulk copy ----------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// ---- kernel parameters -------------------------------------------------------------------------
+struct SweepParams {
+    // objects, SoA [field][band][No_pad]
+    const float* od;      // d_hi
+    const float* ow;      // FS0/FX0: mask/err^2        FX1: err^2 (+inf where masked)
+    const float* ox;      // FS0: d*w
+    const float* odl;     // 2 * d_lo
+    const float* oA;      // [No_pad] (dof/2 - 1) or 0
+    const int32_t* obits; // [No_pad] band-mask bits of the object (model-mask variant)
+    float Atab[16];       // model-mask variant: (dof/2 - 1) by pair dimensionality
+    float Ktab[16];       //                     ndim-dependent constant of the ln-likelihood, log2 units
+    int64_t No_pad;
+    int64_t No;           // objects in this launch (pass 1) / entries of objlist (pass 2)
+    // models
+    const float* recs;    // [nm][REC]
+    int64_t nm;
+    int tiles_per_split;
+    int has_prior;
+    // pass 1 outputs: [nsplit][No_pad]
+    double* pM;
+    double* pS;
+    int32_t* pbest;
+    // pass 2
+    const int32_t* objlist;
+    const float* M2;      // [No_pad] final max (log2 units, without the per-object constant)
+    const float* thr2;    // [No_pad] selection cut in the same units
+    float* hist;          // [No_pad][hist_stride]
+    int64_t hist_stride;
+};
+
+
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pack2(float a, float b) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float lo2(f2 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a;
+}
+__device__ __forceinline__ float hi2(f2 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return b;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    f2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    f2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+
+}  // namespace fzbsweep
+
+// ---- tensor-core sweep (fzb_sweep_tc.cu) ----------------------------------------------------------------------------
+// lin: linear-domain form ((dof/2 - 1) = 1); mlo: the tiles carry the float64 remainder of the model fluxes
+int fzb_launch_sweep_tc(fzb_context* h, const fzbsweep::SweepParams& P, dim3 grid, int nf, bool dp, int pass, bool lin,
+                        bool mlo);
+// build the 256-model tiles (MMA operand + packed pairs + KDE tails) from the sorted model order; sets h->fast.tc_valid
+int fzb_build_tiles_tc(fzb_context* h, const double* lnprior, const int32_t* bins, const float* invnorm, bool mlo);
+int fzb_tc_tile_objects();     // objects per CTA of the tensor-core sweep
+int fzb_tc_split();            // partial results per object and model split

@@ -1,0 +1,73 @@
+// Host side of the tensor-core sweep (kernel: fzb_sweep_tc.cuh): tile building and launch dispatch.  Its own
+// translation unit so that the tcgen05 kernels compile beside the packed-FP32 / float64 sweeps of fzb_fast.cu.
+#include <type_traits>
+
+#include "fzb_sweep_common.cuh"
+
+namespace {
+using namespace fzbsweep;
+#include "fzb_sweep_tc.cuh"
+
+template <int NF, bool DP, int PASS, bool LIN, bool MLO>
+int launch_tc_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prior) {
+    const unsigned char* tiles = h->fast.tiles_tc.as<unsigned char>();
+    if (prior) {
+        auto kern = k_sweep_tc<NF, DP, true, PASS, LIN, MLO>;
+        FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(NF, MLO)));
+        kern<<<grid, TC_THREADS, tc_smem(NF, MLO), h->stream>>>(P, tiles, 128u, 256u);
+    } else {
+        auto kern = k_sweep_tc<NF, DP, false, PASS, LIN, MLO>;
+        FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem(NF, MLO)));
+        kern<<<grid, TC_THREADS, tc_smem(NF, MLO), h->stream>>>(P, tiles, 128u, 256u);
+    }
+    fzb_count_launch(h);
+    FZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int NF, bool DP, bool LIN, bool MLO>
+int launch_tc_p(fzb_context* h, const SweepParams& P, dim3 grid, bool prior, int pass) {
+    return pass == 1 ? launch_tc_t<NF, DP, 1, LIN, MLO>(h, P, grid, prior) : launch_tc_t<NF, DP, 2, LIN, MLO>(h, P, grid, prior);
+}
+
+template <bool MLO>
+int launch_tc_m(fzb_context* h, const SweepParams& P, dim3 grid, int nf, bool dp, int pass, bool lin) {
+    const bool prior = P.has_prior != 0;
+    if (nf == 5) {
+        if (lin && dp) return launch_tc_p<5, true, true, MLO>(h, P, grid, prior, pass);
+        if (dp) return launch_tc_p<5, true, false, MLO>(h, P, grid, prior, pass);
+        return launch_tc_p<5, false, false, MLO>(h, P, grid, prior, pass);
+    }
+    if (nf == 4) return dp ? launch_tc_p<4, true, false, MLO>(h, P, grid, prior, pass) : launch_tc_p<4, false, false, MLO>(h, P, grid, prior, pass);
+    if (nf == 6) return dp ? launch_tc_p<6, true, false, MLO>(h, P, grid, prior, pass) : launch_tc_p<6, false, false, MLO>(h, P, grid, prior, pass);
+    fzb_set_error("tensor-core sweep: unsupported filter count %d", nf);
+    return 2;
+}
+
+}  // namespace
+
+int fzb_tc_tile_objects() { return TC_OBJS; }
+int fzb_tc_split() { return TC_SPLIT; }
+
+// lin: linear-domain form, valid when every object handled by the fp32 pass has (dof/2 - 1) = 1 (Nf = 5, dim_prior)
+int fzb_launch_sweep_tc(fzb_context* h, const SweepParams& P, dim3 grid, int nf, bool dp, int pass, bool lin, bool mlo) {
+    return mlo ? launch_tc_m<true>(h, P, grid, nf, dp, pass, lin) : launch_tc_m<false>(h, P, grid, nf, dp, pass, lin);
+}
+
+int fzb_build_tiles_tc(fzb_context* h, const double* lnprior, const int32_t* bins, const float* invnorm, bool mlo) {
+    FastModels& F = h->fast;
+    const int64_t nm = F.nm;
+    const int nf = F.nf;
+    const int64_t ntile = (nm + TC_TM - 1) / TC_TM;
+    const size_t bytes = (size_t)ntile * tc_tile_bytes(nf, mlo);
+    if (F.tiles_tc.reserve(bytes + 64)) return 1;
+    FZB_CUDA(cudaMemsetAsync(F.tiles_tc.p, 0, bytes, h->stream));
+    TcRecParams T = {};
+    T.m = h->models.as<double>(); T.lnprior = lnprior; T.perm = F.perm.as<int32_t>(); T.bins = bins; T.invnorm = invnorm;
+    T.nm = nm; T.Nf = nf; T.mlo = mlo ? 1 : 0; T.tiles = F.tiles_tc.as<unsigned char>();
+    k_build_tiles_tc<<<(unsigned)((nm + 255) / 256), 256, 0, h->stream>>>(T);
+    fzb_count_launch(h);
+    FZB_CUDA(cudaGetLastError());
+    F.tc_valid = true;
+    return 0;
+}

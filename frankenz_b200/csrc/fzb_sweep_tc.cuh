@@ -29,7 +29,9 @@
 //        k-steps 0-1: m_hi | m_lo | m_hi | 0        (paired with  -x_hi | -x_hi | -x_lo | 0,  x = w d, for inter
 //                                                    and with      g_hi |  g_hi |  g_lo | 0,  g = 2 w d_lo, for G)
 //        k-steps 2-3: q_hi | q_lo | q_hi | 0        (q = m^2;     w_hi |  w_hi |  w_lo | 0)
-//   [model pair (128)][6] float2   (m_even, m_odd) per band, then the prior pair   (48 B, three LDS.128)
+//   [model pair (128)][6] float2   (m_even, m_odd) per band, then the prior pair   (48 B, three LDS.128); with MLO
+//        (models that are not fp32-representable, e.g. the float64 grid of simulate.make_model_grid) the float64
+//        remainders (m - float(m))_even/odd per band sit between the bands and the prior (nf more float2)
 //   [model pair (128)]    {invnorm_even, invnorm_odd, bin_even, bin_odd}
 //   [8 models (32)]       {bin of the first, 1 if all eight share it, 1/norm of that bin (same bin = same kernel
 //                          width and grid position = same edge normalisation), -}
@@ -50,20 +52,22 @@ __host__ __device__ constexpr int tc_slot(int nf) { return nf <= 5 ? 5 : nf; }
 __host__ __device__ constexpr int tc_ks(int nf) { return (3 * tc_slot(nf) + 7) / 8; }
 __host__ __device__ constexpr int tc_ksteps(int nf) { return 2 * tc_ks(nf); }      // model operand: m rows, m^2 rows
 __host__ __device__ constexpr int tc_aksteps(int nf) { return 3 * tc_ks(nf); }     // object operand: -x, w, g
-__host__ __device__ constexpr int tc_pairq(int nf) { return (nf + 2) / 2; }        // 16-byte words per model pair: nf bands + prior
+// 16-byte words per model pair: nf bands (+ nf bands of the float64 remainder, MLO) + prior
+__host__ __device__ constexpr int tc_pairq(int nf, bool mlo = false) { return ((mlo ? 2 * nf : nf) + 2) / 2; }
 __host__ __device__ constexpr int tc_opsec(int nf) { return tc_ksteps(nf) * TC_TM * 32; }
-__host__ __device__ constexpr int tc_pairsec(int nf) { return (TC_TM / 2) * 16 * tc_pairq(nf); }
+__host__ __device__ constexpr int tc_pairsec(int nf, bool mlo = false) { return (TC_TM / 2) * 16 * tc_pairq(nf, mlo); }
 constexpr int TC_TAILSEC = (TC_TM / 2) * 16;
 constexpr int TC_SUBSEC = (TC_TM / 8) * 16;        // per 8 models: {KDE bin of the first, 1 if all eight share it, 1/norm of that bin}
-__host__ __device__ constexpr int tc_tile_bytes(int nf) { return tc_opsec(nf) + tc_pairsec(nf) + TC_TAILSEC + TC_SUBSEC; }
+__host__ __device__ constexpr int tc_tile_bytes(int nf, bool mlo = false) { return tc_opsec(nf) + tc_pairsec(nf, mlo) + TC_TAILSEC + TC_SUBSEC; }
 __host__ __device__ constexpr int tc_obja_tile(int nf) { return tc_aksteps(nf) * 128 * 32; }
 __host__ __device__ constexpr int tc_obja_bytes(int nf) { return TC_MT * tc_obja_tile(nf); }
 constexpr int TC_NSTAGE = 2;
 constexpr int TC_CHUNK_COLS = TC_MT * 3 * TC_NC;  // TMEM columns of one chunk buffer
 constexpr int TC_TMEM_COLS = 512;
-__host__ __device__ constexpr size_t tc_smem(int nf) { return (size_t)tc_obja_bytes(nf) + (size_t)TC_NSTAGE * tc_tile_bytes(nf) + 512; }
+__host__ __device__ constexpr size_t tc_smem(int nf, bool mlo = false) { return (size_t)tc_obja_bytes(nf) + (size_t)TC_NSTAGE * tc_tile_bytes(nf, mlo) + 512; }
 static_assert(tc_tile_bytes(5) == 41472 && tc_tile_bytes(5) % 128 == 0 && tc_tile_bytes(6) % 128 == 0, "tile layout");
-static_assert(tc_smem(6) <= 227 * 1024, "shared memory budget");
+static_assert(tc_tile_bytes(4, true) % 128 == 0 && tc_tile_bytes(5, true) % 128 == 0 && tc_tile_bytes(6, true) % 128 == 0, "tile layout");
+static_assert(tc_smem(6, true) <= 227 * 1024, "shared memory budget");
 static_assert(2 * TC_CHUNK_COLS <= TC_TMEM_COLS, "TMEM budget");
 static_assert(TC_SPLIT == 2 && TC_NSUB == 4, "sub-batch assignment below assumes two warpgroups per M-tile, four sub-batches");
 
@@ -129,7 +133,10 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #define TC_TIE8(v) "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])
 
 // chi2 part of one object against a pair of models: sum_b w_b (d_b - s m_b)^2 + K - s G in the units of the weights
-template <int NF>
+// MLO: m = float(m) + m_lo; the residual d - s m is formed with both parts (the second FMA adds -s m_lo to the already
+// cancelled difference, so nothing of the remainder is lost to rounding; the scale itself needs no correction,
+// envelope theorem)
+template <int NF, bool MLO>
 __device__ __forceinline__ f2 tc_pair_c(f2 B2, f2 C2, f2 G2, const f2* __restrict__ m2, const f2* d2, const f2* w2, f2 K2) {
     const f2 rc = pack2(fast_rcp(lo2(C2)), fast_rcp(hi2(C2)));
     const f2 ns = mul2(B2, rc);          // minus the optimal scale (the A operand of the inter product is negated)
@@ -137,16 +144,17 @@ __device__ __forceinline__ f2 tc_pair_c(f2 B2, f2 C2, f2 G2, const f2* __restric
 #pragma unroll
     for (int b = 0; b < NF; ++b) {
         f2 r = fma2(ns, m2[b], d2[b]);
+        if (MLO) r = fma2(ns, m2[NF + b], r);
         f2 t = mul2(r, w2[b]);
         c = fma2(t, r, c);
     }
     return c;
 }
 // ln-likelihood (log2 units, up to the per-object constant); the weights carry -log2(e)/2: c = -chi2 log2(e)/2
-template <int NF, bool DP, bool PRIOR, bool TAIL>
+template <int NF, bool DP, bool PRIOR, bool TAIL, bool MLO>
 __device__ __forceinline__ f2 tc_pair_l(f2 B2, f2 C2, f2 G2, const f2* __restrict__ m2, f2 prior2, const f2* d2, const f2* w2,
                                         f2 K2, f2 A2) {
-    f2 c = tc_pair_c<NF>(B2, C2, G2, m2, d2, w2, K2);
+    f2 c = tc_pair_c<NF, MLO>(B2, C2, G2, m2, d2, w2, K2);
     const f2 cc = c;
     if (PRIOR) c = add2(c, prior2);
     f2 l = c;
@@ -159,12 +167,13 @@ __device__ __forceinline__ float pow2i(float k) {
     return (k >= -126.f) ? __int_as_float(((int)fminf(k, 127.f) + 127) << 23) : 0.f;
 }
 
-template <int NF, bool DP, bool PRIOR, int PASS, bool LIN = false>
+template <int NF, bool DP, bool PRIOR, int PASS, bool LIN = false, bool MLO = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const unsigned char* __restrict__ tiles, uint32_t lbo,
                                                             uint32_t sbo) {
     static_assert(NF >= 1 && NF <= 6, "filters per object");
-    constexpr int SLOT = tc_slot(NF), KS = tc_ks(NF), AKSTEPS = tc_aksteps(NF), PQ = tc_pairq(NF);
-    constexpr int TILE_BYTES = tc_tile_bytes(NF), OPSEC = tc_opsec(NF), PAIRSEC = tc_pairsec(NF);
+    constexpr int SLOT = tc_slot(NF), KS = tc_ks(NF), AKSTEPS = tc_aksteps(NF), PQ = tc_pairq(NF, MLO);
+    constexpr int TILE_BYTES = tc_tile_bytes(NF, MLO), OPSEC = tc_opsec(NF), PAIRSEC = tc_pairsec(NF, MLO);
+    constexpr int PRI = MLO ? 2 * NF : NF;      // position of the prior pair among the float2 of a model pair
     constexpr int OBJA_TILE = tc_obja_tile(NF), OBJA_BYTES = tc_obja_bytes(NF);
     static_assert(!LIN || DP, "the linear-domain form is the dim_prior likelihood with (dof/2 - 1) = 1");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -348,14 +357,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                 f2 m2[2 * PQ];        // the bands of the two models, then the prior pair
 #pragma unroll
                 for (int i = 0; i < PQ; ++i) { const ulonglong2 q = pairs[p * PQ + i]; m2[2 * i] = q.x; m2[2 * i + 1] = q.y; }
-                const f2 prior2 = m2[NF];
+                const f2 prior2 = m2[PRI];
                 const int idx0 = first_i + 2 * p;
                 const f2 B2 = pack2(Bv[2 * jp], Bv[2 * jp + 1]);
                 const f2 C2 = pack2(Cv[2 * jp], Cv[2 * jp + 1]);
                 const f2 G2 = pack2(Gv[2 * jp], Gv[2 * jp + 1]);
                 f2 l;
-                if (SLOW && tail) l = tc_pair_l<NF, DP, PRIOR, true>(B2, C2, G2, m2, prior2, d2, w2, K2, A2);
-                else l = tc_pair_l<NF, DP, PRIOR, false>(B2, C2, G2, m2, prior2, d2, w2, K2, A2);
+                if (SLOW && tail) l = tc_pair_l<NF, DP, PRIOR, true, MLO>(B2, C2, G2, m2, prior2, d2, w2, K2, A2);
+                else l = tc_pair_l<NF, DP, PRIOR, false, MLO>(B2, C2, G2, m2, prior2, d2, w2, K2, A2);
                 const f2 delta = fma2(M2, kMinusOne, l);
                 if (PASS == 1) {
                     const float e0 = fast_ex2(-fabsf(lo2(delta))), e1 = fast_ex2(-fabsf(hi2(delta)));
@@ -402,11 +411,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                 f2 m2[2 * PQ];
 #pragma unroll
                 for (int i = 0; i < PQ; ++i) { const ulonglong2 q = pairs[p * PQ + i]; m2[2 * i] = q.x; m2[2 * i + 1] = q.y; }
-                pr[jp] = m2[NF];
+                pr[jp] = m2[PRI];
                 const f2 B2 = pack2(Bv[2 * jp], Bv[2 * jp + 1]);
                 const f2 C2 = pack2(Cv[2 * jp], Cv[2 * jp + 1]);
                 const f2 G2 = pack2(Gv[2 * jp], Gv[2 * jp + 1]);
-                f2 x = tc_pair_c<NF>(B2, C2, G2, m2, d2, w2, K2);
+                f2 x = tc_pair_c<NF, MLO>(B2, C2, G2, m2, d2, w2, K2);
                 if (SLOW) {      // padding models (beyond the last one) get x = FLT_MAX: weight 0, never the minimum
                     const int cnt_i = 2 * npair_full + (odd ? 1 : 0);
                     x = pack2(2 * p < cnt_i ? lo2(x) : FLT_MAX, 2 * p + 1 < cnt_i ? hi2(x) : FLT_MAX);
@@ -620,6 +629,7 @@ struct TcRecParams {
     const float* invnorm;
     int64_t nm;
     int Nf;
+    int mlo;
     unsigned char* tiles;
 };
 
@@ -628,9 +638,10 @@ __global__ void k_build_tiles_tc(TcRecParams P) {
     if (p >= P.nm) return;
     const int64_t j = P.perm[p];
     const int r = (int)(p % TC_TM);
-    const int nf = P.Nf, slot = tc_slot(nf), ks = tc_ks(nf), pq = tc_pairq(nf);
-    const int opsec = tc_opsec(nf), pairsec = tc_pairsec(nf);
-    unsigned char* T = P.tiles + (size_t)(p / TC_TM) * tc_tile_bytes(nf);
+    const bool mlo = P.mlo != 0;
+    const int nf = P.Nf, slot = tc_slot(nf), ks = tc_ks(nf), pq = tc_pairq(nf, mlo);
+    const int opsec = tc_opsec(nf), pairsec = tc_pairsec(nf, mlo);
+    unsigned char* T = P.tiles + (size_t)(p / TC_TM) * tc_tile_bytes(nf, mlo);
     float rowv[8 * 6];
     for (int i = 0; i < 8 * 6; ++i) rowv[i] = 0.f;
     float* pr = reinterpret_cast<float*>(T + opsec) + (r >> 1) * (4 * pq);
@@ -642,8 +653,9 @@ __global__ void k_build_tiles_tc(TcRecParams P) {
         rowv[b] = mh; rowv[slot + b] = ml; rowv[2 * slot + b] = mh;
         rowv[8 * ks + b] = qh; rowv[8 * ks + slot + b] = ql; rowv[8 * ks + 2 * slot + b] = qh;
         pr[2 * b + (r & 1)] = mf;
+        if (mlo) pr[2 * (nf + b) + (r & 1)] = (float)(v - (double)mf);
     }
-    pr[2 * nf + (r & 1)] = P.lnprior ? (float)(P.lnprior[j] * 1.4426950408889634) : 0.f;
+    pr[2 * (mlo ? 2 * nf : nf) + (r & 1)] = P.lnprior ? (float)(P.lnprior[j] * 1.4426950408889634) : 0.f;
     float* tl = reinterpret_cast<float*>(T + opsec + pairsec) + (r >> 1) * 4;
     tl[r & 1] = P.invnorm ? P.invnorm[p] : 0.f;
     tl[2 + (r & 1)] = __int_as_float(P.bins ? P.bins[p] : -1);

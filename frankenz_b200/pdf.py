@@ -87,35 +87,23 @@ def gaussian_bin(mu, std, bins):
     return cdf[1:] - cdf[:-1]
 
 
-def _kde_selection_sum(y_wt, wt_thresh, cdf_thresh):
-    """Sum of the weights the reference's threshold rule keeps (pdf.py:508-516 / :589-597)."""
-    if wt_thresh is not None:
-        sel = y_wt > (wt_thresh * np.max(y_wt))
-        return float(np.sum(y_wt[sel])), bool(sel.any())
-    idx_sort = np.argsort(y_wt)
-    y_cdf = np.cumsum(y_wt[idx_sort])
-    y_cdf /= y_cdf[-1]
-    sel = idx_sort[y_cdf <= (1. - cdf_thresh)]
-    return float(np.sum(y_wt[sel])), len(sel) > 0
-
-
 def _kde_on_device(ny, y_wt, wt_thresh, cdf_thresh, setup):
-    """Shared body of gauss_kde / gauss_kde_dict: the device KDE kernels work on log-weights of one pseudo-object and
-    return the normalised PDF; the reference returns the un-normalised stack, whose sum is the sum of the kept weights
-    (every kernel is normalised over its window)."""
+    """Shared body of gauss_kde / gauss_kde_dict: the device KDE kernels work on the log-weights of one pseudo-object
+    (weights exp(logwt - levid), levid = ln sum(y_wt)); the un-normalised stack they return is scaled back by
+    exp(levid) = sum(y_wt), which gives the reference's un-normalised PDF."""
     y_wt = np.ones(ny) if y_wt is None else np.asarray(y_wt, dtype=np.float64)
-    total, any_sel = _kde_selection_sum(y_wt, wt_thresh, cdf_thresh)
     eng = Engine(np.zeros((ny, 1)), np.zeros((ny, 1)), np.ones((ny, 1)))
     try:
         setup(eng)
-        if not any_sel or not np.isfinite(total) or total <= 0.:
-            return np.zeros(eng.Ng)
+        if not np.any(y_wt > 0.) or not np.all(np.isfinite(y_wt)):
+            return np.zeros(eng.Ng)         # nothing passes `wt > wt_thresh * max(wt)` (pdf.py:508-516 / :589-597)
         cfg = make_config(None, dict(wt_thresh=wt_thresh, cdf_thresh=cdf_thresh))
+        cfg.reserved = 1
         with np.errstate(divide="ignore"):
-            pdfs, _, _ = eng.predict_logwt(np.log(y_wt)[None, :], cfg)
+            pdfs, _, levid = eng.predict_logwt(np.log(y_wt)[None, :], cfg)
     finally:
         eng.close()
-    return pdfs[0] * total
+    return pdfs[0] * np.exp(levid[0])
 
 
 def gauss_kde(y, y_std, x, dx=None, y_wt=None, sig_thresh=5., wt_thresh=1e-3, cdf_thresh=2e-4, *args, **kwargs):

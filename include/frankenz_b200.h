@@ -45,7 +45,8 @@ typedef struct FzbConfig {
     double  wt_thresh;         /* default 1e-3 */
     double  cdf_thresh;        /* default 2e-4 */
     int32_t precision;         /* FZB_PREC_* */
-    int32_t reserved;
+    int32_t reserved;          /* bit 0 (fzb_predict_logwt only): return the un-normalised stack of kernels with weights
+                                  exp(logwt - levid), as the module-level gauss_kde / gauss_kde_dict do (pdf.py:519-526) */
 } FzbConfig;
 
 enum {
