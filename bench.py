@@ -482,6 +482,34 @@ def run_c3(ctx, grid, steps, e2e, cpu):
                    "objects_per_s": float(ne) * max(1, world) / te,
                    "call": "BruteForce.fit_predict(numpy..., save_fits=False, return_gof=True) -> (No x 701) float64 PDFs"}
 
+    # ---- end to end with the summaries fused behind fit_predict (the PDFs stay on the device) ---------------------
+    res_summ = None
+    if e2e:
+        times, ms_s = [], []
+        for i in range(1 + max(1, min(steps, 3))):
+            barrier()
+            t0 = time.perf_counter()
+            summ, (lm, le) = bf.fit_predict_summarize(xs, xes, xms, labels, labe, label_dict=rdict, return_gof=True,
+                                                      verbose=False, lprob_kwargs=LPROB, return_pdfs=False,
+                                                      rstate=np.random.RandomState(1))
+            t1 = time.perf_counter()
+            if i > 0:
+                times.append(t1 - t0)
+                ms_s.append(eng.stats()["ms_summarize"])
+        ts = float(np.mean(times))
+        if use_dist:
+            tt = torch.tensor([ts], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ts = float(tt.item())
+        d2h_s = int(sum(a.nbytes for est in summ[:4] for a in est) + sum(a.nbytes for a in summ[4]) + summ[5].nbytes
+                    + lm.nbytes + le.nbytes + 3 * lm.nbytes)
+        assert np.all(np.isfinite(summ[0][0][np.isfinite(lm)]))
+        res_summ = {"value": float(ne) * nm * max(1, world) / ts, "unit": "pairs/s", "seconds_per_step": ts,
+                    "h2d_bytes_per_step": int(3 * xs.nbytes + ne * 8 + eng.Ng * eng.Ng * 8), "d2h_bytes_per_step": d2h_s,
+                    "objects_per_s": float(ne) * max(1, world) / ts, "summarize_ms_device": float(np.mean(ms_s)),
+                    "call": "BruteForce.fit_predict(..., summarize=True, return_pdfs=False): fit + PDF + pdfs_summarize "
+                            "on the device, point estimates / intervals / risks out"}
+
     # ---- roofline of the dominant kernel (the fp32 sweep), measured live ------------------------------
     fp32_peak, mufu_peak = eng.measure_peaks(5)
     ms_scan = float(np.mean([s["ms_scan"] for s in st_acc]))
@@ -537,6 +565,7 @@ def run_c3(ctx, grid, steps, e2e, cpu):
     del d_x, d_xe, d_xm
     torch.cuda.empty_cache()
     return {"value": value, "ms_per_step": t_all / steps, "nm": nm, "clocks": clocks, "e2e": res_e2e,
+            "e2e_summaries": res_summ,
             "gpu_launches": launches, "roofline": roofline, "cpu": res_cpu, "grid_note": grid_note}
 
 

@@ -260,6 +260,30 @@ class Engine(object):
                                             dptr(lmap), dptr(levid), iptr(best), dptr(bchi2), dptr(bscale)))
         return pdfs, lmap, levid, best, bchi2, bscale
 
+    def fit_predict_summarize(self, data, data_err, data_mask, cfg, pgrid, loss, urand, renormalize=True,
+                              wconf_frac=0.03, want_pdf=False):
+        """Fused fit + PDF + pdfs_summarize: the PDFs are summarised on the device; they are
+        downloaded only with want_pdf."""
+        x, xe, xm = self._objects(data, data_err, data_mask)
+        if x.shape[1] != self.Nf:
+            raise ValueError("data has %d filters, models have %d" % (x.shape[1], self.Nf))
+        no = len(x)
+        pgrid, loss, urand = f64(pgrid), f64(loss), f64(urand)
+        if len(pgrid) != self.Ng or loss.shape != (self.Ng, self.Ng) or urand.shape != (no,):
+            raise ValueError("summary tables do not match the PDF grid / the number of objects")
+        pdfs = _pinned_pool.empty((no, self.Ng)) if want_pdf else None
+        lmap, levid = np.empty(no), np.empty(no)
+        best = np.empty(no, dtype=np.int64)
+        bchi2, bscale = np.empty(no), np.empty(no)
+        est, sd, conf, risk, quant = (np.empty((4, no)) for _ in range(5))
+        mc = np.empty(no)
+        _lib.check(self.lib.fzb_fit_predict_summarize(
+            self.h, dptr(x), dptr(xe), dptr(xm), no, C.byref(cfg), dptr(pgrid), dptr(loss), dptr(urand),
+            1 if renormalize else 0, float(wconf_frac), dptr(pdfs), dptr(lmap), dptr(levid), iptr(best), dptr(bchi2),
+            dptr(bscale), dptr(est), dptr(sd), dptr(conf), dptr(risk), dptr(quant), dptr(mc)))
+        summary = tuple((est[k], sd[k], conf[k], risk[k]) for k in range(4)) + ((quant[0], quant[1], quant[2], quant[3]), mc)
+        return summary, pdfs, lmap, levid, best, bchi2, bscale
+
     def predict_logwt(self, logwt, cfg, neighbors=None, nneighbors=None):
         """PDFs from a log-weight matrix (bruteforce.py:358-372; knn.py:541-555 with neighbours)."""
         lw = f64(logwt)

@@ -35,7 +35,7 @@ class FzbStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("pairs_fp32", C.c_int64), ("pairs_fp64", C.c_int64),
                 ("objects_fp64", C.c_int64), ("ms_scan", C.c_double), ("ms_accum", C.c_double),
                 ("ms_finish", C.c_double), ("ms_total", C.c_double), ("sweep_kind", C.c_int64),
-                ("knn_redo", C.c_int64), ("pairs_pass2", C.c_int64)]
+                ("knn_redo", C.c_int64), ("pairs_pass2", C.c_int64), ("ms_summarize", C.c_double)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/frankenz_b200.h
@@ -62,6 +62,10 @@ SIGNATURES = {
     "fzb_fit": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, C.c_int64, _CFG, _OUT]),
     "fzb_fit_predict": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, C.c_int64, _CFG, c_double_p, c_double_p,
                                   c_double_p, c_int64_p, c_double_p, c_double_p]),
+    "fzb_fit_predict_summarize": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, C.c_int64, _CFG, c_double_p,
+                                            c_double_p, c_double_p, C.c_int32, C.c_double, c_double_p, c_double_p,
+                                            c_double_p, c_int64_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                            c_double_p, c_double_p, c_double_p, c_double_p]),
     "fzb_fit_predict_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, _CFG, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fzb_predict_logwt": (C.c_int, [_H, c_double_p, C.c_int64, C.c_int64, c_int64_p, c_int64_p, _CFG, c_double_p,

@@ -162,9 +162,20 @@ class BruteForce(object):
     # ---- fit_predict ---------------------------------------------------------------------------
     def fit_predict(self, data, data_err, data_mask, model_labels, model_label_errs, lprob_func=None,
                     label_dict=None, label_grid=None, kde_args=None, kde_kwargs=None, lprob_args=None,
-                    lprob_kwargs=None, return_gof=False, track_scale=False, verbose=True, save_fits=True):
+                    lprob_kwargs=None, return_gof=False, track_scale=False, verbose=True, save_fits=True,
+                    summarize=False, return_pdfs=True, summarize_kwargs=None):
         """Fit and predict in one go (bruteforce.py:374-503).  With `save_fits=False` the
-        (Ndata x Nmodel) arrays are never formed: the fused kernels reduce on the fly."""
+        (Ndata x Nmodel) arrays are never formed: the fused kernels reduce on the fly.
+
+        Extension (not in the reference): `summarize=True` also returns what `pdf.pdfs_summarize` would compute from the
+        PDFs, evaluated on the device while they are still there (see `fit_predict_summarize`); with
+        `return_pdfs=False` the PDFs themselves are not copied to the host."""
+        if summarize:
+            return self.fit_predict_summarize(data, data_err, data_mask, model_labels, model_label_errs,
+                                              lprob_func=lprob_func, label_dict=label_dict, label_grid=label_grid,
+                                              kde_args=kde_args, kde_kwargs=kde_kwargs, lprob_args=lprob_args,
+                                              lprob_kwargs=lprob_kwargs, return_gof=return_gof, verbose=verbose,
+                                              return_pdfs=return_pdfs, **(summarize_kwargs or {}))
         pdfs, lmap, levid = self._fit_predict_all(data, data_err, data_mask, model_labels, model_label_errs,
                                                   lprob_func, label_dict, label_grid, kde_args, kde_kwargs,
                                                   lprob_args, lprob_kwargs, track_scale, save_fits)
@@ -174,6 +185,45 @@ class BruteForce(object):
         if return_gof:
             return pdfs, (lmap, levid)
         return pdfs
+
+    def fit_predict_summarize(self, data, data_err, data_mask, model_labels, model_label_errs, lprob_func=None,
+                              label_dict=None, label_grid=None, kde_args=None, kde_kwargs=None, lprob_args=None,
+                              lprob_kwargs=None, return_gof=False, verbose=True, return_pdfs=False, renormalize=True,
+                              rstate=None, pkern='lorentz', pkern_grid=None, wconf_frac=0.03):
+        """`fit_predict(save_fits=False)` followed by `pdf.pdfs_summarize(pdfs, grid, ...)` (pdf.py:899-1074; demo 3
+        cells 14 + 21) in one call: the point estimates, intervals and risks are computed on the device from PDFs that
+        never leave it, so ~200 bytes per object cross PCIe instead of Ngrid x 8.
+
+        Returns `summary` (the 6-tuple of pdfs_summarize: (mean, std, conf, risk), (median, ...), (mode, ...),
+        (best, ...), (low95, low68, high68, high95), mc), followed by `pdfs` if `return_pdfs` and by `(lmap, levid)` if
+        `return_gof`.  The random draws come from `rstate` one per object in order, like the reference's; the
+        confidence width is the reference's default wconf_func, `wconf_frac * (1 + estimate)`."""
+        _check_args(kde_args, "kde_args")
+        if label_dict is None and label_grid is None:
+            raise ValueError("`label_dict` or `label_grid` must be specified.")
+        eng, cfg = self._setup(lprob_func, lprob_args, lprob_kwargs, False, kde_kwargs)
+        eng.set_kde(model_labels, model_label_errs, label_dict=label_dict, label_grid=label_grid, kde_kwargs=kde_kwargs)
+        clean_inplace(data, data_err, data_mask)
+        pgrid = np.ascontiguousarray(label_dict.grid if label_dict is not None else label_grid, dtype=np.float64)
+        if rstate is None:
+            rstate = np.random
+        nobj = len(data)
+        urand = np.array([rstate.rand() for _ in range(nobj)]) if nobj < 64 else np.ascontiguousarray(rstate.rand(nobj))
+        loss = np.ascontiguousarray(1.0 - _pdf._loss_kernel(pgrid, pkern, pkern_grid), dtype=np.float64)
+        summary, pdfs, lmap, levid, best, bchi2, bscale = eng.fit_predict_summarize(
+            data, data_err, data_mask, cfg, pgrid, loss, urand, renormalize=renormalize, wconf_frac=wconf_frac,
+            want_pdf=return_pdfs)
+        self.best_idx, self.best_chi2, self.best_scale = best, bchi2, bscale
+        self.NDATA = nobj
+        if verbose:
+            sys.stderr.write('\rGenerating PDF {0}/{1}\n'.format(nobj, nobj))
+            sys.stderr.flush()
+        out = (summary,)
+        if return_pdfs:
+            out = out + (pdfs,)
+        if return_gof:
+            out = out + ((lmap, levid),)
+        return out[0] if len(out) == 1 else out
 
     def _fit_predict_all(self, data, data_err, data_mask, model_labels, model_label_errs, lprob_func, label_dict,
                          label_grid, kde_args, kde_kwargs, lprob_args, lprob_kwargs, track_scale, save_fits):

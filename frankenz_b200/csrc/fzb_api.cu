@@ -672,10 +672,19 @@ int fzb_fit_predict_dev(fzb_handle h, const double* d_data, const double* d_err,
 }
 
 // Host-pointer form.  The objects are processed in chunks; the PDFs of chunk c leave through the staged downloader
-// while the kernels of chunk c+1 run, so PCIe and the host memcpy are hidden behind the compute.
-int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, const double* data_mask, int64_t No,
-                    const FzbConfig* cfg, double* pdfs, double* lmap, double* levid, int64_t* best_idx,
-                    double* best_chi2, double* best_scale) {
+// while the kernels of chunk c+1 run, so PCIe and the host memcpy are hidden behind the compute.  With `summ` the PDF
+// rows of every chunk are summarised where they lie (pdf.pdfs_summarize, pdf.py:899-1074) and `pdfs` may be NULL: then
+// 21 doubles per object cross PCIe instead of Ngrid.
+struct SummArgs {
+    const double *pgrid, *loss, *urand;
+    int renormalize;
+    double wfac;
+    double *est, *sd, *conf, *risk, *quant, *mc;
+};
+
+static int fit_predict_host_impl(fzb_context* h, const double* data, const double* data_err, const double* data_mask,
+                                 int64_t No, const FzbConfig* cfg, double* pdfs, double* lmap, double* levid,
+                                 int64_t* best_idx, double* best_chi2, double* best_scale, const SummArgs* summ) {
     if (use_device(h) || check_models(h)) return 2;
     FZB_CHECK(cfg != nullptr, "null config");
     FZB_CHECK(No >= 0, "negative object count");
@@ -692,6 +701,10 @@ int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, co
         h->out_f64[3].reserve((size_t)No * 8) || h->out_f64[4].reserve((size_t)No * 8) ||
         h->out_i64[0].reserve((size_t)No * 8))
         return 1;
+    if (summ) {
+        FZB_CHECK(h->kde_mode != FZB_KDE_NONE && Ng > 0, "summaries need a configured KDE");
+        if (fzb_summarize_tables(h, summ->pgrid, summ->loss, summ->urand, No, Ng)) return 1;
+    }
     const double* d_x = h->obj_in[0].as<double>();
     const double* d_xe = h->obj_in[1].as<double>();
     const double* d_xm = h->obj_in[2].as<double>();
@@ -700,6 +713,7 @@ int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, co
     double* d_bc = h->out_f64[3].as<double>();
     double* d_bs = h->out_f64[4].as<double>();
     int64_t* d_bi = h->out_i64[0].as<int64_t>();
+    const bool want_rows = pdfs != nullptr || summ != nullptr;     // PDF rows are needed on the device
 
     // chunk size: large enough for long CTAs of the sweep kernels (few model splits), small enough to pipeline; the chunks
     // taper towards the end (below), so the size of the main ones does not set the un-hidden tail
@@ -707,7 +721,7 @@ int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, co
     // (an override is rounded up to the 4096-object granularity of the taper below, floor 8192, so that no chunk of the
     // taper exceeds the reserved staging buffers)
     if (const char* e = getenv("FZB_E2E_CHUNK")) chunk = std::max<int64_t>(8192, (atoll(e) + 4095) / 4096 * 4096);
-    if (!pdfs || No <= chunk + chunk / 2) chunk = No;
+    if (!want_rows || No <= chunk + chunk / 2) chunk = No;
     const size_t chunk_bytes = (size_t)chunk * Ng * sizeof(double);
     StagedDownloader dl(h);
     if (pdfs) {
@@ -716,29 +730,42 @@ int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, co
         const bool pinned_dst = cudaPointerGetAttributes(&pa, pdfs) == cudaSuccess && pa.type == cudaMemoryTypeHost;
         cudaGetLastError();
         if (dl.init((size_t)64 << 20, pinned_dst)) return 1;
-        for (int b = 0; b < 2; ++b)
-            if (h->pdf_dev[b].reserve(chunk_bytes)) return 1;
     }
+    if (want_rows)
+        for (int b = 0; b < (pdfs ? 2 : 1); ++b)
+            if (h->pdf_dev[b].reserve(chunk_bytes)) return 1;
     FZB_CUDA(cudaEventRecord(h->ev[0], h->stream));
     int64_t c = 0;
     int64_t push_id[2] = {-1, -1};
     int64_t nc = 0;
+    FzbStats acc = {};
     for (int64_t o0 = 0; o0 < No; o0 += nc, ++c) {
         // the download of the last chunk is the only one nothing hides: taper the chunk size towards the end
         const int64_t rem = No - o0;
         nc = chunk;
         if (pdfs && rem < 2 * chunk) nc = std::max<int64_t>(std::min<int64_t>(rem, 8192), (rem / 2 + 4095) / 4096 * 4096);
         nc = std::min(std::min(nc, rem), chunk);
-        int b = (int)(c & 1);
+        int b = pdfs ? (int)(c & 1) : 0;
         h->prior_o0 = o0;
         // device buffer b was last read by the download of chunk c-2 (issued before that of chunk c-1)
         if (pdfs && c >= 2 && dl.fence_compute(push_id[b])) return 1;
         int rc = fit_predict_dev_impl(h, d_x + o0 * Nf, d_xe + o0 * Nf, d_xm + o0 * Nf, nc, cfg,
-                                      pdfs ? h->pdf_dev[b].as<double>() : nullptr, d_lmap + o0, d_levid + o0, d_bi + o0,
+                                      want_rows ? h->pdf_dev[b].as<double>() : nullptr, d_lmap + o0, d_levid + o0, d_bi + o0,
                                       d_bc + o0, d_bs + o0);
         if (rc) return rc;
+        if (summ) {
+            FZB_CUDA(cudaEventRecord(h->ev[6], h->stream));
+            if (fzb_summarize_rows_dev(h, h->pdf_dev[b].as<double>(), nc, o0, No, Ng, summ->renormalize, summ->wfac)) return 1;
+            FZB_CUDA(cudaEventRecord(h->ev[7], h->stream));
+        }
         if (pdfs && dl.push(pdfs + (size_t)o0 * Ng, h->pdf_dev[b].p, (size_t)nc * Ng * sizeof(double), &push_id[b]))
             return 1;
+        if (summ) {
+            float ms = 0.f;
+            FZB_CUDA(cudaEventSynchronize(h->ev[7]));
+            FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]));
+            h->stats.ms_summarize += ms;
+        }
     }
     FZB_CUDA(cudaEventRecord(h->ev[1], h->stream));
     consume_prior_bins(h);
@@ -746,12 +773,31 @@ int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, co
         download(h, best_idx, d_bi, (size_t)No) || download(h, best_chi2, d_bc, (size_t)No) ||
         download(h, best_scale, d_bs, (size_t)No))
         return 1;
+    if (summ && fzb_summarize_download(h, No, summ->est, summ->sd, summ->conf, summ->risk, summ->quant, summ->mc)) return 1;
     FZB_CUDA(cudaStreamSynchronize(h->stream));
     FZB_CHECK(dl.finish() == 0, "device-to-host copy of the PDFs failed");
     float ms = 0.f;
     FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
     h->stats.ms_total = ms;
     return check_kde_error(h);
+}
+
+int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, const double* data_mask, int64_t No,
+                    const FzbConfig* cfg, double* pdfs, double* lmap, double* levid, int64_t* best_idx,
+                    double* best_chi2, double* best_scale) {
+    return fit_predict_host_impl(h, data, data_err, data_mask, No, cfg, pdfs, lmap, levid, best_idx, best_chi2, best_scale,
+                                 nullptr);
+}
+
+int fzb_fit_predict_summarize(fzb_handle h, const double* data, const double* data_err, const double* data_mask,
+                              int64_t No, const FzbConfig* cfg, const double* pgrid, const double* loss,
+                              const double* urand, int32_t renormalize, double wconf_frac, double* pdfs, double* lmap,
+                              double* levid, int64_t* best_idx, double* best_chi2, double* best_scale, double* est,
+                              double* std, double* conf, double* risk, double* quant, double* mc) {
+    FZB_CHECK(pgrid && loss && urand && est && std && conf && risk && quant && mc, "null summary argument");
+    SummArgs sa = {pgrid, loss, urand, renormalize, wconf_frac, est, std, conf, risk, quant, mc};
+    return fit_predict_host_impl(h, data, data_err, data_mask, No, cfg, pdfs, lmap, levid, best_idx, best_chi2, best_scale,
+                                 &sa);
 }
 
 int fzb_predict_logwt(fzb_handle h, const double* logwt, int64_t No, int64_t W, const int64_t* neighbors,

@@ -205,6 +205,12 @@ int fzb_summarize_impl(fzb_context* h, const double* pdfs, const double* pgrid, 
                        int64_t No, int32_t Ng, int32_t renormalize, double* rowsum, double* est, double* sd, double* risk,
                        double* quant, double* mc);
 int fzb_conf_impl(fzb_context* h, const double* points, const double* widths, int64_t No, double* conf);
+int fzb_summarize_tables(fzb_context* h, const double* pgrid, const double* loss, const double* urand, int64_t No,
+                         int32_t Ng);
+int fzb_summarize_rows_dev(fzb_context* h, const double* d_pdfs, int64_t n, int64_t o0, int64_t Ntot, int32_t Ng,
+                           int32_t renormalize, double wfac);
+int fzb_summarize_download(fzb_context* h, int64_t No, double* est, double* sd, double* conf, double* risk, double* quant,
+                           double* mc);
 
 // ---- model-sharded merge kernels (fzb_shard.cu) --------------------------------------------------
 int fzb_shard_add_offset_launch(fzb_context* h, int64_t* d_best, int64_t No, int64_t offset);

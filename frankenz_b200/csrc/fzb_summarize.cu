@@ -82,6 +82,8 @@ struct SummParams {
     double* rowsum;         // [No]
     double* cdf;            // (No x Ng) out, kept for stage 2
     double *est, *sd, *risk, *quant, *mc;   // [4][Ntot] each (mc: [Ntot]); column offset o0
+    double* conf;           // nullable [4][Ntot]: probability within +-wfac (1 + estimator), the default `wconf_func`
+    double wfac;            // (pdf.py:1038-1062), formed while the CDF is still in shared memory
     int64_t Ntot, o0;
 };
 
@@ -204,7 +206,14 @@ __global__ void __launch_bounds__(ST, 1) k_summarize(SummParams P) {
         }
         if (lane < 5 && lane != 2) P.quant[(size_t)(lane < 2 ? lane : lane - 1) * P.Ntot + q] = qv;
         if (lane == 5) P.mc[q] = qv;
+        if (P.conf && lane < 4) {
+            const double w = (1. + pts[lane]) * P.wfac;
+            const double lo = np_interp(pts[lane] - w, P.pgrid, c, Ng);
+            const double hi = np_interp(pts[lane] + w, P.pgrid, c, Ng);
+            P.conf[(size_t)lane * P.Ntot + q] = hi - lo;
+        }
     }
+    if (P.cdf == nullptr) return;
     __syncthreads();
     for (int i = tid; i < SB * Ng; i += ST) {
         const int oo = i / Ng;
@@ -297,6 +306,50 @@ int fzb_summarize_impl(fzb_context* h, const double* pdfs, const double* pgrid, 
     h->stats.ms_total = ms;
     h->summ_No = No;
     h->summ_Ng = Ng;
+    return 0;
+}
+
+// ---- summaries of PDF rows that are already on the device (fused behind fit_predict) ------------------------------
+// The tables (grid, loss matrix, random numbers) are uploaded once per call by fzb_summarize_tables; every chunk of PDFs
+// is then summarised where it lies, so that only 21 doubles per object cross PCIe instead of Ngrid.
+int fzb_summarize_tables(fzb_context* h, const double* pgrid, const double* loss, const double* urand, int64_t No,
+                         int32_t Ng) {
+    FZB_CHECK(Ng >= 2 && Ng <= ST * SMAXCOL, "pdfs_summarize: grid of %d points (supported: 2..%d)", Ng, ST * SMAXCOL);
+    if (h->summ[0].reserve((size_t)Ng * 8) || h->summ[1].reserve((size_t)Ng * Ng * 8) ||
+        h->summ[3].reserve((size_t)No * 22 * 8 + 64) || h->summ[5].reserve((size_t)No * 8 + 64))
+        return 1;
+    FZB_CUDA(cudaMemcpyAsync(h->summ[0].p, pgrid, (size_t)Ng * 8, cudaMemcpyHostToDevice, h->stream));
+    FZB_CUDA(cudaMemcpyAsync(h->summ[1].p, loss, (size_t)Ng * Ng * 8, cudaMemcpyHostToDevice, h->stream));
+    FZB_CUDA(cudaMemcpyAsync(h->summ[5].p, urand, (size_t)No * 8, cudaMemcpyHostToDevice, h->stream));
+    h->summ_No = 0;      // no CDFs are kept: fzb_pdfs_conf does not apply to a fused run
+    return 0;
+}
+
+// rows [o0, o0 + n) of the batch of Ntot objects; outputs in h->summ[3]: est, sd, risk, quant, conf [4][Ntot], mc [Ntot]
+int fzb_summarize_rows_dev(fzb_context* h, const double* d_pdfs, int64_t n, int64_t o0, int64_t Ntot, int32_t Ng,
+                           int32_t renormalize, double wfac) {
+    double* o_est = h->summ[3].as<double>();
+    SummParams P = {};
+    P.pdfs = d_pdfs; P.pgrid = h->summ[0].as<double>(); P.loss = h->summ[1].as<double>(); P.urand = h->summ[5].as<double>();
+    P.No = n; P.Ng = Ng; P.renorm = renormalize; P.rowsum = nullptr; P.cdf = nullptr;
+    P.est = o_est; P.sd = o_est + 4 * Ntot; P.risk = o_est + 8 * Ntot; P.quant = o_est + 12 * Ntot;
+    P.conf = o_est + 16 * Ntot; P.mc = o_est + 20 * Ntot; P.wfac = wfac; P.Ntot = Ntot; P.o0 = o0;
+    if (Ng <= ST) return launch_summ<1>(h, P, n);
+    if (Ng <= 2 * ST) return launch_summ<2>(h, P, n);
+    if (Ng <= 3 * ST) return launch_summ<3>(h, P, n);
+    return launch_summ<4>(h, P, n);
+}
+
+int fzb_summarize_download(fzb_context* h, int64_t No, double* est, double* sd, double* conf, double* risk, double* quant,
+                           double* mc) {
+    const double* o = h->summ[3].as<double>();
+    const size_t b4 = (size_t)4 * No * 8;
+    FZB_CUDA(cudaMemcpyAsync(est, o, b4, cudaMemcpyDeviceToHost, h->stream));
+    FZB_CUDA(cudaMemcpyAsync(sd, o + 4 * No, b4, cudaMemcpyDeviceToHost, h->stream));
+    FZB_CUDA(cudaMemcpyAsync(risk, o + 8 * No, b4, cudaMemcpyDeviceToHost, h->stream));
+    FZB_CUDA(cudaMemcpyAsync(quant, o + 12 * No, b4, cudaMemcpyDeviceToHost, h->stream));
+    FZB_CUDA(cudaMemcpyAsync(conf, o + 16 * No, b4, cudaMemcpyDeviceToHost, h->stream));
+    FZB_CUDA(cudaMemcpyAsync(mc, o + 20 * No, (size_t)No * 8, cudaMemcpyDeviceToHost, h->stream));
     return 0;
 }
 

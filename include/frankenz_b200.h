@@ -82,6 +82,7 @@ typedef struct FzbStats {
     int64_t knn_redo;          /* kNN: (query, tree) searches the fp32 scan could not prove exact and the float64
                                   kernel re-did from scratch                                                    */
     int64_t pairs_pass2;       /* object-model pairs pass 2 actually evaluated (after sub-batch pruning)       */
+    double  ms_summarize;      /* CUDA-event time of the fused PDF summaries (fzb_fit_predict_summarize)        */
 } FzbStats;
 
 const char* fzb_last_error(void);
@@ -139,6 +140,18 @@ int fzb_fit(fzb_handle h, const double* data, const double* data_err, const doub
 int fzb_fit_predict(fzb_handle h, const double* data, const double* data_err, const double* data_mask,
                     int64_t No, const FzbConfig* cfg, double* pdfs, double* lmap, double* levid,
                     int64_t* best_idx, double* best_chi2, double* best_scale);
+
+/* fzb_fit_predict with pdf.pdfs_summarize (pdf.py:899-1074; demos/3 cell 21, the immediate consumer of the PDFs) applied
+ * to every PDF while it is still on the device: SURVEY.md section 8f rank 2.  pgrid [Ngrid], loss (Ngrid x Ngrid) =
+ * 1 - kernel[truth, guess], urand [No] as for fzb_pdfs_summarize; the confidence width is the reference's default
+ * wconf_func, wconf_frac * (1 + estimator) with wconf_frac = 0.03 (pdf.py:1040-1042).  Outputs (host): est / std / conf /
+ * risk [4][No] for (mean, median, mode, best), quant [4][No] (2.5, 16, 84, 97.5 %), mc [No].  pdfs may be NULL: then only
+ * ~170 + 40 bytes per object leave the device instead of Ngrid x 8. */
+int fzb_fit_predict_summarize(fzb_handle h, const double* data, const double* data_err, const double* data_mask,
+                              int64_t No, const FzbConfig* cfg, const double* pgrid, const double* loss,
+                              const double* urand, int32_t renormalize, double wconf_frac, double* pdfs, double* lmap,
+                              double* levid, int64_t* best_idx, double* best_chi2, double* best_scale, double* est,
+                              double* std, double* conf, double* risk, double* quant, double* mc);
 
 /* Same, all pointers on the device (inputs resident in HBM; used by bench.py "value"
  * and by the multi-GPU driver). */

@@ -77,3 +77,47 @@ def test_resample_and_batching(fz):
         for j in range(4):
             assert np.array_equal(res[k][j][n:2 * n], one[k][j]) or j == 2 or k == 3, (k, j)
     assert np.array_equal(res[4][0][:n], one[4][0]) and np.array_equal(res[4][3][n:2 * n], one[4][3])
+
+
+def test_summaries_fused_behind_fit_predict(sdss_mock):
+    """SURVEY 8f rank 2 as written: fit_predict(..., summarize=True, return_pdfs=False) computes the summaries on the
+    device from PDFs that never reach the host; they must equal pdfs_summarize applied to the PDFs of fit_predict."""
+    import frankenz_b200 as fz
+    from oracle import fz_oracle as fo
+    phot, err, z = sdss_mock
+    m, me, mm = phot[:3000].copy(), err[:3000].copy(), np.ones((3000, 5))
+    x, xe, xm = phot[3500:3900].copy(), err[3500:3900].copy(), np.ones((400, 5))
+    zgrid = np.arange(0, 7 + 1e-5, 0.01)
+    rdict = fz.pdf.PDFDict(zgrid, np.linspace(0.005, 2, 500))
+    labe = np.full(3000, 0.05)
+    for kw in (dict(), dict(free_scale=True, ignore_model_err=True)):
+        bf = fz.BruteForce(m, me, mm)
+        pdfs, (lm, le) = bf.fit_predict(x.copy(), xe.copy(), xm.copy(), z[:3000], labe, label_dict=rdict, return_gof=True,
+                                        verbose=False, save_fits=False, lprob_kwargs=kw)
+        ref = fz.pdf.pdfs_summarize(pdfs.copy(), zgrid, rstate=np.random.RandomState(3))
+        got, (lm2, le2) = bf.fit_predict(x.copy(), xe.copy(), xm.copy(), z[:3000], labe, label_dict=rdict,
+                                         return_gof=True, verbose=False, save_fits=False, lprob_kwargs=kw,
+                                         summarize=True, return_pdfs=False,
+                                         summarize_kwargs=dict(rstate=np.random.RandomState(3)))
+        assert np.array_equal(lm, lm2) and np.allclose(le, le2, rtol=0, atol=1e-9)
+        for a, b in zip(got[:4], ref[:4]):
+            for u, v in zip(a, b):          # estimate, std, conf, risk: the PDFs of two runs differ by fp32 atomics order
+                assert np.allclose(u, v, rtol=0, atol=2e-5), np.max(np.abs(u - v))
+        for u, v in zip(got[4], ref[4]):
+            assert np.allclose(u, v, rtol=0, atol=2e-5)
+        assert np.allclose(got[5], ref[5], rtol=0, atol=2e-5)
+        # with the PDFs returned as well: summaries of exactly those PDFs, so everything but fp rounding is identical
+        got2, p2 = bf.fit_predict_summarize(x.copy(), xe.copy(), xm.copy(), z[:3000], labe, label_dict=rdict,
+                                            lprob_kwargs=kw, verbose=False, return_pdfs=True,
+                                            rstate=np.random.RandomState(3))
+        ref2 = fz.pdf.pdfs_summarize(p2.copy(), zgrid, rstate=np.random.RandomState(3))
+        for a, b in zip(got2[:4], ref2[:4]):
+            assert np.array_equal(a[0], b[0]) and np.allclose(a[1], b[1], rtol=1e-12, atol=0)     # estimate, std
+            assert np.array_equal(a[2], b[2]) and np.allclose(a[3], b[3], rtol=1e-12, atol=1e-15)  # conf, risk
+        for u, v in zip(got2[4], ref2[4]):
+            assert np.array_equal(u, v)
+        assert np.array_equal(got2[5], ref2[5])
+        # oracle (the reference's arithmetic, bit-exact against its golden vectors) on the same PDFs
+        oref = fo.pdfs_summarize(p2.copy(), zgrid, rstate=np.random.RandomState(3))
+        for a, b in zip(got2[:4], oref[:4]):
+            assert np.allclose(a[0], b[0], rtol=0, atol=1e-12) and np.allclose(a[3], b[3], rtol=1e-10, atol=1e-12)
