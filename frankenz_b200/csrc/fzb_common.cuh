@@ -76,6 +76,8 @@ struct FastModels {
     DevBuf perm;           // int32 [nm_pad]: sorted position -> original model index (-1 = padding)
     DevBuf bins;           // int32 [nm_pad]: KDE histogram bin (slot*Ng + pos) of each sorted model, -1 = none
     DevBuf invnorm;        // float [nm_pad]: 1 / kernel normalisation of each sorted model
+    DevBuf live;           // pass-2 pruning: live bits of the tensor-core sweep, [model tile x half][object] uint16
+    DevBuf sortbuf;        // keys / values / temporary storage of the sort of the pass-2 object list
     int nslot = 0;         // distinct dictionary widths in use
     std::vector<int32_t> slot_sidx;  // slot -> dictionary index
     DevBuf d_slot_sidx;
@@ -199,6 +201,10 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                              const FzbConfig& cfg, double* d_pdfs, double* d_lmap, double* d_levid,
                              int64_t* d_best_idx, double* d_best_chi2, double* d_best_scale, int shard_mode = 0,
                              double* d_psum = nullptr, const double* d_glmap = nullptr);
+
+// pass-2 object order of the tensor-core sweep (fzb_prune.cu)
+int fzb_sort_by_live_bits(fzb_context* h, const unsigned short* live, int64_t nrows, int64_t No_pad, int32_t* list,
+                          int64_t n);
 
 // ---- PDF summaries (fzb_summarize.cu) ---------------------------------------------------------
 int fzb_summarize_impl(fzb_context* h, const double* pdfs, const double* pgrid, const double* loss, const double* urand,

@@ -1203,6 +1203,14 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     int32_t* counts = h->misc[3].as<int32_t>();
     if (kde && h->misc[4].reserve((size_t)chunk_pad * hist_stride * 4 + 256)) return 1;
     float* hist = kde ? h->misc[4].as<float>() : nullptr;
+    // pass-2 pruning of the tensor-core sweep: live bits [model tile][half][object], sort keys of the safe list
+    const bool prune = use_tc && kde && cfg.use_wt_thresh && getenv("FZB_NO_PRUNE") == nullptr;
+    unsigned short* live = nullptr;
+    if (prune) {
+        if (h->fast.live.reserve((size_t)ntiles * fzb_tc_split() * chunk_pad * sizeof(unsigned short) + 256)) return 1;
+        live = h->fast.live.as<unsigned short>();
+        if (h->fast.sortbuf.reserve((size_t)chunk_pad * 16 + 256)) return 1;
+    }
     if (F.aux64.reserve((size_t)chunk_pad * 40 + 64)) return 1;
     double* M2d = F.aux64.as<double>();
     double* thr2d = M2d + chunk_pad;
@@ -1265,6 +1273,8 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         SP.recs = F.recs.as<float>(); SP.nm = nm; SP.has_prior = h->has_lnprior ? 1 : 0;
         SP.tiles_per_split = tiles_per_split;
         SP.pM = pM; SP.pS = pS; SP.pbest = pbest;
+        SP.live = live;
+        SP.live_thr = cfg.use_wt_thresh ? (float)(cfg.wt_thresh * (1.0 - 1e-4)) : 0.f;
         const int64_t tiles1 = (nc + tile_objs - 1) / tile_objs;
         int64_t nsafe = 0, nsafe64 = 0, nunsafe = 0;
         if (shard_mode != 2) {
@@ -1344,6 +1354,8 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             if (nunsafe > 0 && fzb_generic_shard_pass1_dev(h, d_x, d_xe, d_xm, No, unsafe_list, nunsafe, cfg, d_lmap,
                                                            d_psum, d_best_idx))
                 return 1;
+            if (prune && nsafe > 0 && fzb_sort_by_live_bits(h, live, ntiles * fzb_tc_split(), nc_pad, safe_list, nsafe))
+                return 1;
             h->shard_valid = true;
             h->shard_No = No;
             h->shard_counts[0] = (int)nsafe; h->shard_counts[1] = (int)nunsafe; h->shard_counts[3] = (int)nsafe64;
@@ -1377,6 +1389,13 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             FZB_CUDA(cudaEventRecord(h->ev[4], h->stream));
             FZB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nc_pad * hist_stride * 4, h->stream));
             if (nsafe > 0) {
+                if (prune && shard_mode != 2 &&
+                    fzb_sort_by_live_bits(h, live, ntiles * fzb_tc_split(), nc_pad, safe_list, nsafe))
+                    return 1;       // objects with similar survivor sets share a warp (sharded pass 2: sorted by pass 1)
+                if (prune) {
+                    FZB_CUDA(cudaMemsetAsync(counts + 8, 0, 8, h->stream));
+                    SP.pairs_done = reinterpret_cast<unsigned long long*>(counts + 8);
+                }
                 SP.No = nsafe; SP.objlist = safe_list; SP.M2 = M2; SP.thr2 = thr2; SP.hist = hist;
                 SP.hist_stride = hist_stride;
                 const int64_t tiles2 = (nsafe + tile_objs - 1) / tile_objs;
@@ -1420,7 +1439,12 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             }
             FZB_CUDA(cudaGetLastError());
             FZB_CUDA(cudaEventRecord(h->ev[6], h->stream));
+            unsigned long long pdone = 0;
+            if (prune && nsafe > 0)
+                FZB_CUDA(cudaMemcpyAsync(&pdone, counts + 8, 8, cudaMemcpyDeviceToHost, h->stream));
             FZB_CUDA(cudaStreamSynchronize(h->stream));
+            h->stats.pairs_pass2 += (prune && nsafe > 0) ? (int64_t)pdone : nsafe * nm;
+            h->stats.pairs_pass2 += nsafe64 * nm;
             FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));
             h->stats.ms_accum += ms;
             FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]));

@@ -84,6 +84,12 @@ struct SweepParams {
     const float* thr2;    // [No_pad] selection cut in the same units
     float* hist;          // [No_pad][hist_stride]
     int64_t hist_stride;
+    // pass-2 pruning (tensor-core sweep): one bit per (object, 8-model sub-batch), set by pass 1 when a weight of the
+    // sub-batch exceeds live_thr times the running maximum (a superset of the final wt_thresh selection, the running
+    // maximum only grows); layout [model tile][half][No_pad] uint16, bit = 2 * chunk + k.  Null: no pruning.
+    unsigned short* live;
+    float live_thr;
+    unsigned long long* pairs_done;   // pass 2: object-model pairs actually evaluated (statistics)
 };
 
 

@@ -334,6 +334,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + mt * (3 * TC_NC);
         int cur_bin = -1;
         uint32_t gch = 0;
+        uint32_t lbits = 0;                    // pass 1: live sub-batches of the current tile; pass 2: those of the warp
+        unsigned long long npairs = 0;
         auto flush = [&](float v, int bin) {
             if (v != 0.f && oidx >= 0) atomicAdd(P.hist + (int64_t)oidx * P.hist_stride + bin, v);
         };
@@ -402,6 +404,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
         // and a plain max.  Pass 1 keeps R per object (integer valued, so that a change of R rescales the sums by an
         // exact power of two) and lowers it whenever the largest weight passes 2^8; a jump beyond 2^24 (or an
         // overflow) has the weights of the sub-batch formed again in a frame at its minimum.  Pass 2 uses R = -M.
+        uint32_t live_bit = 0;                 // bit of the sub-batch being processed
         auto process_lin = [&](auto slow_tag, const int p0, float (&Bv)[8], float (&Cv)[8], float (&Gv)[8]) {
             constexpr bool SLOW = decltype(slow_tag)::value;
             f2 xs[4], pr[4];
@@ -466,6 +469,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                     weights();
                 }
                 S2 = add2(S2, Ssub);
+                if (P.live && ysub > P.live_thr * lo2(M2)) lbits |= live_bit;     // may pass the final cut: pass 2 looks
                 const float Yt = hi2(M2);
                 if (__any_sync(0xffffffffu, ysub > Yt)) {
                     float Ym = lo2(M2);
@@ -526,8 +530,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                 }
             }
         };
+        // pass 2: the live bits of the next tile are fetched while the current one is processed
+        uint32_t live_next = 0;
+        if (PASS == 2 && P.live && oidx >= 0 && nt > 0)
+            live_next = P.live[((size_t)t0 * TC_SPLIT + half) * (size_t)P.No_pad + oidx];
         for (int it = 0; it < nt; ++it) {
             const int st = it % TC_NSTAGE, n = it / TC_NSTAGE;
+            const uint32_t live_mine = live_next;
+            if (PASS == 2 && P.live && oidx >= 0 && it + 1 < nt)
+                live_next = P.live[((size_t)(t0 + it + 1) * TC_SPLIT + half) * (size_t)P.No_pad + oidx];
             mbar_wait_hint(&tile_full[st], (uint32_t)(n & 1));
             const unsigned char* tile = stage + (size_t)st * TILE_BYTES;
             pairs = reinterpret_cast<const ulonglong2*>(tile + OPSEC);
@@ -539,24 +550,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
             first_i = (int)first;
             npair_full = cnt >> 1;
             odd = (cnt & 1) != 0;
+            const size_t live_at = ((size_t)(t0 + it) * TC_SPLIT + half) * (size_t)P.No_pad;
+            if (PASS == 2) {
+                // sub-batches in which some object of this warp may have a model above the cut (bits of pass 1)
+                lbits = 0xffffffffu;
+                if (P.live) lbits = __reduce_or_sync(0xffffffffu, (oidx >= 0) ? live_mine : 0u);
+            } else {
+                lbits = 0;
+            }
             for (int ch = 0; ch < nch; ++ch, ++gch) {
                 const uint32_t buf = gch & 1, use = gch >> 1;
                 mbar_wait_hint(&acc_full[mt * 2 + buf], use & 1);
                 tc_fence_after();
                 const uint32_t cbase = lane_addr + buf * TC_CHUNK_COLS;
+                if (PASS == 2 && ((lbits >> (2 * ch)) & 3u) == 0u) {      // warp-uniform: nothing of this chunk survives
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[mt * 2 + buf]);
+                    continue;
+                }
 #pragma unroll
                 for (int k = 0; k < TC_NSUB / TC_SPLIT; ++k) {
                     const int sub = half + TC_SPLIT * k;          // this warpgroup's sub-batches of the chunk
+                    live_bit = 1u << (2 * ch + k);
+                    const bool dead = (PASS == 2) && (lbits & live_bit) == 0u;     // warp-uniform
                     float Bv[8], Cv[8], Gv[8];
-                    tmem_ld8(cbase + sub * 8, Bv);
-                    tmem_ld8(cbase + TC_NC + sub * 8, Cv);
-                    tmem_ld8(cbase + 2 * TC_NC + sub * 8, Gv);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" : TC_TIE8(Bv), TC_TIE8(Cv), TC_TIE8(Gv)::"memory");
+                    if (!dead) {
+                        tmem_ld8(cbase + sub * 8, Bv);
+                        tmem_ld8(cbase + TC_NC + sub * 8, Cv);
+                        tmem_ld8(cbase + 2 * TC_NC + sub * 8, Gv);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" : TC_TIE8(Bv), TC_TIE8(Cv), TC_TIE8(Gv)::"memory");
+                    }
                     if (k == TC_NSUB / TC_SPLIT - 1) {   // everything this warp needs of the chunk is in registers
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_empty[mt * 2 + buf]);
                     }
+                    if (dead) continue;
+                    if (PASS == 2) npairs += 8;
                     const int p0 = ch * (TC_NC / 2) + sub * 4;
                     // fast path: four complete model pairs and (pass 2) one KDE bin for all eight models -> one
                     // branch-free block in which the chains of the four pair evaluations interleave
@@ -578,6 +609,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                         else process(std::true_type{}, p0, Bv, Cv, Gv);
                     }
                 }
+            }
+            if (PASS == 1 && P.live) {
+                const int64_t slot = tile_base + (int64_t)mt * 128 + row;
+                if (slot < P.No_pad) P.live[live_at + slot] = (unsigned short)(LIN ? lbits : 0xffffu);
             }
             if (PASS == 1 && LIN) {
                 Sd += (double)(lo2(S2) + hi2(S2));
@@ -611,8 +646,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                     P.pbest[q] = (m0 > m1) ? best0 : ((m1 > m0) ? best1 : min(best0, best1));
                 }
             }
-        } else if (cur_bin >= 0) {
-            flush(lo2(acc2) + hi2(acc2), cur_bin);
+        } else {
+            if (cur_bin >= 0) flush(lo2(acc2) + hi2(acc2), cur_bin);
+            if (P.pairs_done) {
+                const unsigned long long mine = (oidx >= 0) ? npairs : 0ull;
+                unsigned long long tot = mine;
+                for (int sft = 16; sft > 0; sft >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, sft);
+                if (lane == 0 && tot) atomicAdd(P.pairs_done, tot);
+            }
         }
     }
     tc_fence_before();
