@@ -373,7 +373,7 @@ int fzb_destroy(fzb_handle h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->models, &h->models_err, &h->models_mask, &h->lnprior, &h->prior_table, &h->prior_bins, &h->widths, &h->koff, &h->kernels,
                       &h->kcdf, &h->yidx, &h->ysidx, &h->grid, &h->y, &h->ystd, &h->lowers, &h->uppers, &h->rows,
-                      &h->knn_feats, &h->knn_cand, &h->knn_redo, &h->kde_err, &h->summ[0], &h->summ[1], &h->summ[2], &h->summ[3], &h->summ[4], &h->summ[5], &h->fast.recs, &h->fast.tiles_tc, &h->fast.recs64, &h->fast.aux64, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
+                      &h->knn_feats, &h->knn_cand, &h->knn_redo, &h->knn_tiles, &h->knn_aux, &h->kde_err, &h->summ[0], &h->summ[1], &h->summ[2], &h->summ[3], &h->summ[4], &h->summ[5], &h->fast.recs, &h->fast.tiles_tc, &h->fast.recs64, &h->fast.aux64, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
                       &h->fast.d_slot_sidx, &h->fast.live, &h->fast.sortbuf};
     for (auto* b : bufs) b->release();
     for (auto& b : h->obj_in) b.release();
@@ -940,6 +940,8 @@ int fzb_knn_build(fzb_handle h, const float* feats, int32_t K, int64_t Nm, int32
     h->knn_K = K;
     h->knn_Nm = Nm;
     h->knn_Nf = Nf;
+    h->knn_tc_valid = false;
+    if (getenv("FZB_KNN_TC") != nullptr && atoi(getenv("FZB_KNN_TC")) != 0 && fzb_knn_tc_build(h)) return 1;
     return 0;
 }
 

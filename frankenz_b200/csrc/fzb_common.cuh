@@ -160,6 +160,10 @@ struct fzb_context {
     // kNN
     DevBuf knn_feats;       // float32 K x Nm x Nf (+ 64 B pad)
     DevBuf knn_cand, knn_redo;
+    DevBuf knn_tiles;       // tensor-core scan: centred, tf32-split row tiles of every tree (fzb_knn_tc.cu)
+    DevBuf knn_aux;         // double: centre [FZB_FAST_MAXF], max |f'|^2 per tree [K]
+    bool knn_tc_valid = false;
+    int64_t knn_ntile = 0;
     int knn_K = 0;
     int64_t knn_stride = 0;  // floats between consecutive trees (16-byte aligned, >= Nm*Nf + 3)
     int64_t knn_Nm = 0;
@@ -226,5 +230,10 @@ int fzb_shard_normalise_launch(fzb_context* h, const float* d_rows, int64_t n, i
 
 // ---- kNN (fzb_knn.cu) -------------------------------------------------------------------------
 int fzb_knn_query_dev(fzb_context* h, const double* d_q, int64_t No, int k, double p, int64_t* d_idx, double* d_dist);
+int fzb_knn_tc_build(fzb_context* h);
+int fzb_knn_tc_kcmax();
+int fzb_knn_tc_lists();
+int fzb_knn_tc_scan(fzb_context* h, const double* d_q, int64_t No, int KC, int nsp, int tiles_per_split, float* cand_d,
+                    int* cand_i);
 int fzb_knn_union_dev(fzb_context* h, const int64_t* d_idx, int64_t No, int Kk, int64_t* d_neighbors,
                       int64_t* d_nneighbors);

@@ -275,10 +275,14 @@ __global__ void __launch_bounds__(KS_T, 2) k_knn_scan(const float* __restrict__ 
 }
 
 // one warp per (query, tree): exact float64 distances of the candidates, order by (distance, index), verify
+// tc_aux != null: the candidates come from the tensor-core scan (fzb_knn_tc.cu): cand_d holds v = |f'|^2 - 2 f'.q' in the
+// frame centred on tc_aux[0..NF) and its error is absolute, |v - v_true| <= tc_c0 (|q'|^2 + max_j |f'_j|^2)
+// (tc_aux[FZB_FAST_MAXF + tree] = that maximum); tc_stat receives the largest error seen, in the same units.
 __global__ void k_knn_rerank(const float* __restrict__ feats, int64_t tstride, int K, int64_t Nm, int NF, const double* __restrict__ q,
                              int64_t No, int k, int KC, int nsp, const float* __restrict__ cand_d,
                              const int* __restrict__ cand_i, int64_t* __restrict__ out_idx,
-                             double* __restrict__ out_dist, int64_t* __restrict__ redo, int* __restrict__ n_redo) {
+                             double* __restrict__ out_dist, int64_t* __restrict__ redo, int* __restrict__ n_redo,
+                             const double* __restrict__ tc_aux, double tc_c0, unsigned long long* __restrict__ tc_stat) {
     extern __shared__ double rs[];
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, w = threadIdx.x >> 5;
     const int C = KC * nsp;
@@ -290,12 +294,17 @@ __global__ void k_knn_rerank(const float* __restrict__ feats, int64_t tstride, i
     const int t = (int)(item % K);
     const float* F = feats + (size_t)t * tstride;
     const size_t base = (size_t)item * C;
-    double qn = 0.0;
-    for (int b = 0; b < NF; ++b) qn += q[o * NF + b] * q[o * NF + b];
+    double qn = 0.0, qc = 0.0;
+    for (int b = 0; b < NF; ++b) {
+        qn += q[o * NF + b] * q[o * NF + b];
+        if (tc_aux) { const double d = q[o * NF + b] - tc_aux[b]; qc += d * d; }
+    }
     const double eq = sqrt(qn) * 5.9604644775390625e-08;     // 2^-24 |q|
+    const double tc_scale = tc_aux ? qc + tc_aux[FZB_FAST_MAXF + t] : 0.0;
+    double worst = 0.0;
     float tau = CUDART_INF_F;          // smallest per-split threshold = smallest fp32 distance of any excluded row
     for (int s = 0; s < nsp; ++s) {
-        float mx = 0.f;
+        float mx = -CUDART_INF_F;
         for (int c = lane; c < KC; c += 32) mx = fmaxf(mx, cand_d[base + (size_t)s * KC + c]);
         for (int sh = 16; sh > 0; sh >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, sh));
         tau = fminf(tau, mx);
@@ -312,9 +321,15 @@ __global__ void k_knn_rerank(const float* __restrict__ feats, int64_t tstride, i
             }
             if (isnan(acc)) acc = CUDART_INF;
             ++nvalid;
+            if (tc_aux && isfinite(acc)) worst = fmax(worst, fabs((double)cand_d[base + c] + qc - acc));
         }
         sd[c] = acc;
         si[c] = r >= 0 ? r : 0x7fffffffffffffffll;
+    }
+    if (tc_aux && tc_stat) {
+        worst = tc_scale > 0.0 ? worst / tc_scale : 0.0;
+        for (int sh = 16; sh > 0; sh >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, sh));
+        if (lane == 0 && worst > 0.0) atomicMax(tc_stat, (unsigned long long)__double_as_longlong(worst));
     }
     for (int sh = 16; sh > 0; sh >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, sh);
     __syncwarp();
@@ -336,8 +351,12 @@ __global__ void k_knn_rerank(const float* __restrict__ feats, int64_t tstride, i
     // accept only if no excluded row can belong to the top k
     bool ok = nvalid >= k && isfinite(dk);
     if (ok && !isinf(tau)) {
-        double dmin_excl = sqrt((double)tau * (1.0 - 5e-7)) - eq;
-        ok = sqrt(dk) < dmin_excl;
+        if (tc_aux) {
+            ok = dk * (1.0 + 1e-12) < (double)tau + qc - tc_c0 * tc_scale;
+        } else {
+            double dmin_excl = sqrt((double)tau * (1.0 - 5e-7)) - eq;
+            ok = sqrt(dk) < dmin_excl;
+        }
     }
     if (!ok && lane == 0) redo[atomicAdd(n_redo, 1)] = item;
 }
@@ -398,62 +417,82 @@ static int knn_scan_launch(fzb_context* h, const double* d_q, int64_t No, int KC
     return 0;
 }
 
+// error bound of the tensor-core scan's v, in units of (|q'|^2 + max |f'|^2): see fzb_knn_tc.cu
+static double env_c0() {
+    const char* e = getenv("FZB_KNN_TC_C0");
+    return e ? atof(e) : 4e-6;
+}
+
 int fzb_knn_query_dev(fzb_context* h, const double* d_q, int64_t No, int k, double p, int64_t* d_idx, double* d_dist) {
     int pmode = (p == 2.0) ? 2 : (p == 1.0) ? 1 : (!(p > 0) || std::isinf(p)) ? 0 : 3;
     const int nf = h->knn_Nf;
     const int K = h->knn_K;
     const int64_t Nm = h->knn_Nm;
     const int KC = k + 8;
-    const bool fast = pmode == 2 && nf >= 4 && nf <= 6 && KC <= KS_KCMAX && Nm >= 4096 && Nm < ((int64_t)1 << 31) &&
-                      getenv("FZB_KNN_EXACT_ONLY") == nullptr;
+    // tensor-core candidate scan (fzb_knn_tc.cu): measured SLOWER than the fp32 CUDA-core scan on B200 (1.24e12 against
+    // 1.42e12 distance evaluations/s at 1M rows x 20 trees: every accumulator has to be read back from TMEM at 64 B/clk/SM),
+    // so it is opt-in (FZB_KNN_TC=1) and the CUDA-core scan is the product path
+    const bool use_tc = pmode == 2 && h->knn_tc_valid && KC <= fzb_knn_tc_kcmax() && getenv("FZB_KNN_EXACT_ONLY") == nullptr;
+    const bool fast = use_tc || (pmode == 2 && nf >= 4 && nf <= 6 && KC <= KS_KCMAX && Nm >= 4096 &&
+                                 Nm < ((int64_t)1 << 31) && getenv("FZB_KNN_EXACT_ONLY") == nullptr);
     if (!fast) return knn_exact_launch(h, d_q, No, k, p, pmode, d_idx, d_dist, nullptr, nullptr, No * K);
 
     // row splits so that small query batches still fill the GPU
-    int64_t qtiles = (No + KS_T * KS_R - 1) / (KS_T * KS_R);
-    int64_t want = (int64_t)h->sm_count * 8;
+    const int64_t qper = use_tc ? 128 : KS_T * KS_R, rtile = use_tc ? 256 : KS_TM;
+    int64_t qtiles = (No + qper - 1) / qper;
+    int64_t want = (int64_t)h->sm_count * (use_tc ? 2 : 8);
     int64_t nsp = (want + qtiles * K - 1) / (qtiles * K);
-    int64_t max_sp = (Nm + 4 * KS_TM - 1) / (4 * KS_TM);
+    int64_t max_sp = (Nm + 4 * rtile - 1) / (4 * rtile);
     if (nsp > max_sp) nsp = max_sp;
     if (nsp > 32) nsp = 32;
     if (nsp < 1) nsp = 1;
-    int64_t rows_per_split = ((Nm + nsp - 1) / nsp + KS_TM - 1) / KS_TM * KS_TM;
+    int64_t rows_per_split = ((Nm + nsp - 1) / nsp + rtile - 1) / rtile * rtile;
     nsp = (Nm + rows_per_split - 1) / rows_per_split;
     // process the queries in chunks that bound the candidate buffers (~2 GB)
-    size_t per_q = (size_t)K * nsp * KC * 8;
+    const int nlist = (int)nsp * (use_tc ? fzb_knn_tc_lists() : 1);     // candidate lists per (query, tree)
+    size_t per_q = (size_t)K * nlist * KC * 8;
     int64_t chunk = (int64_t)(((size_t)2 << 30) / per_q);
     if (chunk < KS_T * KS_R) chunk = KS_T * KS_R;
     if (chunk > No) chunk = No;
     if (h->knn_cand.reserve((size_t)chunk * per_q + 256) || h->knn_redo.reserve((size_t)chunk * K * 8 + 64)) return 1;
     float* cand_d = h->knn_cand.as<float>();
-    int* cand_i = reinterpret_cast<int*>(cand_d + (size_t)chunk * K * nsp * KC);
+    int* cand_i = reinterpret_cast<int*>(cand_d + (size_t)chunk * K * nlist * KC);
     int* n_redo = h->knn_redo.as<int>();
     int64_t* redo = reinterpret_cast<int64_t*>(n_redo + 4);
     for (int64_t o0 = 0; o0 < No; o0 += chunk) {
         int64_t nc = No - o0 < chunk ? No - o0 : chunk;
         const double* qq = d_q + o0 * nf;
-        int rc = nf == 4 ? knn_scan_launch<4>(h, qq, nc, KC, (int)nsp, rows_per_split, cand_d, cand_i)
+        int rc = use_tc ? fzb_knn_tc_scan(h, qq, nc, KC, (int)nsp, (int)(rows_per_split / rtile), cand_d, cand_i)
+               : nf == 4 ? knn_scan_launch<4>(h, qq, nc, KC, (int)nsp, rows_per_split, cand_d, cand_i)
                : nf == 5 ? knn_scan_launch<5>(h, qq, nc, KC, (int)nsp, rows_per_split, cand_d, cand_i)
                          : knn_scan_launch<6>(h, qq, nc, KC, (int)nsp, rows_per_split, cand_d, cand_i);
         if (rc) return rc;
         FZB_CUDA(cudaMemsetAsync(n_redo, 0, 16, h->stream));
         const int wpb = 4;
-        size_t smem = (size_t)wpb * KC * nsp * 16;
+        size_t smem = (size_t)wpb * KC * nlist * 16;
         FZB_CHECK(smem <= 200 * 1024, "kNN re-rank: too many candidates");
         FZB_CUDA(cudaFuncSetAttribute(k_knn_rerank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int64_t items = nc * K;
         k_knn_rerank<<<(unsigned)((items + wpb - 1) / wpb), wpb * 32, smem, h->stream>>>(
-            h->knn_feats.as<float>(), h->knn_stride, K, Nm, nf, qq, nc, k, KC, (int)nsp, cand_d, cand_i, d_idx + (size_t)o0 * K * k,
-            d_dist ? d_dist + (size_t)o0 * K * k : nullptr, redo, n_redo);
+            h->knn_feats.as<float>(), h->knn_stride, K, Nm, nf, qq, nc, k, KC, nlist, cand_d, cand_i, d_idx + (size_t)o0 * K * k,
+            d_dist ? d_dist + (size_t)o0 * K * k : nullptr, redo, n_redo, use_tc ? h->knn_aux.as<double>() : nullptr,
+            env_c0(), use_tc ? reinterpret_cast<unsigned long long*>(n_redo + 2) : nullptr);
         fzb_count_launch(h);
         FZB_CUDA(cudaGetLastError());
         // the rare (query, tree) pairs that failed the exactness test are re-done by the float64 kernel
         if (knn_exact_launch(h, qq, nc, k, p, pmode, d_idx + (size_t)o0 * K * k,
                              d_dist ? d_dist + (size_t)o0 * K * k : nullptr, redo, n_redo, 4096))
             return 1;
-        int nr = 0;
-        FZB_CUDA(cudaMemcpyAsync(&nr, n_redo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        int nr[4] = {0, 0, 0, 0};
+        FZB_CUDA(cudaMemcpyAsync(nr, n_redo, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         FZB_CUDA(cudaStreamSynchronize(h->stream));
-        h->stats.knn_redo += nr;
+        h->stats.knn_redo += nr[0];
+        if (use_tc) {
+            double w;
+            memcpy(&w, nr + 2, 8);
+            if (w > h->stats.knn_tc_err) h->stats.knn_tc_err = w;
+        }
+        h->stats.knn_tc = use_tc ? 1 : 0;
     }
     return 0;
 }

@@ -83,6 +83,9 @@ typedef struct FzbStats {
                                   kernel re-did from scratch                                                    */
     int64_t pairs_pass2;       /* object-model pairs pass 2 actually evaluated (after sub-batch pruning)       */
     double  ms_summarize;      /* CUDA-event time of the fused PDF summaries (fzb_fit_predict_summarize)        */
+    int64_t knn_tc;            /* 1: the last kNN search generated its candidates on the tensor cores           */
+    double  knn_tc_err;        /* largest error of a tensor-core candidate distance seen by the float64 re-rank, in
+                                  units of (|q'|^2 + max |f'|^2); the exactness test assumes <= 4e-6            */
 } FzbStats;
 
 const char* fzb_last_error(void);

@@ -43,5 +43,8 @@ for rep in range(2):
     t = time.time()
     idx, dist = nn._engine.knn_query(q, k, p=2)
     dt = time.time() - t
-    print("knn_query alone: %.3f s wall, device %.1f ms -> %.3e distance evaluations/s" %
-          (dt, nn._engine.stats()["ms_total"], len(q) * K * ntr / (nn._engine.stats()["ms_total"] * 1e-3)))
+    st = nn._engine.stats()
+    print("knn_query alone: %.3f s wall, device %.1f ms -> %.3e distance evaluations/s; tensor-core scan %d, redo %d of %d, "
+          "largest candidate error %.3g (bound 4e-6)" %
+          (dt, st["ms_total"], len(q) * K * ntr / (st["ms_total"] * 1e-3), st["knn_tc"], st["knn_redo"], len(q) * K,
+           st["knn_tc_err"]))
