@@ -332,6 +332,23 @@ class Engine(object):
         res["neighbors"], res["Nneighbors"] = nb, nn
         return res
 
+    def fit_gather(self, data, data_err, data_mask, neighbors, nneighbors, cfg):
+        """Fits of every object to its own list of models (networks.py:918-923); arrays padded to the widest list."""
+        x, xe, xm = self._objects(data, data_err, data_mask)
+        nb = np.ascontiguousarray(neighbors, dtype=np.int64)
+        nn = np.ascontiguousarray(nneighbors, dtype=np.int64)
+        no, w = nb.shape
+        res = dict(lnprior=np.empty((no, w)), lnlike=np.empty((no, w)), lnprob=np.empty((no, w)),
+                   Ndim=np.empty((no, w), dtype=np.int64), chi2=np.empty((no, w)), scale=np.empty((no, w)),
+                   scale_err=np.empty((no, w)))
+        o = FzbFitOut()
+        for name in ("lnprior", "lnlike", "lnprob", "chi2", "scale", "scale_err"):
+            setattr(o, name, dptr(res[name]))
+        o.Ndim = iptr(res["Ndim"])
+        _lib.check(self.lib.fzb_fit_gather(self.h, dptr(x), dptr(xe), dptr(xm), no, w, iptr(nb), iptr(nn), C.byref(cfg),
+                                           C.byref(o)))
+        return res
+
     def measure_peaks(self, reps=5):
         """FP32-FMA (TFLOP/s) and MUFU (Gop/s) peaks of this device, measured with dependency-free loops."""
         a, b = C.c_double(), C.c_double()
@@ -358,6 +375,14 @@ class SummaryEngine(object):
         self.h = C.c_void_p()
         self.device = default_device() if device is None else int(device)
         _lib.check(self.lib.fzb_create(self.device, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            try:
+                self.lib.fzb_destroy(self.h)
+            except Exception:
+                pass
+            self.h = None
 
     @classmethod
     def get(cls, device=None):

@@ -86,9 +86,14 @@ SIGNATURES = {
     "fzb_knn_query": (C.c_int, [_H, c_double_p, C.c_int64, C.c_int32, C.c_double, c_int64_p, c_double_p]),
     "fzb_knn_fit": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int32, C.c_double,
                               _CFG, c_int64_p, c_int64_p, _OUT]),
+    "fzb_fit_gather": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int64, c_int64_p, c_int64_p, _CFG,
+                                 _OUT]),
     "fzb_pdfs_summarize": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int32, C.c_int32,
                                      c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "fzb_pdfs_conf": (C.c_int, [_H, c_double_p, c_double_p, C.c_int64, c_double_p]),
+    "fzb_nz_set_pdfs": (C.c_int, [_H, c_double_p, C.c_int64, C.c_int32]),
+    "fzb_nz_set_pdfs_dev": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_int32]),
+    "fzb_nz_loglike": (C.c_int, [_H, c_double_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, c_double_p, c_double_p]),
     "fzb_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "fzb_free_pinned": (C.c_int, [C.c_void_p]),
     "fzb_clean_inplace_f64": (C.c_int, [c_double_p, c_double_p, c_double_p, C.c_int64]),

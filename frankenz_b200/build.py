@@ -13,7 +13,7 @@ LIB = os.path.join(LIBDIR, "libfzb200.so")
 # (source, extra flags).  The float64 kernels are compiled without FMA contraction so that their
 # arithmetic is the IEEE sequence numpy executes (e.g. d - (d/m)*m == 0 for a one-band fit).
 SOURCES = [("fzb_api.cu", []), ("fzb_generic.cu", ["-fmad=false"]), ("fzb_fast.cu", []), ("fzb_sweep_tc.cu", []), ("fzb_knn.cu", ["-fmad=false"]), ("fzb_knn_tc.cu", []),
-           ("fzb_summarize.cu", ["-fmad=false"]), ("fzb_shard.cu", ["-fmad=false"]), ("fzb_prune.cu", [])]
+           ("fzb_summarize.cu", ["-fmad=false"]), ("fzb_shard.cu", ["-fmad=false"]), ("fzb_prune.cu", []), ("fzb_samplers.cu", ["-fmad=false"])]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -374,7 +374,7 @@ int fzb_destroy(fzb_handle h) {
     DevBuf* bufs[] = {&h->models, &h->models_err, &h->models_mask, &h->lnprior, &h->prior_table, &h->prior_bins, &h->widths, &h->koff, &h->kernels,
                       &h->kcdf, &h->yidx, &h->ysidx, &h->grid, &h->y, &h->ystd, &h->lowers, &h->uppers, &h->rows,
                       &h->knn_feats, &h->knn_cand, &h->knn_redo, &h->knn_tiles, &h->knn_aux, &h->kde_err, &h->summ[0], &h->summ[1], &h->summ[2], &h->summ[3], &h->summ[4], &h->summ[5], &h->fast.recs, &h->fast.tiles_tc, &h->fast.recs64, &h->fast.aux64, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
-                      &h->fast.d_slot_sidx, &h->fast.live, &h->fast.sortbuf};
+                      &h->fast.d_slot_sidx, &h->fast.live, &h->fast.sortbuf, &h->nz_pdfs, &h->nz_buf};
     for (auto* b : bufs) b->release();
     for (auto& b : h->obj_in) b.release();
     for (auto& b : h->out_f64) b.release();
@@ -1023,6 +1023,102 @@ int fzb_knn_fit(fzb_handle h, const double* qfeats, const double* data, const do
     }
     consume_prior_bins(h);
     return t.stop();
+}
+
+// Likelihood of every object against ITS OWN list of models (host lists): the gather half of fzb_knn_fit without the
+// search.  Used by the SOM / GNG node-fit (networks.py:918-923: lprob_func(x, models[idxs], ...)).
+int fzb_fit_gather(fzb_handle h, const double* data, const double* data_err, const double* data_mask, int64_t No,
+                   int64_t W, const int64_t* neighbors, const int64_t* nneighbors, const FzbConfig* cfg,
+                   const FzbFitOut* out) {
+    if (use_device(h) || check_models(h)) return 2;
+    FZB_CHECK(data && data_err && data_mask && cfg && neighbors && nneighbors && out && W > 0, "bad arguments");
+    reset_stats(h);
+    if (No == 0) return 0;
+    if (check_prior_bins(h, No)) return 2;
+    for (int64_t i = 0; i < No; ++i) {
+        FZB_CHECK(nneighbors[i] >= 0 && nneighbors[i] <= W, "object %lld: %lld neighbours for a row width of %lld",
+                  (long long)i, (long long)nneighbors[i], (long long)W);
+        for (int64_t c = 0; c < nneighbors[i]; ++c)
+            FZB_CHECK(neighbors[i * W + c] >= 0 && neighbors[i * W + c] < h->Nm, "object %lld: model index %lld out of range",
+                      (long long)i, (long long)neighbors[i * W + c]);
+    }
+    const int Nf = h->Nf;
+    int64_t chunk = (int64_t)(((size_t)6 << 30) / ((size_t)W * 8 * 9));
+    chunk = std::max<int64_t>(1, std::min(chunk, No));
+    const size_t cn = (size_t)chunk * W;
+    double* hostp[6] = {out->lnprior, out->lnlike, out->lnprob, out->chi2, out->scale, out->scale_err};
+    double* d_o[6] = {};
+    for (int i = 0; i < 6; ++i)
+        if (hostp[i]) {
+            if (h->out_f64[i].reserve(cn * 8)) return 1;
+            d_o[i] = h->out_f64[i].as<double>();
+        }
+    int64_t* d_nd = nullptr;
+    if (out->Ndim) {
+        if (h->out_i64[1].reserve(cn * 8)) return 1;
+        d_nd = h->out_i64[1].as<int64_t>();
+    }
+    Timer t(h);
+    for (int64_t o0 = 0; o0 < No; o0 += chunk) {
+        const int64_t nc = std::min(chunk, No - o0);
+        const size_t nin = (size_t)nc * Nf, no = (size_t)nc * W;
+        if (upload(h, h->obj_in[0], data + o0 * Nf, nin) || upload(h, h->obj_in[1], data_err + o0 * Nf, nin) ||
+            upload(h, h->obj_in[2], data_mask + o0 * Nf, nin) || upload(h, h->misc[3], neighbors + (size_t)o0 * W, no) ||
+            upload(h, h->misc[4], nneighbors + o0, (size_t)nc))
+            return 1;
+        h->prior_o0 = o0;
+        if (fzb_generic_gather_fit_dev(h, h->obj_in[0].as<double>(), h->obj_in[1].as<double>(), h->obj_in[2].as<double>(),
+                                       nc, W, h->misc[3].as<int64_t>(), h->misc[4].as<int64_t>(), *cfg, d_o[0], d_o[1],
+                                       d_o[2], d_nd, d_o[3], d_o[4], d_o[5]))
+            return 1;
+        for (int i = 0; i < 6; ++i)
+            if (download(h, hostp[i] ? hostp[i] + (size_t)o0 * W : nullptr, d_o[i], no)) return 1;
+        if (download(h, out->Ndim ? out->Ndim + (size_t)o0 * W : nullptr, d_nd, no)) return 1;
+        FZB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    consume_prior_bins(h);
+    return t.stop();
+}
+
+// ---- population likelihood of an N(z) given the PDFs (samplers.py:24-76) ------------------------------------------------
+int fzb_nz_set_pdfs(fzb_handle h, const double* pdfs, int64_t No, int32_t Ng) {
+    if (use_device(h)) return 2;
+    FZB_CHECK(pdfs && No > 0 && Ng > 0, "bad arguments");
+    if (upload(h, h->nz_pdfs, pdfs, (size_t)No * Ng)) return 1;
+    FZB_CUDA(cudaStreamSynchronize(h->stream));
+    h->nz_pdfs_ptr = h->nz_pdfs.as<double>();
+    h->nz_No = No;
+    h->nz_Ng = Ng;
+    return 0;
+}
+
+int fzb_nz_set_pdfs_dev(fzb_handle h, const double* d_pdfs, int64_t No, int32_t Ng) {
+    if (use_device(h)) return 2;
+    FZB_CHECK(d_pdfs && No > 0 && Ng > 0, "bad arguments");
+    h->nz_pdfs_ptr = d_pdfs;
+    h->nz_No = No;
+    h->nz_Ng = Ng;
+    return 0;
+}
+
+int fzb_nz_loglike(fzb_handle h, const double* nz, int32_t Ng, int32_t pair_i, int32_t pair_j, double pair_step,
+                   double* lnlike, double* overlap) {
+    if (use_device(h)) return 2;
+    FZB_CHECK(nz && lnlike, "null argument");
+    FZB_CHECK(h->nz_pdfs_ptr && h->nz_No > 0, "call fzb_nz_set_pdfs first");
+    FZB_CHECK(Ng == h->nz_Ng, "nz has %d bins, the PDFs have %d", Ng, h->nz_Ng);
+    const bool pair = pair_i >= 0 && pair_j >= 0;
+    if (pair) FZB_CHECK(pair_i < Ng && pair_j < Ng, "pair (%d, %d) outside the %d bins", pair_i, pair_j, Ng);
+    reset_stats(h);
+    // samplers.py:63-65: a negative or non-finite N(z) has zero likelihood
+    for (int g = 0; g < Ng; ++g)
+        if (!std::isfinite(nz[g]) || nz[g] < 0.0) {
+            *lnlike = -INFINITY;
+            if (overlap) memset(overlap, 0, (size_t)h->nz_No * sizeof(double));
+            return 0;
+        }
+    return fzb_nz_loglike_impl(h, h->nz_pdfs_ptr, h->nz_No, Ng, nz, pair ? pair_i : -1, pair ? pair_j : -1,
+                               pair ? pair_step : 0.0, lnlike, overlap);
 }
 
 }  // extern "C"

@@ -169,6 +169,12 @@ struct fzb_context {
     int64_t knn_Nm = 0;
     int knn_Nf = 0;
 
+    // population likelihood (fzb_samplers.cu): PDFs resident on the device (own copy or a caller's device pointer)
+    DevBuf nz_pdfs, nz_buf;
+    const double* nz_pdfs_ptr = nullptr;
+    int64_t nz_No = 0;
+    int nz_Ng = 0;
+
     FzbStats stats = {};
 };
 
@@ -227,6 +233,10 @@ int fzb_shard_add_offset_launch(fzb_context* h, int64_t* d_best, int64_t No, int
 int fzb_shard_merge_launch(fzb_context* h, const double* d_gathered, int world, int64_t No, double* d_lmap,
                            double* d_levid, int64_t* d_best);
 int fzb_shard_normalise_launch(fzb_context* h, const float* d_rows, int64_t n, int Ng, double* d_pdfs);
+
+// ---- population likelihood (fzb_samplers.cu) ---------------------------------------------------
+int fzb_nz_loglike_impl(fzb_context* h, const double* d_pdfs, int64_t No, int Ng, const double* nz_host, int pa, int pb,
+                        double step, double* lnlike, double* overlap_host);
 
 // ---- kNN (fzb_knn.cu) -------------------------------------------------------------------------
 int fzb_knn_query_dev(fzb_context* h, const double* d_q, int64_t No, int k, double p, int64_t* d_idx, double* d_dist);

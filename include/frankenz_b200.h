@@ -217,6 +217,13 @@ int fzb_knn_fit(fzb_handle h, const double* qfeats, const double* data, const do
                 const double* data_mask, int64_t No, int32_t k, double p, const FzbConfig* cfg,
                 int64_t* neighbors, int64_t* nneighbors, const FzbFitOut* out);
 
+/* Likelihood of every object against its own list of models (the gather half of fzb_knn_fit, lists from the host):
+ * SOM / GNG node-fit second stage, networks.py:918-923.  neighbors host int64 (No x W), row i uses its first nneighbors[i]
+ * entries; out arrays (No x W), padded like fzb_knn_fit. */
+int fzb_fit_gather(fzb_handle h, const double* data, const double* data_err, const double* data_mask, int64_t No,
+                   int64_t W, const int64_t* neighbors, const int64_t* nneighbors, const FzbConfig* cfg,
+                   const FzbFitOut* out);
+
 /* PDF summary statistics: replaces pdf.pdfs_summarize (pdf.py:899-1074).
  * pdfs: host (No x Ng) float64, not modified; pgrid: host [Ng] (2 <= Ng <= 1024); loss: host (Ng x Ng) float64 =
  * 1 - kernel[truth, guess] as pdf.py:1003-1024 builds it; urand: host [No], the rstate.rand() of each object in order
@@ -230,6 +237,17 @@ int fzb_pdfs_summarize(fzb_handle h, const double* pdfs, const double* pgrid, co
 /* Second stage (pdf.py:1038-1062): conf[e][i] = CDF_i(point + width) - CDF_i(point - width) for points / widths [4][No]
  * (the four estimators and the caller's wconf_func evaluated at them), on the PDFs of the last fzb_pdfs_summarize. */
 int fzb_pdfs_conf(fzb_handle h, const double* points, const double* widths, int64_t No, double* conf);
+
+/* Population likelihood of a redshift distribution given the PDFs (samplers.loglike_nz, samplers.py:24-76; SURVEY 8f
+ * rank 4): overlap_i = sum_g pdfs[i,g] nz[g] (+ pair_step (pdfs[i,pair_i] - pdfs[i,pair_j]) when pair_i, pair_j >= 0),
+ * lnlike = sum_i log(overlap_i); -inf (and zero overlaps) when nz has a negative or non-finite entry.  The PDFs stay
+ * resident on the device between calls (the MCMC samplers call this thousands of times on the same PDFs):
+ * fzb_nz_set_pdfs uploads a host array (No x Ng), fzb_nz_set_pdfs_dev adopts a device pointer (e.g. the output of
+ * fzb_fit_predict_dev; it must stay valid).  overlap: nullable host [No]. */
+int fzb_nz_set_pdfs(fzb_handle h, const double* pdfs, int64_t No, int32_t Ngrid);
+int fzb_nz_set_pdfs_dev(fzb_handle h, const double* d_pdfs, int64_t No, int32_t Ngrid);
+int fzb_nz_loglike(fzb_handle h, const double* nz, int32_t Ngrid, int32_t pair_i, int32_t pair_j, double pair_step,
+                   double* lnlike, double* overlap);
 
 /* Page-locked host memory for large outputs (the (Ndata x Ngrid) PDFs): when the `pdfs` argument of fzb_fit_predict
  * points into such a buffer, the device-to-host copies go straight into it, without the staging buffer and the host-side

@@ -561,3 +561,92 @@ def pdfs_summarize(pdfs, pgrid, renormalize=True, rstate=None, pkern="lorentz", 
         rsk[:, i] = np.interp([p[i] for p in points], pgrid, risk[i])   # pdf.py:1066-1068
     est = tuple((points[k], stds[k], conf[k], rsk[k]) for k in range(4))
     return est + ((quant[:, 0].copy(), quant[:, 1].copy(), quant[:, 3].copy(), quant[:, 4].copy()), quant[:, 5].copy())
+
+
+# ----------------------------------------------------------------------------
+# population likelihood  (frankenz/samplers.py:24-76)
+# ----------------------------------------------------------------------------
+def loglike_nz(nz, pdfs, overlap=None, return_overlap=False, pair=None, pair_step=None):
+    """ln-likelihood of a population N(z) given per-object PDFs (samplers.py:62-76)."""
+    perturb = 0.0
+    if np.any(~np.isfinite(nz) | (nz < 0.0)):
+        lnlike, overlap = -np.inf, np.zeros(len(pdfs))
+    else:
+        if overlap is None:
+            overlap = np.dot(pdfs, nz)
+        if pair is not None and pair_step is not None:
+            perturb = pair_step * (pdfs[:, pair[0]] - pdfs[:, pair[1]])
+        lnlike = np.sum(np.log(overlap + perturb))
+    if return_overlap:
+        return lnlike, overlap + perturb
+    return lnlike
+
+
+# ----------------------------------------------------------------------------
+# SOM / GNG node-fit stages  (frankenz/networks.py:246-356, 782-936)
+# ----------------------------------------------------------------------------
+def _node_select(node_lnprob, wt_thresh, cdf_thresh):
+    """networks.py:322-331 / 888-897: indices of the nodes an object maps to, in the reference's order."""
+    if wt_thresh is None and cdf_thresh is None:
+        wt_thresh = -np.inf
+    if wt_thresh is not None:
+        lwt_min = np.log(wt_thresh) + np.max(node_lnprob)
+        return np.arange(len(node_lnprob))[node_lnprob > lwt_min]
+    idx_sort = np.argsort(node_lnprob)
+    node_prob = np.exp(node_lnprob - logsumexp(node_lnprob))
+    node_cdf = np.cumsum(node_prob[idx_sort])
+    return idx_sort[node_cdf <= (1.0 - cdf_thresh)]
+
+
+def network_populate(models, models_err, models_mask, nodes, wt_thresh=1e-3, cdf_thresh=2e-4, lpnet_kwargs=None):
+    """networks.py:246-356 with track_scale=True: per-node lists of models, ln-weights, scales and BMU lists."""
+    if lpnet_kwargs is None:
+        lpnet_kwargs = dict(free_scale=True, ignore_model_err=True, return_scale=True)
+    nnode = len(nodes)
+    out = dict(nodes_idxs=[[] for _ in range(nnode)], nodes_logwts=[[] for _ in range(nnode)],
+               nodes_bmus=[[] for _ in range(nnode)], nodes_scales=[[] for _ in range(nnode)],
+               nodes_scales_err=[[] for _ in range(nnode)], nodes_Nmatch=np.zeros(nnode, dtype=int),
+               models_lmap=np.zeros(len(models)), models_levid=np.zeros(len(models)))
+    ye, ym = np.zeros_like(nodes), np.ones_like(nodes)
+    for i in range(len(models)):
+        x, xe, xm = models[i].copy(), models_err[i].copy(), np.array(models_mask[i], dtype=float)
+        res = logprob(x, xe, xm, nodes, ye, ym, **lpnet_kwargs)
+        lp = res[2]
+        out["nodes_bmus"][np.argmax(lp)].append(i)
+        n_idxs = _node_select(lp, wt_thresh, cdf_thresh)
+        n_lp = lp[n_idxs]
+        lmap, levid = np.max(n_lp), logsumexp(n_lp)
+        out["models_lmap"][i], out["models_levid"][i] = lmap, levid
+        for j, lw, s, se in zip(n_idxs, n_lp - levid, res[5][n_idxs], res[6][n_idxs]):
+            out["nodes_idxs"][j].append(i)
+            out["nodes_logwts"][j].append(lw)
+            out["nodes_scales"][j].append(s)
+            out["nodes_scales_err"][j].append(se)
+            out["nodes_Nmatch"][j] += 1
+    return out
+
+
+def network_fit(models, models_err, models_mask, nodes, pop, data, data_err, data_mask, nodes_only=False,
+                wt_thresh=1e-3, cdf_thresh=2e-4, lpnet_kwargs=None, lprob_kwargs=None):
+    """networks.py:782-936: neighbour lists and fits of every object through the populated network `pop`."""
+    if lpnet_kwargs is None:
+        lpnet_kwargs = dict(free_scale=True, ignore_model_err=True, return_scale=True)
+    match_sel = np.arange(len(nodes))[pop["nodes_Nmatch"] > 0]
+    y = nodes[match_sel]
+    ye, ym = np.zeros_like(y), np.ones_like(y)
+    neighbors, results = [], []
+    for i in range(len(data)):
+        x, xe, xm = data[i], data_err[i], data_mask[i]
+        clean_inplace(x, xe, xm)
+        node_results = logprob(x, xe, xm, y, ye, ym, **lpnet_kwargs)
+        wsel = _node_select(node_results[2], wt_thresh, cdf_thresh)
+        sel_arr = match_sel[wsel]
+        if nodes_only:
+            neighbors.append(sel_arr)
+            results.append([nr[wsel] for nr in node_results])
+            continue
+        indices = np.array([idx for sidx in sel_arr for idx in pop["nodes_idxs"][sidx]])
+        idxs = ordered_unique(indices)
+        neighbors.append(np.array(idxs))
+        results.append(logprob(x, xe, xm, models[idxs], models_err[idxs], models_mask[idxs], **(lprob_kwargs or {})))
+    return neighbors, results

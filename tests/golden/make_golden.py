@@ -287,7 +287,39 @@ def case_summarize():
     np.savez_compressed(os.path.join(HERE, "pdfs_summarize.npz"), **out)
     print("pdfs_summarize.npz", len(out), "arrays")
 
+def case_loglike_nz():
+    """samplers.loglike_nz (samplers.py:24-76) on seeded PDFs: plain, with a perturbed pair of bins,
+    with overlaps returned, and for an invalid N(z)."""
+    from frankenz import samplers
+    zgrid = np.arange(0, 7 + 1e-5, 0.01)
+    p = mock_pdfs(700, zgrid, 91)
+    p[0] = p[3]                                   # the single-bin spike of row 0 would give overlap 0 with most N(z)
+    p /= p.sum(axis=1)[:, None]
+    rs = np.random.RandomState(92)
+    out = dict(zgrid=zgrid, pdfs=p)
+    nzs = []
+    for k in range(4):
+        nz = rs.gamma(2.0, size=len(zgrid)) * np.exp(-0.5 * ((zgrid - 1.0 - 0.4 * k) / (0.7 + 0.2 * k)) ** 2) + 1e-4
+        nzs.append(nz / nz.sum())
+    nzs = np.array(nzs)
+    out["nz"] = nzs
+    out["lnlike"] = np.array([samplers.loglike_nz(nz, p) for nz in nzs])
+    ll, ov = samplers.loglike_nz(nzs[1], p, return_overlap=True)
+    out["lnlike_ov"], out["overlap"] = ll, ov
+    ll, ov = samplers.loglike_nz(nzs[2], p, return_overlap=True, pair=(120, 260), pair_step=3e-4)
+    out["lnlike_pair"], out["overlap_pair"] = ll, ov
+    bad = nzs[0].copy()
+    bad[5] = -1e-3
+    ll, ov = samplers.loglike_nz(bad, p, return_overlap=True)
+    out["lnlike_bad"], out["overlap_bad"], out["nz_bad"] = ll, ov, bad
+    np.savez_compressed(os.path.join(HERE, "loglike_nz.npz"), **out)
+    print("loglike_nz ok", out["lnlike"])
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "nz":
+        case_loglike_nz()
+        sys.exit(0)
     case_loglike()
     case_degenerate()
     case_bruteforce()
@@ -295,3 +327,4 @@ if __name__ == "__main__":
     case_knn()
     case_fs1_iters()
     case_summarize()
+    case_loglike_nz()

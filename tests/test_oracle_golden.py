@@ -173,3 +173,47 @@ def test_pdfs_summarize_user_kernel_grid_and_resample():
     assert exact(fo.pdfs_resample(g["pdfs"].copy(), g["zgrid"], g["resample_grid"]), g["resampled"])
     assert exact(fo.pdfs_resample(g["pdfs"].copy(), g["zgrid"], g["resample_grid"], renormalize=False, left=0.5,
                                   right=0.25), g["resampled_noren"])
+
+
+def _unragged(g, name):
+    off, flat = g[name + "_off"], g[name]
+    return [flat[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+
+def test_loglike_nz_matches_reference():
+    """samplers.py:24-76."""
+    g = golden("loglike_nz.npz")
+    p = g["pdfs"]
+    for nz, ref in zip(g["nz"], g["lnlike"]):
+        assert fo.loglike_nz(nz, p) == ref
+    ll, ov = fo.loglike_nz(g["nz"][1], p, return_overlap=True)
+    assert ll == g["lnlike_ov"] and np.array_equal(ov, g["overlap"])
+    ll, ov = fo.loglike_nz(g["nz"][2], p, return_overlap=True, pair=(120, 260), pair_step=3e-4)
+    assert ll == g["lnlike_pair"] and np.array_equal(ov, g["overlap_pair"])
+    ll, ov = fo.loglike_nz(g["nz_bad"], p, return_overlap=True)
+    assert ll == -np.inf and not ov.any()
+
+
+def test_network_node_fit_matches_reference():
+    """networks.py:246-356 and :782-936 on the nodes of a reference-trained SOM."""
+    g = golden("som_nodefit.npz")
+    m, me, mm, nodes = g["models"], g["models_err"], g["models_mask"], g["nodes"]
+    pop = fo.network_populate(m, me, mm, nodes)
+    assert np.array_equal(pop["nodes_Nmatch"], g["nodes_Nmatch"])
+    for name in ("nodes_idxs", "nodes_bmus"):
+        for a, b in zip(pop[name], _unragged(g, name)):
+            assert np.array_equal(np.asarray(a, dtype=np.int64), b)
+    for name in ("nodes_logwts", "nodes_scales", "nodes_scales_err"):
+        for a, b in zip(pop[name], _unragged(g, name)):
+            assert np.array_equal(np.asarray(a, dtype=np.float64), b)
+    assert np.array_equal(pop["models_lmap"], g["models_lmap"]) and np.array_equal(pop["models_levid"], g["models_levid"])
+    kw = dict(free_scale=True, ignore_model_err=True, dim_prior=True)
+    for tag, nodes_only in (("nodes", True), ("full", False)):
+        nb, res = fo.network_fit(m, me, mm, nodes, pop, g["data"].copy(), g["data_err"].copy(), g["data_mask"].copy(),
+                                 nodes_only=nodes_only, lprob_kwargs=kw)
+        for a, b in zip(nb, _unragged(g, tag + "_neighbors")):
+            assert np.array_equal(np.asarray(a, dtype=np.int64), b)
+        for r, b in zip(res, _unragged(g, tag + "_lnprob")):
+            assert np.array_equal(r[2], b, equal_nan=True)
+        for r, b in zip(res, _unragged(g, tag + "_chi2")):
+            assert np.array_equal(r[4], b, equal_nan=True)
