@@ -213,6 +213,53 @@ def leg_model_sharded(args, rank, world, local, dist, torch, fz):
                                     "ok": bool(stat[0].item() <= 1e-5 and stat[1].item() <= 1e-5 and stat[2].item() <= 1e-5)}}
 
 
+def leg_default_likelihood(args, rank, world, local, dist, torch, fz):
+    """The reference's DEFAULT likelihood (fixed scale, model errors, dim_prior: pdf.py:27-100), the mode of configs C1,
+    C2 and C5: 6-band LSST training rows with errors (float64), device-resident inputs, one GPU's share.  Per pair
+    6 Nf + 8 = 44 flop and Nf + 2 = 8 MUFU results (one reciprocal per band): MUFU-bound."""
+    from frankenz_b200._engine import make_config
+    n_train, n_obj = args.fx1_models, args.fx1_objects
+    tr, tre, trm, ztr, x, xe, xm = bench_data.c5_dataset(n_train, n_obj, seed=20260107 + rank)
+    zgrid, sig = bench_data.c3_kde()
+    bf = fz.BruteForce(tr, tre, trm)
+    eng = bf._eng()
+    eng.set_kde(ztr, np.full(n_train, 0.05), label_dict=fz.pdf.PDFDict(zgrid, sig))
+    cfg = make_config(dict(), None)
+    dev = torch.device("cuda", local)
+    d = [torch.from_numpy(a).to(dev) for a in (x, xe, xm)]
+    out = [torch.empty((n_obj, eng.Ng), dtype=torch.float64, device=dev)] + \
+          [torch.empty(n_obj, dtype=torch.float64, device=dev) for _ in range(2)] + \
+          [torch.empty(n_obj, dtype=torch.int64, device=dev)] + \
+          [torch.empty(n_obj, dtype=torch.float64, device=dev) for _ in range(2)]
+    sts = []
+    for rep in range(4):
+        torch.cuda.synchronize()
+        eng.fit_predict_dev(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), n_obj, cfg, *[t.data_ptr() for t in out])
+        if rep > 0:
+            sts.append(eng.stats())
+    ms = float(np.mean([s["ms_total"] for s in sts]))
+    ms_scan = float(np.mean([s["ms_scan"] for s in sts]))
+    n64 = float(np.mean([s["objects_fp64"] for s in sts]))
+    fp32_peak, mufu_peak = eng.measure_peaks(3)
+    vals = torch.tensor([ms, ms_scan], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms, ms_scan = float(vals[0].item()), float(vals[1].item())
+    pairs = float(n_obj) * n_train
+    eng.close()
+    return {"workload": "default likelihood (free_scale=False, model errors, dim_prior=True), %d objects x %d training "
+                        "rows per GPU, 6 bands (LSST ugrizY), float64 rows, fit_predict(save_fits=False) on device-resident "
+                        "inputs" % (n_obj, n_train),
+            "value": pairs * max(1, world) / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
+            "objects_routed_to_fp64": n64,
+            "roofline": {"bound": "mufu", "kernel": "k_sweep2<FX1> pass 1", "mufu_per_pair": 8.0,
+                         "achieved_gops": 8.0 * pairs / (ms_scan * 1e-3) / 1e9, "peak_gops": mufu_peak,
+                         "frac": 8.0 * pairs / (ms_scan * 1e-3) / 1e9 / mufu_peak, "pass1_ms": ms_scan,
+                         "flops_per_pair": 44.0, "fp32_tflops": 44.0 * pairs / (ms_scan * 1e-3) / 1e12,
+                         "fp32_peak_tflops": fp32_peak,
+                         "peak_source": "fzb_measure_peaks (dependency-free MUFU.EX2 loop, this run)"}}
+
+
 def leg_knn(args, rank, world, local, dist, torch, fz):
     """C4-shaped: NearestNeighbors over K Monte-Carlo realisations of the training set, queries sharded over the ranks
     (training features replicated), k neighbours per tree; the search is checked against the all-float64 kernel
@@ -290,6 +337,8 @@ def main():
     ap.add_argument("--c5-objects", type=int, default=262144)
     ap.add_argument("--c5-chunk", type=int, default=65536)
     ap.add_argument("--c5-check-objects", type=int, default=16384)
+    ap.add_argument("--fx1-models", type=int, default=262144)
+    ap.add_argument("--fx1-objects", type=int, default=262144)
     ap.add_argument("--knn-train", type=int, default=1000000)
     ap.add_argument("--knn-queries", type=int, default=65536)
     ap.add_argument("--knn-K", type=int, default=20)
@@ -364,6 +413,7 @@ def main():
     if not args.no_legs:
         if use_dist:
             legs["model_sharded"] = leg_model_sharded(args, rank, world, local, dist, torch, fz)
+        legs["default_likelihood"] = leg_default_likelihood(args, rank, world, local, dist, torch, fz)
         legs["knn"] = leg_knn(args, rank, world, local, dist, torch, fz)
 
     if rank == 0:

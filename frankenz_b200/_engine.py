@@ -332,6 +332,19 @@ class Engine(object):
         res["neighbors"], res["Nneighbors"] = nb, nn
         return res
 
+    def knn_fit_predict(self, qfeats, data, data_err, data_mask, k, p, cfg):
+        """Search, union, fits and KDE on the device; only PDFs / lmap / levid / Nneighbors come back."""
+        x, xe, xm = self._objects(data, data_err, data_mask)
+        q = f64(qfeats)
+        no = len(x)
+        pdfs = _pinned_pool.empty((no, self.Ng))
+        lmap, levid = np.empty(no), np.empty(no)
+        nn = np.empty(no, dtype=np.int64)
+        pp = 0.0 if np.isinf(p) else float(p)
+        _lib.check(self.lib.fzb_knn_fit_predict(self.h, dptr(q), dptr(x), dptr(xe), dptr(xm), no, k, pp, C.byref(cfg),
+                                                dptr(pdfs), dptr(lmap), dptr(levid), iptr(nn)))
+        return pdfs, lmap, levid, nn
+
     def fit_gather(self, data, data_err, data_mask, neighbors, nneighbors, cfg):
         """Fits of every object to its own list of models (networks.py:918-923); arrays padded to the widest list."""
         x, xe, xm = self._objects(data, data_err, data_mask)

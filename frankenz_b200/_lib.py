@@ -86,6 +86,8 @@ SIGNATURES = {
     "fzb_knn_query": (C.c_int, [_H, c_double_p, C.c_int64, C.c_int32, C.c_double, c_int64_p, c_double_p]),
     "fzb_knn_fit": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int32, C.c_double,
                               _CFG, c_int64_p, c_int64_p, _OUT]),
+    "fzb_knn_fit_predict": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int32, C.c_double,
+                                      _CFG, c_double_p, c_double_p, c_double_p, c_int64_p]),
     "fzb_fit_gather": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int64, c_int64_p, c_int64_p, _CFG,
                                  _OUT]),
     "fzb_pdfs_summarize": (C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int64, C.c_int32, C.c_int32,

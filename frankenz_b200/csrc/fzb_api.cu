@@ -1025,6 +1025,79 @@ int fzb_knn_fit(fzb_handle h, const double* qfeats, const double* data, const do
     return t.stop();
 }
 
+// kNN search + union + fits + KDE without the (No x K k) fit arrays (knn.py:722-874 with save_fits=False): everything
+// stays on the device, the PDFs leave through the staged downloader while the next chunk is searched.
+int fzb_knn_fit_predict(fzb_handle h, const double* qfeats, const double* data, const double* data_err,
+                        const double* data_mask, int64_t No, int32_t k, double p, const FzbConfig* cfg, double* pdfs,
+                        double* lmap, double* levid, int64_t* nneighbors) {
+    if (use_device(h) || check_models(h)) return 2;
+    FZB_CHECK(h->knn_K > 0, "call fzb_knn_build first");
+    FZB_CHECK(h->knn_Nm == h->Nm && h->knn_Nf == h->Nf, "kNN features (%lld x %d) do not match the model set (%lld x %d)",
+              (long long)h->knn_Nm, h->knn_Nf, (long long)h->Nm, h->Nf);
+    FZB_CHECK(qfeats && data && data_err && data_mask && cfg && pdfs, "null argument");
+    FZB_CHECK(k > 0 && k <= h->knn_Nm, "k=%d must be in [1, Nmodel=%lld]", k, (long long)h->knn_Nm);
+    FZB_CHECK(h->kde_mode != FZB_KDE_NONE, "no KDE configured");
+    reset_stats(h);
+    if (No == 0) return 0;
+    if (check_prior_bins(h, No)) return 2;
+    const int Nf = h->Nf, Ng = h->Ng;
+    const int64_t W = (int64_t)h->knn_K * k;
+    int64_t chunk = std::min<int64_t>(No, 32768);
+    const size_t cn = (size_t)chunk * W;
+    if (h->out_i64[0].reserve(cn * 8) || h->misc[3].reserve(cn * 8) || h->misc[4].reserve((size_t)chunk * 8) ||
+        h->out_f64[1].reserve((size_t)No * 8) || h->out_f64[2].reserve((size_t)No * 8) || h->out_i64[1].reserve((size_t)No * 8))
+        return 1;
+    for (int b = 0; b < 2; ++b)
+        if (h->pdf_dev[b].reserve((size_t)chunk * Ng * 8)) return 1;
+    StagedDownloader dl(h);
+    cudaPointerAttributes pa = {};
+    const bool pinned_dst = cudaPointerGetAttributes(&pa, pdfs) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (dl.init((size_t)64 << 20, pinned_dst)) return 1;
+    double* d_lmap = h->out_f64[1].as<double>();
+    double* d_levid = h->out_f64[2].as<double>();
+    int64_t* d_nn_all = h->out_i64[1].as<int64_t>();
+    FzbStats acc = {};
+    FZB_CUDA(cudaEventRecord(h->ev[0], h->stream));
+    int64_t push_id[2] = {-1, -1};
+    int64_t c = 0;
+    for (int64_t o0 = 0; o0 < No; o0 += chunk, ++c) {
+        const int64_t nc = std::min(chunk, No - o0);
+        const int b = (int)(c & 1);
+        const size_t nin = (size_t)nc * Nf;
+        if (upload(h, h->obj_in[0], data + o0 * Nf, nin) || upload(h, h->obj_in[1], data_err + o0 * Nf, nin) ||
+            upload(h, h->obj_in[2], data_mask + o0 * Nf, nin) || upload(h, h->misc[5], qfeats + o0 * Nf, nin))
+            return 1;
+        h->prior_o0 = o0;
+        int64_t* d_idx = h->out_i64[0].as<int64_t>();
+        int64_t* d_nb = h->misc[3].as<int64_t>();
+        int64_t* d_nn = h->misc[4].as<int64_t>();
+        if (fzb_knn_query_dev(h, h->misc[5].as<double>(), nc, k, p, d_idx, nullptr)) return 1;
+        if (fzb_knn_union_dev(h, d_idx, nc, (int)W, d_nb, d_nn)) return 1;
+        if (c >= 2 && dl.fence_compute(push_id[b])) return 1;
+        if (fzb_generic_gather_fit_predict_dev(h, h->obj_in[0].as<double>(), h->obj_in[1].as<double>(),
+                                               h->obj_in[2].as<double>(), nc, W, d_nb, d_nn, *cfg,
+                                               h->pdf_dev[b].as<double>(), d_lmap + o0, d_levid + o0))
+            return 1;
+        FZB_CUDA(cudaMemcpyAsync(d_nn_all + o0, d_nn, (size_t)nc * 8, cudaMemcpyDeviceToDevice, h->stream));
+        if (dl.push(pdfs + (size_t)o0 * Ng, h->pdf_dev[b].p, (size_t)nc * Ng * sizeof(double), &push_id[b])) return 1;
+        // the next chunk's uploads reuse obj_in / misc: everything of this chunk must have been consumed
+        FZB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    FZB_CUDA(cudaEventRecord(h->ev[1], h->stream));
+    consume_prior_bins(h);
+    if (download(h, lmap, d_lmap, (size_t)No) || download(h, levid, d_levid, (size_t)No) ||
+        download(h, nneighbors, d_nn_all, (size_t)No))
+        return 1;
+    FZB_CUDA(cudaStreamSynchronize(h->stream));
+    FZB_CHECK(dl.finish() == 0, "device-to-host copy of the PDFs failed");
+    float ms = 0.f;
+    FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    h->stats.ms_total = ms;
+    (void)acc;
+    return check_kde_error(h);
+}
+
 // Likelihood of every object against ITS OWN list of models (host lists): the gather half of fzb_knn_fit without the
 // search.  Used by the SOM / GNG node-fit (networks.py:918-923: lprob_func(x, models[idxs], ...)).
 int fzb_fit_gather(fzb_handle h, const double* data, const double* data_err, const double* data_mask, int64_t No,

@@ -191,6 +191,9 @@ int fzb_generic_fit_predict_dev(fzb_context* h, const double* d_x, const double*
 int fzb_generic_predict_logwt_dev(fzb_context* h, const double* d_logwt, int64_t No, int64_t W,
                                   const int64_t* d_neighbors, const int64_t* d_nneighbors, const FzbConfig& cfg,
                                   double* d_pdfs, double* d_lmap, double* d_levid);
+int fzb_generic_gather_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm, int64_t No,
+                                       int64_t W, const int64_t* d_neighbors, const int64_t* d_nneighbors,
+                                       const FzbConfig& cfg, double* d_pdfs, double* d_lmap, double* d_levid);
 int fzb_generic_shard_pass1_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm,
                                 int64_t No, const int32_t* d_objsel, int64_t Nsel, const FzbConfig& cfg,
                                 double* d_pmax, double* d_psum, int64_t* d_pbest);

@@ -274,8 +274,17 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
                     best[2 * p + 1] = g1 ? (int)(first + jj) : best[2 * p + 1];
                 } else {
                     float u0 = fast_ex2(d0), u1 = fast_ex2(d1);
-                    u0 = (lo2(l) > thr[2 * p]) ? u0 : 0.f;
-                    u1 = (hi2(l) > thr[2 * p + 1]) ? u1 : 0.f;
+                    bool s0 = lo2(l) > thr[2 * p], s1 = hi2(l) > thr[2 * p + 1];
+                    if (P.ex.x) {      // weights within the fp32 error of the cut: float64 decides (fzb_sweep_common.cuh)
+                        const float band = P.ex_tol * 1.4427f;
+                        const bool n0 = fabsf(lo2(l) - thr[2 * p]) < band, n1 = fabsf(hi2(l) - thr[2 * p + 1]) < band;
+                        if (n0 || n1) {
+                            if (n0 && oidx[2 * p] >= 0) { s0 = fzb_exact_selected(P.ex, oidx[2 * p], (int)(first + jj)); if (P.ex_count) atomicAdd(P.ex_count, 1u); }
+                            if (n1 && oidx[2 * p + 1] >= 0) { s1 = fzb_exact_selected(P.ex, oidx[2 * p + 1], (int)(first + jj)); if (P.ex_count) atomicAdd(P.ex_count, 1u); }
+                        }
+                    }
+                    u0 = s0 ? u0 : 0.f;
+                    u1 = s1 ? u1 : 0.f;
                     acc[p] = fma2(pack2(u0, u1), invnorm, acc[p]);
                 }
             }
@@ -1395,6 +1404,20 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                 if (prune) {
                     FZB_CUDA(cudaMemsetAsync(counts + 8, 0, 8, h->stream));
                     SP.pairs_done = reinterpret_cast<unsigned long long*>(counts + 8);
+                }
+                if (cfg.use_wt_thresh && !mm && getenv("FZB_NO_EXACT_CUT") == nullptr) {
+                    // weights within the fp32 error of the wt_thresh cut are re-decided in float64
+                    SP.ex.x = PP.x; SP.ex.xe = PP.xe; SP.ex.xm = PP.xm;
+                    SP.ex.m = h->models.as<double>(); SP.ex.me = h->models_err.as<double>(); SP.ex.mm = h->models_mask.as<double>();
+                    SP.ex.lnprior = h->has_lnprior ? h->lnprior.as<double>() : nullptr;
+                    SP.ex.perm = F.perm.as<int32_t>();
+                    SP.ex.lmap = (shard_mode == 2) ? d_glmap : lmap_local;
+                    SP.ex.ln_wt_thresh = std::log(cfg.wt_thresh);
+                    SP.ex.Nf = nf; SP.ex.free_scale = cfg.free_scale; SP.ex.ime = cfg.ignore_model_err != 0;
+                    SP.ex.dim_prior = cfg.dim_prior;
+                    SP.ex_tol = (float)env_double("FZB_EXACT_CUT_TOL", 3e-5);
+                    FZB_CUDA(cudaMemsetAsync(counts + 10, 0, 4, h->stream));
+                    SP.ex_count = reinterpret_cast<unsigned int*>(counts + 10);
                 }
                 SP.No = nsafe; SP.objlist = safe_list; SP.M2 = M2; SP.thr2 = thr2; SP.hist = hist;
                 SP.hist_stride = hist_stride;

@@ -588,6 +588,22 @@ int fzb_generic_fit_predict_dev(fzb_context* h, const double* d_x, const double*
     return launch_generic(h, P, items, true);
 }
 
+// fit_predict of every object against ITS OWN list of models (kNN union): likelihood + KDE in one pass, nothing but the
+// PDFs (and lmap / levid) leaves the kernel.  knn.py:827-872 with save_fits=False.
+int fzb_generic_gather_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_xe, const double* d_xm, int64_t No,
+                                       int64_t W, const int64_t* d_neighbors, const int64_t* d_nneighbors,
+                                       const FzbConfig& cfg, double* d_pdfs, double* d_lmap, double* d_levid) {
+    if (check_kde(h)) return 2;
+    GenParams P = {};
+    fill_common(h, P, d_x, d_xe, d_xm, No, cfg);
+    P.stage = ST_FIT_PREDICT;
+    P.W = W; P.nbr = d_neighbors; P.nnbr = d_nneighbors;
+    P.kde = make_kde(h, cfg);
+    P.pdfs = d_pdfs; P.lmap = d_lmap; P.levid = d_levid;
+    h->stats.pairs_fp64 += No * W;
+    return launch_generic(h, P, No, true);
+}
+
 int fzb_generic_predict_logwt_dev(fzb_context* h, const double* d_logwt, int64_t No, int64_t W,
                                   const int64_t* d_neighbors, const int64_t* d_nneighbors, const FzbConfig& cfg,
                                   double* d_pdfs, double* d_lmap, double* d_levid) {

@@ -377,8 +377,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                     best1 = g1 ? idx0 + 1 : best1;
                 } else {
                     float u0 = fast_ex2(lo2(delta)), u1 = fast_ex2(hi2(delta));
-                    u0 = (lo2(l) > thr) ? u0 : 0.f;
-                    u1 = (hi2(l) > thr) ? u1 : 0.f;
+                    bool s0 = lo2(l) > thr, s1 = hi2(l) > thr;
+                    if (P.ex.x) {      // log2 domain: a band of ex_tol / ln 2 around the cut is re-decided in float64
+                        const float band = P.ex_tol * 1.4427f;
+                        const bool n0 = fabsf(lo2(l) - thr) < band, n1 = fabsf(hi2(l) - thr) < band && !(SLOW && tail);
+                        if (__any_sync(0xffffffffu, n0 || n1)) {
+                            if (n0 && oidx >= 0) { s0 = fzb_exact_selected(P.ex, oidx, idx0); if (P.ex_count) atomicAdd(P.ex_count, 1u); }
+                            if (n1 && oidx >= 0) { s1 = fzb_exact_selected(P.ex, oidx, idx0 + 1); if (P.ex_count) atomicAdd(P.ex_count, 1u); }
+                        }
+                    }
+                    u0 = s0 ? u0 : 0.f;
+                    u1 = s1 ? u1 : 0.f;
                     if (!SLOW) {
                         acc2 = fma2(pack2(u0, u1), pack2(sub_inv, sub_inv), acc2);
                     } else {
@@ -501,13 +510,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                 }
             } else {
                 const f2 R2 = pack2(Rf, Rf);
+                f2 us[4];
+                float uv[8];                    // the weights that pass the cut (0 otherwise)
+                float nearm = FLT_MAX;          // smallest |weight - cut| of the sub-batch
+                const f2 nthr2 = pack2(-thr, -thr);
+#pragma unroll
+                for (int jp = 0; jp < 4; ++jp) {
+                    const f2 arg = fma2(xs[jp], kMinusOne, PRIOR ? add2(pr[jp], R2) : R2);
+                    us[jp] = mul2(xs[jp], pack2(fast_ex2(lo2(arg)), fast_ex2(hi2(arg))));
+                    const f2 dd = add2(us[jp], nthr2);
+                    nearm = fminf(nearm, fminf(fabsf(lo2(dd)), fabsf(hi2(dd))));
+                    uv[2 * jp] = (lo2(us[jp]) > thr) ? lo2(us[jp]) : 0.f;
+                    uv[2 * jp + 1] = (hi2(us[jp]) > thr) ? hi2(us[jp]) : 0.f;
+                }
+                if (P.ex.x && __any_sync(0xffffffffu, nearm < thr * P.ex_tol)) {
+                    // a weight within the fp32 error of the cut: the float64 arithmetic of the reference decides
+                    if (nearm < thr * P.ex_tol && oidx >= 0) {
+                        const int cnt_i = SLOW ? 2 * npair_full + (odd ? 1 : 0) : (1 << 30);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float uq = (q & 1) ? hi2(us[q >> 1]) : lo2(us[q >> 1]);
+                            const int jm = 2 * (p0 + (q >> 1)) + (q & 1);
+                            if (fabsf(uq - thr) < thr * P.ex_tol && jm < cnt_i) {
+                                uv[q] = fzb_exact_selected(P.ex, oidx, first_i + jm) ? uq : 0.f;
+                                if (P.ex_count) atomicAdd(P.ex_count, 1u);
+                            }
+                        }
+                    }
+                }
 #pragma unroll
                 for (int jp = 0; jp < 4; ++jp) {
                     const int p = p0 + jp;
-                    const f2 arg = fma2(xs[jp], kMinusOne, PRIOR ? add2(pr[jp], R2) : R2);
-                    const f2 u = mul2(xs[jp], pack2(fast_ex2(lo2(arg)), fast_ex2(hi2(arg))));
-                    const float u0 = (lo2(u) > thr) ? lo2(u) : 0.f;
-                    const float u1 = (hi2(u) > thr) ? hi2(u) : 0.f;
+                    const float u0 = uv[2 * jp], u1 = uv[2 * jp + 1];
                     if (!SLOW) {
                         acc2 = fma2(pack2(u0, u1), pack2(sub_inv, sub_inv), acc2);
                     } else {

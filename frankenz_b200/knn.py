@@ -202,6 +202,24 @@ class NearestNeighbors(object):
                          label_grid, kde_args, kde_kwargs, lprob_args, lprob_kwargs, track_scale, save_fits, rstate):
         if label_dict is None and label_grid is None:
             raise ValueError("`label_dict` or `label_grid` must be specified.")
+        if not save_fits:
+            # nothing is kept (knn.py:806-815 skips every store): search, union, fits and KDE stay on the device
+            _check_lprob_func(lprob_func)
+            _check_args(lprob_args, "lprob_args")
+            _check_args(kde_args, "kde_args")
+            lk = dict(lprob_kwargs or {})
+            if rstate is None:
+                rstate = np.random
+            self._engine.set_lnprior(lk.get("lnprior", None), lk.get("lnprior_bin", None))
+            self._engine.set_kde(model_labels, model_label_errs, label_dict=label_dict, label_grid=label_grid,
+                                 kde_kwargs=kde_kwargs)
+            cfg = make_config(lk, kde_kwargs, track_scale=False)
+            q = self._query_features(data, data_err, rstate)
+            clean_inplace(data, data_err, data_mask)
+            pdfs, lmap, levid, nn = self._engine.knn_fit_predict(q, data, data_err, data_mask, self.k, self.lp_norm, cfg)
+            self.NDATA = len(data)
+            self.Nneighbors_last = nn
+            return pdfs, lmap, levid
         res = self._run_fit(data, data_err, data_mask, lprob_func, rstate, lprob_args, lprob_kwargs, track_scale,
                             save_fits, self.k, self.lp_norm)
         return self._predict_all(model_labels, model_label_errs, label_dict, label_grid, None, kde_args, kde_kwargs,

@@ -217,6 +217,12 @@ int fzb_knn_fit(fzb_handle h, const double* qfeats, const double* data, const do
                 const double* data_mask, int64_t No, int32_t k, double p, const FzbConfig* cfg,
                 int64_t* neighbors, int64_t* nneighbors, const FzbFitOut* out);
 
+/* Search + union + fits + KDE in one call, without the (No x K k) fit arrays: NearestNeighbors.fit_predict with
+ * save_fits=False (knn.py:722-874).  pdfs host (No x Ngrid); lmap / levid / nneighbors nullable host [No]. */
+int fzb_knn_fit_predict(fzb_handle h, const double* qfeats, const double* data, const double* data_err,
+                        const double* data_mask, int64_t No, int32_t k, double p, const FzbConfig* cfg, double* pdfs,
+                        double* lmap, double* levid, int64_t* nneighbors);
+
 /* Likelihood of every object against its own list of models (the gather half of fzb_knn_fit, lists from the host):
  * SOM / GNG node-fit second stage, networks.py:918-923.  neighbors host int64 (No x W), row i uses its first nneighbors[i]
  * entries; out arrays (No x W), padded like fzb_knn_fit. */

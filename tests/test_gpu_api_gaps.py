@@ -122,3 +122,31 @@ def test_generator_twins_stream_in_chunks(sdss_mock, monkeypatch):
     got = [p.copy() for p, _ in bf2._fit_predict(x.copy(), xe.copy(), xm.copy(), z[:900], labe, label_dict=rdict,
                                                  save_fits=False)]
     assert np.max(np.abs(np.array(got) - ref)) <= 1e-12
+
+
+def test_knn_fit_predict_without_saved_fits(sdss_mock):
+    """NearestNeighbors.fit_predict(save_fits=False) keeps search, union, fits and KDE on the device
+    (fzb_knn_fit_predict); the PDFs must equal those of the fit + predict route, and nothing is stored."""
+    import frankenz_b200 as fz
+    phot, err, z = sdss_mock
+    m, me, mm = phot[:4500].copy(), err[:4500].copy(), np.ones((4500, 5))
+    x, xe, xm = phot[4500:4800].copy(), err[4500:4800].copy(), np.ones((300, 5))
+    x[3, 2] = np.nan
+    depth = golden("sdss_cww_mock.npz")["depth_flux1sig"]
+    kw = dict(skynoise=depth, zeropoints=10 ** (-0.4 * -23.9))
+    zgrid = np.arange(0, 7 + 1e-5, 0.01)
+    rdict = fz.pdf.PDFDict(zgrid, np.linspace(0.005, 2, 500))
+    labe = np.full(4500, 0.05)
+    for lk in (dict(), dict(free_scale=True, ignore_model_err=True)):
+        nn = fz.NearestNeighbors(m, me, mm, K=4, fmap_kwargs=kw, rstate=np.random.RandomState(1), verbose=False)
+        p1, (lm1, le1) = nn.fit_predict(x.copy(), xe.copy(), xm.copy(), z[:4500], labe, label_dict=rdict, k=12, eps=0,
+                                        rstate=np.random.RandomState(2), return_gof=True, verbose=False, lprob_kwargs=lk)
+        nnb = nn.Nneighbors.copy()
+        nn2 = fz.NearestNeighbors(m, me, mm, K=4, fmap_kwargs=kw, rstate=np.random.RandomState(1), verbose=False)
+        p2, (lm2, le2) = nn2.fit_predict(x.copy(), xe.copy(), xm.copy(), z[:4500], labe, label_dict=rdict, k=12, eps=0,
+                                         rstate=np.random.RandomState(2), return_gof=True, verbose=False,
+                                         lprob_kwargs=lk, save_fits=False)
+        assert nn2.fit_lnprob is None and nn2.neighbors is None
+        assert np.array_equal(nn2.Nneighbors_last, nnb)
+        assert np.allclose(p1, p2, rtol=0, atol=1e-13) and np.array_equal(lm1, lm2)
+        assert np.allclose(le1, le2, rtol=1e-14, atol=0)

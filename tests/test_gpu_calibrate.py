@@ -1,0 +1,52 @@
+"""Parity of the fused fp32 / tensor-core path at scale (the former tools/calibrate_fast.py): the C3
+workload on 65,536 objects against all 199,950 models of the reference's FLOAT64 template grid, fused path against the
+float64 reference-order kernels for every object and against the CPU oracle on spot rows.  Bounds are the north_star's:
+PDFs 1e-5 L1, lmap / levid 1e-5 max(1, |x|)."""
+import numpy as np
+import pytest
+
+import bench_data
+from oracle import fz_oracle as fo
+
+pytestmark = pytest.mark.gpu
+LPROB = dict(free_scale=True, ignore_model_err=True, dim_prior=True)
+
+
+@pytest.mark.parametrize("float64_grid", [True, False])
+def test_c3_fused_path_against_float64_at_65k_objects(float64_grid):
+    import frankenz_b200 as fz
+    n = 65536
+    models, labels, depth = bench_data.c3_models(float64_grid=float64_grid)
+    assert np.array_equal(models.astype(np.float32).astype(np.float64), models) == (not float64_grid)
+    x, xe, xm, _, _ = bench_data.c3_objects(n, models, depth, seed=20260103)
+    zgrid, sig = bench_data.c3_kde()
+    rdict = fz.pdf.PDFDict(zgrid, sig)
+    labe = np.full(len(models), 0.05)
+    bf = fz.BruteForce(models, np.zeros_like(models), np.ones_like(models))
+    res = {}
+    for mode in ("auto", "fp64"):
+        p, (lm, le) = bf.fit_predict(x.copy(), xe.copy(), xm.copy(), labels, labe, label_dict=rdict, return_gof=True,
+                                     verbose=False, save_fits=False, lprob_kwargs=dict(LPROB, precision=mode))
+        res[mode] = (p, lm, le, bf.best_idx.copy(), bf._eng().stats())
+    p, lm, le, bi, st = res["auto"]
+    p64, lm64, le64, bi64, _ = res["fp64"]
+    assert st["sweep_kind"] == 3 and st["pairs_fp32"] > 1.5 * n * len(models)       # the tensor-core sweep did the work
+    l1 = np.sum(np.abs(p - p64), axis=1)
+    dl = np.abs(lm - lm64) / np.maximum(1, np.abs(lm64))
+    de = np.abs(le - le64) / np.maximum(1, np.abs(le64))
+    print("float64_grid=%s: max L1 %.3g (99.9%% %.3g, median %.3g), max dlmap %.3g, max dlevid %.3g, arg-max mismatches %d"
+          % (float64_grid, l1.max(), np.percentile(l1, 99.9), np.median(l1), dl.max(), de.max(), int(np.sum(bi != bi64))))
+    assert l1.max() <= 1e-5 and dl.max() <= 1e-5 and de.max() <= 1e-5
+    assert np.percentile(l1, 99.9) <= 2e-6
+    # where the arg-max differs the two models are equally good to the tolerance (lmap agrees); it must stay rare
+    assert np.mean(bi != bi64) < 0.02
+    # oracle (numpy restatement of the reference, pinned to its golden vectors) on spot rows incl. the worst ones
+    spot = np.unique(np.concatenate([np.argsort(l1)[-3:], [0, 777, 40001]]))
+    kd = fo.KernelDict(zgrid, sig)
+    with np.errstate(all="ignore"):
+        po, lmo, leo = fo.bruteforce_fit_predict(models, np.zeros_like(models), np.ones_like(models), x[spot].copy(),
+                                                 xe[spot].copy(), xm[spot].copy(), labels, labe, label_dict=kd, **LPROB)
+    assert np.max(np.sum(np.abs(p[spot] - po), axis=1)) <= 1e-5
+    assert np.max(np.sum(np.abs(p64[spot] - po), axis=1)) <= 1e-9
+    assert np.all(np.abs(lm[spot] - lmo) <= 1e-5 * np.maximum(1, np.abs(lmo)))
+    assert np.all(np.abs(le[spot] - leo) <= 1e-5 * np.maximum(1, np.abs(leo)))
