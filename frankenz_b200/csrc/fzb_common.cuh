@@ -78,6 +78,7 @@ struct FastModels {
     DevBuf invnorm;        // float [nm_pad]: 1 / kernel normalisation of each sorted model
     DevBuf live;           // pass-2 pruning: live bits of the tensor-core sweep, [model tile x half][object] uint16
     DevBuf sortbuf;        // keys / values / temporary storage of the sort of the pass-2 object list
+    DevBuf cutlist;        // weights recorded at the wt_thresh cut by pass 2 (CutRecord), re-decided in float64
     int nslot = 0;         // distinct dictionary widths in use
     std::vector<int32_t> slot_sidx;  // slot -> dictionary index
     DevBuf d_slot_sidx;

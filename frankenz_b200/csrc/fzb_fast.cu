@@ -274,14 +274,12 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
                     best[2 * p + 1] = g1 ? (int)(first + jj) : best[2 * p + 1];
                 } else {
                     float u0 = fast_ex2(d0), u1 = fast_ex2(d1);
-                    bool s0 = lo2(l) > thr[2 * p], s1 = hi2(l) > thr[2 * p + 1];
-                    if (P.ex.x) {      // weights within the fp32 error of the cut: float64 decides (fzb_sweep_common.cuh)
+                    const bool s0 = lo2(l) > thr[2 * p], s1 = hi2(l) > thr[2 * p + 1];
+                    if (P.ex_list) {   // weights within the fp32 error of the cut: recorded for k_exact_cut_fix
                         const float band = P.ex_tol * 1.4427f;
                         const bool n0 = fabsf(lo2(l) - thr[2 * p]) < band, n1 = fabsf(hi2(l) - thr[2 * p + 1]) < band;
-                        if (n0 || n1) {
-                            if (n0 && oidx[2 * p] >= 0) { s0 = fzb_exact_selected(P.ex, oidx[2 * p], (int)(first + jj)); if (P.ex_count) atomicAdd(P.ex_count, 1u); }
-                            if (n1 && oidx[2 * p + 1] >= 0) { s1 = fzb_exact_selected(P.ex, oidx[2 * p + 1], (int)(first + jj)); if (P.ex_count) atomicAdd(P.ex_count, 1u); }
-                        }
+                        if (n0 && oidx[2 * p] >= 0) record_cut(P, oidx[2 * p], (int)(first + jj), u0, s0);
+                        if (n1 && oidx[2 * p + 1] >= 0) record_cut(P, oidx[2 * p + 1], (int)(first + jj), u1, s1);
                     }
                     u0 = s0 ? u0 : 0.f;
                     u1 = s1 ? u1 : 0.f;
@@ -827,6 +825,52 @@ __global__ void __launch_bounds__(256) k_finish(FinishParams P) {
     for (int g = tid; g < P.Ng; g += 256) out[g] = pdf[g] / tot;
 }
 
+// ---- float64 re-decision of the weights recorded at the wt_thresh cut (CutRecord, fzb_sweep_common.cuh) -------------
+struct CutFixParams {
+    const CutRecord* list;
+    const unsigned int* count;
+    unsigned int cap;
+    const double *x, *xe, *xm;      // raw objects of the chunk
+    const double *m, *me, *mm;      // models, original order
+    const double* lnprior;          // nullable
+    const int32_t* perm;            // sorted position -> original model
+    const int32_t* bins;            // sorted position -> histogram bin
+    const float* invnorm;           // sorted position -> 1 / kernel normalisation
+    const double* lmap;             // [chunk] exact maximum of the ln-posterior (the global one in a sharded pass 2)
+    double ln_wt_thresh;
+    int Nf, free_scale, ime, dim_prior;
+    float* hist;
+    int64_t hist_stride;
+    unsigned int* changed;          // statistics
+};
+
+__global__ void k_exact_cut_fix(CutFixParams P) {
+    const unsigned int n = min(*P.count, P.cap);
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const CutRecord r = P.list[i];
+        double sx[FZB_FAST_MAXF], sxe[FZB_FAST_MAXF], sxm[FZB_FAST_MAXF];
+        for (int b = 0; b < P.Nf; ++b) {
+            const double d = P.x[(size_t)r.obj * P.Nf + b], e = P.xe[(size_t)r.obj * P.Nf + b], k = P.xm[(size_t)r.obj * P.Nf + b];
+            const bool clean = isfinite(d) && isfinite(e) && (e > 0.0);
+            sx[b] = clean ? d : 0.0;
+            sxe[b] = clean ? e : 1.0;
+            sxm[b] = clean ? k : 0.0;
+        }
+        const int64_t j = P.perm[r.model];
+        fzb64::PairState st;
+        fzb64::pair_first(sx, sxe, sxm, P.m + j * P.Nf, P.me + j * P.Nf, P.mm + j * P.Nf, P.Nf, P.free_scale, P.ime, st);
+        const double a = P.free_scale ? 0.5 * (st.ndim - 1.0) : 0.5 * st.ndim;
+        double l = P.dim_prior ? fzb64::chi2_logpdf(st.chi2, a) : st.lnl;
+        if (P.lnprior) l += P.lnprior[j];
+        const bool sel = l > P.lmap[r.obj] + P.ln_wt_thresh;        // what the float64 path decides (pdf.py:589-591)
+        if (sel != (r.selected != 0)) {
+            const float delta = (sel ? r.weight : -r.weight) * P.invnorm[r.model];
+            atomicAdd(P.hist + (int64_t)r.obj * P.hist_stride + P.bins[r.model], delta);
+            if (P.changed) atomicAdd(P.changed, 1u);
+        }
+    }
+}
+
 // ---- record building ------------------------------------------------------------------------------
 struct RecParams {
     const double *m, *me, *lnprior;
@@ -1220,6 +1264,10 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         live = h->fast.live.as<unsigned short>();
         if (h->fast.sortbuf.reserve((size_t)chunk_pad * 16 + 256)) return 1;
     }
+    // weights at the wt_thresh cut are recorded by pass 2 and re-decided in float64 (k_exact_cut_fix)
+    const bool exact_cut = kde && cfg.use_wt_thresh && getenv("FZB_NO_EXACT_CUT") == nullptr;
+    const unsigned int cut_cap = (unsigned int)std::min<int64_t>((int64_t)1 << 26, std::max<int64_t>(1 << 16, 8 * chunk_pad));
+    if (exact_cut && h->fast.cutlist.reserve((size_t)cut_cap * sizeof(CutRecord) + 64)) return 1;
     if (F.aux64.reserve((size_t)chunk_pad * 40 + 64)) return 1;
     double* M2d = F.aux64.as<double>();
     double* thr2d = M2d + chunk_pad;
@@ -1405,19 +1453,12 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                     FZB_CUDA(cudaMemsetAsync(counts + 8, 0, 8, h->stream));
                     SP.pairs_done = reinterpret_cast<unsigned long long*>(counts + 8);
                 }
-                if (cfg.use_wt_thresh && !mm && getenv("FZB_NO_EXACT_CUT") == nullptr) {
-                    // weights within the fp32 error of the wt_thresh cut are re-decided in float64
-                    SP.ex.x = PP.x; SP.ex.xe = PP.xe; SP.ex.xm = PP.xm;
-                    SP.ex.m = h->models.as<double>(); SP.ex.me = h->models_err.as<double>(); SP.ex.mm = h->models_mask.as<double>();
-                    SP.ex.lnprior = h->has_lnprior ? h->lnprior.as<double>() : nullptr;
-                    SP.ex.perm = F.perm.as<int32_t>();
-                    SP.ex.lmap = (shard_mode == 2) ? d_glmap : lmap_local;
-                    SP.ex.ln_wt_thresh = std::log(cfg.wt_thresh);
-                    SP.ex.Nf = nf; SP.ex.free_scale = cfg.free_scale; SP.ex.ime = cfg.ignore_model_err != 0;
-                    SP.ex.dim_prior = cfg.dim_prior;
-                    SP.ex_tol = (float)env_double("FZB_EXACT_CUT_TOL", 3e-5);
-                    FZB_CUDA(cudaMemsetAsync(counts + 10, 0, 4, h->stream));
+                if (exact_cut) {
+                    FZB_CUDA(cudaMemsetAsync(counts + 10, 0, 8, h->stream));
+                    SP.ex_list = h->fast.cutlist.as<CutRecord>();
                     SP.ex_count = reinterpret_cast<unsigned int*>(counts + 10);
+                    SP.ex_cap = cut_cap;
+                    SP.ex_tol = (float)env_double("FZB_EXACT_CUT_TOL", 3e-5);
                 }
                 SP.No = nsafe; SP.objlist = safe_list; SP.M2 = M2; SP.thr2 = thr2; SP.hist = hist;
                 SP.hist_stride = hist_stride;
@@ -1437,6 +1478,21 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                 S6.tiles_per_split = tps64;
                 if (launch_sweep64(h, S6, dim3((unsigned)t64, (unsigned)ns64), nf, mode, cfg.dim_prior != 0, 2)) return 1;
                 h->stats.pairs_fp64 += nsafe64 * nm;
+            }
+            if (exact_cut && nsafe > 0) {
+                CutFixParams CF = {};
+                CF.list = h->fast.cutlist.as<CutRecord>(); CF.count = reinterpret_cast<unsigned int*>(counts + 10);
+                CF.cap = cut_cap; CF.x = PP.x; CF.xe = PP.xe; CF.xm = PP.xm;
+                CF.m = h->models.as<double>(); CF.me = h->models_err.as<double>(); CF.mm = h->models_mask.as<double>();
+                CF.lnprior = h->has_lnprior ? h->lnprior.as<double>() : nullptr;
+                CF.perm = F.perm.as<int32_t>(); CF.bins = F.bins.as<int32_t>(); CF.invnorm = F.invnorm.as<float>();
+                CF.lmap = (shard_mode == 2) ? d_glmap : lmap_local;
+                CF.ln_wt_thresh = std::log(cfg.wt_thresh);
+                CF.Nf = nf; CF.free_scale = cfg.free_scale; CF.ime = cfg.ignore_model_err != 0; CF.dim_prior = cfg.dim_prior;
+                CF.hist = hist; CF.hist_stride = hist_stride; CF.changed = reinterpret_cast<unsigned int*>(counts + 11);
+                k_exact_cut_fix<<<h->sm_count * 2, 256, 0, h->stream>>>(CF);
+                fzb_count_launch(h);
+                FZB_CUDA(cudaGetLastError());
             }
             FZB_CUDA(cudaEventRecord(h->ev[5], h->stream));
             FinishParams FP = {};
@@ -1463,9 +1519,14 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             FZB_CUDA(cudaGetLastError());
             FZB_CUDA(cudaEventRecord(h->ev[6], h->stream));
             unsigned long long pdone = 0;
+            unsigned int cutc[2] = {0, 0};
             if (prune && nsafe > 0)
                 FZB_CUDA(cudaMemcpyAsync(&pdone, counts + 8, 8, cudaMemcpyDeviceToHost, h->stream));
+            if (exact_cut && nsafe > 0)
+                FZB_CUDA(cudaMemcpyAsync(cutc, counts + 10, 8, cudaMemcpyDeviceToHost, h->stream));
             FZB_CUDA(cudaStreamSynchronize(h->stream));
+            h->stats.cut_recorded += cutc[0];
+            h->stats.cut_changed += cutc[1];
             h->stats.pairs_pass2 += (prune && nsafe > 0) ? (int64_t)pdone : nsafe * nm;
             h->stats.pairs_pass2 += nsafe64 * nm;
             FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]));

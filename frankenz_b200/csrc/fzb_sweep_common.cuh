@@ -4,43 +4,22 @@
 #include <cfloat>
 
 #include "fzb_common.cuh"
-#include "fzb_pair64.cuh"
 
 namespace fzbsweep {
 
-// ---- exact decision for weights at the wt_thresh cut ------------------------------------------------------------------
+// ---- weights at the wt_thresh cut -------------------------------------------------------------------------------------
 // The selection wt > wt_thresh max(wt) (pdf.py:589-591) is a hard cut: a model whose fp32 weight lies within the fp32
 // error of the cut could fall on the other side than in float64 and move wt_thresh / sum(wt) of the PDF.  Pass 2 of the
-// sweeps therefore re-decides every weight within ExactSel::tol (relative) of the cut with the float64 pair arithmetic
-// of the reference (fzb_pair64.cuh) against the exact maximum: rare (a few per thousand objects), so it runs in a
-// non-inlined slow path.
-struct ExactSel {
-    const double *x, *xe, *xm;      // raw objects of the chunk (No x Nf); null = no exact re-decision
-    const double *m, *me, *mm;      // models, original order
-    const double* lnprior;          // nullable
-    const int32_t* perm;            // sorted position -> original model
-    const double* lmap;             // [chunk] exact maximum of ln-posterior (global maximum in a model-sharded pass 2)
-    double ln_wt_thresh;
-    int Nf, free_scale, ime, dim_prior;
+// sweeps therefore RECORDS every weight within ex_tol (relative) of the cut - (object, model, weight, fp32 decision), a
+// few per thousand sub-batches - and k_exact_cut_fix (fzb_fast.cu) re-decides them with the float64 pair arithmetic of
+// the reference against the exact maximum, correcting the histogram where the decision changes.  The hot loop only pays
+// for the detection (one packed add and one 3-input minimum per two weights).
+struct CutRecord {
+    int obj;          // chunk-local object
+    int model;        // sorted model position
+    float weight;     // the fp32 weight (relative to the pass-2 maximum)
+    int selected;     // the fp32 decision
 };
-
-static __device__ __noinline__ bool fzb_exact_selected(const ExactSel& E, int o, int sorted_j) {
-    double sx[FZB_FAST_MAXF], sxe[FZB_FAST_MAXF], sxm[FZB_FAST_MAXF];
-    for (int b = 0; b < E.Nf; ++b) {
-        const double d = E.x[(size_t)o * E.Nf + b], e = E.xe[(size_t)o * E.Nf + b], k = E.xm[(size_t)o * E.Nf + b];
-        const bool clean = isfinite(d) && isfinite(e) && (e > 0.0);
-        sx[b] = clean ? d : 0.0;
-        sxe[b] = clean ? e : 1.0;
-        sxm[b] = clean ? k : 0.0;
-    }
-    const int64_t j = E.perm[sorted_j];
-    fzb64::PairState st;
-    fzb64::pair_first(sx, sxe, sxm, E.m + j * E.Nf, E.me + j * E.Nf, E.mm + j * E.Nf, E.Nf, E.free_scale, E.ime, st);
-    const double a = E.free_scale ? 0.5 * (st.ndim - 1.0) : 0.5 * st.ndim;
-    double l = E.dim_prior ? fzb64::chi2_logpdf(st.chi2, a) : st.lnl;
-    if (E.lnprior) l += E.lnprior[j];
-    return l > E.lmap[o] + E.ln_wt_thresh;
-}
 
 constexpr int TM = 256;          // models per shared-memory tile
 constexpr int NSTAGE = 2;
@@ -125,10 +104,16 @@ struct SweepParams {
     unsigned short* live;
     float live_thr;
     unsigned long long* pairs_done;   // pass 2: object-model pairs actually evaluated (statistics)
-    ExactSel ex;                      // pass 2: float64 re-decision of the weights at the cut (ex.x null: off)
-    float ex_tol;                     // relative half-width of the band around the cut that is re-decided
-    unsigned int* ex_count;           // statistics: re-decided weights
+    CutRecord* ex_list;               // pass 2: weights within ex_tol of the cut (null: off), see CutRecord
+    unsigned int* ex_count;
+    unsigned int ex_cap;
+    float ex_tol;                     // relative half-width of the band around the cut
 };
+
+__device__ __forceinline__ void record_cut(const SweepParams& P, int obj, int model, float weight, bool selected) {
+    const unsigned int at = atomicAdd(P.ex_count, 1u);
+    if (at < P.ex_cap) P.ex_list[at] = CutRecord{obj, model, weight, selected ? 1 : 0};
+}
 
 
 typedef unsigned long long f2;

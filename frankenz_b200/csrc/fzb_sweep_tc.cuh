@@ -377,13 +377,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                     best1 = g1 ? idx0 + 1 : best1;
                 } else {
                     float u0 = fast_ex2(lo2(delta)), u1 = fast_ex2(hi2(delta));
-                    bool s0 = lo2(l) > thr, s1 = hi2(l) > thr;
-                    if (P.ex.x) {      // log2 domain: a band of ex_tol / ln 2 around the cut is re-decided in float64
+                    const bool s0 = lo2(l) > thr, s1 = hi2(l) > thr;
+                    if (P.ex_list) {   // log2 domain: a band of ex_tol / ln 2 around the cut is recorded for float64
                         const float band = P.ex_tol * 1.4427f;
                         const bool n0 = fabsf(lo2(l) - thr) < band, n1 = fabsf(hi2(l) - thr) < band && !(SLOW && tail);
                         if (__any_sync(0xffffffffu, n0 || n1)) {
-                            if (n0 && oidx >= 0) { s0 = fzb_exact_selected(P.ex, oidx, idx0); if (P.ex_count) atomicAdd(P.ex_count, 1u); }
-                            if (n1 && oidx >= 0) { s1 = fzb_exact_selected(P.ex, oidx, idx0 + 1); if (P.ex_count) atomicAdd(P.ex_count, 1u); }
+                            if (n0 && oidx >= 0) record_cut(P, oidx, idx0, u0, s0);
+                            if (n1 && oidx >= 0) record_cut(P, oidx, idx0 + 1, u1, s1);
                         }
                     }
                     u0 = s0 ? u0 : 0.f;
@@ -523,18 +523,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                     uv[2 * jp] = (lo2(us[jp]) > thr) ? lo2(us[jp]) : 0.f;
                     uv[2 * jp + 1] = (hi2(us[jp]) > thr) ? hi2(us[jp]) : 0.f;
                 }
-                if (P.ex.x && __any_sync(0xffffffffu, nearm < thr * P.ex_tol)) {
-                    // a weight within the fp32 error of the cut: the float64 arithmetic of the reference decides
+                if (P.ex_list && __any_sync(0xffffffffu, nearm < thr * P.ex_tol)) {
+                    // weights within the fp32 error of the cut: recorded, re-decided in float64 by k_exact_cut_fix
                     if (nearm < thr * P.ex_tol && oidx >= 0) {
                         const int cnt_i = SLOW ? 2 * npair_full + (odd ? 1 : 0) : (1 << 30);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const float uq = (q & 1) ? hi2(us[q >> 1]) : lo2(us[q >> 1]);
                             const int jm = 2 * (p0 + (q >> 1)) + (q & 1);
-                            if (fabsf(uq - thr) < thr * P.ex_tol && jm < cnt_i) {
-                                uv[q] = fzb_exact_selected(P.ex, oidx, first_i + jm) ? uq : 0.f;
-                                if (P.ex_count) atomicAdd(P.ex_count, 1u);
-                            }
+                            if (fabsf(uq - thr) < thr * P.ex_tol && jm < cnt_i) record_cut(P, oidx, first_i + jm, uq, uq > thr);
                         }
                     }
                 }

@@ -84,6 +84,8 @@ typedef struct FzbStats {
     int64_t pairs_pass2;       /* object-model pairs pass 2 actually evaluated (after sub-batch pruning)       */
     double  ms_summarize;      /* CUDA-event time of the fused PDF summaries (fzb_fit_predict_summarize)        */
     int64_t knn_tc;            /* 1: the last kNN search generated its candidates on the tensor cores           */
+    int64_t cut_recorded;      /* pass 2: weights within the fp32 error of the wt_thresh cut, re-decided in float64   */
+    int64_t cut_changed;       /* ... of which the float64 decision differed from the fp32 one                 */
     double  knn_tc_err;        /* largest error of a tensor-core candidate distance seen by the float64 re-rank, in
                                   units of (|q'|^2 + max |f'|^2); the exactness test assumes <= 4e-6            */
 } FzbStats;

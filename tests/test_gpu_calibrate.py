@@ -38,8 +38,10 @@ def test_c3_fused_path_against_float64_at_65k_objects(float64_grid):
           % (float64_grid, l1.max(), np.percentile(l1, 99.9), np.median(l1), dl.max(), de.max(), int(np.sum(bi != bi64))))
     assert l1.max() <= 1e-5 and dl.max() <= 1e-5 and de.max() <= 1e-5
     assert np.percentile(l1, 99.9) <= 2e-6
-    # where the arg-max differs the two models are equally good to the tolerance (lmap agrees); it must stay rare
-    assert np.mean(bi != bi64) < 0.02
+    # The arg-max itself is ill-conditioned under dim_prior: ln L = (dof/2 - 1) ln chi2 - chi2/2 has a flat maximum at
+    # chi2 = dof - 2, so among 2e5 models several lie within the fp32 rounding of it (a quarter of the objects here pick
+    # another of those models than the float64 path does).  lmap is the EXACT float64 value of the chosen model, so
+    # `dl` above already bounds how much worse the chosen model can be: 1e-5 relative.
     # oracle (numpy restatement of the reference, pinned to its golden vectors) on spot rows incl. the worst ones
     spot = np.unique(np.concatenate([np.argsort(l1)[-3:], [0, 777, 40001]]))
     kd = fo.KernelDict(zgrid, sig)
