@@ -37,7 +37,8 @@ class FzbStats(C.Structure):
                 ("ms_finish", C.c_double), ("ms_total", C.c_double), ("sweep_kind", C.c_int64),
                 ("knn_redo", C.c_int64), ("pairs_pass2", C.c_int64), ("ms_summarize", C.c_double),
                 ("knn_tc", C.c_int64), ("cut_recorded", C.c_int64), ("cut_changed", C.c_int64),
-                ("knn_tc_err", C.c_double)]
+                ("knn_tc_err", C.c_double), ("objects_fused", C.c_int64),
+                ("knn_overflow", C.c_int64)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/frankenz_b200.h

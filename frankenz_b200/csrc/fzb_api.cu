@@ -373,7 +373,7 @@ int fzb_destroy(fzb_handle h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->models, &h->models_err, &h->models_mask, &h->lnprior, &h->prior_table, &h->prior_bins, &h->widths, &h->koff, &h->kernels,
                       &h->kcdf, &h->yidx, &h->ysidx, &h->grid, &h->y, &h->ystd, &h->lowers, &h->uppers, &h->rows,
-                      &h->knn_feats, &h->knn_cand, &h->knn_redo, &h->knn_tiles, &h->knn_aux, &h->kde_err, &h->summ[0], &h->summ[1], &h->summ[2], &h->summ[3], &h->summ[4], &h->summ[5], &h->fast.recs, &h->fast.tiles_tc, &h->fast.recs64, &h->fast.aux64, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
+                      &h->knn_feats, &h->knn_scan, &h->knn_buf, &h->knn_centre, &h->knn_cand, &h->knn_redo, &h->knn_tiles, &h->knn_aux, &h->kde_err, &h->summ[0], &h->summ[1], &h->summ[2], &h->summ[3], &h->summ[4], &h->summ[5], &h->fast.recs, &h->fast.tiles_tc, &h->fast.tiles_tc_coarse, &h->fast.fuse, &h->fast.recs64, &h->fast.aux64, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
                       &h->fast.d_slot_sidx, &h->fast.live, &h->fast.sortbuf, &h->fast.cutlist, &h->nz_pdfs, &h->nz_buf};
     for (auto* b : bufs) b->release();
     for (auto& b : h->obj_in) b.release();
@@ -941,6 +941,7 @@ int fzb_knn_build(fzb_handle h, const float* feats, int32_t K, int64_t Nm, int32
     h->knn_Nm = Nm;
     h->knn_Nf = Nf;
     h->knn_tc_valid = false;
+    if (fzb_knn_scan_build(h)) return 1;
     if (getenv("FZB_KNN_TC") != nullptr && atoi(getenv("FZB_KNN_TC")) != 0 && fzb_knn_tc_build(h)) return 1;
     return 0;
 }
@@ -1042,7 +1043,7 @@ int fzb_knn_fit_predict(fzb_handle h, const double* qfeats, const double* data, 
     if (check_prior_bins(h, No)) return 2;
     const int Nf = h->Nf, Ng = h->Ng;
     const int64_t W = (int64_t)h->knn_K * k;
-    int64_t chunk = std::min<int64_t>(No, 32768);
+    int64_t chunk = std::min<int64_t>(No, 65536);
     const size_t cn = (size_t)chunk * W;
     if (h->out_i64[0].reserve(cn * 8) || h->misc[3].reserve(cn * 8) || h->misc[4].reserve((size_t)chunk * 8) ||
         h->out_f64[1].reserve((size_t)No * 8) || h->out_f64[2].reserve((size_t)No * 8) || h->out_i64[1].reserve((size_t)No * 8))

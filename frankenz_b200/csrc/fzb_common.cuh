@@ -71,7 +71,10 @@ struct FastModels {
     DevBuf recs;           // [nm_pad][rec] float: see fzb_fast.cu for the record layout
     DevBuf recs64;         // [nm][rec64] double records of the float64 sweep
     DevBuf tiles_tc;       // tensor-core sweep: 256-model tiles (MMA operand + packed pairs + tails), fzb_sweep_tc.cuh
+    DevBuf tiles_tc_coarse; // the same for every FZB_TC_COARSE-th model of the sorted order (pre-pass of the fused sweep)
+    int64_t nm_coarse = 0;
     bool tc_valid = false;
+    DevBuf fuse;           // fused sweep: per-thread records, counts, seeds, object flags
     DevBuf aux64;          // per-object float64 pass-2 inputs
     DevBuf perm;           // int32 [nm_pad]: sorted position -> original model index (-1 = padding)
     DevBuf bins;           // int32 [nm_pad]: KDE histogram bin (slot*Ng + pos) of each sorted model, -1 = none
@@ -163,6 +166,12 @@ struct fzb_context {
     DevBuf knn_cand, knn_redo;
     DevBuf knn_tiles;       // tensor-core scan: centred, tf32-split row tiles of every tree (fzb_knn_tc.cu)
     DevBuf knn_aux;         // double: centre [FZB_FAST_MAXF], max |f'|^2 per tree [K]
+    DevBuf knn_scan;        // filter scan: interleaved, value-duplicated copy of the features (fzb_knn.cu)
+    DevBuf knn_buf;         // filter scan: per-(query, tree) row buffers, thresholds, counts
+    DevBuf knn_centre;      // filter scan, dot form: mean feature (double[Nf])
+    int knn_form = 0;       // fp32 distance form of the scan copy (fzb_knn.cu: KS_DIFF / KS_DOT)
+    bool knn_scan_valid = false;
+    int64_t knn_m = 0, knn_Ns = 0;   // interleave stride / rows of the scan copy
     bool knn_tc_valid = false;
     int64_t knn_ntile = 0;
     int knn_K = 0;
@@ -244,6 +253,7 @@ int fzb_nz_loglike_impl(fzb_context* h, const double* d_pdfs, int64_t No, int Ng
 
 // ---- kNN (fzb_knn.cu) -------------------------------------------------------------------------
 int fzb_knn_query_dev(fzb_context* h, const double* d_q, int64_t No, int k, double p, int64_t* d_idx, double* d_dist);
+int fzb_knn_scan_build(fzb_context* h);
 int fzb_knn_tc_build(fzb_context* h);
 int fzb_knn_tc_kcmax();
 int fzb_knn_tc_lists();

@@ -644,6 +644,15 @@ struct MergeParams {
     // routing: counts[0] fp32-safe (chunk-local), counts[1] degenerate -> generic kernel (absolute),
     //          counts[2] needs the float64 sweep (chunk-local), counts[3] float64-sweep objects ready for pass 2
     int32_t *safe_list, *unsafe_list, *prec_list, *safe64_list, *counts;
+    // fused single pass (k_sweep_tc<..., FUSE>): an fp32-safe object keeps its histogram when every thread that worked on
+    // it stayed in the frame of M0 without overflowing its record segment and the final maximum is within the recorded
+    // band above M0 -> fuse_list (counts[5]); otherwise safe_list (row cleared, pruned pass 2)
+    const int* fz_cnt;                  // [nsplit][No_pad], null: not a fused pass
+    const float* fz_M0;
+    int fz_cap;
+    double fz_glog2;                    // log2 of the band's upper edge, less a margin
+    unsigned char* fz_ok;               // [No_pad] out: 1 = histogram of the fused pass stands
+    int32_t* fuse_list;
 };
 
 __global__ void k_merge(MergeParams P) {
@@ -717,7 +726,17 @@ __global__ void k_merge(MergeParams P) {
     if (P.stage == 0) {
         P.M2[o] = (float)M;
         P.thr2[o] = (float)(M + P.log2_wt_thresh);
-        if (finite && precise) P.safe_list[atomicAdd(&P.counts[0], 1)] = (int32_t)o;
+        bool fok = false;
+        if (P.fz_cnt && finite && precise) {
+            fok = (M - (double)P.fz_M0[o]) <= P.fz_glog2;
+            for (int s = 0; s < P.nsplit; ++s) {
+                const int c = P.fz_cnt[(size_t)s * P.No_pad + o];
+                if (c < 0 || c > P.fz_cap) fok = false;
+            }
+        }
+        if (P.fz_ok) P.fz_ok[o] = fok ? 1 : 0;
+        if (fok) P.fuse_list[atomicAdd(&P.counts[5], 1)] = (int32_t)o;
+        else if (finite && precise) P.safe_list[atomicAdd(&P.counts[0], 1)] = (int32_t)o;
         else if (finite && P.prec_list) P.prec_list[atomicAdd(&P.counts[2], 1)] = (int32_t)o;
         else P.unsafe_list[atomicAdd(&P.counts[1], 1)] = (int32_t)og;
     } else {
@@ -844,31 +863,98 @@ struct CutFixParams {
     unsigned int* changed;          // statistics
 };
 
+__device__ __forceinline__ void cutfix_object(const CutFixParams& P, int obj, double* sx, double* sxe, double* sxm) {
+    for (int b = 0; b < P.Nf; ++b) {
+        const double d = P.x[(size_t)obj * P.Nf + b], e = P.xe[(size_t)obj * P.Nf + b], k = P.xm[(size_t)obj * P.Nf + b];
+        const bool clean = isfinite(d) && isfinite(e) && (e > 0.0);
+        sx[b] = clean ? d : 0.0;
+        sxe[b] = clean ? e : 1.0;
+        sxm[b] = clean ? k : 0.0;
+    }
+}
+// the float64 decision for one recorded weight (pdf.py:589-591); corrects the histogram where it differs
+__device__ __forceinline__ void cutfix_apply(const CutFixParams& P, int obj, int model, float weight, bool selected,
+                                             const double* sx, const double* sxe, const double* sxm) {
+    const int64_t j = P.perm[model];
+    fzb64::PairState st;
+    fzb64::pair_first(sx, sxe, sxm, P.m + j * P.Nf, P.me + j * P.Nf, P.mm + j * P.Nf, P.Nf, P.free_scale, P.ime, st);
+    const double a = P.free_scale ? 0.5 * (st.ndim - 1.0) : 0.5 * st.ndim;
+    double l = P.dim_prior ? fzb64::chi2_logpdf(st.chi2, a) : st.lnl;
+    if (P.lnprior) l += P.lnprior[j];
+    const bool sel = l > P.lmap[obj] + P.ln_wt_thresh;
+    if (sel != selected) {
+        const float delta = (sel ? weight : -weight) * P.invnorm[model];
+        atomicAdd(P.hist + (int64_t)obj * P.hist_stride + P.bins[model], delta);
+        if (P.changed) atomicAdd(P.changed, 1u);
+    }
+}
+
 __global__ void k_exact_cut_fix(CutFixParams P) {
     const unsigned int n = min(*P.count, P.cap);
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const CutRecord r = P.list[i];
         double sx[FZB_FAST_MAXF], sxe[FZB_FAST_MAXF], sxm[FZB_FAST_MAXF];
-        for (int b = 0; b < P.Nf; ++b) {
-            const double d = P.x[(size_t)r.obj * P.Nf + b], e = P.xe[(size_t)r.obj * P.Nf + b], k = P.xm[(size_t)r.obj * P.Nf + b];
-            const bool clean = isfinite(d) && isfinite(e) && (e > 0.0);
-            sx[b] = clean ? d : 0.0;
-            sxe[b] = clean ? e : 1.0;
-            sxm[b] = clean ? k : 0.0;
-        }
-        const int64_t j = P.perm[r.model];
-        fzb64::PairState st;
-        fzb64::pair_first(sx, sxe, sxm, P.m + j * P.Nf, P.me + j * P.Nf, P.mm + j * P.Nf, P.Nf, P.free_scale, P.ime, st);
-        const double a = P.free_scale ? 0.5 * (st.ndim - 1.0) : 0.5 * st.ndim;
-        double l = P.dim_prior ? fzb64::chi2_logpdf(st.chi2, a) : st.lnl;
-        if (P.lnprior) l += P.lnprior[j];
-        const bool sel = l > P.lmap[r.obj] + P.ln_wt_thresh;        // what the float64 path decides (pdf.py:589-591)
-        if (sel != (r.selected != 0)) {
-            const float delta = (sel ? r.weight : -r.weight) * P.invnorm[r.model];
-            atomicAdd(P.hist + (int64_t)r.obj * P.hist_stride + P.bins[r.model], delta);
-            if (P.changed) atomicAdd(P.changed, 1u);
+        cutfix_object(P, r.obj, sx, sxe, sxm);
+        cutfix_apply(P, r.obj, r.model, r.weight, r.selected != 0, sx, sxe, sxm);
+    }
+}
+
+// ---- fused single pass: seed, float64 re-decision of the recorded band, clearing of the rows that take pass 2 -------
+// seed of the running cut: the pre-pass maximum (two partials: the two threads of an object), lowered by a margin
+__global__ void k_fuse_seed(const double* __restrict__ pM, int64_t No, int64_t No_pad, float* __restrict__ M0) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= No_pad) return;
+    float v = -FLT_MAX;
+    if (o < No) {
+        const double m = fmax(pM[o], pM[No_pad + o]);
+        if (m > -1e30 && m < 1e30) v = (float)(m - 2e-4 - 1e-6 * fabs(m));
+    }
+    M0[o] = v;
+}
+
+struct FuseFixParams {
+    CutFixParams C;
+    const uint4* rec;        // [part][No_pad][cap] x 3
+    const int* cnt;          // [part][No_pad]
+    const unsigned char* ok;
+    int64_t No, No_pad, nm;
+    int nparts, cap;
+    float mid, half;         // the band in units of the record's cut
+    unsigned int* recorded;  // statistics
+};
+__global__ void k_fuse_fix(FuseFixParams P) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.No * P.nparts) return;
+    const int part = (int)(i / P.No);
+    const int obj = (int)(i - (int64_t)part * P.No);
+    if (!P.ok[obj]) return;
+    const int n = P.cnt[(size_t)part * P.No_pad + obj];
+    if (n <= 0) return;
+    double sx[FZB_FAST_MAXF], sxe[FZB_FAST_MAXF], sxm[FZB_FAST_MAXF];
+    cutfix_object(P.C, obj, sx, sxe, sxm);
+    const uint4* r = P.rec + ((size_t)part * P.No_pad + obj) * P.cap * 3;
+    unsigned int nw = 0;
+    for (int k = 0; k < n; ++k) {
+        const uint4 a = r[3 * k], b = r[3 * k + 1], c = r[3 * k + 2];
+        const int64_t first = a.x;
+        const float cut = __uint_as_float(a.y);
+        const float w[8] = {__uint_as_float(a.z), __uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y),
+                            __uint_as_float(b.z), __uint_as_float(b.w), __uint_as_float(c.x), __uint_as_float(c.y)};
+        const float cmid = cut * P.mid, chalf = cut * P.half;         // the kernel's own arithmetic
+        for (int q = 0; q < 8; ++q) {
+            if (first + q >= P.nm || !(fabsf(w[q] - cmid) <= chalf)) continue;
+            cutfix_apply(P.C, obj, (int)(first + q), w[q], w[q] > cut, sx, sxe, sxm);
+            ++nw;
         }
     }
+    if (P.recorded && nw) atomicAdd(P.recorded, nw);
+}
+
+__global__ void k_fuse_clear_rows(const unsigned char* __restrict__ ok, float* __restrict__ hist, int64_t hist_stride) {
+    const int64_t o = blockIdx.x;
+    if (ok[o]) return;
+    float* row = hist + o * hist_stride;
+    for (int64_t g = threadIdx.x; g < hist_stride; g += blockDim.x) row[g] = 0.f;
 }
 
 // ---- record building ------------------------------------------------------------------------------
@@ -1268,6 +1354,32 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     const bool exact_cut = kde && cfg.use_wt_thresh && getenv("FZB_NO_EXACT_CUT") == nullptr;
     const unsigned int cut_cap = (unsigned int)std::min<int64_t>((int64_t)1 << 26, std::max<int64_t>(1 << 16, 8 * chunk_pad));
     if (exact_cut && h->fast.cutlist.reserve((size_t)cut_cap * sizeof(CutRecord) + 64)) return 1;
+    // fused single pass (tensor-core sweep, linear-domain form): coarse pre-pass + one sweep that also fills the
+    // histogram; see k_sweep_tc<..., FUSE>
+    const bool fuse_on = use_tc && kde && cfg.use_wt_thresh && exact_cut && shard_mode == 0 && F.nm_coarse > 0 &&
+                         getenv("FZB_NO_FUSE") == nullptr;
+    const int fz_cap = (int)std::max<int64_t>(8, std::min<int64_t>(64, 512 / npart));      // sub-batch records per thread
+    const double fz_g = env_double("FZB_FUSE_BAND", 0.006);          // recorded band above the running cut, natural log units
+    uint4* fz_rec = nullptr;
+    int* fz_cnt = nullptr;
+    float* fz_M0 = nullptr;
+    unsigned char* fz_ok = nullptr;
+    int32_t* fuse_list = nullptr;
+    double *pS_c = nullptr, *pM_c = nullptr;
+    int32_t* pbest_c = nullptr;
+    if (fuse_on) {
+        const size_t n_rec = (size_t)npart * chunk_pad * fz_cap * 48, n_cnt = (size_t)npart * chunk_pad * 4;
+        const size_t n_c = (size_t)fzb_tc_split() * chunk_pad;
+        if (F.fuse.reserve(n_rec + n_cnt + (size_t)chunk_pad * (4 + 4 + 1) + n_c * 20 + 1024)) return 1;
+        fz_rec = F.fuse.as<uint4>();
+        pS_c = reinterpret_cast<double*>(fz_rec + (size_t)npart * chunk_pad * fz_cap * 3);
+        pM_c = pS_c + n_c;
+        pbest_c = reinterpret_cast<int32_t*>(pM_c + n_c);
+        fz_cnt = pbest_c + n_c;
+        fz_M0 = reinterpret_cast<float*>(fz_cnt + (size_t)npart * chunk_pad);
+        fuse_list = reinterpret_cast<int32_t*>(fz_M0 + chunk_pad);
+        fz_ok = reinterpret_cast<unsigned char*>(fuse_list + chunk_pad);
+    }
     if (F.aux64.reserve((size_t)chunk_pad * 40 + 64)) return 1;
     double* M2d = F.aux64.as<double>();
     double* thr2d = M2d + chunk_pad;
@@ -1333,16 +1445,35 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         SP.live = live;
         SP.live_thr = cfg.use_wt_thresh ? (float)(cfg.wt_thresh * (1.0 - 1e-4)) : 0.f;
         const int64_t tiles1 = (nc + tile_objs - 1) / tile_objs;
-        int64_t nsafe = 0, nsafe64 = 0, nunsafe = 0;
+        int64_t nsafe = 0, nsafe64 = 0, nunsafe = 0, nfuse = 0;
+        const bool fuse = fuse_on && use_lin;
         if (shard_mode != 2) {
         FZB_CUDA(cudaEventRecord(h->ev[2], h->stream));
-        if (use_tc ? fzb_launch_sweep_tc(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, cfg.dim_prior != 0, 1, use_lin, mlo)
+        if (fuse) {
+            // pre-pass over every FZB_TC_COARSE-th model -> lower bound of every object's maximum
+            SweepParams SC = SP;
+            SC.nm = F.nm_coarse; SC.tiles_per_split = (int)((F.nm_coarse + TM - 1) / TM);
+            SC.pM = pM_c; SC.pS = pS_c; SC.pbest = pbest_c; SC.live = nullptr;
+            if (fzb_launch_sweep_tc(h, SC, dim3((unsigned)tiles1, 1u), nf, true, 1, true, mlo, F.tiles_tc_coarse.as<unsigned char>()))
+                return 1;
+            k_fuse_seed<<<(unsigned)((nc_pad + 255) / 256), 256, 0, h->stream>>>(pM_c, nc, nc_pad, fz_M0);
+            fzb_count_launch(h);
+            FZB_CUDA(cudaGetLastError());
+            FZB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nc_pad * hist_stride * 4, h->stream));
+            SP.fz_M0 = fz_M0; SP.fz_thr = (float)cfg.wt_thresh;
+            SP.fz_lofac = 1.f - (float)env_double("FZB_EXACT_CUT_TOL", 3e-5); SP.fz_gfac = (float)std::exp(fz_g);
+            SP.fz_mid = 0.5f * (SP.fz_lofac + SP.fz_gfac); SP.fz_half = 0.5f * (SP.fz_gfac - SP.fz_lofac);
+            SP.fz_rec = fz_rec; SP.fz_cnt = fz_cnt; SP.fz_cap = fz_cap;
+            SP.hist = hist; SP.hist_stride = hist_stride;
+            h->stats.pairs_fp32 += nc * F.nm_coarse;
+        }
+        if (use_tc ? fzb_launch_sweep_tc(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, cfg.dim_prior != 0, 1, use_lin, mlo, nullptr, fuse)
                    : launch_sweep(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 1))
             return 1;
         FZB_CUDA(cudaEventRecord(h->ev[3], h->stream));
         h->stats.pairs_fp32 += nc * nm;
 
-        FZB_CUDA(cudaMemsetAsync(counts, 0, 16, h->stream));
+        FZB_CUDA(cudaMemsetAsync(counts, 0, 32, h->stream));
         MergeParams MP = {};
         MP.x = PP.x; MP.xe = PP.xe; MP.xm = PP.xm;
         MP.m = h->models.as<double>(); MP.me = h->models_err.as<double>(); MP.mm = h->models_mask.as<double>();
@@ -1365,14 +1496,23 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         MP.M2 = M2; MP.thr2 = thr2; MP.M2d = M2d; MP.thr2d = thr2d;
         MP.safe_list = safe_list; MP.unsafe_list = unsafe_list; MP.prec_list = use_sweep64 ? prec_list : nullptr;
         MP.safe64_list = safe64_list; MP.counts = counts;
+        if (fuse) {
+            MP.fz_cnt = fz_cnt; MP.fz_M0 = fz_M0; MP.fz_cap = fz_cap; MP.fz_ok = fz_ok; MP.fuse_list = fuse_list;
+            MP.fz_glog2 = (fz_g - 1e-3) * 1.4426950408889634 - 4e-4;     // the seed's margin and the fp32 error of the weights
+        }
         k_merge<<<(unsigned)((nc + 255) / 256), 256, 0, h->stream>>>(MP);
         fzb_count_launch(h);
         FZB_CUDA(cudaGetLastError());
-        FZB_CUDA(cudaMemcpyAsync(hc, counts, 16, cudaMemcpyDeviceToHost, h->stream));
+        int32_t hc8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        FZB_CUDA(cudaMemcpyAsync(hc8, counts, 32, cudaMemcpyDeviceToHost, h->stream));
         FZB_CUDA(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < 4; ++i) hc[i] = hc8[i];
         FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
         h->stats.ms_scan += ms;
         nsafe = hc[0];
+        nfuse = fuse ? hc8[5] : 0;
+        h->stats.objects_fused += nfuse;
+        MP.fz_cnt = nullptr; MP.fz_ok = nullptr;      // stage 1 (float64 sweep) routes as before
         const int64_t nprec = hc[2];
 
         // ---- objects whose fp32 result is not trusted: float64 sweep, pass 1 ---------------------------
@@ -1442,9 +1582,15 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                                                    d_levid, d_best_idx, d_best_chi2, d_best_scale))
                 return 1;
         }
-        if (kde && (nsafe > 0 || nsafe64 > 0)) {
+        if (kde && (nsafe > 0 || nsafe64 > 0 || nfuse > 0)) {
             FZB_CUDA(cudaEventRecord(h->ev[4], h->stream));
-            FZB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nc_pad * hist_stride * 4, h->stream));
+            if (fuse) {      // rows of the objects that did not keep their fused histogram start from zero again
+                k_fuse_clear_rows<<<(unsigned)nc, 256, 0, h->stream>>>(fz_ok, hist, hist_stride);
+                fzb_count_launch(h);
+                FZB_CUDA(cudaGetLastError());
+            } else {
+                FZB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nc_pad * hist_stride * 4, h->stream));
+            }
             if (nsafe > 0) {
                 if (prune && shard_mode != 2 &&
                     fzb_sort_by_live_bits(h, live, ntiles * fzb_tc_split(), nc_pad, safe_list, nsafe))
@@ -1494,6 +1640,25 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                 fzb_count_launch(h);
                 FZB_CUDA(cudaGetLastError());
             }
+            if (nfuse > 0) {
+                FuseFixParams FF = {};
+                CutFixParams& CF = FF.C;
+                CF.x = PP.x; CF.xe = PP.xe; CF.xm = PP.xm;
+                CF.m = h->models.as<double>(); CF.me = h->models_err.as<double>(); CF.mm = h->models_mask.as<double>();
+                CF.lnprior = h->has_lnprior ? h->lnprior.as<double>() : nullptr;
+                CF.perm = F.perm.as<int32_t>(); CF.bins = F.bins.as<int32_t>(); CF.invnorm = F.invnorm.as<float>();
+                CF.lmap = lmap_local;
+                CF.ln_wt_thresh = std::log(cfg.wt_thresh);
+                CF.Nf = nf; CF.free_scale = cfg.free_scale; CF.ime = cfg.ignore_model_err != 0; CF.dim_prior = cfg.dim_prior;
+                CF.hist = hist; CF.hist_stride = hist_stride; CF.changed = reinterpret_cast<unsigned int*>(counts + 11);
+                FF.rec = fz_rec; FF.cnt = fz_cnt; FF.ok = fz_ok; FF.No = nc; FF.No_pad = nc_pad; FF.nparts = (int)npart; FF.nm = nm;
+                FF.cap = fz_cap; FF.recorded = reinterpret_cast<unsigned int*>(counts + 10);
+                FF.mid = SP.fz_mid; FF.half = SP.fz_half;
+                if (!(exact_cut && nsafe > 0)) FZB_CUDA(cudaMemsetAsync(counts + 10, 0, 8, h->stream));
+                k_fuse_fix<<<(unsigned)((nc * npart + 127) / 128), 128, 0, h->stream>>>(FF);
+                fzb_count_launch(h);
+                FZB_CUDA(cudaGetLastError());
+            }
             FZB_CUDA(cudaEventRecord(h->ev[5], h->stream));
             FinishParams FP = {};
             FP.hist = hist; FP.hist_stride = hist_stride; FP.o_base = o0;
@@ -1510,6 +1675,12 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                 k_finish<<<(unsigned)nsafe, 256, smem, h->stream>>>(FP);
                 fzb_count_launch(h);
             }
+            if (nfuse > 0) {
+                FP.objlist = fuse_list;
+                FP.scale = nullptr;
+                k_finish<<<(unsigned)nfuse, 256, smem, h->stream>>>(FP);
+                fzb_count_launch(h);
+            }
             if (nsafe64 > 0) {
                 FP.objlist = safe64_list;
                 FP.scale = nullptr;
@@ -1522,7 +1693,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             unsigned int cutc[2] = {0, 0};
             if (prune && nsafe > 0)
                 FZB_CUDA(cudaMemcpyAsync(&pdone, counts + 8, 8, cudaMemcpyDeviceToHost, h->stream));
-            if (exact_cut && nsafe > 0)
+            if (exact_cut && (nsafe > 0 || nfuse > 0))
                 FZB_CUDA(cudaMemcpyAsync(cutc, counts + 10, 8, cudaMemcpyDeviceToHost, h->stream));
             FZB_CUDA(cudaStreamSynchronize(h->stream));
             h->stats.cut_recorded += cutc[0];

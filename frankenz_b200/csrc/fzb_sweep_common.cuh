@@ -108,6 +108,14 @@ struct SweepParams {
     unsigned int* ex_count;
     unsigned int ex_cap;
     float ex_tol;                     // relative half-width of the band around the cut
+    // fused single pass (k_sweep_tc<..., FUSE>): see the kernel's header comment
+    const float* fz_M0;               // [No_pad] lower bound of the object's maximum (sweep units), -FLT_MAX: none
+    float fz_thr;                     // wt_thresh
+    float fz_lofac, fz_gfac;          // recorded band relative to the running cut: (lofac, gfac]
+    float fz_mid, fz_half;            // (lofac + gfac) / 2, (gfac - lofac) / 2
+    uint4* fz_rec;                    // [part][No_pad][fz_cap] x 3: {first model position, cut, eight weights, -, -}
+    int* fz_cnt;                      // [part][No_pad] records of the thread (> fz_cap: overflow; -1: frame changed)
+    int fz_cap;
 };
 
 __device__ __forceinline__ void record_cut(const SweepParams& P, int obj, int model, float weight, bool selected) {
@@ -153,9 +161,11 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b) {
 
 // ---- tensor-core sweep (fzb_sweep_tc.cu) ----------------------------------------------------------------------------
 // lin: linear-domain form ((dof/2 - 1) = 1); mlo: the tiles carry the float64 remainder of the model fluxes
+// tiles: null = the full tile set of the context; fuse: the single-pass variant (pass 1, lin)
 int fzb_launch_sweep_tc(fzb_context* h, const fzbsweep::SweepParams& P, dim3 grid, int nf, bool dp, int pass, bool lin,
-                        bool mlo);
+                        bool mlo, const unsigned char* tiles = nullptr, bool fuse = false);
 // build the 256-model tiles (MMA operand + packed pairs + KDE tails) from the sorted model order; sets h->fast.tc_valid
 int fzb_build_tiles_tc(fzb_context* h, const double* lnprior, const int32_t* bins, const float* invnorm, bool mlo);
+constexpr int FZB_TC_COARSE = 16;     // the coarse tile set (h->fast.tiles_tc_coarse) holds every 16th model of the sorted order
 int fzb_tc_tile_objects();     // objects per CTA of the tensor-core sweep
 int fzb_tc_split();            // partial results per object and model split

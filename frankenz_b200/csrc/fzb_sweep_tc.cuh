@@ -167,10 +167,20 @@ __device__ __forceinline__ float pow2i(float k) {
     return (k >= -126.f) ? __int_as_float(((int)fminf(k, 127.f) + 127) << 23) : 0.f;
 }
 
-template <int NF, bool DP, bool PRIOR, int PASS, bool LIN = false, bool MLO = false>
+// FUSE (pass 1 of the linear-domain form only): the single-pass variant.  A coarse pre-pass (every 16th model, the same
+// kernel) has left a lower bound M0 of the object's maximum; the frame of the weights is fixed to R = -floor(M0) and
+// every weight above the RUNNING cut wt_thresh max(2^(M0 + R), largest weight so far) goes into the KDE histogram right
+// away.  The running cut never exceeds the final one, so the histogram holds a superset of the selection, and the
+// surplus - weights between the cut of their moment and the final cut - lies within a factor fz_gfac above the former
+// as long as the final maximum stays within that factor of 2^M0 (k_merge checks it).  Those weights (and the ones
+// within the fp32 error below the cut) are recorded per thread and re-decided in float64 by k_fuse_fix.  Objects that
+// break the assumptions (frame change, record overflow, maximum far above M0: the bright ones, whose posteriors are
+// narrow) get their histogram row cleared and take the pruned pass 2 as before.
+template <int NF, bool DP, bool PRIOR, int PASS, bool LIN = false, bool MLO = false, bool FUSE = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const unsigned char* __restrict__ tiles, uint32_t lbo,
                                                             uint32_t sbo) {
     static_assert(NF >= 1 && NF <= 6, "filters per object");
+    static_assert(!FUSE || (LIN && PASS == 1), "the fused variant is pass 1 of the linear-domain form");
     constexpr int SLOT = tc_slot(NF), KS = tc_ks(NF), AKSTEPS = tc_aksteps(NF), PQ = tc_pairq(NF, MLO);
     constexpr int TILE_BYTES = tc_tile_bytes(NF, MLO), OPSEC = tc_opsec(NF), PAIRSEC = tc_pairsec(NF, MLO);
     constexpr int PRI = MLO ? 2 * NF : NF;      // position of the prior pair among the float2 of a model pair
@@ -216,6 +226,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
     float Rf = 0.f;                             // LIN: reference exponent of the linear-domain weights
     double Sd = 0.0;
     int best0 = 0, best1 = 0, oidx = -1;
+    float Yc = 0.f;                             // FUSE: running maximum of the weights behind the cut (seeded by M0)
+    float fcut = FLT_MAX;                       // FUSE: the running cut wt_thresh Yc (FLT_MAX: object not fused)
+    bool fuse_ok = false;                       // FUSE: frame still the one fixed by M0
+    int rcnt = 0, fz_seg = 0;                   // FUSE: records written by this thread, its record segment
     if (warp < TC_CW) {
         const int64_t slot = tile_base + (int64_t)mt * 128 + row;
         int64_t o;
@@ -255,8 +269,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                         make_float4(arow[s * 8 + c * 4], arow[s * 8 + c * 4 + 1], arow[s * 8 + c * 4 + 2], arow[s * 8 + c * 4 + 3]);
         }
         thr = (PASS == 2) ? P.thr2[oo] : 0.f;
-        if (PASS == 1) { M2 = LIN ? pack2(0.f, 0.f) : pack2(-FLT_MAX, -FLT_MAX); S2 = pack2(0.f, 0.f); Rf = FLT_MAX; }
-        else {
+        if (PASS == 1) {
+            M2 = LIN ? pack2(0.f, 0.f) : pack2(-FLT_MAX, -FLT_MAX); S2 = pack2(0.f, 0.f); Rf = FLT_MAX;
+            if (FUSE) {
+                const float m0 = P.fz_M0[oo];
+                fuse_ok = m0 > -1e30f && m0 < 1e30f && slot < P.No;
+                if (fuse_ok) { Rf = -floorf(m0); Yc = exp2f(m0 + Rf); fcut = P.fz_thr * Yc; }
+                fz_seg = (int)((int64_t)(blockIdx.y * TC_SPLIT + half) * P.No_pad + oo);
+            }
+        } else {
             const float m = P.M2[oo];
             M2 = pack2(m, m);
             acc2 = pack2(0.f, 0.f);
@@ -337,7 +358,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
         uint32_t lbits = 0;                    // pass 1: live sub-batches of the current tile; pass 2: those of the warp
         unsigned long long npairs = 0;
         auto flush = [&](float v, int bin) {
-            if (v != 0.f && oidx >= 0) atomicAdd(P.hist + (int64_t)oidx * P.hist_stride + bin, v);
+            if (v != 0.f && oidx >= 0 && (!FUSE || fuse_ok)) atomicAdd(P.hist + (int64_t)oidx * P.hist_stride + bin, v);
         };
         const ulonglong2* pairs = nullptr;
         const float4* tails = nullptr;
@@ -413,6 +434,73 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
         // and a plain max.  Pass 1 keeps R per object (integer valued, so that a change of R rescales the sums by an
         // exact power of two) and lowers it whenever the largest weight passes 2^8; a jump beyond 2^24 (or an
         // overflow) has the weights of the sub-batch formed again in a frame at its minimum.  Pass 2 uses R = -M.
+        // Weights of one sub-batch (four model pairs, linear domain) -> KDE histogram: those above `cut` are summed per
+        // bin in a register and flushed with one RED per (thread, bin run).  A weight with |u - cmid| <= chalf is
+        // recorded for the float64 re-decision (pass 2: the band of the fp32 error around the final cut, global list;
+        // fused pass: from just below the running cut up to fz_gfac above it, per-thread segment).  chalf < 0: off.
+        auto lin_accumulate = [&](auto slow_tag, const int p0, const f2 (&us)[4], const float cut, const float cmid,
+                                  const float chalf) {
+            constexpr bool SLOW = decltype(slow_tag)::value;
+            float uv[8];                    // the weights that pass the cut (0 otherwise)
+            float nearm = FLT_MAX;          // smallest |weight - cmid| of the sub-batch
+            const f2 nmid2 = pack2(-cmid, -cmid);
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                const f2 dd = add2(us[jp], nmid2);
+                nearm = fminf(nearm, fminf(fabsf(lo2(dd)), fabsf(hi2(dd))));
+                uv[2 * jp] = (lo2(us[jp]) > cut) ? lo2(us[jp]) : 0.f;
+                uv[2 * jp + 1] = (hi2(us[jp]) > cut) ? hi2(us[jp]) : 0.f;
+            }
+            if (__any_sync(0xffffffffu, nearm <= chalf)) {
+                if (FUSE) {
+                    // the whole sub-batch (first model, cut of the moment, eight weights: 48 bytes, three vector stores)
+                    // goes to the thread's segment; k_fuse_fix works out which of the weights lie in the band
+                    if (nearm <= chalf && fuse_ok) {
+                        if (rcnt < P.fz_cap) {
+                            uint4* dst = reinterpret_cast<uint4*>(P.fz_rec) + ((size_t)fz_seg * P.fz_cap + rcnt) * 3;
+                            dst[0] = make_uint4((unsigned)(first_i + 2 * p0), __float_as_uint(cut), __float_as_uint(lo2(us[0])),
+                                                __float_as_uint(hi2(us[0])));
+                            dst[1] = make_uint4(__float_as_uint(lo2(us[1])), __float_as_uint(hi2(us[1])), __float_as_uint(lo2(us[2])),
+                                                __float_as_uint(hi2(us[2])));
+                            dst[2] = make_uint4(__float_as_uint(lo2(us[3])), __float_as_uint(hi2(us[3])), 0u, 0u);
+                        }
+                        ++rcnt;
+                    }
+                } else if (nearm <= chalf && oidx >= 0) {
+                    const int cnt_i = SLOW ? 2 * npair_full + (odd ? 1 : 0) : (1 << 30);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float uq = (q & 1) ? hi2(us[q >> 1]) : lo2(us[q >> 1]);
+                        const int jm = 2 * (p0 + (q >> 1)) + (q & 1);
+                        if (fabsf(uq - cmid) <= chalf && jm < cnt_i) record_cut(P, oidx, first_i + jm, uq, uq > cut);
+                    }
+                }
+            }
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                const int p = p0 + jp;
+                const float u0 = uv[2 * jp], u1 = uv[2 * jp + 1];
+                if (!SLOW) {
+                    acc2 = fma2(pack2(u0, u1), pack2(sub_inv, sub_inv), acc2);
+                } else {
+                    const float4 tl = tails[p];
+                    if (p > npair_full || (p == npair_full && !odd)) continue;      // warp-uniform: nothing but padding
+                    const bool tail = (p == npair_full);
+                    const int bin0 = __float_as_int(tl.z), bin1 = tail ? bin0 : __float_as_int(tl.w);
+                    if (bin0 != cur_bin) {             // warp-uniform
+                        if (cur_bin >= 0) { flush(lo2(acc2) + hi2(acc2), cur_bin); acc2 = pack2(0.f, 0.f); }
+                        cur_bin = bin0;
+                    }
+                    if (bin1 == bin0) {
+                        acc2 = fma2(pack2(u0, u1), pack2(tl.x, tl.y), acc2);
+                    } else {                           // the pair straddles a bin boundary
+                        flush(fmaf(u0, tl.x, lo2(acc2) + hi2(acc2)), bin0);
+                        acc2 = pack2(0.f, u1 * tl.y);
+                        cur_bin = bin1;
+                    }
+                }
+            }
+        };
         uint32_t live_bit = 0;                 // bit of the sub-batch being processed
         auto process_lin = [&](auto slow_tag, const int p0, float (&Bv)[8], float (&Cv)[8], float (&Gv)[8]) {
             constexpr bool SLOW = decltype(slow_tag)::value;
@@ -474,11 +562,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                         M2 = mul2(M2, pack2(f, f));
                         Sd *= (double)f;
                         Rf = Rn;
+                        if (FUSE) { fuse_ok = false; fcut = FLT_MAX; Yc *= f; }      // the histogram was being filled in the old frame
                     }
                     weights();
                 }
                 S2 = add2(S2, Ssub);
-                if (P.live && ysub > P.live_thr * lo2(M2)) lbits |= live_bit;     // may pass the final cut: pass 2 looks
+                // may pass the final cut: pass 2 looks (FUSE: the seeded maximum makes the bits nearly the final selection)
+                if (P.live && ysub > P.live_thr * (FUSE ? fmaxf(lo2(M2), Yc) : lo2(M2))) lbits |= live_bit;
                 const float Yt = hi2(M2);
                 if (__any_sync(0xffffffffu, ysub > Yt)) {
                     float Ym = lo2(M2);
@@ -505,60 +595,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                         Sd *= (double)f;
                         Ym *= f;
                         Rf -= (float)k;
+                        if (FUSE) { fuse_ok = false; fcut = FLT_MAX; Yc *= f; }
                     }
                     M2 = pack2(Ym, Ym * 0.99999618530273438f);
+                    if (FUSE && fuse_ok && Ym > Yc) { Yc = Ym; fcut = P.fz_thr * Ym; }
+                }
+                if (FUSE) {
+                    // every weight above the running cut goes into the histogram now; the band from just below the cut
+                    // to fz_gfac above it is recorded for k_fuse_fix (fz_mid / fz_half: centre / half-width of the band
+                    // in units of the cut)
+                    if (__any_sync(0xffffffffu, ysub > fcut * P.fz_lofac))
+                        lin_accumulate(slow_tag, p0, ys, fcut, fcut * P.fz_mid, fcut * P.fz_half);
                 }
             } else {
                 const f2 R2 = pack2(Rf, Rf);
                 f2 us[4];
-                float uv[8];                    // the weights that pass the cut (0 otherwise)
-                float nearm = FLT_MAX;          // smallest |weight - cut| of the sub-batch
-                const f2 nthr2 = pack2(-thr, -thr);
 #pragma unroll
                 for (int jp = 0; jp < 4; ++jp) {
                     const f2 arg = fma2(xs[jp], kMinusOne, PRIOR ? add2(pr[jp], R2) : R2);
                     us[jp] = mul2(xs[jp], pack2(fast_ex2(lo2(arg)), fast_ex2(hi2(arg))));
-                    const f2 dd = add2(us[jp], nthr2);
-                    nearm = fminf(nearm, fminf(fabsf(lo2(dd)), fabsf(hi2(dd))));
-                    uv[2 * jp] = (lo2(us[jp]) > thr) ? lo2(us[jp]) : 0.f;
-                    uv[2 * jp + 1] = (hi2(us[jp]) > thr) ? hi2(us[jp]) : 0.f;
                 }
-                if (P.ex_list && __any_sync(0xffffffffu, nearm < thr * P.ex_tol)) {
-                    // weights within the fp32 error of the cut: recorded, re-decided in float64 by k_exact_cut_fix
-                    if (nearm < thr * P.ex_tol && oidx >= 0) {
-                        const int cnt_i = SLOW ? 2 * npair_full + (odd ? 1 : 0) : (1 << 30);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float uq = (q & 1) ? hi2(us[q >> 1]) : lo2(us[q >> 1]);
-                            const int jm = 2 * (p0 + (q >> 1)) + (q & 1);
-                            if (fabsf(uq - thr) < thr * P.ex_tol && jm < cnt_i) record_cut(P, oidx, first_i + jm, uq, uq > thr);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int jp = 0; jp < 4; ++jp) {
-                    const int p = p0 + jp;
-                    const float u0 = uv[2 * jp], u1 = uv[2 * jp + 1];
-                    if (!SLOW) {
-                        acc2 = fma2(pack2(u0, u1), pack2(sub_inv, sub_inv), acc2);
-                    } else {
-                        const float4 tl = tails[p];
-                        if (p > npair_full || (p == npair_full && !odd)) continue;      // warp-uniform: nothing but padding
-                        const bool tail = (p == npair_full);
-                        const int bin0 = __float_as_int(tl.z), bin1 = tail ? bin0 : __float_as_int(tl.w);
-                        if (bin0 != cur_bin) {             // warp-uniform
-                            if (cur_bin >= 0) { flush(lo2(acc2) + hi2(acc2), cur_bin); acc2 = pack2(0.f, 0.f); }
-                            cur_bin = bin0;
-                        }
-                        if (bin1 == bin0) {
-                            acc2 = fma2(pack2(u0, u1), pack2(tl.x, tl.y), acc2);
-                        } else {                           // the pair straddles a bin boundary
-                            flush(fmaf(u0, tl.x, lo2(acc2) + hi2(acc2)), bin0);
-                            acc2 = pack2(0.f, u1 * tl.y);
-                            cur_bin = bin1;
-                        }
-                    }
-                }
+                // weights within the fp32 error of the cut: recorded, re-decided in float64 by k_exact_cut_fix
+                lin_accumulate(slow_tag, p0, us, thr, thr, P.ex_list ? thr * P.ex_tol : -1.f);
             }
         };
         // pass 2: the live bits of the next tile are fetched while the current one is processed
@@ -623,7 +681,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                     // fast path: four complete model pairs and (pass 2) one KDE bin for all eight models -> one
                     // branch-free block in which the chains of the four pair evaluations interleave
                     bool fast = p0 + 4 <= npair_full;
-                    if (PASS == 2) {
+                    if (PASS == 2 || FUSE) {
                         const int4 si = subs[ch * TC_NSUB + sub];
                         fast = fast && (si.y != 0);
                         sub_inv = __int_as_float(si.z);
@@ -671,6 +729,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                     P.pM[q] = (double)Mfl;
                     P.pS[q] = any ? Sd * exp2(-((double)Mfl + (double)Rf)) : 0.0;
                     P.pbest[q] = best0;
+                    if (FUSE) {
+                        if (cur_bin >= 0) flush(lo2(acc2) + hi2(acc2), cur_bin);
+                        P.fz_cnt[q] = fuse_ok ? rcnt : -1;
+                    }
                 } else {
                     P.pM[q] = (double)Mfl;
                     P.pS[q] = Sd;
@@ -703,12 +765,14 @@ struct TcRecParams {
     int Nf;
     int mlo;
     unsigned char* tiles;
+    int stride;              // tile position p holds the model at sorted position p * stride (coarse tile set)
 };
 
 __global__ void k_build_tiles_tc(TcRecParams P) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.nm) return;
-    const int64_t j = P.perm[p];
+    const int64_t ps = p * P.stride;          // sorted position
+    const int64_t j = P.perm[ps];
     const int r = (int)(p % TC_TM);
     const bool mlo = P.mlo != 0;
     const int nf = P.Nf, slot = tc_slot(nf), ks = tc_ks(nf), pq = tc_pairq(nf, mlo);
@@ -729,14 +793,15 @@ __global__ void k_build_tiles_tc(TcRecParams P) {
     }
     pr[2 * (mlo ? 2 * nf : nf) + (r & 1)] = P.lnprior ? (float)(P.lnprior[j] * 1.4426950408889634) : 0.f;
     float* tl = reinterpret_cast<float*>(T + opsec + pairsec) + (r >> 1) * 4;
-    tl[r & 1] = P.invnorm ? P.invnorm[p] : 0.f;
-    tl[2 + (r & 1)] = __int_as_float(P.bins ? P.bins[p] : -1);
+    const bool kde = P.bins != nullptr && P.stride == 1;      // the coarse set serves pass 1 only
+    tl[r & 1] = kde ? P.invnorm[p] : 0.f;
+    tl[2 + (r & 1)] = __int_as_float(kde ? P.bins[p] : -1);
     if ((r & 7) == 0) {
-        int uniform = (P.bins != nullptr && p + 8 <= P.nm) ? 1 : 0;
-        const int b0 = P.bins ? P.bins[p] : -1;
+        int uniform = (kde && p + 8 <= P.nm) ? 1 : 0;
+        const int b0 = kde ? P.bins[p] : -1;
         for (int i = 1; i < 8 && uniform; ++i) uniform = (P.bins[p + i] == b0) ? 1 : 0;
         reinterpret_cast<int4*>(T + opsec + pairsec + TC_TAILSEC)[r >> 3] =
-            make_int4(b0, uniform, __float_as_int(P.invnorm ? P.invnorm[p] : 0.f), 0);
+            make_int4(b0, uniform, __float_as_int(kde ? P.invnorm[p] : 0.f), 0);
     }
     unsigned char* dst = T + (r >> 3) * 256 + (r & 7) * 16;
     for (int s = 0; s < 2 * ks; ++s)

@@ -73,7 +73,7 @@ typedef struct FzbStats {
     int64_t pairs_fp32;        /* object-model pairs evaluated by fp32 kernels          */
     int64_t pairs_fp64;        /* object-model pairs evaluated by fp64 kernels          */
     int64_t objects_fp64;      /* objects routed to the fp64 path by the error bound    */
-    double  ms_scan;           /* CUDA-event time of pass 1 (max / logsumexp / argmax)   */
+    double  ms_scan;           /* CUDA-event time of pass 1 (max / logsumexp / argmax); kNN calls: of the search */
     double  ms_accum;          /* CUDA-event time of pass 2 (weights -> histogram)       */
     double  ms_finish;         /* CUDA-event time of histogram (*) kernel + normalise    */
     double  ms_total;          /* CUDA-event time of all device work of the call        */
@@ -86,8 +86,13 @@ typedef struct FzbStats {
     int64_t knn_tc;            /* 1: the last kNN search generated its candidates on the tensor cores           */
     int64_t cut_recorded;      /* pass 2: weights within the fp32 error of the wt_thresh cut, re-decided in float64   */
     int64_t cut_changed;       /* ... of which the float64 decision differed from the fp32 one                 */
-    double  knn_tc_err;        /* largest error of a tensor-core candidate distance seen by the float64 re-rank, in
-                                  units of (|q'|^2 + max |f'|^2); the exactness test assumes <= 4e-6            */
+    double  knn_tc_err;        /* largest error of a candidate's fp32 value seen by the float64 re-rank, in units of
+                                  the scale of the exactness test: tensor-core scan (|q'|^2 + max |f'|^2), bound 4e-6;
+                                  dot-form filter scan (|q'|^2 + |f'|^2), bound 2e-6                              */
+    int64_t objects_fused;     /* fused single pass of the tensor-core sweep: objects whose histogram it completed (the others
+                                  took the pruned pass 2)                                                         */
+    int64_t knn_overflow;      /* kNN filter scan: (query, tree) searches whose row buffer overflowed (re-done by the
+                                  float64 kernel, counted in knn_redo as well)                                  */
 } FzbStats;
 
 const char* fzb_last_error(void);

@@ -35,7 +35,7 @@ def test_struct_layouts(lib):
     from frankenz_b200 import _lib
     assert C.sizeof(_lib.FzbConfig) == 56
     assert C.sizeof(_lib.FzbFitOut) == 7 * 8
-    assert C.sizeof(_lib.FzbStats) == 16 * 8
+    assert C.sizeof(_lib.FzbStats) == 18 * 8
     assert lib.fzb_version() >= 100
 
 

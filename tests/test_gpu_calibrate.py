@@ -30,12 +30,15 @@ def test_c3_fused_path_against_float64_at_65k_objects(float64_grid):
         res[mode] = (p, lm, le, bf.best_idx.copy(), bf._eng().stats())
     p, lm, le, bi, st = res["auto"]
     p64, lm64, le64, bi64, _ = res["fp64"]
-    assert st["sweep_kind"] == 3 and st["pairs_fp32"] > 1.5 * n * len(models)       # the tensor-core sweep did the work
+    assert st["sweep_kind"] == 3 and st["pairs_fp32"] > 1.0 * n * len(models)       # the tensor-core sweep did the work
     l1 = np.sum(np.abs(p - p64), axis=1)
     dl = np.abs(lm - lm64) / np.maximum(1, np.abs(lm64))
     de = np.abs(le - le64) / np.maximum(1, np.abs(le64))
-    print("float64_grid=%s: max L1 %.3g (99.9%% %.3g, median %.3g), max dlmap %.3g, max dlevid %.3g, arg-max mismatches %d"
-          % (float64_grid, l1.max(), np.percentile(l1, 99.9), np.median(l1), dl.max(), de.max(), int(np.sum(bi != bi64))))
+    print("float64_grid=%s: max L1 %.3g (99.9%% %.3g, median %.3g), max dlmap %.3g, max dlevid %.3g, arg-max mismatches %d; "
+          "objects completed by the fused single pass %d of %d, weights re-decided in float64 %d (changed %d)"
+          % (float64_grid, l1.max(), np.percentile(l1, 99.9), np.median(l1), dl.max(), de.max(), int(np.sum(bi != bi64)),
+             st["objects_fused"], n, st["cut_recorded"], st["cut_changed"]))
+    assert st["objects_fused"] >= 0.3 * n          # the single-pass variant carries the faint objects
     assert l1.max() <= 1e-5 and dl.max() <= 1e-5 and de.max() <= 1e-5
     assert np.percentile(l1, 99.9) <= 2e-6
     # The arg-max itself is ill-conditioned under dim_prior: ln L = (dof/2 - 1) ln chi2 - chi2/2 has a flat maximum at

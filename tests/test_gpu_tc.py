@@ -123,6 +123,42 @@ def test_batch_and_split_invariance(fz):
         assert np.max(np.abs(le - le0[sel])) <= 2e-6 and np.max(np.sum(np.abs(p - p0[sel]), axis=1)) <= 2e-6
 
 
+def test_fused_single_pass_matches_two_pass(fz, monkeypatch):
+    """The single-pass variant (coarse pre-pass, histogram filled under the running cut, float64 re-decision of the
+    recorded band) against the two-pass sweep on the same objects, with and without a per-model prior: same best model
+    and lmap, evidence and PDFs within the fp32 noise of the two summation orders, and both within the bounds of the
+    oracle.  The counters say that the fused pass really carried most objects."""
+    m, lab, depth = bench_data.c3_models(float64_grid=True)      # the full 199,950-model grid: the coarse pre-pass needs a
+    x, xe, xm, _, _ = bench_data.c3_objects(2048, m, depth, seed=77)   # dense model set to bound the maximum closely
+    zgrid, sig = bench_data.c3_kde()
+    rdict = fz.pdf.PDFDict(zgrid, sig)
+    labe = np.full(len(m), 0.05)
+    for lnprior in (None, np.random.RandomState(4).uniform(-3, 0, len(m))):
+        kw = dict(FS) if lnprior is None else dict(FS, lnprior=lnprior)
+        bf = fz.BruteForce(m, np.zeros_like(m), np.ones_like(m))
+        res = {}
+        for fused in (True, False):
+            if not fused:
+                monkeypatch.setenv("FZB_NO_FUSE", "1")
+            p, (lm, le) = bf.fit_predict(x.copy(), xe.copy(), xm.copy(), lab, labe, label_dict=rdict, return_gof=True,
+                                         verbose=False, save_fits=False, lprob_kwargs=kw)
+            monkeypatch.delenv("FZB_NO_FUSE", raising=False)
+            res[fused] = (p, lm, le, bf.best_idx.copy(), bf._eng().stats())
+        (p1, lm1, le1, b1, st1), (p2, lm2, le2, b2, st2) = res[True], res[False]
+        assert st1["sweep_kind"] == 3 and st2["sweep_kind"] == 3
+        assert st2["objects_fused"] == 0 and st1["objects_fused"] >= (0.4 if lnprior is None else 0.1) * len(x), (st1, st2)
+        assert st1["pairs_pass2"] < st2["pairs_pass2"], (st1["pairs_pass2"], st2["pairs_pass2"])
+        assert np.array_equal(b1, b2) and np.array_equal(lm1, lm2)
+        assert np.max(np.abs(le1 - le2)) <= 2e-6
+        assert np.max(np.sum(np.abs(p1 - p2), axis=1)) <= 2e-6
+        sub = np.arange(0, len(x), 128)
+        kd = fo.KernelDict(zgrid, sig)
+        with np.errstate(all="ignore"):
+            po, lmo, leo = fo.bruteforce_fit_predict(m, np.zeros_like(m), np.ones_like(m), x[sub].copy(), xe[sub].copy(),
+                                                     xm[sub].copy(), lab, labe, label_dict=kd, lnprior=lnprior, **FS)
+        _check(p1[sub], lm1[sub], le1[sub], po, lmo, leo)
+
+
 def test_object_conditioned_prior_table_on_the_fused_path(fz, monkeypatch):
     """SURVEY 8f rank 1 at scale: fit_predict(save_fits=False) with lnprior[i, j] = table[bin_i, j] runs the fused sweep
     once per table row; it must agree with the float64 kernel that reads the table per pair and with the oracle."""

@@ -44,7 +44,7 @@ for rep in range(2):
     idx, dist = nn._engine.knn_query(q, k, p=2)
     dt = time.time() - t
     st = nn._engine.stats()
-    print("knn_query alone: %.3f s wall, device %.1f ms -> %.3e distance evaluations/s; tensor-core scan %d, redo %d of %d, "
-          "largest candidate error %.3g (bound 4e-6)" %
-          (dt, st["ms_total"], len(q) * K * ntr / (st["ms_total"] * 1e-3), st["knn_tc"], st["knn_redo"], len(q) * K,
-           st["knn_tc_err"]))
+    print("knn_query alone: %.3f s wall, call %.1f ms, search %.1f ms -> %.3e distance evaluations/s; tensor-core scan %d, "
+          "redo %d (overflow %d) of %d, largest candidate error %.3g" %
+          (dt, st["ms_total"], st["ms_scan"], len(q) * K * ntr / (st["ms_scan"] * 1e-3), st["knn_tc"], st["knn_redo"],
+           st["knn_overflow"], len(q) * K, st["knn_tc_err"]))
