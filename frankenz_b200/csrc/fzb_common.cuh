@@ -72,6 +72,8 @@ struct FastModels {
     DevBuf recs64;         // [nm][rec64] double records of the float64 sweep
     DevBuf tiles_tc;       // tensor-core sweep: 256-model tiles (MMA operand + packed pairs + tails), fzb_sweep_tc.cuh
     DevBuf tiles_tc_coarse; // the same for every FZB_TC_COARSE-th model of the sorted order (pre-pass of the fused sweep)
+    DevBuf tiles_tc_f32, tiles_tc_f32_coarse;   // models not fp32-representable: the same sets without the float64 remainder
+    bool tc_f32_valid = false;
     int64_t nm_coarse = 0;
     bool tc_valid = false;
     DevBuf fuse;           // fused sweep: per-thread records, counts, seeds, object flags
@@ -80,6 +82,7 @@ struct FastModels {
     DevBuf bins;           // int32 [nm_pad]: KDE histogram bin (slot*Ng + pos) of each sorted model, -1 = none
     DevBuf invnorm;        // float [nm_pad]: 1 / kernel normalisation of each sorted model
     DevBuf live;           // pass-2 pruning: live bits of the tensor-core sweep, [model tile x half][object] uint16
+    DevBuf tmask;          // pass-2 pruning: live bits per (model tile, pass-2 CTA), see fzb_tile_masks
     DevBuf sortbuf;        // keys / values / temporary storage of the sort of the pass-2 object list
     DevBuf cutlist;        // weights recorded at the wt_thresh cut by pass 2 (CutRecord), re-decided in float64
     int nslot = 0;         // distinct dictionary widths in use
@@ -226,6 +229,8 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                              double* d_psum = nullptr, const double* d_glmap = nullptr);
 
 // pass-2 object order of the tensor-core sweep (fzb_prune.cu)
+int fzb_tile_masks(fzb_context* h, const unsigned short* live, int64_t ntiles, int64_t No_pad, const int32_t* list, int64_t n,
+                   int tile_objs, unsigned int** out);
 int fzb_sort_by_live_bits(fzb_context* h, const unsigned short* live, int64_t nrows, int64_t No_pad, int32_t* list,
                           int64_t n);
 

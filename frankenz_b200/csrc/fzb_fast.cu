@@ -912,6 +912,26 @@ __global__ void k_fuse_seed(const double* __restrict__ pM, int64_t No, int64_t N
     M0[o] = v;
 }
 
+// objects of a chunk by total S/N: list A (<= snr_cut: swept without the float64 remainder of the models), list B
+__global__ void k_split_snr(const float* __restrict__ osnr, int64_t No, float snr_cut, int32_t* __restrict__ list_a,
+                            int32_t* __restrict__ list_b, int32_t* __restrict__ counts) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = o < No;
+    const bool a = valid && osnr[o] <= snr_cut;         // NaN S/N: list B
+    const unsigned ma = __ballot_sync(0xffffffffu, a), mb = __ballot_sync(0xffffffffu, valid && !a);
+    const int lane = threadIdx.x & 31;
+    int base_a = 0, base_b = 0;
+    if (lane == 0) {
+        if (ma) base_a = atomicAdd(&counts[0], __popc(ma));
+        if (mb) base_b = atomicAdd(&counts[1], __popc(mb));
+    }
+    base_a = __shfl_sync(0xffffffffu, base_a, 0);
+    base_b = __shfl_sync(0xffffffffu, base_b, 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (a) list_a[base_a + __popc(ma & below)] = (int32_t)o;
+    else if (valid) list_b[base_b + __popc(mb & below)] = (int32_t)o;
+}
+
 struct FuseFixParams {
     CutFixParams C;
     const uint4* rec;        // [part][No_pad][cap] x 3
@@ -922,32 +942,71 @@ struct FuseFixParams {
     float mid, half;         // the band in units of the record's cut
     unsigned int* recorded;  // statistics
 };
-__global__ void k_fuse_fix(FuseFixParams P) {
+// One thread per (part, object) segment: the weights of its sub-batch records that lie in the band go to the compact
+// CutRecord list (warp-aggregated append), which k_exact_cut_fix then re-decides with every lane busy.  Records beyond
+// the list's capacity are only counted: the host falls back to k_fuse_fix_direct for the chunk.
+__global__ void k_fuse_collect(FuseFixParams P, CutRecord* __restrict__ list, unsigned int* __restrict__ count, unsigned int cap) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int n = 0, obj = 0;
+    const uint4* r = nullptr;
+    if (i < P.No * P.nparts) {
+        const int part = (int)(i / P.No);
+        obj = (int)(i - (int64_t)part * P.No);
+        if (P.ok[obj]) n = max(0, min(P.cnt[(size_t)part * P.No_pad + obj], P.cap));
+        r = P.rec + ((size_t)part * P.No_pad + obj) * P.cap * 3;
+    }
+    const int nmax = __reduce_max_sync(0xffffffffu, n);
+    for (int k = 0; k < nmax; ++k) {
+        const bool has = k < n;
+        uint4 a = make_uint4(0, 0, 0, 0), b = a, c = a;
+        if (has) { a = r[3 * k]; b = r[3 * k + 1]; c = r[3 * k + 2]; }
+        const int64_t first = a.x;
+        const float cut = __uint_as_float(a.y);
+        const float w[8] = {__uint_as_float(a.z), __uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y),
+                            __uint_as_float(b.z), __uint_as_float(b.w), __uint_as_float(c.x), __uint_as_float(c.y)};
+        const float cmid = cut * P.mid, chalf = cut * P.half;         // the kernel's own arithmetic
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const bool hit = has && first + q < P.nm && fabsf(w[q] - cmid) <= chalf;
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m == 0u) continue;
+            unsigned int base = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) base = atomicAdd(count, (unsigned int)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (hit) {
+                const unsigned int at = base + __popc(m & ((1u << lane) - 1u));
+                if (at < cap) list[at] = CutRecord{obj, (int)(first + q), w[q], w[q] > cut ? 1 : 0};
+            }
+        }
+    }
+}
+
+// the same without the list (fallback when the list would overflow)
+__global__ void k_fuse_fix_direct(FuseFixParams P) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.No * P.nparts) return;
     const int part = (int)(i / P.No);
     const int obj = (int)(i - (int64_t)part * P.No);
     if (!P.ok[obj]) return;
-    const int n = P.cnt[(size_t)part * P.No_pad + obj];
+    const int n = min(P.cnt[(size_t)part * P.No_pad + obj], P.cap);
     if (n <= 0) return;
     double sx[FZB_FAST_MAXF], sxe[FZB_FAST_MAXF], sxm[FZB_FAST_MAXF];
     cutfix_object(P.C, obj, sx, sxe, sxm);
     const uint4* r = P.rec + ((size_t)part * P.No_pad + obj) * P.cap * 3;
-    unsigned int nw = 0;
     for (int k = 0; k < n; ++k) {
         const uint4 a = r[3 * k], b = r[3 * k + 1], c = r[3 * k + 2];
         const int64_t first = a.x;
         const float cut = __uint_as_float(a.y);
         const float w[8] = {__uint_as_float(a.z), __uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y),
                             __uint_as_float(b.z), __uint_as_float(b.w), __uint_as_float(c.x), __uint_as_float(c.y)};
-        const float cmid = cut * P.mid, chalf = cut * P.half;         // the kernel's own arithmetic
+        const float cmid = cut * P.mid, chalf = cut * P.half;
         for (int q = 0; q < 8; ++q) {
             if (first + q >= P.nm || !(fabsf(w[q] - cmid) <= chalf)) continue;
             cutfix_apply(P.C, obj, (int)(first + q), w[q], w[q] > cut, sx, sxe, sxm);
-            ++nw;
         }
     }
-    if (P.recorded && nw) atomicAdd(P.recorded, nw);
 }
 
 __global__ void k_fuse_clear_rows(const unsigned char* __restrict__ ok, float* __restrict__ hist, int64_t hist_stride) {
@@ -1352,7 +1411,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     }
     // weights at the wt_thresh cut are recorded by pass 2 and re-decided in float64 (k_exact_cut_fix)
     const bool exact_cut = kde && cfg.use_wt_thresh && getenv("FZB_NO_EXACT_CUT") == nullptr;
-    const unsigned int cut_cap = (unsigned int)std::min<int64_t>((int64_t)1 << 26, std::max<int64_t>(1 << 16, 8 * chunk_pad));
+    const unsigned int cut_cap = (unsigned int)std::min<int64_t>((int64_t)1 << 27, std::max<int64_t>(1 << 16, 48 * chunk_pad));
     if (exact_cut && h->fast.cutlist.reserve((size_t)cut_cap * sizeof(CutRecord) + 64)) return 1;
     // fused single pass (tensor-core sweep, linear-domain form): coarse pre-pass + one sweep that also fills the
     // histogram; see k_sweep_tc<..., FUSE>
@@ -1365,12 +1424,13 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     float* fz_M0 = nullptr;
     unsigned char* fz_ok = nullptr;
     int32_t* fuse_list = nullptr;
+    int32_t* snr_list[2] = {nullptr, nullptr};
     double *pS_c = nullptr, *pM_c = nullptr;
     int32_t* pbest_c = nullptr;
     if (fuse_on) {
         const size_t n_rec = (size_t)npart * chunk_pad * fz_cap * 48, n_cnt = (size_t)npart * chunk_pad * 4;
         const size_t n_c = (size_t)fzb_tc_split() * chunk_pad;
-        if (F.fuse.reserve(n_rec + n_cnt + (size_t)chunk_pad * (4 + 4 + 1) + n_c * 20 + 1024)) return 1;
+        if (F.fuse.reserve(n_rec + n_cnt + (size_t)chunk_pad * (4 + 4 + 1 + 8) + n_c * 20 + 1024)) return 1;
         fz_rec = F.fuse.as<uint4>();
         pS_c = reinterpret_cast<double*>(fz_rec + (size_t)npart * chunk_pad * fz_cap * 3);
         pM_c = pS_c + n_c;
@@ -1378,8 +1438,14 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         fz_cnt = pbest_c + n_c;
         fz_M0 = reinterpret_cast<float*>(fz_cnt + (size_t)npart * chunk_pad);
         fuse_list = reinterpret_cast<int32_t*>(fz_M0 + chunk_pad);
-        fz_ok = reinterpret_cast<unsigned char*>(fuse_list + chunk_pad);
+        snr_list[0] = fuse_list + chunk_pad;
+        snr_list[1] = snr_list[0] + chunk_pad;
+        fz_ok = reinterpret_cast<unsigned char*>(snr_list[1] + chunk_pad);
     }
+    // models that are not fp32-representable: only the brighter objects need the float64 remainder of the fluxes in the
+    // sweep (its effect on ln L is ~2e-8 S/N); the others are swept on the fp32-rounded tile sets
+    const double mlo_snr = env_double("FZB_TC_MLO_SNR", 32.0);
+    const bool snr_split = fuse_on && mlo && F.tc_f32_valid && mlo_snr > 0.0;
     if (F.aux64.reserve((size_t)chunk_pad * 40 + 64)) return 1;
     double* M2d = F.aux64.as<double>();
     double* thr2d = M2d + chunk_pad;
@@ -1446,29 +1512,58 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         SP.live_thr = cfg.use_wt_thresh ? (float)(cfg.wt_thresh * (1.0 - 1e-4)) : 0.f;
         const int64_t tiles1 = (nc + tile_objs - 1) / tile_objs;
         int64_t nsafe = 0, nsafe64 = 0, nunsafe = 0, nfuse = 0;
+        unsigned int fuse_recorded = 0;
         const bool fuse = fuse_on && use_lin;
         if (shard_mode != 2) {
         FZB_CUDA(cudaEventRecord(h->ev[2], h->stream));
         if (fuse) {
-            // pre-pass over every FZB_TC_COARSE-th model -> lower bound of every object's maximum
-            SweepParams SC = SP;
-            SC.nm = F.nm_coarse; SC.tiles_per_split = (int)((F.nm_coarse + TM - 1) / TM);
-            SC.pM = pM_c; SC.pS = pS_c; SC.pbest = pbest_c; SC.live = nullptr;
-            if (fzb_launch_sweep_tc(h, SC, dim3((unsigned)tiles1, 1u), nf, true, 1, true, mlo, F.tiles_tc_coarse.as<unsigned char>()))
-                return 1;
-            k_fuse_seed<<<(unsigned)((nc_pad + 255) / 256), 256, 0, h->stream>>>(pM_c, nc, nc_pad, fz_M0);
-            fzb_count_launch(h);
-            FZB_CUDA(cudaGetLastError());
-            FZB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nc_pad * hist_stride * 4, h->stream));
+            // object lists of the two tile kinds (one list = all objects when the models are fp32-representable)
+            int64_t nlist[2] = {0, nc};
+            if (snr_split) {
+                FZB_CUDA(cudaMemsetAsync(counts + 6, 0, 8, h->stream));
+                k_split_snr<<<(unsigned)((nc + 255) / 256), 256, 0, h->stream>>>(osnr, nc, (float)mlo_snr, snr_list[0], snr_list[1],
+                                                                                counts + 6);
+                fzb_count_launch(h);
+                FZB_CUDA(cudaGetLastError());
+                int32_t hn[2] = {0, 0};
+                FZB_CUDA(cudaMemcpyAsync(hn, counts + 6, 8, cudaMemcpyDeviceToHost, h->stream));
+                FZB_CUDA(cudaStreamSynchronize(h->stream));
+                nlist[0] = hn[0]; nlist[1] = hn[1];
+            }
             SP.fz_M0 = fz_M0; SP.fz_thr = (float)cfg.wt_thresh;
             SP.fz_lofac = 1.f - (float)env_double("FZB_EXACT_CUT_TOL", 3e-5); SP.fz_gfac = (float)std::exp(fz_g);
             SP.fz_mid = 0.5f * (SP.fz_lofac + SP.fz_gfac); SP.fz_half = 0.5f * (SP.fz_gfac - SP.fz_lofac);
             SP.fz_rec = fz_rec; SP.fz_cnt = fz_cnt; SP.fz_cap = fz_cap;
             SP.hist = hist; SP.hist_stride = hist_stride;
+            // pre-pass over every FZB_TC_COARSE-th model -> lower bound of every object's maximum
+            for (int v = 0; v < 2; ++v) {
+                if (nlist[v] == 0) continue;
+                const bool vm = (v == 1) ? mlo : false;
+                SweepParams SC = SP;
+                SC.nm = F.nm_coarse; SC.tiles_per_split = (int)((F.nm_coarse + TM - 1) / TM);
+                SC.pM = pM_c; SC.pS = pS_c; SC.pbest = pbest_c; SC.live = nullptr;
+                if (snr_split) { SC.objlist = snr_list[v]; SC.No = nlist[v]; }
+                const unsigned char* tl = (v == 1) ? F.tiles_tc_coarse.as<unsigned char>() : F.tiles_tc_f32_coarse.as<unsigned char>();
+                if (fzb_launch_sweep_tc(h, SC, dim3((unsigned)((nlist[v] + tile_objs - 1) / tile_objs), 1u), nf, true, 1, true, vm, tl))
+                    return 1;
+            }
+            k_fuse_seed<<<(unsigned)((nc_pad + 255) / 256), 256, 0, h->stream>>>(pM_c, nc, nc_pad, fz_M0);
+            fzb_count_launch(h);
+            FZB_CUDA(cudaGetLastError());
+            FZB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nc_pad * hist_stride * 4, h->stream));
             h->stats.pairs_fp32 += nc * F.nm_coarse;
-        }
-        if (use_tc ? fzb_launch_sweep_tc(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, cfg.dim_prior != 0, 1, use_lin, mlo, nullptr, fuse)
-                   : launch_sweep(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 1))
+            for (int v = 0; v < 2; ++v) {
+                if (nlist[v] == 0) continue;
+                const bool vm = (v == 1) ? mlo : false;
+                SweepParams SF = SP;
+                if (snr_split) { SF.objlist = snr_list[v]; SF.No = nlist[v]; }
+                const unsigned char* tl = (v == 1) ? nullptr : F.tiles_tc_f32.as<unsigned char>();
+                if (fzb_launch_sweep_tc(h, SF, dim3((unsigned)((nlist[v] + tile_objs - 1) / tile_objs), (unsigned)nsplit), nf, true, 1,
+                                        true, vm, tl, true))
+                    return 1;
+            }
+        } else if (use_tc ? fzb_launch_sweep_tc(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, cfg.dim_prior != 0, 1, use_lin, mlo)
+                          : launch_sweep(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 1))
             return 1;
         FZB_CUDA(cudaEventRecord(h->ev[3], h->stream));
         h->stats.pairs_fp32 += nc * nm;
@@ -1598,6 +1693,11 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                 if (prune) {
                     FZB_CUDA(cudaMemsetAsync(counts + 8, 0, 8, h->stream));
                     SP.pairs_done = reinterpret_cast<unsigned long long*>(counts + 8);
+                    unsigned int* tm = nullptr;      // chunks / tiles no object of an M-tile needs: no MMA, no TMA
+                    if (getenv("FZB_NO_TILE_SKIP") == nullptr) {
+                        if (fzb_tile_masks(h, live, ntiles, nc_pad, safe_list, nsafe, (int)tile_objs, &tm)) return 1;
+                    }
+                    SP.tmask = tm;
                 }
                 if (exact_cut) {
                     FZB_CUDA(cudaMemsetAsync(counts + 10, 0, 8, h->stream));
@@ -1652,10 +1752,27 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                 CF.Nf = nf; CF.free_scale = cfg.free_scale; CF.ime = cfg.ignore_model_err != 0; CF.dim_prior = cfg.dim_prior;
                 CF.hist = hist; CF.hist_stride = hist_stride; CF.changed = reinterpret_cast<unsigned int*>(counts + 11);
                 FF.rec = fz_rec; FF.cnt = fz_cnt; FF.ok = fz_ok; FF.No = nc; FF.No_pad = nc_pad; FF.nparts = (int)npart; FF.nm = nm;
-                FF.cap = fz_cap; FF.recorded = reinterpret_cast<unsigned int*>(counts + 10);
+                FF.cap = fz_cap; FF.recorded = nullptr;
                 FF.mid = SP.fz_mid; FF.half = SP.fz_half;
                 if (!(exact_cut && nsafe > 0)) FZB_CUDA(cudaMemsetAsync(counts + 10, 0, 8, h->stream));
-                k_fuse_fix<<<(unsigned)((nc * npart + 127) / 128), 128, 0, h->stream>>>(FF);
+                // in-band weights -> compact list (after pass 2's own records have been consumed) -> float64 re-decision
+                unsigned int* fcount = reinterpret_cast<unsigned int*>(counts + 12);
+                FZB_CUDA(cudaMemsetAsync(fcount, 0, 4, h->stream));
+                k_fuse_collect<<<(unsigned)((nc * npart + 255) / 256), 256, 0, h->stream>>>(FF, h->fast.cutlist.as<CutRecord>(), fcount,
+                                                                                       cut_cap);
+                fzb_count_launch(h);
+                FZB_CUDA(cudaGetLastError());
+                unsigned int nrec = 0;
+                FZB_CUDA(cudaMemcpyAsync(&nrec, fcount, 4, cudaMemcpyDeviceToHost, h->stream));
+                FZB_CUDA(cudaStreamSynchronize(h->stream));
+                fuse_recorded = nrec;
+                if (nrec <= cut_cap) {
+                    CutFixParams CL = FF.C;
+                    CL.list = h->fast.cutlist.as<CutRecord>(); CL.count = fcount; CL.cap = cut_cap;
+                    k_exact_cut_fix<<<h->sm_count * 8, 256, 0, h->stream>>>(CL);
+                } else {
+                    k_fuse_fix_direct<<<(unsigned)((nc * npart + 127) / 128), 128, 0, h->stream>>>(FF);
+                }
                 fzb_count_launch(h);
                 FZB_CUDA(cudaGetLastError());
             }
@@ -1696,7 +1813,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             if (exact_cut && (nsafe > 0 || nfuse > 0))
                 FZB_CUDA(cudaMemcpyAsync(cutc, counts + 10, 8, cudaMemcpyDeviceToHost, h->stream));
             FZB_CUDA(cudaStreamSynchronize(h->stream));
-            h->stats.cut_recorded += cutc[0];
+            h->stats.cut_recorded += cutc[0] + fuse_recorded;
             h->stats.cut_changed += cutc[1];
             h->stats.pairs_pass2 += (prune && nsafe > 0) ? (int64_t)pdone : nsafe * nm;
             h->stats.pairs_pass2 += nsafe64 * nm;

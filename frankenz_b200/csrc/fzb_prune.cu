@@ -30,7 +30,44 @@ __global__ void k_live_key(const unsigned short* __restrict__ live, int64_t nrow
     keys[i] = ((uint32_t)level << 24) | sig;
 }
 
+// live bits of every (model tile, pass-2 CTA): OR over the 128 list objects of each M-tile and both halves; one warp per entry
+__global__ void k_tile_masks(const unsigned short* __restrict__ live, int64_t ntiles, int64_t No_pad, const int32_t* __restrict__ list,
+                             int64_t n, int64_t ncta, int tile_objs, unsigned int* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= ntiles * ncta) return;
+    const int64_t t = w / ncta, c = w - t * ncta;
+    const unsigned short* r0 = live + (size_t)(2 * t) * No_pad;
+    const unsigned short* r1 = r0 + No_pad;
+    unsigned int m0 = 0, m1 = 0;
+    for (int i = lane; i < tile_objs; i += 32) {
+        const int64_t idx = c * tile_objs + i;
+        if (idx < n) {
+            const int64_t o = list[idx];
+            const unsigned int v = (unsigned int)r0[o] | (unsigned int)r1[o];
+            if (i < tile_objs / 2) m0 |= v; else m1 |= v;
+        }
+    }
+    m0 = __reduce_or_sync(0xffffffffu, m0);
+    m1 = __reduce_or_sync(0xffffffffu, m1);
+    if (lane == 0) out[w] = m0 | (m1 << 16);
+}
+
 }  // namespace
+
+// masks for the pass-2 launch over `list` (n objects, tile_objs per CTA, two M-tiles per CTA, two halves per tile row pair)
+int fzb_tile_masks(fzb_context* h, const unsigned short* live, int64_t ntiles, int64_t No_pad, const int32_t* list, int64_t n,
+                   int tile_objs, unsigned int** out) {
+    const int64_t ncta = (n + tile_objs - 1) / tile_objs;
+    if (h->fast.tmask.reserve((size_t)ntiles * ncta * 4 + 64)) return 1;
+    const int64_t warps = ntiles * ncta;
+    k_tile_masks<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, h->stream>>>(live, ntiles, No_pad, list, n, ncta, tile_objs,
+                                                                           h->fast.tmask.as<unsigned int>());
+    fzb_count_launch(h);
+    FZB_CUDA(cudaGetLastError());
+    *out = h->fast.tmask.as<unsigned int>();
+    return 0;
+}
 
 int fzb_sort_by_live_bits(fzb_context* h, const unsigned short* live, int64_t nrows, int64_t No_pad, int32_t* list,
                           int64_t n) {

@@ -62,26 +62,30 @@ int fzb_launch_sweep_tc(fzb_context* h, const SweepParams& P, dim3 grid, int nf,
 }
 
 // Tile sets of the sorted model order: the full one and a coarse one (every FZB_TC_COARSE-th model: the pre-pass of the
-// fused sweep, which only needs a lower bound of every object's maximum)
+// fused sweep, which only needs a lower bound of every object's maximum).  A model grid that is not fp32-representable
+// (mlo) gets both sets twice: with the float64 remainder of the fluxes and without it (the faint objects' sweep, whose
+// likelihoods do not feel the 2^-25 relative rounding of the models: fzb_fast.cu, FZB_TC_MLO_SNR).
 int fzb_build_tiles_tc(fzb_context* h, const double* lnprior, const int32_t* bins, const float* invnorm, bool mlo) {
     FastModels& F = h->fast;
     const int nf = F.nf;
-    for (int coarse = 0; coarse < 2; ++coarse) {
+    for (int v = 0; v < (mlo ? 4 : 2); ++v) {
+        const bool coarse = (v & 1) != 0, with_lo = mlo && v < 2;
         const int stride = coarse ? FZB_TC_COARSE : 1;
         const int64_t nm = (F.nm + stride - 1) / stride;
         const int64_t ntile = (nm + TC_TM - 1) / TC_TM;
-        const size_t bytes = (size_t)ntile * tc_tile_bytes(nf, mlo);
-        DevBuf& dst = coarse ? F.tiles_tc_coarse : F.tiles_tc;
+        const size_t bytes = (size_t)ntile * tc_tile_bytes(nf, with_lo);
+        DevBuf& dst = v == 0 ? F.tiles_tc : v == 1 ? F.tiles_tc_coarse : v == 2 ? F.tiles_tc_f32 : F.tiles_tc_f32_coarse;
         if (dst.reserve(bytes + 64)) return 1;
         FZB_CUDA(cudaMemsetAsync(dst.p, 0, bytes, h->stream));
         TcRecParams T = {};
         T.m = h->models.as<double>(); T.lnprior = lnprior; T.perm = F.perm.as<int32_t>(); T.bins = bins; T.invnorm = invnorm;
-        T.nm = nm; T.Nf = nf; T.mlo = mlo ? 1 : 0; T.tiles = dst.as<unsigned char>(); T.stride = stride;
+        T.nm = nm; T.Nf = nf; T.mlo = with_lo ? 1 : 0; T.tiles = dst.as<unsigned char>(); T.stride = stride;
         k_build_tiles_tc<<<(unsigned)((nm + 255) / 256), 256, 0, h->stream>>>(T);
         fzb_count_launch(h);
         FZB_CUDA(cudaGetLastError());
     }
     F.nm_coarse = (F.nm + FZB_TC_COARSE - 1) / FZB_TC_COARSE;
+    F.tc_f32_valid = mlo;
     F.tc_valid = true;
     return 0;
 }

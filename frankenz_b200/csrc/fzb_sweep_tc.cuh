@@ -233,8 +233,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
     if (warp < TC_CW) {
         const int64_t slot = tile_base + (int64_t)mt * 128 + row;
         int64_t o;
-        if (PASS == 1) o = slot < P.No_pad ? slot : P.No_pad - 1;
-        else o = slot < P.No ? P.objlist[slot] : -1;
+        if (PASS == 1 && !P.objlist) o = slot < P.No_pad ? slot : P.No_pad - 1;
+        else o = slot < P.No ? P.objlist[slot] : -1;      // pass 2, or pass 1 over a list of objects
         oidx = (int)o;
         const int64_t oo = o < 0 ? 0 : o;
         float arow[8 * AKSTEPS];
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
             M2 = LIN ? pack2(0.f, 0.f) : pack2(-FLT_MAX, -FLT_MAX); S2 = pack2(0.f, 0.f); Rf = FLT_MAX;
             if (FUSE) {
                 const float m0 = P.fz_M0[oo];
-                fuse_ok = m0 > -1e30f && m0 < 1e30f && slot < P.No;
+                fuse_ok = m0 > -1e30f && m0 < 1e30f && slot < P.No && o >= 0;
                 if (fuse_ok) { Rf = -floorf(m0); Yc = exp2f(m0 + Rf); fcut = P.fz_thr * Yc; }
                 fz_seg = (int)((int64_t)(blockIdx.y * TC_SPLIT + half) * P.No_pad + oo);
             }
@@ -293,8 +293,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
     if (warp == TC_CW) {
         // ===== TMA producer ======================================================================================
         if (lane == 0) {
+            int lt = 0;                          // tiles actually staged (pass 2 skips the ones without a live sub-batch)
             for (int it = 0; it < nt; ++it) {
-                const int st = it % TC_NSTAGE, n = it / TC_NSTAGE;
+                if (PASS == 2 && P.tmask && P.tmask[(size_t)(t0 + it) * gridDim.x + blockIdx.x] == 0u) continue;
+                const int st = lt % TC_NSTAGE, n = lt / TC_NSTAGE;
+                ++lt;
                 if (n > 0) mbar_wait_hint(&tile_empty[st], (uint32_t)((n - 1) & 1));
                 mbar_expect_tx(&tile_full[st], TILE_BYTES);
                 bulk_g2s(stage + (size_t)st * TILE_BYTES, tiles + (size_t)(t0 + it) * TILE_BYTES, TILE_BYTES, &tile_full[st]);
@@ -307,20 +310,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_NC >> 3) << 17) | ((128u >> 4) << 24);
         const uint64_t d0 = tc_desc(smem_u32(objA), lbo, sbo);
         const uint32_t a_lo = (uint32_t)d0, desc_hi = (uint32_t)(d0 >> 32);
-        uint32_t gch = 0;
+        uint32_t gchm[TC_MT] = {0, 0};      // chunks issued per M-tile (pass 2 skips the chunks without a live sub-batch)
+        int lt = 0;
         for (int it = 0; it < nt; ++it) {
-            const int st = it % TC_NSTAGE, n = it / TC_NSTAGE;
+            uint32_t tm = 0xffffffffu;      // live bits of the tile, OR over the objects of each M-tile (16 bits each)
+            if (PASS == 2 && P.tmask) {
+                tm = P.tmask[(size_t)(t0 + it) * gridDim.x + blockIdx.x];
+                if (tm == 0u) continue;
+            }
+            const int st = lt % TC_NSTAGE, n = lt / TC_NSTAGE;
+            ++lt;
             mbar_wait_hint(&tile_full[st], (uint32_t)(n & 1));
             tc_fence_after();
             const int64_t first = (t0 + it) * TC_TM;
             const int cnt = (int)((P.nm - first) < TC_TM ? (P.nm - first) : TC_TM);
             const int nch = (cnt + TC_NC - 1) / TC_NC;
             const uint32_t b_lo = (uint32_t)tc_desc(smem_u32(stage + (size_t)st * TILE_BYTES), lbo, sbo);
-            for (int ch = 0; ch < nch; ++ch, ++gch) {
-                const uint32_t buf = gch & 1, use = gch >> 1;
+            for (int ch = 0; ch < nch; ++ch) {
                 const uint32_t b0 = b_lo + ch * ((TC_NC / 8) * 256 >> 4);
 #pragma unroll
                 for (int m = 0; m < TC_MT; ++m) {
+                    if (((tm >> (16 * m + 2 * ch)) & 3u) == 0u) continue;      // warp-uniform
+                    const uint32_t buf = gchm[m] & 1, use = gchm[m] >> 1;
+                    ++gchm[m];
                     mbar_wait_hint(&acc_empty[m * 2 + buf], (use & 1) ^ 1);
                     tc_fence_after();
                     if (elect_one()) {
@@ -623,11 +635,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
         uint32_t live_next = 0;
         if (PASS == 2 && P.live && oidx >= 0 && nt > 0)
             live_next = P.live[((size_t)t0 * TC_SPLIT + half) * (size_t)P.No_pad + oidx];
+        int lt = 0;                            // tiles actually staged (see the TMA producer)
         for (int it = 0; it < nt; ++it) {
-            const int st = it % TC_NSTAGE, n = it / TC_NSTAGE;
             const uint32_t live_mine = live_next;
             if (PASS == 2 && P.live && oidx >= 0 && it + 1 < nt)
                 live_next = P.live[((size_t)(t0 + it + 1) * TC_SPLIT + half) * (size_t)P.No_pad + oidx];
+            uint32_t tmm = 0xffffu;            // live bits of the tile for this M-tile (all of its objects, both halves)
+            if (PASS == 2 && P.tmask) {
+                const uint32_t tm = P.tmask[(size_t)(t0 + it) * gridDim.x + blockIdx.x];
+                if (tm == 0u) continue;        // neither M-tile needs the tile: it was not staged
+                tmm = (tm >> (16 * mt)) & 0xffffu;
+            }
+            const int st = lt % TC_NSTAGE, n = lt / TC_NSTAGE;
+            ++lt;
             mbar_wait_hint(&tile_full[st], (uint32_t)(n & 1));
             const unsigned char* tile = stage + (size_t)st * TILE_BYTES;
             pairs = reinterpret_cast<const ulonglong2*>(tile + OPSEC);
@@ -647,8 +667,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
             } else {
                 lbits = 0;
             }
-            for (int ch = 0; ch < nch; ++ch, ++gch) {
+            for (int ch = 0; ch < nch; ++ch) {
+                if (((tmm >> (2 * ch)) & 3u) == 0u) continue;      // no object of the M-tile needs the chunk: no MMA was issued
                 const uint32_t buf = gch & 1, use = gch >> 1;
+                ++gch;
                 mbar_wait_hint(&acc_full[mt * 2 + buf], use & 1);
                 tc_fence_after();
                 const uint32_t cbase = lane_addr + buf * TC_CHUNK_COLS;
@@ -701,7 +723,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
             }
             if (PASS == 1 && P.live) {
                 const int64_t slot = tile_base + (int64_t)mt * 128 + row;
-                if (slot < P.No_pad) P.live[live_at + slot] = (unsigned short)(LIN ? lbits : 0xffffu);
+                const int64_t wo = P.objlist ? (int64_t)oidx : slot;      // outputs are indexed by object
+                if (P.objlist ? oidx >= 0 : slot < P.No_pad) P.live[live_at + wo] = (unsigned short)(LIN ? lbits : 0xffffu);
             }
             if (PASS == 1 && LIN) {
                 Sd += (double)(lo2(S2) + hi2(S2));
@@ -719,10 +742,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
         }
         if (PASS == 1) {
             const int64_t slot = tile_base + (int64_t)mt * 128 + row;
-            if (slot < P.No_pad) {
+            const int64_t wo = P.objlist ? (int64_t)oidx : slot;          // outputs are indexed by object
+            if (P.objlist ? oidx >= 0 : slot < P.No_pad) {
                 const float m0 = lo2(M2), m1 = hi2(M2);
                 // the two threads of an object report like two model splits
-                const size_t q = ((size_t)blockIdx.y * TC_SPLIT + half) * P.No_pad + slot;
+                const size_t q = ((size_t)blockIdx.y * TC_SPLIT + half) * P.No_pad + wo;
                 if (LIN) {
                     // y = 2^(l + R): sum 2^(l - max l) = sum y / 2^(max l + R)
                     const bool any = Mfl > -FLT_MAX;
