@@ -1444,8 +1444,11 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     }
     // models that are not fp32-representable: only the brighter objects need the float64 remainder of the fluxes in the
     // sweep (its effect on ln L is ~2e-8 S/N); the others are swept on the fp32-rounded tile sets
+    // The same cut routes the sweeps: the faint objects (broad posteriors, maximum well bounded by the pre-pass) take the
+    // fused single pass, the bright ones (narrow posteriors: pass 2 prunes almost everything, the fused pass would mostly
+    // be repeated) the seeded pass 1 + pruned pass 2.
     const double mlo_snr = env_double("FZB_TC_MLO_SNR", 32.0);
-    const bool snr_split = fuse_on && mlo && F.tc_f32_valid && mlo_snr > 0.0;
+    const bool snr_split = fuse_on && mlo_snr > 0.0;
     if (F.aux64.reserve((size_t)chunk_pad * 40 + 64)) return 1;
     double* M2d = F.aux64.as<double>();
     double* thr2d = M2d + chunk_pad;
@@ -1543,7 +1546,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                 SC.nm = F.nm_coarse; SC.tiles_per_split = (int)((F.nm_coarse + TM - 1) / TM);
                 SC.pM = pM_c; SC.pS = pS_c; SC.pbest = pbest_c; SC.live = nullptr;
                 if (snr_split) { SC.objlist = snr_list[v]; SC.No = nlist[v]; }
-                const unsigned char* tl = (v == 1) ? F.tiles_tc_coarse.as<unsigned char>() : F.tiles_tc_f32_coarse.as<unsigned char>();
+                const unsigned char* tl = (v == 1 || !mlo) ? F.tiles_tc_coarse.as<unsigned char>() : F.tiles_tc_f32_coarse.as<unsigned char>();
                 if (fzb_launch_sweep_tc(h, SC, dim3((unsigned)((nlist[v] + tile_objs - 1) / tile_objs), 1u), nf, true, 1, true, vm, tl))
                     return 1;
             }
@@ -1557,9 +1560,10 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                 const bool vm = (v == 1) ? mlo : false;
                 SweepParams SF = SP;
                 if (snr_split) { SF.objlist = snr_list[v]; SF.No = nlist[v]; }
-                const unsigned char* tl = (v == 1) ? nullptr : F.tiles_tc_f32.as<unsigned char>();
+                const unsigned char* tl = (v == 1 || !mlo) ? nullptr : F.tiles_tc_f32.as<unsigned char>();
+                const int variant = (snr_split && v == 1 && getenv("FZB_FUSE_BRIGHT") == nullptr) ? 2 : 1;
                 if (fzb_launch_sweep_tc(h, SF, dim3((unsigned)((nlist[v] + tile_objs - 1) / tile_objs), (unsigned)nsplit), nf, true, 1,
-                                        true, vm, tl, true))
+                                        true, vm, tl, variant))
                     return 1;
             }
         } else if (use_tc ? fzb_launch_sweep_tc(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, cfg.dim_prior != 0, 1, use_lin, mlo)

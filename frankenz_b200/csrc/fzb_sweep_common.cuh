@@ -163,9 +163,9 @@ __device__ __forceinline__ f2 add2(f2 a, f2 b) {
 
 // ---- tensor-core sweep (fzb_sweep_tc.cu) ----------------------------------------------------------------------------
 // lin: linear-domain form ((dof/2 - 1) = 1); mlo: the tiles carry the float64 remainder of the model fluxes
-// tiles: null = the full tile set of the context; fuse: the single-pass variant (pass 1, lin)
+// tiles: null = the full tile set of the context; fuse (pass 1, lin): 1 = the single-pass variant, 2 = seeded pass 1
 int fzb_launch_sweep_tc(fzb_context* h, const fzbsweep::SweepParams& P, dim3 grid, int nf, bool dp, int pass, bool lin,
-                        bool mlo, const unsigned char* tiles = nullptr, bool fuse = false);
+                        bool mlo, const unsigned char* tiles = nullptr, int fuse = 0);
 // build the 256-model tiles (MMA operand + packed pairs + KDE tails) from the sorted model order; sets h->fast.tc_valid
 int fzb_build_tiles_tc(fzb_context* h, const double* lnprior, const int32_t* bins, const float* invnorm, bool mlo);
 constexpr int FZB_TC_COARSE = 16;     // the coarse tile set (h->fast.tiles_tc_coarse) holds every 16th model of the sorted order

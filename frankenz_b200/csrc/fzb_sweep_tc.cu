@@ -8,7 +8,7 @@ namespace {
 using namespace fzbsweep;
 #include "fzb_sweep_tc.cuh"
 
-template <int NF, bool DP, int PASS, bool LIN, bool MLO, bool FUSE = false>
+template <int NF, bool DP, int PASS, bool LIN, bool MLO, int FUSE = 0>
 int launch_tc_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prior, const unsigned char* tiles) {
     if (!tiles) tiles = h->fast.tiles_tc.as<unsigned char>();
     if (prior) {
@@ -32,10 +32,12 @@ int launch_tc_p(fzb_context* h, const SweepParams& P, dim3 grid, bool prior, int
 
 template <bool MLO>
 int launch_tc_m(fzb_context* h, const SweepParams& P, dim3 grid, int nf, bool dp, int pass, bool lin, const unsigned char* tiles,
-                bool fuse) {
+                int fuse) {
     const bool prior = P.has_prior != 0;
     if (fuse) {
-        if (nf == 5 && lin && dp && pass == 1) return launch_tc_t<5, true, 1, true, MLO, true>(h, P, grid, prior, tiles);
+        if (nf == 5 && lin && dp && pass == 1)
+            return fuse == 1 ? launch_tc_t<5, true, 1, true, MLO, 1>(h, P, grid, prior, tiles)
+                             : launch_tc_t<5, true, 1, true, MLO, 2>(h, P, grid, prior, tiles);
         fzb_set_error("tensor-core sweep: the fused pass needs the linear-domain form");
         return 2;
     }
@@ -57,7 +59,7 @@ int fzb_tc_split() { return TC_SPLIT; }
 
 // lin: linear-domain form, valid when every object handled by the fp32 pass has (dof/2 - 1) = 1 (Nf = 5, dim_prior)
 int fzb_launch_sweep_tc(fzb_context* h, const SweepParams& P, dim3 grid, int nf, bool dp, int pass, bool lin, bool mlo,
-                        const unsigned char* tiles, bool fuse) {
+                        const unsigned char* tiles, int fuse) {
     return mlo ? launch_tc_m<true>(h, P, grid, nf, dp, pass, lin, tiles, fuse) : launch_tc_m<false>(h, P, grid, nf, dp, pass, lin, tiles, fuse);
 }
 

@@ -176,7 +176,9 @@ __device__ __forceinline__ float pow2i(float k) {
 // within the fp32 error below the cut) are recorded per thread and re-decided in float64 by k_fuse_fix.  Objects that
 // break the assumptions (frame change, record overflow, maximum far above M0: the bright ones, whose posteriors are
 // narrow) get their histogram row cleared and take the pruned pass 2 as before.
-template <int NF, bool DP, bool PRIOR, int PASS, bool LIN = false, bool MLO = false, bool FUSE = false>
+// FUSE = 2 is the same sweep without the histogram: M0 only seeds the frame and the live bits of pass 2, which then are
+// nearly the final selection instead of the superset under the running maximum - the variant for the bright objects.
+template <int NF, bool DP, bool PRIOR, int PASS, bool LIN = false, bool MLO = false, int FUSE = 0>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const unsigned char* __restrict__ tiles, uint32_t lbo,
                                                             uint32_t sbo) {
     static_assert(NF >= 1 && NF <= 6, "filters per object");
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
             if (FUSE) {
                 const float m0 = P.fz_M0[oo];
                 fuse_ok = m0 > -1e30f && m0 < 1e30f && slot < P.No && o >= 0;
-                if (fuse_ok) { Rf = -floorf(m0); Yc = exp2f(m0 + Rf); fcut = P.fz_thr * Yc; }
+                if (fuse_ok) { Rf = -floorf(m0); Yc = exp2f(m0 + Rf); if (FUSE == 1) fcut = P.fz_thr * Yc; }
                 fz_seg = (int)((int64_t)(blockIdx.y * TC_SPLIT + half) * P.No_pad + oo);
             }
         } else {
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
         uint32_t lbits = 0;                    // pass 1: live sub-batches of the current tile; pass 2: those of the warp
         unsigned long long npairs = 0;
         auto flush = [&](float v, int bin) {
-            if (v != 0.f && oidx >= 0 && (!FUSE || fuse_ok)) atomicAdd(P.hist + (int64_t)oidx * P.hist_stride + bin, v);
+            if (v != 0.f && oidx >= 0 && (FUSE != 1 || fuse_ok)) atomicAdd(P.hist + (int64_t)oidx * P.hist_stride + bin, v);
         };
         const ulonglong2* pairs = nullptr;
         const float4* tails = nullptr;
@@ -464,7 +466,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                 uv[2 * jp + 1] = (hi2(us[jp]) > cut) ? hi2(us[jp]) : 0.f;
             }
             if (__any_sync(0xffffffffu, nearm <= chalf)) {
-                if (FUSE) {
+                if (FUSE == 1) {
                     // the whole sub-batch (first model, cut of the moment, eight weights: 48 bytes, three vector stores)
                     // goes to the thread's segment; k_fuse_fix works out which of the weights lie in the band
                     if (nearm <= chalf && fuse_ok) {
@@ -610,9 +612,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                         if (FUSE) { fuse_ok = false; fcut = FLT_MAX; Yc *= f; }
                     }
                     M2 = pack2(Ym, Ym * 0.99999618530273438f);
-                    if (FUSE && fuse_ok && Ym > Yc) { Yc = Ym; fcut = P.fz_thr * Ym; }
+                    if (FUSE && fuse_ok && Ym > Yc) { Yc = Ym; if (FUSE == 1) fcut = P.fz_thr * Ym; }
                 }
-                if (FUSE) {
+                if (FUSE == 1) {
                     // every weight above the running cut goes into the histogram now; the band from just below the cut
                     // to fz_gfac above it is recorded for k_fuse_fix (fz_mid / fz_half: centre / half-width of the band
                     // in units of the cut)
@@ -703,7 +705,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                     // fast path: four complete model pairs and (pass 2) one KDE bin for all eight models -> one
                     // branch-free block in which the chains of the four pair evaluations interleave
                     bool fast = p0 + 4 <= npair_full;
-                    if (PASS == 2 || FUSE) {
+                    if (PASS == 2 || FUSE == 1) {
                         const int4 si = subs[ch * TC_NSUB + sub];
                         fast = fast && (si.y != 0);
                         sub_inv = __int_as_float(si.z);
@@ -753,9 +755,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                     P.pM[q] = (double)Mfl;
                     P.pS[q] = any ? Sd * exp2(-((double)Mfl + (double)Rf)) : 0.0;
                     P.pbest[q] = best0;
-                    if (FUSE) {
+                    if (FUSE == 1) {
                         if (cur_bin >= 0) flush(lo2(acc2) + hi2(acc2), cur_bin);
                         P.fz_cnt[q] = fuse_ok ? rcnt : -1;
+                    } else if (FUSE == 2) {
+                        P.fz_cnt[q] = -1;
                     }
                 } else {
                     P.pM[q] = (double)Mfl;
