@@ -571,6 +571,9 @@ def run_c3(ctx, grid, steps, e2e, cpu):
     achieved = FLOPS_PER_PAIR * dom_pairs / (dom_ms * 1e-3) / 1e12
     kind = int(st_acc[-1].get("sweep_kind", 1))
     kname = {1: "k_sweep2", 2: "k_sweep_tc", 3: "k_sweep_tc<LIN>"}.get(kind, "k_sweep2")
+    n_fused = float(np.mean([s.get("objects_fused", 0) for s in st_acc]))
+    if n_fused > 0:
+        kname = "k_sweep_tc<LIN, fused single pass / seeded pass 1 by S/N, incl. the 1/16 pre-pass>"
     tc = kind >= 2
     mufu_per_pair = 2.0 if kind == 3 else MUFU_PER_PAIR
     traffic = ncu_traffic_per_object(tc)
@@ -578,6 +581,10 @@ def run_c3(ctx, grid, steps, e2e, cpu):
                 "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                 "peak_source": "fzb_measure_peaks (dependency-free FFMA loop, this run; MEASURED_PEAKS.json has no "
                                "fp32 entry)",
+                "step_structure": ("pass1_scan = coarse pre-pass (every 16th model) + ONE sweep over all pairs that also fills the "
+                                   "KDE histogram for the faint objects (S/N <= 32); pass2_accumulate = pruned second sweep of "
+                                   "the bright objects + float64 re-decision of the weights recorded at the cut") if n_fused > 0
+                                  else "pass 1 (max / evidence / arg-max) + pass 2 (weights above the cut -> histogram)",
                 "note": ("algorithmic 54 flop/pair (SURVEY 8d) against the FP32 FMA peak; the tensor-core sweep executes "
                          "30 of them (the three K=Nf dot products, as tf32x3 tcgen05 MMAs) on the tensor pipe and ~40 "
                          "on the FMA pipe, so the fraction is a figure of merit of the whole SM, not an FMA-pipe "
@@ -593,7 +600,8 @@ def run_c3(ctx, grid, steps, e2e, cpu):
                 "pass2_pairs_evaluated_frac": float(np.mean([s.get("pairs_pass2", 0) for s in st_acc])) / (float(no) * nm),
                 "ms": {"pass1_scan": ms_scan, "pass2_accumulate": ms_acc, "finish": ms_fin,
                        "step_total": float(np.mean(ms_steps))},
-                "objects_routed_to_fp64": n64}
+                "objects_routed_to_fp64": n64, "objects_completed_by_the_fused_pass_frac": n_fused / float(no),
+                "weights_redecided_in_float64_per_object": float(np.mean([s.get("cut_recorded", 0) for s in st_acc])) / float(no)}
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_file):
         try:
@@ -629,17 +637,19 @@ def ncu_traffic_per_object(tc):
         if not os.path.exists(path):
             continue
         txt = open(path).read()
-        sec = txt.split("## ")[1] if "## " in txt else txt      # first kernel section = pass 1
+        mark = txt.find("Objects in this launch:")
+        sec = txt[mark:] if mark >= 0 else (txt.split("## ")[1] if "## " in txt else txt)      # the dominant sweep launch
         rd = re.search(r"dram__bytes_read\.sum`\) \| ([0-9.]+) (\w+)", sec)
         wr = re.search(r"dram__bytes_write\.sum`\) \| ([0-9.]+) (\w+)", sec)
-        ob = re.search(r"--objects (\d+)", txt)
+        ob = re.search(r"Objects in this launch: (\d+)", txt) or re.search(r"--objects (\d+)", txt)
         if not (rd and wr and ob):
             continue
         unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
         tot = float(rd.group(1)) * unit.get(rd.group(2), 1.0) + float(wr.group(1)) * unit.get(wr.group(2), 1.0)
-        return tot / float(ob.group(1)), ("dram__bytes_read.sum + dram__bytes_write.sum of the pass-1 launch in "
-                                          "profiles/%s, per object x objects of this run (photometry planes in, "
-                                          "per-split partials out; the kernel is compute-bound)" % name)
+        return tot / float(ob.group(1)), ("dram__bytes_read.sum + dram__bytes_write.sum of the dominant sweep launch in "
+                                          "profiles/%s, per object x objects of this run (photometry planes in; "
+                                          "partials, live bits, records and histogram REDs out; the kernel is "
+                                          "compute-bound)" % name)
     return None
 
 

@@ -717,10 +717,12 @@ static int fit_predict_host_impl(fzb_context* h, const double* data, const doubl
 
     // chunk size: large enough for long CTAs of the sweep kernels (few model splits), small enough to pipeline; the chunks
     // taper towards the end (below), so the size of the main ones does not set the un-hidden tail
-    int64_t chunk = 196608;
+    int64_t chunk = 262144;
     // (an override is rounded up to the 4096-object granularity of the taper below, floor 8192, so that no chunk of the
     // taper exceeds the reserved staging buffers)
     if (const char* e = getenv("FZB_E2E_CHUNK")) chunk = std::max<int64_t>(8192, (atoll(e) + 4095) / 4096 * 4096);
+    // nothing to overlap when the PDFs stay on the device (summaries only): one chunk, bounded by the row buffer (12 GB)
+    if (!pdfs) chunk = std::max<int64_t>(chunk, ((int64_t)12 << 30) / std::max<int64_t>(1, (int64_t)Ng * 8));
     if (!want_rows || No <= chunk + chunk / 2) chunk = No;
     const size_t chunk_bytes = (size_t)chunk * Ng * sizeof(double);
     StagedDownloader dl(h);
@@ -743,7 +745,8 @@ static int fit_predict_host_impl(fzb_context* h, const double* data, const doubl
         // the download of the last chunk is the only one nothing hides: taper the chunk size towards the end
         const int64_t rem = No - o0;
         nc = chunk;
-        if (pdfs && rem < 2 * chunk) nc = std::max<int64_t>(std::min<int64_t>(rem, 8192), (rem / 2 + 4095) / 4096 * 4096);
+        // (down to ~32k objects = 180 MB of PDFs: every chunk costs a few ms of launch tails and host round trips)
+        if (pdfs && rem < 2 * chunk) nc = rem <= 49152 ? rem : std::max<int64_t>(32768, (rem / 2 + 4095) / 4096 * 4096);
         nc = std::min(std::min(nc, rem), chunk);
         int b = pdfs ? (int)(c & 1) : 0;
         h->prior_o0 = o0;
