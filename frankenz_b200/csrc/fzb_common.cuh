@@ -174,6 +174,7 @@ struct fzb_context {
     DevBuf knn_centre;      // filter scan, dot form: mean feature (double[Nf])
     int knn_form = 0;       // fp32 distance form of the scan copy (fzb_knn.cu: KS_DIFF / KS_DOT)
     bool knn_scan_valid = false;
+    bool knn_share_off = false;   // filter scan: the threshold of tree 0 does not serve the other trees of this set
     int64_t knn_m = 0, knn_Ns = 0;   // interleave stride / rows of the scan copy
     bool knn_tc_valid = false;
     int64_t knn_ntile = 0;

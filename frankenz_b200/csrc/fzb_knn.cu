@@ -234,18 +234,22 @@ __global__ void k_knn_mean_finish(double* sums, int Nf) {
 // One thread owns R queries (features in registers) of one tree and one row split; the rows are staged tile by
 // tile into shared memory with TMA bulk copies and broadcast to all threads.  Rows with distance <= tau are appended
 // (fp32 distance, scan row) to the buffer of the (query, tree, split).
+// A launch covers the trees [t0, t0 + gridDim.y); buffers, counts and thresholds are indexed (query, tree - t0).
+// tau_q != null: the threshold of every tree of the launch is tau_fac x the squared-distance threshold tau_q[query]
+// (the k+8-th smallest distance found in another tree: the trees are noise realisations of one training set).
 template <int NF, int FORM, int R>
 __global__ void __launch_bounds__(KS_T, 2) k_knn_filter(const float* __restrict__ scan, int64_t Ns, int64_t nrows,
                                                         const double* __restrict__ q, const double* __restrict__ centre,
                                                         int64_t No, const float* __restrict__ tau_in, int64_t rows_per_split,
-                                                        int cap, uint2* __restrict__ buf, int* __restrict__ cnt_out) {
+                                                        int cap, uint2* __restrict__ buf, int* __restrict__ cnt_out, int t0,
+                                                        const float* __restrict__ tau_q, float tau_fac) {
     constexpr int RQ = ks_rowq(NF, FORM);
     extern __shared__ __align__(128) unsigned char ks_raw[];
     ulonglong2* stage = reinterpret_cast<ulonglong2*>(ks_raw);                        // 2 x KS_TM x RQ
     uint64_t* bars = reinterpret_cast<uint64_t*>(ks_raw + (size_t)2 * KS_TM * RQ * 16);
     const int tid = threadIdx.x;
     const int t = blockIdx.y, sp = blockIdx.z, nsp = gridDim.z, K = gridDim.y;
-    const ulonglong2* F = reinterpret_cast<const ulonglong2*>(scan) + (size_t)t * Ns * RQ;
+    const ulonglong2* F = reinterpret_cast<const ulonglong2*>(scan) + (size_t)(t0 + t) * Ns * RQ;
     // DIFF: (-q, -q') of query pairs, f - q = f + (-q) with the same rounding; DOT: (-2 q', -2 q'')
     kf2 nq2[R / 2][NF];
     float tau[R];
@@ -254,6 +258,13 @@ __global__ void __launch_bounds__(KS_T, 2) k_knn_filter(const float* __restrict_
     for (int r = 0; r < R; ++r) {
         const int64_t o = (int64_t)blockIdx.x * (KS_T * R) + (int64_t)r * KS_T + tid;
         tau[r] = (o < No) ? (tau_in ? tau_in[o * K + t] : CUDART_INF_F) : -CUDART_INF_F;     // padding queries append nothing
+        if (tau_q && o < No) {
+            // DOT: the thresholds are v = d^2 - |q'|^2, so d^2 is scaled: v' = fac v + (fac - 1) |q'|^2
+            float qq = 0.f;
+            if (FORM == KS_DOT)
+                for (int b = 0; b < NF; ++b) { const float qc = (float)(q[o * NF + b] - centre[b]); qq = fmaf(qc, qc, qq); }
+            tau[r] = fmaf(tau_fac, tau_q[o], (tau_fac - 1.f) * qq);
+        }
         cnt[r] = 0;
     }
 #pragma unroll
@@ -358,12 +369,14 @@ __device__ __forceinline__ unsigned int ks_unkey(unsigned int k) { return (k & 0
 __global__ void __launch_bounds__(256) k_knn_select(const uint2* __restrict__ buf, const int* __restrict__ cnt, int nsp, int cap,
                                                     int64_t nitems, int KC, float* __restrict__ tau_out,
                                                     float* __restrict__ cand_d, int* __restrict__ cand_i, int64_t m,
-                                                    unsigned int* __restrict__ n_overflow) {
+                                                    unsigned int* __restrict__ n_overflow, int Kw, int t0, int Ktot) {
     extern __shared__ unsigned int sel_sm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     unsigned int* keys = sel_sm + (size_t)w * KS_CAP;
     const int64_t item = (int64_t)blockIdx.x * wpb + w;
     if (item >= nitems) return;
+    // candidates go to the slot of (query, tree) among all Ktot trees; the launch covers the trees [t0, t0 + Kw)
+    const int64_t oitem = (item / Kw) * Ktot + t0 + (item % Kw);
     int n = 0;
     bool over = false;
     for (int s = 0; s < nsp; ++s) {
@@ -378,7 +391,7 @@ __global__ void __launch_bounds__(256) k_knn_select(const uint2* __restrict__ bu
     if (bad) {
         if (tau_out && lane == 0) tau_out[item] = CUDART_INF_F;
         if (cand_d)
-            for (int c = lane; c < KC; c += 32) { cand_d[(size_t)item * KC + c] = CUDART_INF_F; cand_i[(size_t)item * KC + c] = -1; }
+            for (int c = lane; c < KC; c += 32) { cand_d[(size_t)oitem * KC + c] = CUDART_INF_F; cand_i[(size_t)oitem * KC + c] = -1; }
         if (over && cand_d && lane == 0 && n_overflow) atomicAdd(n_overflow, 1u);
         return;
     }
@@ -414,8 +427,8 @@ __global__ void __launch_bounds__(256) k_knn_select(const uint2* __restrict__ bu
                 else if (eq) { pos = at_eq + __popc(be & below); if (pos >= KC) pos = -1; }
                 if (pos >= 0) {
                     const int64_t rp = e.y;
-                    cand_d[(size_t)item * KC + pos] = __uint_as_float(e.x);
-                    cand_i[(size_t)item * KC + pos] = (int)((rp % KS_IL) * m + rp / KS_IL);
+                    cand_d[(size_t)oitem * KC + pos] = __uint_as_float(e.x);
+                    cand_i[(size_t)oitem * KC + pos] = (int)((rp % KS_IL) * m + rp / KS_IL);
                 }
                 at_less += __popc(bl);
                 at_eq += __popc(be);
@@ -575,6 +588,7 @@ int fzb_knn_scan_build(fzb_context* h) {
     const int nf = h->knn_Nf, K = h->knn_K;
     const int64_t Nm = h->knn_Nm;
     h->knn_scan_valid = false;
+    h->knn_share_off = false;
     if (nf < 4 || nf > 6 || Nm < 4096 || Nm >= ((int64_t)1 << 31) - KS_IL) return 0;
     const char* e = getenv("FZB_KNN_FORM");
     const int form = (e && strcmp(e, "diff") == 0) ? KS_DIFF : KS_DOT;
@@ -600,14 +614,20 @@ int fzb_knn_scan_build(fzb_context* h) {
     return 0;
 }
 
+struct KnnWindow {
+    int t0, Kw;              // trees [t0, t0 + Kw)
+    const float* tau_q;      // per-query squared-distance threshold shared by the trees of the window (null: per item)
+    float tau_fac;
+};
+
 template <int NF, int FORM, int R>
 static int knn_filter_launch(fzb_context* h, const double* d_q, int64_t No, int64_t nrows, const float* tau_in, int nsp,
-                             int64_t rows_per_split, int cap, uint2* buf, int* cnt) {
+                             int64_t rows_per_split, int cap, uint2* buf, int* cnt, const KnnWindow& W) {
     size_t smem = (size_t)2 * KS_TM * ks_rowq(NF, FORM) * 16 + 2 * sizeof(uint64_t);
     FZB_CUDA(cudaFuncSetAttribute(k_knn_filter<NF, FORM, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((No + KS_T * R - 1) / (KS_T * R)), (unsigned)h->knn_K, (unsigned)nsp);
+    dim3 grid((unsigned)((No + KS_T * R - 1) / (KS_T * R)), (unsigned)W.Kw, (unsigned)nsp);
     k_knn_filter<NF, FORM, R><<<grid, KS_T, smem, h->stream>>>(h->knn_scan.as<float>(), h->knn_Ns, nrows, d_q, h->knn_centre.as<double>(),
-                                                               No, tau_in, rows_per_split, cap, buf, cnt);
+                                                               No, tau_in, rows_per_split, cap, buf, cnt, W.t0, W.tau_q, W.tau_fac);
     fzb_count_launch(h);
     FZB_CUDA(cudaGetLastError());
     return 0;
@@ -616,23 +636,52 @@ static int knn_filter_launch(fzb_context* h, const double* d_q, int64_t No, int6
 // loads and the branch of a row are spread over more distances)
 static int knn_filter_r(int form) { return form == KS_DOT ? KS_RDOT : KS_R; }
 static int knn_filter_dispatch(fzb_context* h, const double* d_q, int64_t No, int64_t nrows, const float* tau_in, int nsp,
-                               int64_t rows_per_split, int cap, uint2* buf, int* cnt) {
+                               int64_t rows_per_split, int cap, uint2* buf, int* cnt, const KnnWindow& W) {
     const int nf = h->knn_Nf;
 #define FZB_KF(NF_) \
-    return h->knn_form == KS_DOT ? knn_filter_launch<NF_, KS_DOT, KS_RDOT>(h, d_q, No, nrows, tau_in, nsp, rows_per_split, cap, buf, cnt) \
-                                 : knn_filter_launch<NF_, KS_DIFF, KS_R>(h, d_q, No, nrows, tau_in, nsp, rows_per_split, cap, buf, cnt)
+    return h->knn_form == KS_DOT ? knn_filter_launch<NF_, KS_DOT, KS_RDOT>(h, d_q, No, nrows, tau_in, nsp, rows_per_split, cap, buf, cnt, W) \
+                                 : knn_filter_launch<NF_, KS_DIFF, KS_R>(h, d_q, No, nrows, tau_in, nsp, rows_per_split, cap, buf, cnt, W)
     if (nf == 4) { FZB_KF(4); }
     if (nf == 5) { FZB_KF(5); }
     FZB_KF(6);
 #undef FZB_KF
 }
 
-// Candidate search of one query chunk by nested prefixes (see above): leaves the KC smallest rows per (query, tree)
-// in cand_d / cand_i.  buf: items x KS_CAP uint2; aux: 2 x items floats (tau) + items x 32 ints (counts).
-static int knn_filter_search(fzb_context* h, const double* d_q, int64_t No, int KC, uint2* buf, float* tau2, int* cnt,
-                             float* cand_d, int* cand_i, unsigned int* n_overflow) {
-    const int K = h->knn_K;
-    const int64_t Ns = h->knn_Ns, items = No * K;
+// row splits of a filter launch: fill the GPU and even out the last wave
+static void knn_row_splits(fzb_context* h, int64_t ctas_per_split, int64_t nrows, bool split, int64_t* nsp_out, int64_t* rps_out) {
+    const int64_t tiles = (nrows + KS_TM - 1) / KS_TM, slots = (int64_t)h->sm_count * 2;
+    int64_t nsp = 1;
+    if (split) {
+        double best = 1e30;
+        for (int64_t c = 1; c <= 32 && c <= tiles; ++c) {
+            if ((tiles + c - 1) / c < 4 && c > 1) break;            // at least four tiles per split
+            const double waves = (double)(ctas_per_split * c) / (double)slots;
+            const double cost = std::ceil(waves) / waves * (1.0 + 0.01 * c);
+            if (cost < best - 1e-9) { best = cost; nsp = c; }
+        }
+    }
+    const int64_t rows_per_split = ((nrows + nsp - 1) / nsp + KS_TM - 1) / KS_TM * KS_TM;
+    *nsp_out = (nrows + rows_per_split - 1) / rows_per_split;
+    *rps_out = rows_per_split;
+}
+
+static int knn_select_launch(fzb_context* h, const uint2* buf, const int* cnt, int nsp, int cap, int64_t items, int KC, float* tau_out,
+                             float* cand_d, int* cand_i, unsigned int* n_overflow, const KnnWindow& W) {
+    const int wpb = 8;
+    const size_t smem = (size_t)wpb * KS_CAP * sizeof(unsigned int);
+    FZB_CUDA(cudaFuncSetAttribute(k_knn_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_select<<<(unsigned)((items + wpb - 1) / wpb), wpb * 32, smem, h->stream>>>(buf, cnt, nsp, cap, items, KC, tau_out, cand_d, cand_i,
+                                                                                 h->knn_m, n_overflow, W.Kw, W.t0, h->knn_K);
+    fzb_count_launch(h);
+    FZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Candidate search of the trees of a window by nested prefixes (see above): leaves the KC smallest rows per (query, tree)
+// in cand_d / cand_i and, if asked, the KC-th smallest distance in tau_final[query x tree of the window].
+static int knn_staged_search(fzb_context* h, const double* d_q, int64_t No, int KC, uint2* buf, float* tau2, int* cnt,
+                             float* cand_d, int* cand_i, unsigned int* n_overflow, const KnnWindow& W, float* tau_final) {
+    const int64_t Ns = h->knn_Ns, items = No * W.Kw;
     // prefixes: KS_P0 rows, then a constant ratio up to all rows; a stage appends KC x ratio rows on average (relative
     // scatter 1 / sqrt(KC)), kept below 3/8 of the buffer
     double ratio_max = std::min(16.0, 0.375 * KS_CAP / KC);
@@ -642,40 +691,44 @@ static int knn_filter_search(fzb_context* h, const double* d_q, int64_t No, int 
     const double ratio = std::pow((double)Ns / KS_P0, 1.0 / J);
     const int64_t qper = (int64_t)KS_T * knn_filter_r(h->knn_form);
     const int64_t qtiles = (No + qper - 1) / qper;
-    const int64_t slots = (int64_t)h->sm_count * 2;
     for (int j = 0; j <= J; ++j) {
         int64_t nrows = j == J ? Ns : (int64_t)std::ceil(KS_P0 * std::pow(ratio, j));
         if (nrows > Ns) nrows = Ns;
-        // row splits: fill the GPU and even out the last wave
-        const int64_t tiles = (nrows + KS_TM - 1) / KS_TM;
-        int64_t nsp = 1;
-        if (j > 0) {
-            const int64_t base = qtiles * K;
-            double best = 1e30;
-            for (int64_t c = 1; c <= 32 && c <= tiles; ++c) {
-                if ((tiles + c - 1) / c < 4 && c > 1) break;            // at least four tiles per split
-                const double waves = (double)(base * c) / (double)slots;
-                const double cost = std::ceil(waves) / waves * (1.0 + 0.01 * c);
-                if (cost < best - 1e-9) { best = cost; nsp = c; }
-            }
-        }
-        int64_t rows_per_split = ((nrows + nsp - 1) / nsp + KS_TM - 1) / KS_TM * KS_TM;
-        nsp = (nrows + rows_per_split - 1) / rows_per_split;
+        int64_t nsp, rows_per_split;
+        knn_row_splits(h, qtiles * W.Kw, nrows, j > 0, &nsp, &rows_per_split);
         const int cap = KS_CAP / (int)nsp;
         const float* tin = j == 0 ? nullptr : tau2 + (size_t)((j - 1) & 1) * items;
         float* tout = tau2 + (size_t)(j & 1) * items;
-        if (knn_filter_dispatch(h, d_q, No, nrows, tin, (int)nsp, rows_per_split, cap, buf, cnt)) return 1;
-        const int wpb = 8;
-        const size_t smem = (size_t)wpb * KS_CAP * sizeof(unsigned int);
-        FZB_CUDA(cudaFuncSetAttribute(k_knn_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (knn_filter_dispatch(h, d_q, No, nrows, tin, (int)nsp, rows_per_split, cap, buf, cnt, W)) return 1;
         const bool last = j == J;
-        k_knn_select<<<(unsigned)((items + wpb - 1) / wpb), wpb * 32, smem, h->stream>>>(
-            buf, cnt, (int)nsp, cap, items, KC, last ? nullptr : tout, last ? cand_d : nullptr, last ? cand_i : nullptr, h->knn_m,
-            n_overflow);
-        fzb_count_launch(h);
-        FZB_CUDA(cudaGetLastError());
+        if (knn_select_launch(h, buf, cnt, (int)nsp, cap, items, KC, last ? tau_final : tout, last ? cand_d : nullptr,
+                              last ? cand_i : nullptr, n_overflow, W))
+            return 1;
     }
     return 0;
+}
+
+// All trees of one query chunk.  The K trees are Monte-Carlo realisations of ONE training set (knn.py:175-188), so the
+// k+8-th smallest distance of a query is nearly the same in all of them (C4: within +-25 %, 99.9 % below x1.32): the
+// staged search runs for tree 0 only and 1.5 x its threshold filters the other trees in a single sweep (a quarter of the
+// appended rows, no prefix stages).  A pair whose sweep finds fewer than k+8 rows (or overflows) is re-done by the
+// float64 kernel like any failed exactness test; if that ever exceeds 1 % of a chunk the shortcut is switched off
+// for the handle.  aux: tau2 = 2 x items floats, tauq = No floats.
+static int knn_filter_search(fzb_context* h, const double* d_q, int64_t No, int KC, uint2* buf, float* tau2, float* tauq, int* cnt,
+                             float* cand_d, int* cand_i, unsigned int* n_overflow, bool* shared) {
+    const int K = h->knn_K;
+    const bool share = K > 1 && !h->knn_share_off && getenv("FZB_KNN_NO_SHARE") == nullptr;
+    *shared = share;
+    if (!share) return knn_staged_search(h, d_q, No, KC, buf, tau2, cnt, cand_d, cand_i, n_overflow, KnnWindow{0, K, nullptr, 1.f}, nullptr);
+    if (knn_staged_search(h, d_q, No, KC, buf, tau2, cnt, cand_d, cand_i, n_overflow, KnnWindow{0, 1, nullptr, 1.f}, tauq)) return 1;
+    const char* e = getenv("FZB_KNN_SHARE_FAC");
+    const KnnWindow W{1, K - 1, tauq, e ? (float)atof(e) : 1.5f};
+    const int64_t qper = (int64_t)KS_T * knn_filter_r(h->knn_form);
+    int64_t nsp, rows_per_split;
+    knn_row_splits(h, ((No + qper - 1) / qper) * W.Kw, h->knn_Ns, true, &nsp, &rows_per_split);
+    const int cap = KS_CAP / (int)nsp;
+    if (knn_filter_dispatch(h, d_q, No, h->knn_Ns, nullptr, (int)nsp, rows_per_split, cap, buf, cnt, W)) return 1;
+    return knn_select_launch(h, buf, cnt, (int)nsp, cap, No * W.Kw, KC, nullptr, cand_d, cand_i, n_overflow, W);
 }
 
 // error bound of the tensor-core scan's v, in units of (|q'|^2 + max |f'|^2): see fzb_knn_tc.cu
@@ -715,7 +768,7 @@ int fzb_knn_query_dev(fzb_context* h, const double* d_q, int64_t No, int k, doub
     // KS_CAP buffered rows per (query, tree), up to 12 GB)
     const int nlist = use_tc ? (int)nsp * fzb_knn_tc_lists() : 1;     // candidate lists per (query, tree)
     const size_t per_q = (size_t)K * nlist * KC * 8;
-    const size_t per_q_buf = use_tc ? 0 : (size_t)K * (KS_CAP * 8 + 8 + 32 * 4);
+    const size_t per_q_buf = use_tc ? 0 : (size_t)K * (KS_CAP * 8 + 8 + 32 * 4) + 4;
     int64_t chunk = use_tc ? (int64_t)(((size_t)2 << 30) / per_q) : (int64_t)(((size_t)12 << 30) / per_q_buf);
     const int64_t qtile = use_tc ? 128 : (int64_t)KS_T * knn_filter_r(h->knn_form);
     chunk = chunk / qtile * qtile;        // whole query tiles
@@ -729,16 +782,18 @@ int fzb_knn_query_dev(fzb_context* h, const double* d_q, int64_t No, int k, doub
     int64_t* redo = reinterpret_cast<int64_t*>(n_redo + 4);
     uint2* fbuf = h->knn_buf.as<uint2>();
     float* ftau = reinterpret_cast<float*>(fbuf + (size_t)chunk * K * KS_CAP);
-    int* fcnt = reinterpret_cast<int*>(ftau + (size_t)2 * chunk * K);
+    float* ftauq = ftau + (size_t)2 * chunk * K;
+    int* fcnt = reinterpret_cast<int*>(ftauq + chunk);
     double ms_search = 0.0;
+    bool shared = false;
     for (int64_t o0 = 0; o0 < No; o0 += chunk) {
         int64_t nc = No - o0 < chunk ? No - o0 : chunk;
         const double* qq = d_q + o0 * nf;
         FZB_CUDA(cudaEventRecord(h->ev[2], h->stream));
         FZB_CUDA(cudaMemsetAsync(n_redo, 0, 16, h->stream));
         int rc = use_tc ? fzb_knn_tc_scan(h, qq, nc, KC, (int)nsp, (int)(rows_per_split / rtile), cand_d, cand_i)
-                        : knn_filter_search(h, qq, nc, KC, fbuf, ftau, fcnt, cand_d, cand_i,
-                                            reinterpret_cast<unsigned int*>(n_redo + 1));
+                        : knn_filter_search(h, qq, nc, KC, fbuf, ftau, ftauq, fcnt, cand_d, cand_i,
+                                            reinterpret_cast<unsigned int*>(n_redo + 1), &shared);
         if (rc) return rc;
         const int wpb = 4;
         size_t smem = (size_t)wpb * KC * nlist * 16;
@@ -764,6 +819,7 @@ int fzb_knn_query_dev(fzb_context* h, const double* d_q, int64_t No, int k, doub
         FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]));
         ms_search += ms;
         h->stats.knn_redo += nr[0];
+        if (shared && (int64_t)nr[0] * 100 > nc * K) h->knn_share_off = true;      // the trees are not alike: staged search for all
         {   // largest error of the candidates' fp32 values in units of the bound's scale (tensor-core / dot forms)
             double w;
             memcpy(&w, nr + 2, 8);

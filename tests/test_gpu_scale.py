@@ -174,8 +174,9 @@ def test_knn_filter_scan_adversarial_inputs(monkeypatch, form):
         monkeypatch.delenv("FZB_KNN_EXACT_ONLY")
         assert np.array_equal(idx_fast, idx_exact), (form, k, st)
         assert np.array_equal(dist_fast, dist_exact)
-        # the fast path must have carried (nearly) all searches: the NaN query and the ties go to the float64 kernel
-        assert st["knn_redo"] <= 8 and st["knn_overflow"] == 0, st
+        # the fast path must have carried (nearly) all searches: the NaN query and the ties go to the float64 kernel, and
+        # so does the far-away query in the tree that borrows the threshold of tree 0 (1.5 x its radius holds every row)
+        assert st["knn_redo"] <= 8 and st["knn_overflow"] <= 2, st
         if form == "dot":
             assert st["knn_tc_err"] <= 2e-6, st                  # measured error of the fp32 values vs the bound
     for i in (0, 5, 7, 2499):
