@@ -5,6 +5,9 @@ Two partitions:
 * objects sharded, models replicated (`fit_predict_object_sharded`): every rank fits a contiguous
   slice of the objects against all models.  Objects are independent (bruteforce.py:192), so there
   is NO data-path collective; an optional all-gather assembles the outputs.
+* kNN with the training rows sharded (`knn_query_row_sharded`): every rank searches its slice of every tree exactly,
+  one all-gather of the per-shard top-k (distance, global row) and a k-way merge by (distance, index) give the
+  neighbours of the whole set - the reference's `KDTree.query` call site (knn.py:362-365) for trees too large for one GPU.
 * models sharded (`fit_predict_model_sharded`): every rank holds a slice of the models and sees all
   objects.  Per object the three associative reductions of the path are merged across ranks:
       lmap  = max_g pmax_g                                         one all-gather of the packed partials
@@ -105,6 +108,59 @@ def merge_gathered(gathered, group=None):
     lmap = torch.where(poisoned, torch.full_like(gmax, float("nan")), gmax)
     levid = torch.where(poisoned, torch.full_like(levid, float("nan")), levid)
     return lmap, levid, best
+
+
+def merge_topk(dist_local, idx_global, k, group=None):
+    """k-way merge of per-rank nearest-neighbour lists.
+
+    dist_local float64 [No, K, k] (ascending per list, inf = missing), idx_global int64 [No, K, k] (row indices of the WHOLE
+    training set, i.e. already offset by the rank's first row).  Every rank gets the k smallest of the union ordered by
+    (distance, index), the order of the single-GPU search (exact ties go to the lowest row index)."""
+    rank, world = _world(group)
+    d, i = dist_local.contiguous(), idx_global.contiguous()
+    if world > 1:
+        gd = [torch.empty_like(d) for _ in range(world)]
+        gi = [torch.empty_like(i) for _ in range(world)]
+        dist.all_gather(gd, d, group=group)
+        dist.all_gather(gi, i, group=group)
+        d, i = torch.cat(gd, dim=-1), torch.cat(gi, dim=-1)
+    return topk_lex(d, i, k)
+
+
+def topk_lex(d, i, k):
+    """The k smallest (distance, index) pairs along the last axis, lexicographic: stable sort by index, then by distance."""
+    o1 = torch.argsort(i, dim=-1, stable=True)
+    d, i = torch.gather(d, -1, o1), torch.gather(i, -1, o1)
+    o2 = torch.argsort(d, dim=-1, stable=True)
+    d, i = torch.gather(d, -1, o2), torch.gather(i, -1, o2)
+    return d[..., :k].contiguous(), i[..., :k].contiguous()
+
+
+def knn_query_row_sharded(features, qfeats, k, p=2, group=None, device=None, engine=None):
+    """Exact k nearest rows per tree with the training rows sharded over the ranks.
+
+    `features` float32 [K, Nrows, Nf]: the WHOLE feature set (every rank keeps its `shard_bounds` slice of the rows of
+    every tree on its GPU); `qfeats` float64 [No, Nf] on every rank.  Returns (idx int64 [No, K, k], dist float64 [No, K, k])
+    as `Engine.knn_query` would for the unsharded set.  Rows per rank must be >= k."""
+    rank, world = _world(group)
+    feats = np.asarray(features, dtype=np.float32)
+    lo, hi = shard_bounds(feats.shape[1], world, rank)
+    if hi - lo < k:
+        raise ValueError("every rank needs at least k=%d training rows, rank %d has %d" % (k, rank, hi - lo))
+    own = engine is None
+    if own:
+        nf = feats.shape[2]
+        ones = np.ones((hi - lo, nf))
+        engine = Engine(ones, ones, ones, device=device)
+        engine.knn_build(np.ascontiguousarray(feats[:, lo:hi]))
+    try:
+        idx, dd = engine.knn_query(qfeats, k, p=p)
+    finally:
+        if own:
+            engine.close()
+    dev = torch.device("cuda", engine.device) if torch.cuda.is_available() else torch.device("cpu")
+    dt, it = merge_topk(torch.from_numpy(dd).to(dev), torch.from_numpy(idx + lo).to(dev), k, group=group)
+    return it.cpu().numpy(), dt.cpu().numpy()
 
 
 def owned_rows(n, world, rank):

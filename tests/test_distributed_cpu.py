@@ -178,3 +178,46 @@ def test_merge_single_process_identity():
     assert levid[1] == -float("inf") and best.tolist() == [14, 10, 11]
     p = merge_pdfs(torch.tensor([[1.0, 3.0], [2.0, 2.0]], dtype=torch.float64))
     assert torch.allclose(p, torch.tensor([[0.25, 0.75], [0.5, 0.5]], dtype=torch.float64))
+
+
+def _knn_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from frankenz_b200.distributed import merge_topk, shard_bounds
+        rs = np.random.RandomState(3)
+        feats = rs.normal(size=(2, 400, 5)).astype(np.float32)
+        feats[1, 300] = feats[1, 20]                    # an exact tie across the two shards
+        qf = rs.normal(size=(6, 5))
+        qf[0] = feats[1, 20].astype(np.float64)
+        k = 7
+        lo, hi = shard_bounds(feats.shape[1], world, rank)
+        idx = np.empty((len(qf), 2, k), dtype=np.int64)
+        dd = np.empty((len(qf), 2, k))
+        for i in range(len(qf)):                        # the per-shard exact search (the GPU kernel's job), by the oracle
+            oi, od = fo.knn_query_exact(feats[:, lo:hi], qf[i], k, 2)
+            idx[i], dd[i] = oi, od
+        dm, im = merge_topk(torch.from_numpy(dd), torch.from_numpy(idx + lo), k)
+        if rank == 0:
+            q.put((feats, qf, im.numpy(), dm.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_knn_row_sharded_merge_gloo():
+    """Per-shard top-k lists merged over two gloo ranks = the exact search of the whole set (knn.py:362-365), ties to the
+    lowest row index."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_knn_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    feats, qf, im, dm = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for i in range(len(qf)):
+        oi, od = fo.knn_query_exact(feats, qf[i], 7, 2)
+        assert np.array_equal(im[i], oi) and np.array_equal(dm[i], od)

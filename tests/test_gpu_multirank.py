@@ -191,3 +191,89 @@ def test_single_rank_driver_chunks_and_ragged_tail():
     assert np.max(np.sum(np.abs(p[good] - p1[good]), axis=1)) <= 1e-5
     assert np.allclose(lm[good], lm1[good], rtol=0, atol=1e-6) and np.array_equal(best[good], bf.best_idx[good])
     sb.close()
+
+
+def _knn_problem():
+    rs = np.random.RandomState(21)
+    base = rs.normal(size=(30000, 5)) * np.array([1.0, 0.7, 0.5, 0.9, 1.3]) + 20.0
+    feats = np.stack([base + rs.normal(size=base.shape) * 0.02 for _ in range(3)]).astype(np.float32)
+    feats[2, 29000] = feats[2, 40]                       # an exact tie between the first and the last shard
+    q = base[rs.choice(len(base), 600)] + rs.normal(size=(600, 5)) * 0.05
+    q[3] = feats[2, 40].astype(np.float64)
+    return feats, q
+
+
+def test_knn_row_shards_merge_like_the_whole_set():
+    """Row-sharded kNN (distributed.knn_query_row_sharded) with the all-gather replaced by a concatenation: three
+    shards searched on one GPU and merged by `topk_lex` give the neighbours of the unsharded search, bit for bit."""
+    import torch
+    from frankenz_b200._engine import Engine
+    from frankenz_b200.distributed import shard_bounds, topk_lex
+    feats, q = _knn_problem()
+    k = 25
+    ones = np.ones((feats.shape[1], 5))
+    e = Engine(ones, ones, ones)
+    e.knn_build(feats)
+    idx_all, dist_all = e.knn_query(q, k, p=2)
+    e.close()
+    ds, ix = [], []
+    for r in range(3):
+        lo, hi = shard_bounds(feats.shape[1], 3, r)
+        es = Engine(ones[lo:hi], ones[lo:hi], ones[lo:hi])
+        es.knn_build(np.ascontiguousarray(feats[:, lo:hi]))
+        i, d = es.knn_query(q, k, p=2)
+        es.close()
+        ds.append(torch.from_numpy(d).cuda())
+        ix.append(torch.from_numpy(i + lo).cuda())
+    dm, im = topk_lex(torch.cat(ds, dim=-1), torch.cat(ix, dim=-1), k)
+    assert np.array_equal(im.cpu().numpy(), idx_all) and np.array_equal(dm.cpu().numpy(), dist_all)
+
+
+def _knn_nccl_worker(rank, world, port, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), FZB_DEVICE=str(rank))
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        try:
+            from frankenz_b200.distributed import knn_query_row_sharded
+            feats, qf = _knn_problem()
+            idx, dd = knn_query_row_sharded(feats, qf, 25, device=rank)
+            q.put((rank, (idx, dd)))
+        finally:
+            dist.destroy_process_group()
+    except BaseException:
+        import traceback
+        q.put((rank, "ERROR: " + traceback.format_exc()))
+
+
+@pytest.mark.timeout(600)
+def test_knn_row_sharded_over_two_nccl_ranks():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    from frankenz_b200._engine import Engine
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_knn_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        items = [q.get(timeout=300), q.get(timeout=300)]
+    finally:
+        for p in procs:
+            p.join(30)
+            if p.is_alive():
+                p.kill()
+    for rank, payload in items:
+        assert not isinstance(payload, str), "rank %d failed:\n%s" % (rank, payload)
+    feats, qf = _knn_problem()
+    ones = np.ones((feats.shape[1], 5))
+    e = Engine(ones, ones, ones)
+    e.knn_build(feats)
+    idx_all, dist_all = e.knn_query(qf, 25, p=2)
+    for rank, (idx, dd) in items:
+        assert np.array_equal(idx, idx_all) and np.array_equal(dd, dist_all)
