@@ -184,6 +184,30 @@ def test_knn_filter_scan_adversarial_inputs(monkeypatch, form):
         assert np.array_equal(idx_fast[i], oi) and np.allclose(dist_fast[i], od, rtol=1e-14, atol=0)
 
 
+def test_knn_trees_that_are_not_alike(monkeypatch):
+    """The filter scan borrows the threshold of tree 0 for the other trees (they are noise realisations of one training
+    set).  Trees that are NOT alike break that shortcut, never the result: the pairs whose borrowed threshold holds too few
+    (or too many) rows are re-done by the float64 kernel, and the handle switches to the staged search of every tree."""
+    from frankenz_b200._engine import Engine
+    rs = np.random.RandomState(5)
+    base = rs.normal(size=(20000, 5)) + 20.0
+    feats = np.stack([base, 20.0 + (base - 20.0) * 6.0, 20.0 + (base - 20.0) * 0.2]).astype(np.float32)   # radii x6, x0.2
+    q = base[rs.choice(len(base), 1500)] + rs.normal(size=(1500, 5)) * 0.05
+    ones = np.ones((len(base), 5))
+    eng = Engine(ones, ones, ones)
+    eng.knn_build(feats)
+    monkeypatch.setenv("FZB_KNN_EXACT_ONLY", "1")
+    idx_exact, dist_exact = eng.knn_query(q, 10, p=2)
+    monkeypatch.delenv("FZB_KNN_EXACT_ONLY")
+    idx1, dist1 = eng.knn_query(q, 10, p=2)
+    st1 = eng.stats()
+    idx2, dist2 = eng.knn_query(q, 10, p=2)
+    st2 = eng.stats()
+    assert np.array_equal(idx1, idx_exact) and np.array_equal(dist1, dist_exact)
+    assert np.array_equal(idx2, idx_exact) and np.array_equal(dist2, dist_exact)
+    assert st1["knn_redo"] > 0.3 * len(q) and st2["knn_redo"] <= 8, (st1["knn_redo"], st2["knn_redo"])
+
+
 def test_float64_sweep_route_matches_generic(c3):
     """Fixed-scale fits of the C3 objects: most best-fit chi2 are far above the fp32 bound, so the objects take the
     register-tiled float64 sweep (k_sweep64).  Its PDFs must agree with the reference-order float64 kernel."""
