@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libfzb200.so")
+LIB_PATH = os.environ.get("FZB_LIB_PATH") or os.path.join(HERE, "lib", "libfzb200.so")   # override: kernel experiments
 
 c_double_p = C.POINTER(C.c_double)
 c_float_p = C.POINTER(C.c_float)

@@ -715,24 +715,37 @@ static int fit_predict_host_impl(fzb_context* h, const double* data, const doubl
     int64_t* d_bi = h->out_i64[0].as<int64_t>();
     const bool want_rows = pdfs != nullptr || summ != nullptr;     // PDF rows are needed on the device
 
-    // chunk size: large enough for long CTAs of the sweep kernels (few model splits), small enough to pipeline; the chunks
-    // taper towards the end (below), so the size of the main ones does not set the un-hidden tail
-    int64_t chunk = 262144;
-    // (an override is rounded up to the 4096-object granularity of the taper below, floor 8192, so that no chunk of the
-    // taper exceeds the reserved staging buffers)
+    // Chunks pipeline the device-to-host copy of the PDFs behind the next chunk's kernels.  Every chunk costs a few ms
+    // (launch tails, host round trips, less efficient small sweeps) and only the download of the last one is exposed.
+    // Pageable destination (staged copy, ~19 GB/s measured on a B200 host: 0.29 us / object against 0.41 us / object of
+    // sweep): chunks of 262,144 objects halving towards the end, down to 32k.  Page-locked destination (direct DMA,
+    // ~50 GB/s): a chunk is 60 % of what remains, i.e. 2.5 times the next one.  FZB_E2E_CHUNK caps the chunk size (floor
+    // 8192, multiples of 4096).
+    bool pinned_dst = false;
+    if (pdfs) {
+        cudaPointerAttributes pa = {};
+        pinned_dst = cudaPointerGetAttributes(&pa, pdfs) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+    }
+    const bool geom = pinned_dst ? getenv("FZB_E2E_HALVING") == nullptr : getenv("FZB_E2E_GEOM") != nullptr;
+    int64_t chunk = geom ? 1048576 : 262144;
     if (const char* e = getenv("FZB_E2E_CHUNK")) chunk = std::max<int64_t>(8192, (atoll(e) + 4095) / 4096 * 4096);
     // nothing to overlap when the PDFs stay on the device (summaries only): one chunk, bounded by the row buffer (12 GB)
     if (!pdfs) chunk = std::max<int64_t>(chunk, ((int64_t)12 << 30) / std::max<int64_t>(1, (int64_t)Ng * 8));
-    if (!want_rows || No <= chunk + chunk / 2) chunk = No;
+    if (!want_rows || (!pdfs && No <= chunk + chunk / 2)) chunk = No;
+    auto next_chunk = [&](int64_t rem) -> int64_t {
+        if (!pdfs) return std::min(rem, chunk);
+        if (rem <= 49152) return rem;
+        int64_t nc = chunk;
+        if (geom) nc = std::max<int64_t>(32768, (rem * 6 / 10 + 4095) / 4096 * 4096);
+        else if (rem < 2 * chunk) nc = std::max<int64_t>(32768, (rem / 2 + 4095) / 4096 * 4096);
+        return std::min(std::min(nc, rem), chunk);
+    };
+    chunk = std::min(chunk, next_chunk(No));          // the largest chunk = the first one
     const size_t chunk_bytes = (size_t)chunk * Ng * sizeof(double);
     StagedDownloader dl(h);
-    if (pdfs) {
-        // a destination from fzb_alloc_pinned takes the DMA directly (no staging buffer, no host-side copy)
-        cudaPointerAttributes pa = {};
-        const bool pinned_dst = cudaPointerGetAttributes(&pa, pdfs) == cudaSuccess && pa.type == cudaMemoryTypeHost;
-        cudaGetLastError();
-        if (dl.init((size_t)64 << 20, pinned_dst)) return 1;
-    }
+    // a destination from fzb_alloc_pinned takes the DMA directly (no staging buffer, no host-side copy)
+    if (pdfs && dl.init((size_t)64 << 20, pinned_dst)) return 1;
     if (want_rows)
         for (int b = 0; b < (pdfs ? 2 : 1); ++b)
             if (h->pdf_dev[b].reserve(chunk_bytes)) return 1;
@@ -742,12 +755,7 @@ static int fit_predict_host_impl(fzb_context* h, const double* data, const doubl
     int64_t nc = 0;
     FzbStats acc = {};
     for (int64_t o0 = 0; o0 < No; o0 += nc, ++c) {
-        // the download of the last chunk is the only one nothing hides: taper the chunk size towards the end
-        const int64_t rem = No - o0;
-        nc = chunk;
-        // (down to ~32k objects = 180 MB of PDFs: every chunk costs a few ms of launch tails and host round trips)
-        if (pdfs && rem < 2 * chunk) nc = rem <= 49152 ? rem : std::max<int64_t>(32768, (rem / 2 + 4095) / 4096 * 4096);
-        nc = std::min(std::min(nc, rem), chunk);
+        nc = next_chunk(No - o0);
         int b = pdfs ? (int)(c & 1) : 0;
         h->prior_o0 = o0;
         // device buffer b was last read by the download of chunk c-2 (issued before that of chunk c-1)

@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_sweep_tc(SweepParams P, const
                     if (lane == 0) mbar_arrive(&acc_empty[mt * 2 + buf]);
                     continue;
                 }
-#pragma unroll
+#pragma unroll        // (rolling this loop in the fused pass to halve its code measured 6 % slower)
                 for (int k = 0; k < TC_NSUB / TC_SPLIT; ++k) {
                     const int sub = half + TC_SPLIT * k;          // this warpgroup's sub-batches of the chunk
                     live_bit = 1u << (2 * ch + k);

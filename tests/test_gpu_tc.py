@@ -161,6 +161,28 @@ def test_fused_single_pass_matches_two_pass(fz, monkeypatch):
         _check(p1[sub], lm1[sub], le1[sub], po, lmo, leo)
 
 
+@pytest.mark.parametrize("wt_thresh", [1e-2, 1e-5])
+def test_fused_single_pass_other_weight_thresholds(fz, wt_thresh):
+    """The running-cut logic of the single pass with cuts other than the default 1e-3 (kde_kwargs wt_thresh, pdf.py:589-591):
+    the fused path against the float64 kernels on the full model grid."""
+    m, lab, depth = bench_data.c3_models(float64_grid=True)
+    x, xe, xm, _, _ = bench_data.c3_objects(768, m, depth, seed=91)
+    zgrid, sig = bench_data.c3_kde()
+    rdict = fz.pdf.PDFDict(zgrid, sig)
+    labe = np.full(len(m), 0.05)
+    bf = fz.BruteForce(m, np.zeros_like(m), np.ones_like(m))
+    out = {}
+    for prec in ("auto", "fp64"):
+        p, (lm, le) = bf.fit_predict(x.copy(), xe.copy(), xm.copy(), lab, labe, label_dict=rdict, return_gof=True, verbose=False,
+                                     save_fits=False, lprob_kwargs=dict(FS, precision=prec), kde_kwargs=dict(wt_thresh=wt_thresh))
+        out[prec] = (p, lm, le, bf._eng().stats())
+    (p, lm, le, st), (p64, lm64, le64, _) = out["auto"], out["fp64"]
+    assert st["sweep_kind"] == 3 and st["objects_fused"] > 0.3 * len(x), st
+    assert np.max(np.sum(np.abs(p - p64), axis=1)) <= 1e-5
+    assert np.all(np.abs(lm - lm64) <= 1e-5 * np.maximum(1, np.abs(lm64)))
+    assert np.all(np.abs(le - le64) <= 1e-5 * np.maximum(1, np.abs(le64)))
+
+
 def test_object_conditioned_prior_table_on_the_fused_path(fz, monkeypatch):
     """SURVEY 8f rank 1 at scale: fit_predict(save_fits=False) with lnprior[i, j] = table[bin_i, j] runs the fused sweep
     once per table row; it must agree with the float64 kernel that reads the table per pair and with the oracle."""
