@@ -1,4 +1,4 @@
-"""Rebuild the tracked round-2 profile documents under profiles/ from the scratch outputs of tools/gpu_r2z.sh (tensor-core sweep
+"""Rebuild the tracked round-2 profile documents under profiles/ from the scratch outputs of tools/gpu_r2_ncu.sh (tensor-core sweep
 report) and tools/gpu_r2_final.sh (kNN report, launch lists, bench lines) in gpurun_out/.  Reads reports, profiles nothing."""
 import csv
 import os
@@ -60,7 +60,7 @@ issue, 6 GB of DRAM writes - 85 % of the issued warp instructions were the diver
 """ + old + """
 After (`k_knn_filter<5, DOT, 8>`: no list, rows below a threshold are appended, `k_knn_select` picks the k+8 smallest; the launch is
 the sweep over all 761k rows of 4 trees for 16,384 queries; `ncu ... -k regex:k_knn_filter -s 3 -c 1 python tools/bench_knn.py 1000000
-16384 4 25`, tools/gpu_r2z.sh - taken before the threshold of tree 0 was shared with the other trees, which changed the launch
+16384 4 25`, tools/gpu_r2_ncu.sh - taken before the threshold of tree 0 was shared with the other trees, which changed the launch
 plan, not the kernel's loop): 6.55e10 distances in 14.4 ms = 4.5e12 distances/s in this launch, 3.45 thread instructions per distance,
 28.4 active threads per instruction, no local memory.  Launch list of a whole search at HEAD: profiles/r2_knn_launches.md.
 
