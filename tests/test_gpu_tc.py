@@ -183,6 +183,33 @@ def test_fused_single_pass_other_weight_thresholds(fz, wt_thresh):
     assert np.all(np.abs(le - le64) <= 1e-5 * np.maximum(1, np.abs(le64)))
 
 
+@pytest.mark.parametrize("which", ["faint", "bright", "one"])
+def test_fused_pass_with_one_sided_batches(fz, which):
+    """Batches in which one of the two object lists of the sweep (faint: fused single pass; bright: seeded pass 1 + pass 2) is
+    empty, and a batch of a single object: against the float64 kernels."""
+    m, lab, depth = bench_data.c3_models(float64_grid=True)
+    x, xe, xm, _, _ = bench_data.c3_objects(6000, m, depth, seed=123)
+    snr = np.sqrt(np.sum((x / xe) ** 2, axis=1))
+    order = np.argsort(snr)
+    sel = {"faint": order[:700], "bright": order[-700:], "one": order[2500:2501]}[which]
+    assert (which != "faint" or snr[sel].max() < 32) and (which != "bright" or snr[sel].min() > 32)
+    zgrid, sig = bench_data.c3_kde()
+    rdict = fz.pdf.PDFDict(zgrid, sig)
+    labe = np.full(len(m), 0.05)
+    bf = fz.BruteForce(m, np.zeros_like(m), np.ones_like(m))
+    out = {}
+    for prec in ("auto", "fp64"):
+        p, (lm, le) = bf.fit_predict(x[sel].copy(), xe[sel].copy(), xm[sel].copy(), lab, labe, label_dict=rdict, return_gof=True,
+                                     verbose=False, save_fits=False, lprob_kwargs=dict(FS, precision=prec))
+        out[prec] = (p, lm, le, bf._eng().stats())
+    (p, lm, le, st), (p64, lm64, le64, _) = out["auto"], out["fp64"]
+    assert st["sweep_kind"] == 3
+    assert (st["objects_fused"] > 0.5 * len(sel)) == (which != "bright"), st
+    assert np.max(np.sum(np.abs(p - p64), axis=1)) <= 1e-5
+    assert np.all(np.abs(lm - lm64) <= 1e-5 * np.maximum(1, np.abs(lm64)))
+    assert np.all(np.abs(le - le64) <= 1e-5 * np.maximum(1, np.abs(le64)))
+
+
 def test_object_conditioned_prior_table_on_the_fused_path(fz, monkeypatch):
     """SURVEY 8f rank 1 at scale: fit_predict(save_fits=False) with lnprior[i, j] = table[bin_i, j] runs the fused sweep
     once per table row; it must agree with the float64 kernel that reads the table per pair and with the oracle."""
