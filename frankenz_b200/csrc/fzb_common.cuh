@@ -82,6 +82,7 @@ struct FastModels {
     DevBuf bins;           // int32 [nm_pad]: KDE histogram bin (slot*Ng + pos) of each sorted model, -1 = none
     DevBuf invnorm;        // float [nm_pad]: 1 / kernel normalisation of each sorted model
     DevBuf live;           // pass-2 pruning: live bits of the tensor-core sweep, [model tile x half][object] uint16
+    DevBuf live64;         // pass-2 pruning of the float64 sweep: one bit per (model tile, object), uint16 [tile][object]
     DevBuf tmask;          // pass-2 pruning: live bits per (model tile, pass-2 CTA), see fzb_tile_masks
     DevBuf sortbuf;        // keys / values / temporary storage of the sort of the pass-2 object list
     DevBuf cutlist;        // weights recorded at the wt_thresh cut by pass 2 (CutRecord), re-decided in float64
@@ -233,7 +234,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
 int fzb_tile_masks(fzb_context* h, const unsigned short* live, int64_t ntiles, int64_t No_pad, const int32_t* list, int64_t n,
                    int tile_objs, unsigned int** out);
 int fzb_sort_by_live_bits(fzb_context* h, const unsigned short* live, int64_t nrows, int64_t No_pad, int32_t* list,
-                          int64_t n);
+                          int64_t n, int bits_per_row = 16);
 
 // ---- PDF summaries (fzb_summarize.cu) ---------------------------------------------------------
 int fzb_summarize_impl(fzb_context* h, const double* pdfs, const double* pgrid, const double* loss, const double* urand,

@@ -146,6 +146,12 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
     // rounding error of the evidence does not grow with the number of models
     double Sd[R];
     float Mfl[R];
+    // pass-2 pruning (same idea as the tensor-core sweep, one bit per object and 256-model tile): pass 1 notes the tiles in
+    // which some weight exceeds wt_thresh x the running maximum (a superset of the final selection); pass 2, whose objects are
+    // sorted by live signature, skips a tile when none of the 32 x R objects of a warp has the bit.  The reference's default
+    // likelihood on training rows (C1 / C2 / C5) gives narrow posteriors: most tiles are dead.
+    bool lv[R];
+    const float lthr = P.live_lthr;           // log2 of the cut, relative to the running maximum
     const int64_t tile_base = (int64_t)blockIdx.x * (FT2 * R);
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
@@ -201,12 +207,35 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
     const f2 kNegHalfLog2e = pack2(-kHalfLog2e, -kHalfLog2e);
     const f2 kMinusOne = pack2(-1.f, -1.f);
     int cur_bin = -1;
+    unsigned long long npairs = 0;            // pass 2: models this warp really evaluated (statistics)
+    unsigned int live_next = 0;
+    if (PASS == 2 && P.live && nt > 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (oidx[r] >= 0) live_next |= P.live[(size_t)t0 * (size_t)P.No_pad + oidx[r]];
+    }
     for (int it = 0; it < nt; ++it) {
         const int st = it % NSTAGE;
+        bool skip = false;
+        if (PASS == 2 && P.live) {
+            // warp-uniform: no object of this warp has a weight above the cut in this tile
+            skip = __reduce_or_sync(0xffffffffu, live_next) == 0u;
+            live_next = 0;
+            if (it + 1 < nt) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (oidx[r] >= 0) live_next |= P.live[(size_t)(t0 + it + 1) * (size_t)P.No_pad + oidx[r]];
+            }
+        }
+        if (PASS == 1) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) lv[r] = false;
+        }
         mbar_wait(&bars[st], (uint32_t)((it / NSTAGE) & 1));
         const float* tile = stage + (size_t)st * TM * REC;
         const int64_t first = (t0 + it) * TM;
-        const int cnt = (int)((P.nm - first) < TM ? (P.nm - first) : TM);
+        const int cnt = skip ? 0 : (int)((P.nm - first) < TM ? (P.nm - first) : TM);
+        if (PASS == 2 && !skip) npairs += cnt;
 #pragma unroll 2
         for (int jj = 0; jj < cnt; ++jj) {
             const float* rec = tile + jj * REC;       // same record for every thread: shared-memory broadcast
@@ -272,6 +301,8 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
                     M[p] = pack2(g0 ? lo2(l) : lo2(M[p]), g1 ? hi2(l) : hi2(M[p]));
                     best[2 * p] = g0 ? (int)(first + jj) : best[2 * p];
                     best[2 * p + 1] = g1 ? (int)(first + jj) : best[2 * p + 1];
+                    lv[2 * p] = lv[2 * p] || d0 > lthr;
+                    lv[2 * p + 1] = lv[2 * p + 1] || d1 > lthr;
                 } else {
                     float u0 = fast_ex2(d0), u1 = fast_ex2(d1);
                     const bool s0 = lo2(l) > thr[2 * p], s1 = hi2(l) > thr[2 * p + 1];
@@ -297,6 +328,13 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
                 Mfl[2 * p + 1] = m1;
                 S[p] = pack2(0.f, 0.f);
             }
+            if (P.live) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int64_t slot = tile_base + (int64_t)r * FT2 + tid;
+                    if (slot < P.No_pad) P.live[(size_t)(t0 + it) * (size_t)P.No_pad + slot] = lv[r] ? 1 : 0;
+                }
+            }
         }
         __syncthreads();
         if (tid == 0 && it + NSTAGE < nt) issue(it + NSTAGE);
@@ -312,13 +350,23 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
                 P.pbest[q] = best[r];
             }
         }
-    } else if (cur_bin >= 0) {
+    } else {
+        if (cur_bin >= 0) {
 #pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            float a0 = lo2(acc[p]), a1 = hi2(acc[p]);
-            if (a0 != 0.f && oidx[2 * p] >= 0) atomicAdd(P.hist + (int64_t)oidx[2 * p] * P.hist_stride + cur_bin, a0);
-            if (a1 != 0.f && oidx[2 * p + 1] >= 0)
-                atomicAdd(P.hist + (int64_t)oidx[2 * p + 1] * P.hist_stride + cur_bin, a1);
+            for (int p = 0; p < NP; ++p) {
+                float a0 = lo2(acc[p]), a1 = hi2(acc[p]);
+                if (a0 != 0.f && oidx[2 * p] >= 0) atomicAdd(P.hist + (int64_t)oidx[2 * p] * P.hist_stride + cur_bin, a0);
+                if (a1 != 0.f && oidx[2 * p + 1] >= 0)
+                    atomicAdd(P.hist + (int64_t)oidx[2 * p + 1] * P.hist_stride + cur_bin, a1);
+            }
+        }
+        if (P.pairs_done) {
+            int nobj = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) nobj += oidx[r] >= 0 ? 1 : 0;
+            unsigned long long tot = npairs * (unsigned long long)nobj;
+            for (int sft = 16; sft > 0; sft >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, sft);
+            if ((tid & 31) == 0 && tot) atomicAdd(P.pairs_done, tot);
         }
     }
 }
@@ -359,6 +407,9 @@ struct Sweep64Params {
     const double* thr2;
     float* hist;
     int64_t hist_stride;
+    // pass-2 pruning by whole tiles, as in k_sweep2: [model tile][No_pad] by object, one bit; null: off
+    unsigned short* live;
+    double live_lthr;
 };
 
 template <int NF, int MODE, bool DP, int PASS>
@@ -419,12 +470,33 @@ __global__ void __launch_bounds__(FT64, 2) k_sweep64(Sweep64Params P) {
         for (int it = 0; it < NSTAGE && it < nt; ++it) issue(it);
     }
     int cur_bin = -1;
+    bool lv[R64];
+    unsigned int live_next = 0;
+    if (PASS == 2 && P.live && nt > 0) {
+#pragma unroll
+        for (int r = 0; r < R64; ++r)
+            if (oidx[r] >= 0) live_next |= P.live[(size_t)t0 * (size_t)P.No_pad + oidx[r]];
+    }
     for (int it = 0; it < nt; ++it) {
         const int st = it % NSTAGE;
+        bool skip = false;
+        if (PASS == 2 && P.live) {       // warp-uniform: no object of this warp has a weight above the cut in this tile
+            skip = __reduce_or_sync(0xffffffffu, live_next) == 0u;
+            live_next = 0;
+            if (it + 1 < nt) {
+#pragma unroll
+                for (int r = 0; r < R64; ++r)
+                    if (oidx[r] >= 0) live_next |= P.live[(size_t)(t0 + it + 1) * (size_t)P.No_pad + oidx[r]];
+            }
+        }
+        if (PASS == 1) {
+#pragma unroll
+            for (int r = 0; r < R64; ++r) lv[r] = false;
+        }
         mbar_wait(&bars[st], (uint32_t)((it / NSTAGE) & 1));
         const double* tile = stage + (size_t)st * TM * REC;
         const int64_t first = (t0 + it) * TM;
-        const int cnt = (int)((P.nm - first) < TM ? (P.nm - first) : TM);
+        const int cnt = skip ? 0 : (int)((P.nm - first) < TM ? (P.nm - first) : TM);
 #pragma unroll 1
         for (int jj = 0; jj < cnt; ++jj) {
             const double* rec = tile + jj * REC;
@@ -480,6 +552,7 @@ __global__ void __launch_bounds__(FT64, 2) k_sweep64(Sweep64Params P) {
                     S[r] = __fmaf_rn(S[r], gt ? e : 1.f, gt ? 1.f : e);
                     M[r] = gt ? l : M[r];
                     best[r] = gt ? (int)(first + jj) : best[r];
+                    lv[r] = lv[r] || delta > P.live_lthr;
                 } else {
                     float u = fast_ex2((float)delta);
                     u = (l > thr[r]) ? u : 0.f;
@@ -493,6 +566,7 @@ __global__ void __launch_bounds__(FT64, 2) k_sweep64(Sweep64Params P) {
                 Sd[r] = Sd[r] * exp2(Mfl[r] - M[r]) + (double)S[r];
                 Mfl[r] = M[r];
                 S[r] = 0.f;
+                if (P.live && oidx[r] >= 0) P.live[(size_t)(t0 + it) * (size_t)P.No_pad + oidx[r]] = lv[r] ? 1 : 0;
             }
         }
         __syncthreads();
@@ -1418,11 +1492,23 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     if (kde && h->misc[4].reserve((size_t)chunk_pad * hist_stride * 4 + 256)) return 1;
     float* hist = kde ? h->misc[4].as<float>() : nullptr;
     // pass-2 pruning of the tensor-core sweep: live bits [model tile][half][object], sort keys of the safe list
-    const bool prune = use_tc && kde && cfg.use_wt_thresh && getenv("FZB_NO_PRUNE") == nullptr;
+    // (the packed sweep prunes by whole tiles: one uint16 per (tile, object) holding a single bit, so that both kernels share
+    // the sort of the pass-2 list)
+    const bool prune = (use_tc || packed) && !(!use_tc && !h->mask_all_one) && kde && cfg.use_wt_thresh &&
+                       getenv("FZB_NO_PRUNE") == nullptr;
+    const int64_t live_rows = ntiles * (use_tc ? fzb_tc_split() : 1);
+    const int live_bits = use_tc ? 16 : 1;
     unsigned short* live = nullptr;
     if (prune) {
-        if (h->fast.live.reserve((size_t)ntiles * fzb_tc_split() * chunk_pad * sizeof(unsigned short) + 256)) return 1;
+        if (h->fast.live.reserve((size_t)live_rows * chunk_pad * sizeof(unsigned short) + 256)) return 1;
         live = h->fast.live.as<unsigned short>();
+        if (h->fast.sortbuf.reserve((size_t)chunk_pad * 16 + 256)) return 1;
+    }
+    // the float64 sweep prunes its pass 2 the same way (its objects are the bright / badly fitted ones: narrow posteriors)
+    unsigned short* live64 = nullptr;
+    if (kde && cfg.use_wt_thresh && getenv("FZB_NO_PRUNE") == nullptr && getenv("FZB_NO_SWEEP64") == nullptr && h->mask_all_one) {
+        if (h->fast.live64.reserve((size_t)ntiles * chunk_pad * sizeof(unsigned short) + 256)) return 1;
+        live64 = h->fast.live64.as<unsigned short>();
         if (h->fast.sortbuf.reserve((size_t)chunk_pad * 16 + 256)) return 1;
     }
     // weights at the wt_thresh cut are recorded by pass 2 and re-decided in float64 (k_exact_cut_fix)
@@ -1513,6 +1599,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         S6.free_scale = cfg.free_scale; S6.dim_prior = cfg.dim_prior;
         S6.recs = F.recs64.as<double>(); S6.nm = nm; S6.tiles_per_split = tiles_per_split;
         S6.pM = pM; S6.pS = pS; S6.pbest = pbest;
+        S6.live = live64; S6.live_lthr = cfg.use_wt_thresh ? std::log2(cfg.wt_thresh) - 2e-4 : -DBL_MAX;
         SweepParams SP = {};
         SP.od = od; SP.ow = ow; SP.ox = ox; SP.odl = odl; SP.oA = oA;
         SP.obits = mm ? obits : nullptr;
@@ -1529,6 +1616,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         SP.pM = pM; SP.pS = pS; SP.pbest = pbest;
         SP.live = live;
         SP.live_thr = cfg.use_wt_thresh ? (float)(cfg.wt_thresh * (1.0 - 1e-4)) : 0.f;
+        SP.live_lthr = cfg.use_wt_thresh ? (float)(std::log2(cfg.wt_thresh) - 2e-4) : -FLT_MAX;
         const int64_t tiles1 = (nc + tile_objs - 1) / tile_objs;
         int64_t nsafe = 0, nsafe64 = 0, nunsafe = 0, nfuse = 0;
         unsigned int fuse_recorded = 0;
@@ -1666,8 +1754,9 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             if (nunsafe > 0 && fzb_generic_shard_pass1_dev(h, d_x, d_xe, d_xm, No, unsafe_list, nunsafe, cfg, d_lmap,
                                                            d_psum, d_best_idx))
                 return 1;
-            if (prune && nsafe > 0 && fzb_sort_by_live_bits(h, live, ntiles * fzb_tc_split(), nc_pad, safe_list, nsafe))
+            if (prune && nsafe > 0 && fzb_sort_by_live_bits(h, live, live_rows, nc_pad, safe_list, nsafe, live_bits))
                 return 1;
+            if (live64 && nsafe64 > 0 && fzb_sort_by_live_bits(h, live64, ntiles, nc_pad, safe64_list, nsafe64, 1)) return 1;
             h->shard_valid = true;
             h->shard_No = No;
             h->shard_counts[0] = (int)nsafe; h->shard_counts[1] = (int)nunsafe; h->shard_counts[3] = (int)nsafe64;
@@ -1708,13 +1797,13 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
             }
             if (nsafe > 0) {
                 if (prune && shard_mode != 2 &&
-                    fzb_sort_by_live_bits(h, live, ntiles * fzb_tc_split(), nc_pad, safe_list, nsafe))
+                    fzb_sort_by_live_bits(h, live, live_rows, nc_pad, safe_list, nsafe, live_bits))
                     return 1;       // objects with similar survivor sets share a warp (sharded pass 2: sorted by pass 1)
                 if (prune) {
                     FZB_CUDA(cudaMemsetAsync(counts + 8, 0, 8, h->stream));
                     SP.pairs_done = reinterpret_cast<unsigned long long*>(counts + 8);
                     unsigned int* tm = nullptr;      // chunks / tiles no object of an M-tile needs: no MMA, no TMA
-                    if (getenv("FZB_NO_TILE_SKIP") == nullptr) {
+                    if (use_tc && getenv("FZB_NO_TILE_SKIP") == nullptr) {
                         if (fzb_tile_masks(h, live, ntiles, nc_pad, safe_list, nsafe, (int)tile_objs, &tm)) return 1;
                     }
                     SP.tmask = tm;
@@ -1735,6 +1824,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                 h->stats.pairs_fp32 += nsafe * nm;
             }
             if (nsafe64 > 0) {
+                if (live64 && shard_mode != 2 && fzb_sort_by_live_bits(h, live64, ntiles, nc_pad, safe64_list, nsafe64, 1)) return 1;
                 S6.objlist = safe64_list; S6.nlist = nsafe64; S6.M2 = M2d; S6.thr2 = thr2d; S6.hist = hist;
                 S6.hist_stride = hist_stride;
                 const int64_t t64 = (nsafe64 + FT64 * R64 - 1) / (FT64 * R64);

@@ -13,7 +13,7 @@
 namespace {
 
 __global__ void k_live_key(const unsigned short* __restrict__ live, int64_t nrows, int64_t No_pad,
-                           const int32_t* __restrict__ list, int64_t n, uint32_t* __restrict__ keys) {
+                           const int32_t* __restrict__ list, int64_t n, uint32_t* __restrict__ keys, int bits) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t o = list[i];
@@ -24,9 +24,9 @@ __global__ void k_live_key(const unsigned short* __restrict__ live, int64_t nrow
         int c = 0;
         for (int64_t r = r0; r < r1; ++r) c += __popc((unsigned)live[(size_t)r * No_pad + o]);
         total += c;
-        if ((int64_t)c * 50 > (r1 - r0) * 16) sig |= 1u << seg;       // more than 2 % of the segment's sub-batches
+        if ((int64_t)c * 50 > (r1 - r0) * bits) sig |= 1u << seg;     // more than 2 % of the segment's bits
     }
-    const int64_t level = min((int64_t)15, total * 16 / max((int64_t)1, nrows * 16));
+    const int64_t level = min((int64_t)15, total * 16 / max((int64_t)1, nrows * bits));
     keys[i] = ((uint32_t)level << 24) | sig;
 }
 
@@ -70,7 +70,7 @@ int fzb_tile_masks(fzb_context* h, const unsigned short* live, int64_t ntiles, i
 }
 
 int fzb_sort_by_live_bits(fzb_context* h, const unsigned short* live, int64_t nrows, int64_t No_pad, int32_t* list,
-                          int64_t n) {
+                          int64_t n, int bits_per_row) {
     if (n <= 32) return 0;
     DevBuf& sb = h->fast.sortbuf;
     size_t tmp_bytes = 0;
@@ -82,7 +82,7 @@ int fzb_sort_by_live_bits(fzb_context* h, const unsigned short* live, int64_t nr
     uint32_t* keys_out = keys_in + n;
     int32_t* vals_out = reinterpret_cast<int32_t*>(keys_out + n);
     void* tmp = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(vals_out + n) + 255) & ~(uintptr_t)255);
-    k_live_key<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(live, nrows, No_pad, list, n, keys_in);
+    k_live_key<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(live, nrows, No_pad, list, n, keys_in, bits_per_row);
     fzb_count_launch(h);
     FZB_CUDA(cudaGetLastError());
     FZB_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_in, keys_out, list, vals_out, (int)n, 0, 28, h->stream));

@@ -103,6 +103,7 @@ struct SweepParams {
     // maximum only grows); layout [model tile][half][No_pad] uint16, bit = 2 * chunk + k.  Null: no pruning.
     unsigned short* live;
     float live_thr;
+    float live_lthr;                  // the same cut as a log2 difference (packed sweep: one bit per object and tile)
     const unsigned int* tmask;        // pass 2: [model tile][CTA] live bits OR-ed over the 128 objects of each M-tile (16 bits
                                       // each, both halves): chunks and tiles nobody needs are not multiplied / staged at all
     unsigned long long* pairs_done;   // pass 2: object-model pairs actually evaluated (statistics)
