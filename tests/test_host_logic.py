@@ -119,3 +119,29 @@ def test_clean_inplace_threaded_helper_matches_numpy_rule():
     a2, b2, c2 = x[:100].copy(), xe[:100].copy(), xm[:100].astype(bool)       # small + bool mask: numpy form
     clean_inplace(a2, b2, c2)
     assert np.array_equal(a2, a[:100]) and np.array_equal(b2, b[:100]) and np.array_equal(c2, c[:100].astype(bool))
+
+
+def test_page_pool_recycles_buffers_only_when_every_view_is_gone():
+    """PagePool (_engine.py): the large pageable output arrays are handed out again once the array AND its views have been
+    garbage collected; small requests and a zero budget fall back to numpy.empty."""
+    import gc
+    from frankenz_b200._engine import PagePool
+    pool = PagePool(max_bytes=1 << 30)
+    a = pool.empty((100000, 120))                    # 96 MB: pooled
+    addr = a.ctypes.data
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.flags["WRITEABLE"] and pool.total == a.nbytes
+    a[:] = 3.0
+    view = a[10:20]
+    del a
+    gc.collect()
+    assert not pool.free and view[0, 0] == 3.0       # a view keeps the block out of the pool
+    del view
+    gc.collect()
+    assert len(pool.free) == 1
+    b = pool.empty((100000, 120))
+    assert b.ctypes.data == addr and not pool.free   # same memory, already mapped
+    c = pool.empty((100000, 120))                    # a second live array gets its own block
+    assert c.ctypes.data != addr and pool.total == 2 * b.nbytes
+    small = pool.empty((10, 10))
+    assert small.base is None and pool.total == 2 * b.nbytes
+    assert PagePool(max_bytes=0).empty((100000, 120)).base is None

@@ -1,13 +1,16 @@
 #!/bin/bash
+# default-likelihood leg: phases and launch list
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/r2am_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2am_pytest.log
-tail -6 gpurun_out/r2am_pytest.log
-timeout 900 python bench.py --no-e2e --no-cpu --grid float64 --steps 2 > gpurun_out/r2am_bench.json 2> gpurun_out/r2am_bench.err; echo "bench rc=$?"
-FZB_NO_PRUNE=1 timeout 900 python bench.py --no-e2e --no-cpu --grid float64 --steps 2 > gpurun_out/r2am_bench_noprune.json 2> gpurun_out/r2am_bench_noprune.err; echo "bench noprune rc=$?"
+timeout 300 python tools/bench_fx1.py > gpurun_out/r2_fx1.log 2>&1; tail -3 gpurun_out/r2_fx1.log
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 90 --csv --log-file gpurun_out/r2_fx1_launches.csv python tools/bench_fx1.py > gpurun_out/r2_fx1_ncu.log 2>&1; echo "ncu rc=$?"
 python - <<'PY'
-import json
-for f in ('gpurun_out/r2am_bench.json','gpurun_out/r2am_bench_noprune.json'):
-    d=json.loads([l for l in open(f) if l.startswith('{')][-1])
-    x=d['default_likelihood']
-    print(f, 'fx1 %.4g pairs/s, %.1f ms/step, fp64 objs %d' % (x['value'], x['ms_per_step'], x['objects_routed_to_fp64']), 'headline %.4g' % d['value'])
+import csv
+rows=[r for r in csv.reader(open('gpurun_out/r2_fx1_launches.csv'))]
+hdr=[r for r in rows if 'Kernel Name' in r][0]
+ki=hdr.index('Kernel Name'); vi=hdr.index('Metric Value'); gi=hdr.index('Grid Size')
+data=[r for r in rows if len(r)>10 and r[0].isdigit()]
+preps=[i for i,r in enumerate(data) if 'k_prep_objects' in r[ki]]
+for r in data[preps[1]:preps[2]]:
+    print(r[ki].replace('<unnamed>::','').replace('void ','')[:70], r[gi], '%.3f ms' % (float(r[vi].replace(',',''))/1e6))
 PY
+timeout 300 python tests/scripts/bench_c1.py 2>&1 | head -3 | cut -c1-250
