@@ -295,7 +295,7 @@ class Engine(object):
         res = dict(out or {})
         for name in want:
             if name not in res:
-                res[name] = np.empty((no, self.Nm), dtype=np.int64) if name == "Ndim" else _page_pool.empty((no, self.Nm))
+                res[name] = np.empty((no, self.Nm), dtype=np.int64 if name == "Ndim" else np.float64)
         o = FzbFitOut()
         for name in ("lnprior", "lnlike", "lnprob", "chi2", "scale", "scale_err"):
             setattr(o, name, dptr(res.get(name)))
