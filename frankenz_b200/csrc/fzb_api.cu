@@ -373,7 +373,7 @@ int fzb_destroy(fzb_handle h) {
     cudaStreamSynchronize(h->stream);
     DevBuf* bufs[] = {&h->models, &h->models_err, &h->models_mask, &h->lnprior, &h->prior_table, &h->prior_bins, &h->widths, &h->koff, &h->kernels,
                       &h->kcdf, &h->yidx, &h->ysidx, &h->grid, &h->y, &h->ystd, &h->lowers, &h->uppers, &h->rows,
-                      &h->knn_feats, &h->knn_scan, &h->knn_buf, &h->knn_centre, &h->knn_cand, &h->knn_redo, &h->knn_tiles, &h->knn_aux, &h->kde_err, &h->summ[0], &h->summ[1], &h->summ[2], &h->summ[3], &h->summ[4], &h->summ[5], &h->fast.recs, &h->fast.tiles_tc, &h->fast.tiles_tc_coarse, &h->fast.tiles_tc_f32, &h->fast.tiles_tc_f32_coarse, &h->fast.fuse, &h->fast.recs64, &h->fast.aux64, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
+                      &h->knn_feats, &h->knn_scan, &h->knn_buf, &h->knn_centre, &h->knn_cand, &h->knn_redo, &h->knn_tiles, &h->knn_aux, &h->kde_err, &h->summ[0], &h->summ[1], &h->summ[2], &h->summ[3], &h->summ[4], &h->summ[5], &h->fast.recs, &h->fast.recs_coarse, &h->fast.tiles_tc, &h->fast.tiles_tc_coarse, &h->fast.tiles_tc_f32, &h->fast.tiles_tc_f32_coarse, &h->fast.fuse, &h->fast.recs64, &h->fast.aux64, &h->fast.perm, &h->fast.bins, &h->fast.invnorm,
                       &h->fast.d_slot_sidx, &h->fast.live, &h->fast.live64, &h->fast.sortbuf, &h->fast.cutlist, &h->nz_pdfs, &h->nz_buf};
     for (auto* b : bufs) b->release();
     for (auto& b : h->obj_in) b.release();

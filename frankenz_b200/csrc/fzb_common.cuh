@@ -69,6 +69,7 @@ struct FastModels {
     int64_t nm_pad = 0;    // padded to a multiple of the tile
     int rec = 0;           // floats per model record
     DevBuf recs;           // [nm_pad][rec] float: see fzb_fast.cu for the record layout
+    DevBuf recs_coarse;    // the same records for every FZB_TC_COARSE-th model of the sorted order (pre-pass of the fused sweep)
     DevBuf recs64;         // [nm][rec64] double records of the float64 sweep
     DevBuf tiles_tc;       // tensor-core sweep: 256-model tiles (MMA operand + packed pairs + tails), fzb_sweep_tc.cuh
     DevBuf tiles_tc_coarse; // the same for every FZB_TC_COARSE-th model of the sorted order (pre-pass of the fused sweep)

@@ -114,9 +114,17 @@ __device__ __forceinline__ f2 pack_chi2(const ObjPack<NF, MODE>& o, const f2* __
     return chi2;
 }
 
-template <int NF, int MODE, bool DP, bool MLO, bool PRIOR, int R, int PASS, bool MM = false>
+// FUSE (pass 1): the single-pass variant, as in the tensor-core sweep (fzb_sweep_tc.cuh) but in the log domain.  The running
+// maximum starts at M0, a lower bound of the object's maximum from a pre-pass over every 16th model, so the sums, the live
+// bits and the selection all refer to max(M0, maximum so far): every weight above the RUNNING cut is added to a per-bin
+// register sum kept in the frame of the current maximum (rescaled by the same factor as the evidence sum when the maximum
+// moves; flushed to the histogram in the fixed frame of M0), and weights between just below the cut and fz_gfac above it are
+// recorded (CutRecord list) for the float64 re-decision.  k_merge accepts the histogram when the final maximum is within the
+// band above M0; the other objects take the pruned pass 2.
+template <int NF, int MODE, bool DP, bool MLO, bool PRIOR, int R, int PASS, bool MM = false, bool FUSE = false>
 __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P) {
     static_assert(R % 2 == 0, "objects come in packed pairs");
+    static_assert(!FUSE || (PASS == 1 && !MM), "the fused variant is pass 1 without model masks");
     constexpr int FT2 = ft2_of(R);
     constexpr int NP = R / 2;
     constexpr int REC = rec2_floats(NF, MODE, MLO, MM);
@@ -152,6 +160,7 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
     // likelihood on training rows (C1 / C2 / C5) gives narrow posteriors: most tiles are dead.
     bool lv[R];
     const float lthr = P.live_lthr;           // log2 of the cut, relative to the running maximum
+    float m0f[R];                             // FUSE: the seed of the running maximum = frame of the histogram
     const int64_t tile_base = (int64_t)blockIdx.x * (FT2 * R);
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
@@ -179,8 +188,14 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
             if (MODE == FM_FS0) ob[p].x[b] = pack2(P.ox[b * P.No_pad + oo[0]], P.ox[b * P.No_pad + oo[1]]);
         }
         ob[p].A = pack2(P.oA[oo[0]], P.oA[oo[1]]);
-        if (PASS == 1) { M[p] = pack2(-FLT_MAX, -FLT_MAX); S[p] = pack2(0.f, 0.f); }
-        else { M[p] = pack2(P.M2[oo[0]], P.M2[oo[1]]); acc[p] = pack2(0.f, 0.f); }
+        if (PASS == 1) {
+            M[p] = pack2(-FLT_MAX, -FLT_MAX); S[p] = pack2(0.f, 0.f);
+            if (FUSE) {
+                m0f[2 * p] = P.fz_M0[oo[0]]; m0f[2 * p + 1] = P.fz_M0[oo[1]];     // -FLT_MAX: no seed (k_merge rejects the object)
+                M[p] = pack2(m0f[2 * p], m0f[2 * p + 1]);
+                acc[p] = pack2(0.f, 0.f);
+            }
+        } else { M[p] = pack2(P.M2[oo[0]], P.M2[oo[1]]); acc[p] = pack2(0.f, 0.f); }
     }
 
     const int64_t ntiles_all = (P.nm + TM - 1) / TM;
@@ -242,7 +257,7 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
             const f2* rec2 = reinterpret_cast<const f2*>(rec);
             const f2 prior2 = PRIOR ? rec2[TAILOFF / 2] : 0;
             f2 invnorm = 0;
-            if (PASS == 2) {
+            if (PASS == 2 || FUSE) {
                 invnorm = rec2[TAILOFF / 2 + 1];
                 const int bin = __float_as_int(rec[TAILOFF + 4]);
                 if (bin != cur_bin) {                  // warp-uniform
@@ -250,6 +265,10 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
 #pragma unroll
                         for (int p = 0; p < NP; ++p) {
                             float a0 = lo2(acc[p]), a1 = hi2(acc[p]);
+                            if (FUSE) {      // register sums are in the frame of the current maximum, the histogram in that of M0
+                                if (a0 != 0.f) a0 *= fast_ex2(lo2(M[p]) - m0f[2 * p]);
+                                if (a1 != 0.f) a1 *= fast_ex2(hi2(M[p]) - m0f[2 * p + 1]);
+                            }
                             if (a0 != 0.f && oidx[2 * p] >= 0)
                                 atomicAdd(P.hist + (int64_t)oidx[2 * p] * P.hist_stride + cur_bin, a0);
                             if (a1 != 0.f && oidx[2 * p + 1] >= 0)
@@ -303,6 +322,21 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
                     best[2 * p + 1] = g1 ? (int)(first + jj) : best[2 * p + 1];
                     lv[2 * p] = lv[2 * p] || d0 > lthr;
                     lv[2 * p + 1] = lv[2 * p + 1] || d1 > lthr;
+                    if (FUSE) {
+                        // above the running cut (a new maximum always is); P.fz_thr = log2(wt_thresh) in this kernel
+                        const bool s0 = d0 > P.fz_thr, s1 = d1 > P.fz_thr;
+                        // weight relative to the maximum AFTER this model: 1 for a new maximum, e otherwise; the sum so far is
+                        // rescaled like the evidence sum
+                        const float w0 = g0 ? 1.f : e0, w1 = g1 ? 1.f : e1;
+                        acc[p] = fma2(acc[p], pack2(g0 ? e0 : 1.f, g1 ? e1 : 1.f), mul2(pack2(s0 ? w0 : 0.f, s1 ? w1 : 0.f), invnorm));
+                        const bool n0 = fabsf(d0 - P.fz_mid) <= P.fz_half, n1 = fabsf(d1 - P.fz_mid) <= P.fz_half;
+                        if (n0 || n1) {      // rare: in the band around the running cut -> float64 re-decision (weight in the frame of M0)
+                            if (n0 && oidx[2 * p] >= 0 && m0f[2 * p] > -1e30f)
+                                record_cut(P, oidx[2 * p], (int)(first + jj), fast_ex2(lo2(l) - m0f[2 * p]), s0);
+                            if (n1 && oidx[2 * p + 1] >= 0 && m0f[2 * p + 1] > -1e30f)
+                                record_cut(P, oidx[2 * p + 1], (int)(first + jj), fast_ex2(hi2(l) - m0f[2 * p + 1]), s1);
+                        }
+                    }
                 } else {
                     float u0 = fast_ex2(d0), u1 = fast_ex2(d1);
                     const bool s0 = lo2(l) > thr[2 * p], s1 = hi2(l) > thr[2 * p + 1];
@@ -348,6 +382,16 @@ __global__ void __launch_bounds__(ft2_of(R), minb2_of(R)) k_sweep2(SweepParams P
                 P.pM[q] = (double)Mfl[r];
                 P.pS[q] = Sd[r];
                 P.pbest[q] = best[r];
+            }
+        }
+        if (FUSE && cur_bin >= 0) {
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                float a0 = lo2(acc[p]), a1 = hi2(acc[p]);
+                if (a0 != 0.f && oidx[2 * p] < P.No)
+                    atomicAdd(P.hist + (int64_t)oidx[2 * p] * P.hist_stride + cur_bin, a0 * fast_ex2(lo2(M[p]) - m0f[2 * p]));
+                if (a1 != 0.f && oidx[2 * p + 1] < P.No)
+                    atomicAdd(P.hist + (int64_t)oidx[2 * p + 1] * P.hist_stride + cur_bin, a1 * fast_ex2(hi2(M[p]) - m0f[2 * p + 1]));
             }
         }
     } else {
@@ -721,8 +765,10 @@ struct MergeParams {
     // fused single pass (k_sweep_tc<..., FUSE>): an fp32-safe object keeps its histogram when every thread that worked on
     // it stayed in the frame of M0 without overflowing its record segment and the final maximum is within the recorded
     // band above M0 -> fuse_list (counts[5]); otherwise safe_list (row cleared, pruned pass 2)
-    const int* fz_cnt;                  // [nsplit][No_pad], null: not a fused pass
-    const float* fz_M0;
+    const int* fz_cnt;                  // [nsplit][No_pad] (tensor-core sweep), nullable
+    const unsigned int* fz_count;       // packed sweep: records written to the CutRecord list, and its capacity
+    unsigned int fz_count_cap;
+    const float* fz_M0;                 // null: not a fused pass
     int fz_cap;
     double fz_glog2;                    // log2 of the band's upper edge, less a margin
     unsigned char* fz_ok;               // [No_pad] out: 1 = histogram of the fused pass stands
@@ -801,12 +847,14 @@ __global__ void k_merge(MergeParams P) {
         P.M2[o] = (float)M;
         P.thr2[o] = (float)(M + P.log2_wt_thresh);
         bool fok = false;
-        if (P.fz_cnt && finite && precise) {
+        if (P.fz_M0 && finite && precise) {
             fok = (M - (double)P.fz_M0[o]) <= P.fz_glog2;
-            for (int s = 0; s < P.nsplit; ++s) {
-                const int c = P.fz_cnt[(size_t)s * P.No_pad + o];
-                if (c < 0 || c > P.fz_cap) fok = false;
-            }
+            if (P.fz_cnt)            // tensor-core sweep: per-thread record segments, frame changes
+                for (int s = 0; s < P.nsplit; ++s) {
+                    const int c = P.fz_cnt[(size_t)s * P.No_pad + o];
+                    if (c < 0 || c > P.fz_cap) fok = false;
+                }
+            if (P.fz_count && *P.fz_count > P.fz_count_cap) fok = false;      // packed sweep: one list, it must hold every record
         }
         if (P.fz_ok) P.fz_ok[o] = fok ? 1 : 0;
         if (fok) P.fuse_list[atomicAdd(&P.counts[5], 1)] = (int32_t)o;
@@ -949,6 +997,7 @@ struct CutFixParams {
     float* hist;
     int64_t hist_stride;
     unsigned int* changed;          // statistics
+    const unsigned char* ok;        // nullable: only the records of objects with ok[obj] != 0 (fused pass of the packed sweep)
 };
 
 __device__ __forceinline__ void cutfix_object(const CutFixParams& P, int obj, double* sx, double* sxe, double* sxm) {
@@ -981,6 +1030,7 @@ __global__ void k_exact_cut_fix(CutFixParams P) {
     const unsigned int n = min(*P.count, P.cap);
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const CutRecord r = P.list[i];
+        if (P.ok && !P.ok[r.obj]) continue;
         double sx[FZB_FAST_MAXF], sxe[FZB_FAST_MAXF], sxm[FZB_FAST_MAXF];
         cutfix_object(P, r.obj, sx, sxe, sxm);
         cutfix_apply(P, r.obj, r.model, r.weight, r.selected != 0, sx, sxe, sxm);
@@ -989,12 +1039,13 @@ __global__ void k_exact_cut_fix(CutFixParams P) {
 
 // ---- fused single pass: seed, float64 re-decision of the recorded band, clearing of the rows that take pass 2 -------
 // seed of the running cut: the pre-pass maximum (two partials: the two threads of an object), lowered by a margin
-__global__ void k_fuse_seed(const double* __restrict__ pM, int64_t No, int64_t No_pad, float* __restrict__ M0) {
+__global__ void k_fuse_seed(const double* __restrict__ pM, int64_t No, int64_t No_pad, float* __restrict__ M0, int nparts) {
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= No_pad) return;
     float v = -FLT_MAX;
     if (o < No) {
-        const double m = fmax(pM[o], pM[No_pad + o]);
+        double m = pM[o];
+        for (int s = 1; s < nparts; ++s) m = fmax(m, pM[(size_t)s * No_pad + o]);
         if (m > -1e30 && m < 1e30) v = (float)(m - 2e-4 - 1e-6 * fabs(m));
     }
     M0[o] = v;
@@ -1116,12 +1167,14 @@ struct RecParams {
     int Nf, mode, rec, mlo, packed, mm;
     const double* mask;     // model masks (MM)
     float* recs;
+    int stride;             // record p holds the model at sorted position p * stride (coarse set: pre-pass of the fused sweep)
 };
 
 __global__ void k_build_records(RecParams P) {
     int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P.nm) return;
-    int64_t j = P.perm[p];
+    const int64_t ps = p * P.stride;
+    int64_t j = P.perm[ps];
     float* r = P.recs + p * P.rec;
     {
         // packed layout (k_sweep2): every model value duplicated (v, v); fixed-scale modes store -m and -2*m_lo
@@ -1149,8 +1202,8 @@ __global__ void k_build_records(RecParams P) {
         }
         int tail = kmoff + (P.mm ? 2 * nf : 0);
         r[tail] = r[tail + 1] = P.lnprior ? (float)(P.lnprior[j] * 1.4426950408889634) : 0.f;
-        r[tail + 2] = r[tail + 3] = P.invnorm ? P.invnorm[p] : 0.f;
-        r[tail + 4] = __int_as_float(P.bins ? P.bins[p] : -1);
+        r[tail + 2] = r[tail + 3] = P.invnorm ? P.invnorm[ps] : 0.f;
+        r[tail + 4] = __int_as_float(P.bins ? P.bins[ps] : -1);
         int used = tail + 5;
         if (P.mm) r[used++] = __int_as_float(mbits);
         for (int i = used; i < P.rec; ++i) r[i] = 0.f;
@@ -1181,16 +1234,16 @@ int launch_sweep2_mm(fzb_context* h, const SweepParams& P, dim3 grid) {
     return 0;
 }
 
-template <int NF, int MODE, bool DP, bool MLO, int R, int PASS>
+template <int NF, int MODE, bool DP, bool MLO, int R, int PASS, bool FUSE = false>
 int launch_sweep2_t(fzb_context* h, const SweepParams& P, dim3 grid, bool prior) {
     constexpr int REC = rec2_floats(NF, MODE, MLO);
     size_t smem = (size_t)NSTAGE * TM * REC * sizeof(float) + NSTAGE * sizeof(uint64_t) + 128;
     if (prior) {
-        auto kern = k_sweep2<NF, MODE, DP, MLO, true, R, PASS>;
+        auto kern = k_sweep2<NF, MODE, DP, MLO, true, R, PASS, false, FUSE>;
         FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, ft2_of(R), smem, h->stream>>>(P);
     } else {
-        auto kern = k_sweep2<NF, MODE, DP, MLO, false, R, PASS>;
+        auto kern = k_sweep2<NF, MODE, DP, MLO, false, R, PASS, false, FUSE>;
         FZB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<grid, ft2_of(R), smem, h->stream>>>(P);
     }
@@ -1208,6 +1261,13 @@ int launch_sweep_r(fzb_context* h, const SweepParams& P, dim3 grid, int R, int p
             return (R == -4) ? launch_sweep2_mm<NF, MODE, DP, 4, 2>(h, P, grid)
                              : launch_sweep2_mm<NF, MODE, DP, 2, 2>(h, P, grid);
         }
+    }
+    if (pass == 3) {   // fused single pass: the default likelihood, four objects per thread
+        if constexpr (MODE == FM_FX1 && DP) {
+            if (R == -4 && P.obits == nullptr) return launch_sweep2_t<NF, MODE, DP, MLO, 4, 1, true>(h, P, grid, P.has_prior != 0);
+        }
+        fzb_set_error("fp32 path: no fused variant of this sweep");
+        return 2;
     }
     if (R < 0) {   // packed kernels: R = -objects per thread
         if (pass == 1) {
@@ -1383,9 +1443,19 @@ static int fast_prepare_mode(fzb_context* h, int mode) {
     R.nm = nm; R.Nf = nf; R.mode = mode; R.rec = F.rec; R.mlo = mlo ? 1 : 0; R.packed = packed ? 1 : 0;
     R.mm = mm ? 1 : 0; R.mask = h->models_mask.as<double>();
     R.recs = F.recs.as<float>();
+    R.stride = 1;
     k_build_records<<<(unsigned)((nm + 255) / 256), 256, 0, h->stream>>>(R);
     fzb_count_launch(h);
     FZB_CUDA(cudaGetLastError());
+    {   // every FZB_TC_COARSE-th model of the sorted order: the pre-pass of the fused sweeps
+        F.nm_coarse = (nm + FZB_TC_COARSE - 1) / FZB_TC_COARSE;
+        if (F.recs_coarse.reserve((size_t)F.nm_coarse * F.rec * sizeof(float) + 64)) return 1;
+        RecParams RC = R;
+        RC.nm = F.nm_coarse; RC.stride = FZB_TC_COARSE; RC.recs = F.recs_coarse.as<float>();
+        k_build_records<<<(unsigned)((F.nm_coarse + 255) / 256), 256, 0, h->stream>>>(RC);
+        fzb_count_launch(h);
+        FZB_CUDA(cudaGetLastError());
+    }
     {
         Rec64Params R6 = {};
         R6.m = R.m; R6.me = R.me; R6.lnprior = R.lnprior; R6.perm = R.perm; R6.bins = R.bins; R6.invnorm = R.invnorm;
@@ -1517,8 +1587,11 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     if (exact_cut && h->fast.cutlist.reserve((size_t)cut_cap * sizeof(CutRecord) + 64)) return 1;
     // fused single pass (tensor-core sweep, linear-domain form): coarse pre-pass + one sweep that also fills the
     // histogram; see k_sweep_tc<..., FUSE>
-    const bool fuse_on = use_tc && kde && cfg.use_wt_thresh && exact_cut && shard_mode == 0 && F.nm_coarse > 0 &&
-                         getenv("FZB_NO_FUSE") == nullptr;
+    const bool fuse_any = kde && cfg.use_wt_thresh && exact_cut && shard_mode == 0 && F.nm_coarse > 0 &&
+                          getenv("FZB_NO_FUSE") == nullptr;
+    const bool fuse_on = use_tc && fuse_any;
+    // packed sweep: the reference's default likelihood (fixed scale, model errors), four objects per thread, no model masks
+    const bool fuse_pk = !use_tc && packed && Robj == 4 && mode == FM_FX1 && cfg.dim_prior && h->mask_all_one && fuse_any;
     const int fz_cap = (int)std::max<int64_t>(8, std::min<int64_t>(64, 512 / npart));      // sub-batch records per thread
     const double fz_g = env_double("FZB_FUSE_BAND", 0.006);          // recorded band above the running cut, natural log units
     uint4* fz_rec = nullptr;
@@ -1529,12 +1602,12 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
     int32_t* snr_list[2] = {nullptr, nullptr};
     double *pS_c = nullptr, *pM_c = nullptr;
     int32_t* pbest_c = nullptr;
-    if (fuse_on) {
-        const size_t n_rec = (size_t)npart * chunk_pad * fz_cap * 48, n_cnt = (size_t)npart * chunk_pad * 4;
+    if (fuse_on || fuse_pk) {
+        const size_t n_rec = fuse_on ? (size_t)npart * chunk_pad * fz_cap * 48 : 0, n_cnt = (size_t)npart * chunk_pad * 4;
         const size_t n_c = (size_t)fzb_tc_split() * chunk_pad;
         if (F.fuse.reserve(n_rec + n_cnt + (size_t)chunk_pad * (4 + 4 + 1 + 8) + n_c * 20 + 1024)) return 1;
         fz_rec = F.fuse.as<uint4>();
-        pS_c = reinterpret_cast<double*>(fz_rec + (size_t)npart * chunk_pad * fz_cap * 3);
+        pS_c = reinterpret_cast<double*>(fz_rec + (fuse_on ? (size_t)npart * chunk_pad * fz_cap * 3 : 0));
         pM_c = pS_c + n_c;
         pbest_c = reinterpret_cast<int32_t*>(pM_c + n_c);
         fz_cnt = pbest_c + n_c;
@@ -1620,10 +1693,31 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         const int64_t tiles1 = (nc + tile_objs - 1) / tile_objs;
         int64_t nsafe = 0, nsafe64 = 0, nunsafe = 0, nfuse = 0;
         unsigned int fuse_recorded = 0;
-        const bool fuse = fuse_on && use_lin;
+        const bool fuse_t = fuse_on && use_lin;
+        const bool fuse = fuse_t || fuse_pk;
         if (shard_mode != 2) {
         FZB_CUDA(cudaEventRecord(h->ev[2], h->stream));
-        if (fuse) {
+        if (fuse_pk) {
+            // pre-pass over every FZB_TC_COARSE-th model (one split) -> seed of the running maximum
+            SweepParams SC = SP;
+            SC.recs = F.recs_coarse.as<float>(); SC.nm = F.nm_coarse; SC.tiles_per_split = (int)((F.nm_coarse + TM - 1) / TM);
+            SC.pM = pM_c; SC.pS = pS_c; SC.pbest = pbest_c; SC.live = nullptr;
+            if (launch_sweep(h, SC, dim3((unsigned)tiles1, 1u), nf, mode, cfg.dim_prior != 0, mlo, R, 1)) return 1;
+            k_fuse_seed<<<(unsigned)((nc_pad + 255) / 256), 256, 0, h->stream>>>(pM_c, nc, nc_pad, fz_M0, 1);
+            fzb_count_launch(h);
+            FZB_CUDA(cudaGetLastError());
+            FZB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nc_pad * hist_stride * 4, h->stream));
+            FZB_CUDA(cudaMemsetAsync(counts + 10, 0, 8, h->stream));
+            h->stats.pairs_fp32 += nc * F.nm_coarse;
+            // log2 domain: cut, and the recorded band from the fp32 error below it to exp(fz_g) above it
+            const double l2e = 1.4426950408889634, elo = env_double("FZB_EXACT_CUT_TOL", 3e-5) * l2e, ehi = fz_g * l2e;
+            SP.fz_M0 = fz_M0; SP.fz_thr = (float)std::log2(cfg.wt_thresh);
+            SP.fz_mid = (float)(std::log2(cfg.wt_thresh) + 0.5 * (ehi - elo)); SP.fz_half = (float)(0.5 * (ehi + elo));
+            SP.hist = hist; SP.hist_stride = hist_stride;
+            SP.ex_list = h->fast.cutlist.as<CutRecord>(); SP.ex_count = reinterpret_cast<unsigned int*>(counts + 10); SP.ex_cap = cut_cap;
+            if (launch_sweep(h, SP, dim3((unsigned)tiles1, (unsigned)nsplit), nf, mode, cfg.dim_prior != 0, mlo, R, 3)) return 1;
+            SP.ex_list = nullptr;
+        } else if (fuse) {
             // object lists of the two tile kinds (one list = all objects when the models are fp32-representable)
             int64_t nlist[2] = {0, nc};
             if (snr_split) {
@@ -1654,7 +1748,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                 if (fzb_launch_sweep_tc(h, SC, dim3((unsigned)((nlist[v] + tile_objs - 1) / tile_objs), 1u), nf, true, 1, true, vm, tl))
                     return 1;
             }
-            k_fuse_seed<<<(unsigned)((nc_pad + 255) / 256), 256, 0, h->stream>>>(pM_c, nc, nc_pad, fz_M0);
+            k_fuse_seed<<<(unsigned)((nc_pad + 255) / 256), 256, 0, h->stream>>>(pM_c, nc, nc_pad, fz_M0, fzb_tc_split());
             fzb_count_launch(h);
             FZB_CUDA(cudaGetLastError());
             FZB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nc_pad * hist_stride * 4, h->stream));
@@ -1700,7 +1794,8 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         MP.safe_list = safe_list; MP.unsafe_list = unsafe_list; MP.prec_list = use_sweep64 ? prec_list : nullptr;
         MP.safe64_list = safe64_list; MP.counts = counts;
         if (fuse) {
-            MP.fz_cnt = fz_cnt; MP.fz_M0 = fz_M0; MP.fz_cap = fz_cap; MP.fz_ok = fz_ok; MP.fuse_list = fuse_list;
+            MP.fz_cnt = fuse_t ? fz_cnt : nullptr; MP.fz_M0 = fz_M0; MP.fz_cap = fz_cap; MP.fz_ok = fz_ok; MP.fuse_list = fuse_list;
+            if (fuse_pk) { MP.fz_count = reinterpret_cast<unsigned int*>(counts + 10); MP.fz_count_cap = cut_cap; }
             MP.fz_glog2 = (fz_g - 1e-3) * 1.4426950408889634 - 4e-4;     // the seed's margin and the fp32 error of the weights
         }
         k_merge<<<(unsigned)((nc + 255) / 256), 256, 0, h->stream>>>(MP);
@@ -1715,7 +1810,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
         nsafe = hc[0];
         nfuse = fuse ? hc8[5] : 0;
         h->stats.objects_fused += nfuse;
-        MP.fz_cnt = nullptr; MP.fz_ok = nullptr;      // stage 1 (float64 sweep) routes as before
+        MP.fz_cnt = nullptr; MP.fz_ok = nullptr; MP.fz_M0 = nullptr;      // stage 1 (float64 sweep) routes as before
         const int64_t nprec = hc[2];
 
         // ---- objects whose fp32 result is not trusted: float64 sweep, pass 1 ---------------------------
@@ -1792,6 +1887,29 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                 k_fuse_clear_rows<<<(unsigned)nc, 256, 0, h->stream>>>(fz_ok, hist, hist_stride);
                 fzb_count_launch(h);
                 FZB_CUDA(cudaGetLastError());
+                if (fuse_pk && nfuse > 0) {
+                    // the band records of the fused pass (objects that keep their histogram only), before pass 2 reuses the list
+                    CutFixParams CA = {};
+                    CA.list = h->fast.cutlist.as<CutRecord>(); CA.count = reinterpret_cast<unsigned int*>(counts + 10);
+                    CA.cap = cut_cap; CA.x = PP.x; CA.xe = PP.xe; CA.xm = PP.xm;
+                    CA.m = h->models.as<double>(); CA.me = h->models_err.as<double>(); CA.mm = h->models_mask.as<double>();
+                    CA.lnprior = h->has_lnprior ? h->lnprior.as<double>() : nullptr;
+                    CA.perm = F.perm.as<int32_t>(); CA.bins = F.bins.as<int32_t>(); CA.invnorm = F.invnorm.as<float>();
+                    CA.lmap = lmap_local; CA.ln_wt_thresh = std::log(cfg.wt_thresh);
+                    CA.Nf = nf; CA.free_scale = cfg.free_scale; CA.ime = cfg.ignore_model_err != 0; CA.dim_prior = cfg.dim_prior;
+                    CA.hist = hist; CA.hist_stride = hist_stride; CA.changed = reinterpret_cast<unsigned int*>(counts + 13);
+                    CA.ok = fz_ok;
+                    FZB_CUDA(cudaMemsetAsync(counts + 13, 0, 4, h->stream));
+                    k_exact_cut_fix<<<h->sm_count * 8, 256, 0, h->stream>>>(CA);
+                    fzb_count_launch(h);
+                    FZB_CUDA(cudaGetLastError());
+                    unsigned int na[4] = {0, 0, 0, 0};
+                    FZB_CUDA(cudaMemcpyAsync(na, counts + 10, 16, cudaMemcpyDeviceToHost, h->stream));
+                    FZB_CUDA(cudaStreamSynchronize(h->stream));
+                    fuse_recorded = na[0];
+                    h->stats.cut_changed += na[3];
+                    FZB_CUDA(cudaMemsetAsync(counts + 10, 0, 8, h->stream));      // pass 2 (if any) starts its own list
+                }
             } else {
                 FZB_CUDA(cudaMemsetAsync(hist, 0, (size_t)nc_pad * hist_stride * 4, h->stream));
             }
@@ -1850,7 +1968,7 @@ int fzb_fast_fit_predict_dev(fzb_context* h, const double* d_x, const double* d_
                 fzb_count_launch(h);
                 FZB_CUDA(cudaGetLastError());
             }
-            if (nfuse > 0) {
+            if (nfuse > 0 && fuse_t) {
                 FuseFixParams FF = {};
                 CutFixParams& CF = FF.C;
                 CF.x = PP.x; CF.xe = PP.xe; CF.xm = PP.xm;

@@ -208,6 +208,40 @@ def test_knn_trees_that_are_not_alike(monkeypatch):
     assert st1["knn_redo"] > 0.3 * len(q) and st2["knn_redo"] <= 8, (st1["knn_redo"], st2["knn_redo"])
 
 
+def test_default_likelihood_fused_single_pass(monkeypatch):
+    """The reference's default likelihood (fixed scale, model errors, dim_prior) on a batch large enough for the fused single
+    pass of the packed sweep (>= 49,152 objects, four per thread): against the two-pass sweep on every object and against the
+    float64 kernels on a sub-sample; the counters say that the single pass carried most objects."""
+    import frankenz_b200 as fz
+    tr, tre, trm, ztr, x, xe, xm = bench_data.c5_dataset(98304, 120000, seed=77)     # dense enough for the coarse pre-pass;
+    # the host pipeline splits 120,000 objects into chunks of 61,440 (four objects per thread: fused) + 32,768 + 25,792
+    zgrid, sig = bench_data.c3_kde()
+    rdict = fz.pdf.PDFDict(zgrid, sig)
+    labe = np.full(len(tr), 0.05)
+    bf = fz.BruteForce(tr, tre, trm)
+    res = {}
+    for fused in (True, False):
+        if not fused:
+            monkeypatch.setenv("FZB_NO_FUSE", "1")
+        p, (lm, le) = bf.fit_predict(x.copy(), xe.copy(), xm.copy(), ztr, labe, label_dict=rdict, return_gof=True,
+                                     verbose=False, save_fits=False)
+        monkeypatch.delenv("FZB_NO_FUSE", raising=False)
+        res[fused] = (p, lm, le, bf.best_idx.copy(), bf._eng().stats())
+    (p1, lm1, le1, b1, st1), (p2, lm2, le2, b2, st2) = res[True], res[False]
+    assert st1["sweep_kind"] == 1 and st2["objects_fused"] == 0 and st1["objects_fused"] > 0.1 * len(x), (st1, st2)
+    assert st1["pairs_pass2"] < 0.95 * st2["pairs_pass2"], (st1["pairs_pass2"], st2["pairs_pass2"])
+    assert np.array_equal(b1, b2) and np.array_equal(lm1, lm2)
+    ok = np.isfinite(lm1)
+    assert np.max(np.abs(le1[ok] - le2[ok])) <= 2e-6 and np.max(np.sum(np.abs(p1[ok] - p2[ok]), axis=1)) <= 2e-6
+    sub = np.arange(0, len(x), 60)
+    p64, (lm64, le64) = bf.fit_predict(x[sub].copy(), xe[sub].copy(), xm[sub].copy(), ztr, labe, label_dict=rdict,
+                                       return_gof=True, verbose=False, save_fits=False, lprob_kwargs=dict(precision="fp64"))
+    good = np.isfinite(lm64)
+    assert np.max(np.sum(np.abs(p1[sub][good] - p64[good]), axis=1)) <= 1e-5
+    assert np.all(np.abs(lm1[sub][good] - lm64[good]) <= 1e-5 * np.maximum(1, np.abs(lm64[good])))
+    assert np.all(np.abs(le1[sub][good] - le64[good]) <= 1e-5 * np.maximum(1, np.abs(le64[good])))
+
+
 def test_float64_sweep_route_matches_generic(c3):
     """Fixed-scale fits of the C3 objects: most best-fit chi2 are far above the fp32 bound, so the objects take the
     register-tiled float64 sweep (k_sweep64).  Its PDFs must agree with the reference-order float64 kernel."""
