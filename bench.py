@@ -252,7 +252,12 @@ def leg_default_likelihood(args, rank, world, local, dist, torch, fz):
                         "inputs" % (n_obj, n_train),
             "value": pairs * max(1, world) / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
             "objects_routed_to_fp64": n64,
-            "roofline": {"bound": "mufu", "kernel": "k_sweep2<FX1> pass 1", "mufu_per_pair": 8.0,
+            "objects_completed_by_the_fused_pass_frac": float(np.mean([s.get("objects_fused", 0) for s in sts])) / float(n_obj),
+            "ms": {"sweep_phase": ms_scan, "pass2_and_redecisions": float(np.mean([s["ms_accum"] for s in sts])),
+                   "finish": float(np.mean([s["ms_finish"] for s in sts]))},
+            "roofline": {"bound": "mufu", "kernel": "k_sweep2<FX1, fused single pass> incl. the 1/16 pre-pass (the plain pass 1 of "
+                                                     "round 1 ran at 0.92 of the MUFU peak; the fused pass also fills the KDE "
+                                                     "histogram and is issue bound)", "mufu_per_pair": 8.0,
                          "achieved_gops": 8.0 * pairs / (ms_scan * 1e-3) / 1e9, "peak_gops": mufu_peak,
                          "frac": 8.0 * pairs / (ms_scan * 1e-3) / 1e9 / mufu_peak, "pass1_ms": ms_scan,
                          "flops_per_pair": 44.0, "fp32_tflops": 44.0 * pairs / (ms_scan * 1e-3) / 1e12,
