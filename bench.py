@@ -209,7 +209,11 @@ def leg_model_sharded(args, rank, world, local, dist, torch, fz):
             "independent_gpus_pairs_per_s": float(ts.item()), "efficiency_vs_independent_gpus": value / float(ts.item()),
             "parity_vs_unsharded": {"objects_checked": int(nsub), "pdf_l1_max": float(stat[0].item()),
                                     "lmap_rel_max": float(stat[1].item()), "levid_rel_max": float(stat[2].item()),
-                                    "best_index_mismatch_fraction": float(stat[3].item()), "bound": 1e-5,
+                                    "best_index_mismatch_fraction": float(stat[3].item()),
+                                    "best_index_note": "not a reference output; with dim_prior the log-posterior is flat at chi2 = "
+                                                       "Nband-2, so among 1M rows several lie within fp32 rounding of the maximum; the "
+                                                       "picks differ by <= 2e-7 in float64 log-posterior (tools/diag_shard_best.py)",
+                                    "bound": 1e-5,
                                     "ok": bool(stat[0].item() <= 1e-5 and stat[1].item() <= 1e-5 and stat[2].item() <= 1e-5)}}
 
 
