@@ -46,6 +46,9 @@ __device__ __forceinline__ void sm_bar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void sm_bar_expect(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void sm_bar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void sm_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sm_u32(dst)),
                  "l"(src), "r"(bytes), "r"(sm_u32(bar))
@@ -162,7 +165,7 @@ __host__ __device__ inline size_t summ_ring_doubles(int Ng, int LP, int nobj) {
 }
 __host__ __device__ inline size_t summ_smem_bytes(int Ng, int LP, int nobj) {
     return ((size_t)((Ng + 3) / 4 * 4) * nobj + summ_ring_doubles(Ng, LP, nobj) + (size_t)((Ng + CKS - 1) / CKS) * nobj +
-            (size_t)8 * nobj) * 8 + (size_t)2 * nobj * 4 + 2 * 8;
+            (size_t)8 * nobj) * 8 + (size_t)2 * nobj * 4 + 4 * 8;
 }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -194,12 +197,14 @@ __global__ void __launch_bounds__(ST2, 1) k_summarize(SummParams P) {
     int* s_imax = reinterpret_cast<int*>(s_pts + 5 * NOBJ);     // [NOBJ] (+ NOBJ spare)
     int* s_cnt = s_imax + NOBJ;                                 // [2]: GEMM warps that hold their fragments of the half
     uint64_t* full = reinterpret_cast<uint64_t*>(s_imax + 2 * NOBJ);   // [2]: the four rows of a half have landed
+    uint64_t* empty = full + 2;                                        // [2]: every GEMM warp holds its fragments of the half
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t ob = (int64_t)blockIdx.x * NOBJ;
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
             sm_bar_init(&full[s], 1);
+            sm_bar_init(&empty[s], GW * 32);
             s_cnt[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -286,12 +291,13 @@ __global__ void __launch_bounds__(ST2, 1) k_summarize(SummParams P) {
             const int t = 4 * j + lr;
 #pragma unroll
             for (int mb = 0; mb < NMB; ++mb) af[mb] = spdf[pidx<NOBJ>(t, mb * 8 + lq)];
+            sm_bar_arrive(&empty[h]);                           // every lane: its own reads of the half are done
             __syncwarp();
             if (lane == 0) {
-                __threadfence_block();
-                if (atomicAdd(&s_cnt[h], 1) == GW - 1) {        // the last warp to hold its fragments refills the half
-                    s_cnt[h] = 0;
-                    if (j + 2 < NK) {
+                if (atomicAdd(&s_cnt[h], 1) == GW - 1) {        // the last warp to hold its fragments refills the half:
+                    s_cnt[h] = 0;                               // every other warp arrived before it counted, so the
+                    if (j + 2 < NK) {                           // wait below returns at once (it is the acquire)
+                        sm_bar_wait(&empty[h], (uint32_t)(j >> 1) & 1u);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         issue(j + 2);
                     }
