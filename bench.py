@@ -568,6 +568,14 @@ def run_c3(ctx, grid, steps, e2e, cpu):
                     "objects_per_s": float(ne) * max(1, world) / ts, "summarize_ms_device": float(np.mean(ms_s)),
                     "call": "BruteForce.fit_predict(..., summarize=True, return_pdfs=False): fit + PDF + pdfs_summarize "
                             "on the device, point estimates / intervals / risks out"}
+        ms_dev = float(np.mean(ms_s))
+        if ms_dev > 0:
+            # k_summarize: the risk product pdf . (1 - kernel) is 2 Ng^2 flop per object in float64 on the FP64 tensor cores
+            tf = 2.0 * eng.Ng * eng.Ng * ne / (ms_dev * 1e-3) * 1e-12
+            res_summ["summarize_roofline"] = {
+                "kernel": "k_summarize (DMMA m8n8k4 risk product + numpy-order CDF / quantiles / estimators)", "bound": "fp64 tensor",
+                "achieved": tf, "peak": 37.1, "unit": "TFLOP/s", "frac": tf / 37.1,
+                "peak_source": "mma.sync.m8n8k4.f64 microbenchmark on B200 (tools/fp64_rate.cu: DMMA 37.1, DFMA 33.9 TFLOP/s)"}
 
     # ---- roofline of the dominant kernel (the fp32 sweep), measured live ------------------------------
     fp32_peak, mufu_peak = eng.measure_peaks(5)
