@@ -329,11 +329,12 @@ class Engine(object):
         if len(pgrid) != self.Ng or loss.shape != (self.Ng, self.Ng) or urand.shape != (no,):
             raise ValueError("summary tables do not match the PDF grid / the number of objects")
         pdfs = _out_array((no, self.Ng)) if want_pdf else None
-        lmap, levid = np.empty(no), np.empty(no)
+        # one recycled block for the 25 per-object float64 outputs (200 bytes per object): a fresh numpy.empty per array
+        # would be first-touched, page by page, by the download
+        blk = _page_pool.empty((25, no))
+        est, sd, conf, risk, quant = (blk[4 * i:4 * i + 4] for i in range(5))
+        mc, lmap, levid, bchi2, bscale = (blk[20 + i] for i in range(5))
         best = np.empty(no, dtype=np.int64)
-        bchi2, bscale = np.empty(no), np.empty(no)
-        est, sd, conf, risk, quant = (np.empty((4, no)) for _ in range(5))
-        mc = np.empty(no)
         _lib.check(self.lib.fzb_fit_predict_summarize(
             self.h, dptr(x), dptr(xe), dptr(xm), no, C.byref(cfg), dptr(pgrid), dptr(loss), dptr(urand),
             1 if renormalize else 0, float(wconf_frac), dptr(pdfs), dptr(lmap), dptr(levid), iptr(best), dptr(bchi2),

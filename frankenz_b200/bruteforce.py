@@ -209,7 +209,7 @@ class BruteForce(object):
             rstate = np.random
         nobj = len(data)
         urand = np.array([rstate.rand() for _ in range(nobj)]) if nobj < 64 else np.ascontiguousarray(rstate.rand(nobj))
-        loss = np.ascontiguousarray(1.0 - _pdf._loss_kernel(pgrid, pkern, pkern_grid), dtype=np.float64)
+        loss = _pdf._loss_matrix(pgrid, pkern, pkern_grid)
         summary, pdfs, lmap, levid, best, bchi2, bscale = eng.fit_predict_summarize(
             data, data_err, data_mask, cfg, pgrid, loss, urand, renormalize=renormalize, wconf_frac=wconf_frac,
             want_pdf=return_pdfs)
