@@ -753,7 +753,6 @@ static int fit_predict_host_impl(fzb_context* h, const double* data, const doubl
     int64_t c = 0;
     int64_t push_id[2] = {-1, -1};
     int64_t nc = 0;
-    FzbStats acc = {};
     for (int64_t o0 = 0; o0 < No; o0 += nc, ++c) {
         nc = next_chunk(No - o0);
         int b = pdfs ? (int)(c & 1) : 0;
@@ -1069,7 +1068,6 @@ int fzb_knn_fit_predict(fzb_handle h, const double* qfeats, const double* data, 
     double* d_lmap = h->out_f64[1].as<double>();
     double* d_levid = h->out_f64[2].as<double>();
     int64_t* d_nn_all = h->out_i64[1].as<int64_t>();
-    FzbStats acc = {};
     FZB_CUDA(cudaEventRecord(h->ev[0], h->stream));
     int64_t push_id[2] = {-1, -1};
     int64_t c = 0;
@@ -1106,7 +1104,6 @@ int fzb_knn_fit_predict(fzb_handle h, const double* qfeats, const double* data, 
     float ms = 0.f;
     FZB_CUDA(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
     h->stats.ms_total = ms;
-    (void)acc;
     return check_kde_error(h);
 }
 

@@ -145,3 +145,34 @@ def test_page_pool_recycles_buffers_only_when_every_view_is_gone():
     small = pool.empty((10, 10))
     assert small.base is None and pool.total == 2 * b.nbytes
     assert PagePool(max_bytes=0).empty((100000, 120)).base is None
+
+
+def test_loss_matrix_cache_is_keyed_by_kernel_and_grid():
+    """pdf._loss_matrix: named kernels on the default argument are cached per grid (read-only, most recent first, at
+    most 4); callables and user kernel grids are evaluated on every call like the reference does (pdf.py:1003-1023)."""
+    from frankenz_b200 import pdf
+    del pdf._LOSS_CACHE[:]
+    g = np.linspace(0., 6., 61)
+    a = pdf._loss_matrix(g, "lorentz", None)
+    assert np.array_equal(a, 1.0 - pdf._loss_kernel(g, "lorentz", None)) and not a.flags.writeable
+    assert pdf._loss_matrix(g.copy(), "lorentz", None) is a                   # same values, another array object
+    assert pdf._loss_matrix(g, "gaussian", None) is not a
+    g2 = g.copy()
+    g2[7] += 1e-9
+    b = pdf._loss_matrix(g2, "lorentz", None)
+    assert b is not a and not np.array_equal(a, b)
+    calls = []
+
+    def kern(x):
+        calls.append(1)
+        return np.exp(-np.abs(x))
+    pdf._loss_matrix(g, kern, None)
+    pdf._loss_matrix(g, kern, None)
+    assert len(calls) == 2
+    kg = np.subtract.outer(g, g)
+    assert pdf._loss_matrix(g, "tophat", kg) is not pdf._loss_matrix(g, "tophat", kg)
+    for i in range(6):
+        pdf._loss_matrix(g + i, "lorentz", None)
+    assert len(pdf._LOSS_CACHE) == 4
+    with pytest.raises(RuntimeError):
+        pdf._loss_matrix(g, "no such kernel", None)
