@@ -583,7 +583,9 @@ int fzb_summarize_impl(fzb_context* h, const double* pdfs, const double* pgrid, 
     double* o_quant = o_risk + 4 * No;
     double* o_mc = o_quant + 4 * No;
     double* o_sum = o_mc + No;
-    const int64_t chunk = std::max<int64_t>(32, std::min<int64_t>(No, ((int64_t)256 << 20) / ((int64_t)Ng * 8) / 32 * 32));
+    int64_t chunk = std::max<int64_t>(32, std::min<int64_t>(No, ((int64_t)256 << 20) / ((int64_t)Ng * 8) / 32 * 32));
+    const int64_t wave = (int64_t)std::max(1, h->sm_count) * 32;          // whole waves of one 32-object CTA per SM
+    if (chunk > wave) chunk = chunk / wave * wave;
     if (d_in.reserve((size_t)chunk * Ng * 8)) return 1;
     FZB_CUDA(cudaEventRecord(h->ev[0], h->stream));
     for (int64_t o0 = 0; o0 < No; o0 += chunk) {
