@@ -281,16 +281,16 @@ __global__ void __launch_bounds__(ST2, 1) k_summarize(SummParams P) {
             for (int nb = 0; nb < NNB; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
         const int lr = lane & 3, lq = lane >> 2;
         const int colbase = warp * 8 * NNB + lq;
+        double af[NMB];
+#pragma unroll
+        for (int mb = 0; mb < NMB; ++mb) af[mb] = spdf[pidx<NOBJ>(lr, mb * 8 + lq)];
         for (int j = 0; j < NK; ++j) {
             const int h = j & 1;
             sm_bar_wait(&full[h], (uint32_t)(j >> 1) & 1u);
             const double* rb = ring + (size_t)(h * 4 + lr) * RP + colbase;
-            double bf[NNB], af[NMB];
+            double bf[NNB];
 #pragma unroll
             for (int nb = 0; nb < NNB; ++nb) bf[nb] = rb[nb * 8];
-            const int t = 4 * j + lr;
-#pragma unroll
-            for (int mb = 0; mb < NMB; ++mb) af[mb] = spdf[pidx<NOBJ>(t, mb * 8 + lq)];
             sm_bar_arrive(&empty[h]);                           // every lane: its own reads of the half are done
             __syncwarp();
             if (lane == 0) {
@@ -303,10 +303,14 @@ __global__ void __launch_bounds__(ST2, 1) k_summarize(SummParams P) {
                     }
                 }
             }
+            // the PDF fragments of the next step do not wait for anything: they are loaded behind this step's DMMAs
+            const int tn = min(4 * (j + 1), 4 * (NK - 1)) + lr;
 #pragma unroll
-            for (int mb = 0; mb < NMB; ++mb)
+            for (int mb = 0; mb < NMB; ++mb) {
 #pragma unroll
                 for (int nb = 0; nb < NNB; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], af[mb], bf[nb]);
+                af[mb] = spdf[pidx<NOBJ>(tn, mb * 8 + lq)];
+            }
         }
     } else if (lane < NOBJ) {
         // ---- the one sequential piece, lane = object: the CDF in numpy.cumsum order, one checkpoint per CKS grid points
